@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py — coverage fwd+bwd point x pose evals/s (BASELINE.json metric) on N B200s of one node.
+
+Workload (config.workload): BASELINE config 4 — trajectory optimisation forward+backward,
+64 body waypoints x 5 cameras = 320 evaluated poses, 100M-point synthetic box cloud.  The cloud is
+point-sharded over the ranks (STRONG scaling: the total cloud is fixed, a rank holds N/G points);
+per step every rank runs pass A (per-pose min/max) -> NCCL MIN/MAX all-reduce -> pass B (fused
+log-odds fusion + gradient accumulators) -> NCCL SUM all-reduce -> O(W) epilogue -> torch chain
+rule through the multi-camera front end to the 64x4 body parameters.
+
+One JSON line on rank 0:
+  value       evals/s with the cloud resident in HBM (CUDA events, barrier + sync both sides, max over ranks)
+  e2e         same, through the public API with HOST (pinned) inputs: every step copies this rank's cloud
+              shard and the body parameters host->device and reads loss + gradients back
+  roofline    pass-B kernel (cov_traj_fused): algorithmic FP32 flops / CUDA-event duration vs the FP32 peak
+              (FMA probe measured live; nominal alongside), plus its HBM fraction
+  cpu_baseline  oracle/torch_port.py (torch CPU autograd port of the reference) on a bounded sample, N=1 only
+--impl reference times that CPU port alone (all host threads) on the same config/metric.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+# frozen algorithmic work constants
+FLOP_FWD, FLOP_BWD = 64, 86
+BYTES_PASS_A, BYTES_PASS_B = 12, 16          # per point: xyz read; xyz read + rewards written
+FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
+N_WAYPOINTS, N_CAMS = 64, 5
+N_POINTS_C4 = 100_000_000
+CHUNKS = 64                                   # cloud = 64 seeded chunks, so 1/2/4/8-rank clouds are identical
+BOX_LO, BOX_HI = (-10.0, -10.0, -1.0), (30.0, 30.0, 4.0)
+
+
+def body_waypoints(n=N_WAYPOINTS, length=35.0):
+    """Gentle S-curve, spacing >= 0.5 m (so wps_step = 1), yaw = path tangent."""
+    xs = np.linspace(0.0, length, n)
+    ys = 0.5 * xs + 0.3 * np.sin(xs) - 8.0
+    yaw = np.arctan2(0.5 + 0.3 * np.cos(xs), 1.0)
+    return torch.tensor(np.stack([xs - 5.0, ys, np.zeros(n), yaw], 1), dtype=torch.float32)
+
+
+def make_cloud_shard(n_total, rank, world, device):
+    per_chunk = n_total // CHUNKS
+    assert per_chunk * CHUNKS == n_total and CHUNKS % world == 0
+    lo = torch.tensor(BOX_LO, device=device)
+    hi = torch.tensor(BOX_HI, device=device)
+    own = range(rank * CHUNKS // world, (rank + 1) * CHUNKS // world)
+    out = torch.empty(per_chunk * len(own), 3, device=device)
+    g = torch.Generator(device=device)
+    for i, c in enumerate(own):
+        g.manual_seed(1000 + c)
+        out[i * per_chunk:(i + 1) * per_chunk] = torch.rand(per_chunk, 3, generator=g, device=device) * (hi - lo) + lo
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi SM clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.path = gpu_index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_rate(body, rig, steps, warmup, budget_s):
+    """evals/s of the torch-CPU port on a bounded sample of the same workload (all 320 poses, a
+    subsample of the cloud sized so the whole run takes about `budget_s` seconds)."""
+    from oracle import torch_port, coverage_oracle as orc
+    from trajectory_optimization_b200 import multicam
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    K = torch.from_numpy(orc.K_DEFAULT.copy())
+    with torch.no_grad():
+        t, q = multicam.camera_poses_from_body(body, rig)
+    P, Q = t.reshape(-1, 3).contiguous(), q.reshape(-1, 4).contiguous()
+    W = P.shape[0]
+    g = torch.Generator().manual_seed(1000)
+    lo, hi = torch.tensor(BOX_LO), torch.tensor(BOX_HI)
+
+    def cloud(n):
+        return torch.rand(n, 3, generator=g) * (hi - lo) + lo
+
+    # calibrate on a small sample, then size the real one (autograd keeps ~240 B per point per pose)
+    n_cal = 8000
+    pts = cloud(n_cal)
+    t0 = time.perf_counter()
+    torch_port.traj_step(pts, P, Q, K, orc.IMG_WIDTH, orc.IMG_HEIGHT)
+    rate_cal = n_cal * W / (time.perf_counter() - t0)
+    n = int(rate_cal * budget_s / ((steps + warmup) * W))
+    n = max(2000, min(n, 60_000))
+    pts = cloud(n)
+    for _ in range(warmup):
+        torch_port.traj_step(pts, P, Q, K, orc.IMG_WIDTH, orc.IMG_HEIGHT)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        torch_port.traj_step(pts, P, Q, K, orc.IMG_WIDTH, orc.IMG_HEIGHT)
+    dt = time.perf_counter() - t0
+    return dict(value=n * W * steps / dt, unit="point*pose evals/s", cores=threads, kind="port",
+                sample=f"{n} points x {W} poses, {steps} fwd+bwd steps of oracle/torch_port.py (torch {torch.__version__} "
+                       f"CPU autograd, {threads} threads), {dt / steps * 1e3:.0f} ms/step"), dt / steps
+
+
+def config_dict(n_total, world):
+    return {"workload": "c4: trajectory optimisation fwd+bwd, 64 waypoints x 5 cams = 320 poses, "
+                        f"{n_total / 1e6:g}M-point synthetic box cloud, point-sharded over {world} GPU(s)",
+            "n_points": n_total, "n_poses": N_WAYPOINTS * N_CAMS, "parallelism": f"points/{world}",
+            "l2_policy": "inputs larger than L2 (>=150 MB of points per rank streamed twice per step)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from trajectory_optimization_b200 import multicam
+    body, rig = body_waypoints(), multicam.ring_rig(N_CAMS)
+    base, ms = cpu_reference_rate(body, rig, args.steps, args.warmup, budget_s=90.0)
+    line = {"impl": "reference", "metric": "coverage fwd+bwd point*pose evals/s", "value": base["value"],
+            "unit": "point*pose evals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config_dict(args.points, args.gpus),
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": base["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--points", type=int, default=N_POINTS_C4, help="total cloud size (default: config 4)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    from trajectory_optimization_b200 import _lib, multicam, ops, tools
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    L = _lib.lib()
+    n_total = args.points
+    W = N_WAYPOINTS * N_CAMS
+    K, img_w, img_h = tools.load_intrinsics(dev)
+    rig = multicam.ring_rig(N_CAMS)
+    body0 = body_waypoints()
+    body = body0.to(dev).requires_grad_(True)
+    pts = make_cloud_shard(n_total, rank, world, dev)
+    n_local = pts.shape[0]
+
+    def step(points):
+        body.grad = None
+        t, q = multicam.camera_poses_from_body(body, rig)
+        rewards, mean = ops.coverage_traj(points, t.reshape(-1, 3), q.reshape(-1, 4), K, img_w, img_h,
+                                          n_total=n_total, group=group)
+        loss = 1.0 / (mean + 1e-6)
+        loss.backward()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- device-resident throughput (value) ----
+    for _ in range(args.warmup):
+        step(pts)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(lambda: step(pts), args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    value = n_total * W * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end: host (pinned) inputs in, loss + gradients out, every step ----
+    host_pts = torch.empty(pts.shape, dtype=torch.float32, pin_memory=True)
+    host_pts.copy_(pts)
+    host_body = torch.empty(body0.shape, dtype=torch.float32, pin_memory=True)
+    host_body.copy_(body0)
+    host_out = torch.empty(1 + body0.numel(), dtype=torch.float32, pin_memory=True)
+    dev_pts = torch.empty_like(pts)
+
+    def e2e_step():
+        dev_pts.copy_(host_pts, non_blocking=True)
+        with torch.no_grad():
+            body.copy_(host_body, non_blocking=True)
+        loss = step(dev_pts)
+        host_out[:1].copy_(loss.detach().reshape(1), non_blocking=True)
+        host_out[1:].copy_(body.grad.reshape(-1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e_value = n_total * W * args.steps / (ms_e2e * 1e-3)
+    h2d = host_pts.numel() * 4 * world + host_body.numel() * 4 * world
+    d2h = host_out.numel() * 4 * world
+
+    # ---- per-kernel timing for the roofline (pass B = cov_traj_fused, pass A = cov_traj_minmax) ----
+    import ctypes
+    with torch.no_grad():
+        t, q = multicam.camera_poses_from_body(body, rig)
+    P, Q = t.reshape(-1, 3).contiguous(), q.reshape(-1, 4).contiguous()
+    cam = _lib.camera(img_w, img_h, 1.0, 5.0, 1e-6)
+    minmax = torch.empty(2 * W, device=dev)
+    acc = torch.empty(W * _lib.ACC_STRIDE + 1, dtype=torch.float64, device=dev)
+    rewards = torch.empty(n_local, device=dev)
+    wsb = L.cov_traj_workspace_bytes(n_local, W)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def pass_a():
+        _lib.check(L.cov_traj_minmax(pts.data_ptr(), n_local, P.data_ptr(), Q.data_ptr(), W, K.data_ptr(),
+                                     ctypes.byref(cam), minmax.data_ptr(), stream), "cov_traj_minmax")
+
+    def pass_b():
+        _lib.check(L.cov_traj_fused(pts.data_ptr(), n_local, P.data_ptr(), Q.data_ptr(), W, K.data_ptr(),
+                                    ctypes.byref(cam), minmax.data_ptr(), None, rewards.data_ptr(), acc.data_ptr(),
+                                    ws.data_ptr(), wsb, stream), "cov_traj_fused")
+
+    pass_a()
+    if group is not None:
+        dist.all_reduce(minmax[:W], op=dist.ReduceOp.MIN)
+        dist.all_reduce(minmax[W:], op=dist.ReduceOp.MAX)
+    pass_b()
+    reps = max(3, min(args.steps, 10))
+    ms_a = timed(pass_a, reps) / reps
+    ms_b = timed(pass_b, reps) / reps
+    gated = float((rewards != 0.5).float().mean().item())  # fraction of points with at least one gated pose
+
+    # FP32 / MUFU probes (measured peak for the roofline denominator)
+    sink = torch.zeros(1, device=dev)
+    iters = 4096
+    L.cov_probe_fma(iters, sink.data_ptr(), stream)
+    L.cov_probe_ex2(iters, sink.data_ptr(), stream)
+    n_fma = [0]
+    n_ex2 = [0]
+    ms_fma = timed(lambda: n_fma.__setitem__(0, L.cov_probe_fma(iters, sink.data_ptr(), stream)), 3) / 3
+    ms_ex2 = timed(lambda: n_ex2.__setitem__(0, L.cov_probe_ex2(iters, sink.data_ptr(), stream)), 3) / 3
+    fp32_meas = 2.0 * n_fma[0] / (ms_fma * 1e-3) / 1e12
+    mufu_meas = n_ex2[0] / (ms_ex2 * 1e-3) / 1e12
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    evals_local = n_local * W
+    flops_b = evals_local * FLOP_FWD  # pass B does one forward per pair; the gated backward (<1 % of pairs) is not counted
+    achieved_tf = flops_b / (ms_b * 1e-3) / 1e12
+    roofline = {
+        "kernel": "cov_traj_fused_kernel (pass B: fused log-odds forward + gated gradient accumulators)",
+        "bound": "fp32", "achieved": achieved_tf, "peak": fp32_meas, "unit": "TFLOP/s", "frac": achieved_tf / fp32_meas,
+        "peak_source": "FP32 FMA probe measured live in this run (cov_probe_fma); MEASURED_PEAKS.json has no FP32 entry",
+        "peak_nominal": FP32_NOMINAL_TFLOPS, "frac_of_nominal": achieved_tf / FP32_NOMINAL_TFLOPS,
+        "flop_per_eval": FLOP_FWD, "ms_per_launch": ms_b, "traffic": None,
+        "hbm": {"achieved": n_local * BYTES_PASS_B / (ms_b * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": n_local * BYTES_PASS_B / (ms_b * 1e-3) / 1e9 / hbm_peak,
+                "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s"},
+        "mufu_T_per_s_measured": mufu_meas, "mufu_per_eval": 3,
+        "pass_a": {"kernel": "cov_traj_minmax_kernel", "ms_per_launch": ms_a,
+                   "achieved": evals_local * FLOP_FWD / (ms_a * 1e-3) / 1e12,
+                   "frac": evals_local * FLOP_FWD / (ms_a * 1e-3) / 1e12 / fp32_meas},
+        "points_with_gated_pose_frac": gated,
+    }
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu_baseline, _ = cpu_reference_rate(body0, rig, steps=3, warmup=1, budget_s=20.0)
+    line = {"metric": "coverage fwd+bwd point*pose evals/s", "value": value, "unit": "point*pose evals/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(n_total, world), "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "point*pose evals/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": 5 * args.steps,  # per step: minmax_init, minmax, fused, reduce, epilogue
+            "roofline": roofline, "cpu_baseline": cpu_baseline}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

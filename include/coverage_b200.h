@@ -1,0 +1,142 @@
+/*
+ * coverage_b200.h — C ABI of libcovb200.so: the B200 (sm_100a) implementation of the
+ * differentiable visibility/coverage hot path of ctu-vras/trajectory_optimization.
+ *
+ * Conventions (all entry points):
+ *   - plain C: pointers, sizes and scalars only; no C++/torch types cross the boundary;
+ *   - `const float* x_dev` / `*_dev` arguments are DEVICE pointers, everything else is by value;
+ *   - the caller owns every buffer (outputs, accumulators, workspace); the library never
+ *     allocates or frees device memory, never synchronises the device and launches only on
+ *     the stream passed as `stream` (a cudaStream_t cast to void*; NULL = legacy default);
+ *   - return value 0 = success, negative = COV_ERR_*; cov_last_error() returns a
+ *     thread-local message for the most recent failure on the calling thread;
+ *   - re-entrant: no global mutable state besides that thread-local string.
+ *   - quaternions are (w, x, y, z), unnormalised (the kernels apply F.normalize, eps 1e-12);
+ *     point clouds are row-major (N,3) fp32, 16-byte aligned (COV_ERR_ALIGN otherwise).
+ *
+ * "ref:" lines cite the reference interface each entry point replaces
+ * (paths relative to the reference repository root).
+ */
+#ifndef COVERAGE_B200_H
+#define COVERAGE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define COV_OK 0
+#define COV_ERR_ARG (-1)         /* null pointer / negative size / bad enum            */
+#define COV_ERR_UNSUPPORTED (-2) /* pose count exceeds what fits in shared memory      */
+#define COV_ERR_WORKSPACE (-3)   /* workspace too small                                */
+#define COV_ERR_CUDA (-4)        /* a CUDA runtime call or launch failed               */
+#define COV_ERR_ALIGN (-5)       /* a device pointer is not 16-byte aligned            */
+
+/* Layout of the per-pose accumulator rows produced by cov_traj_fused (doubles). */
+#define COV_ACC_STRIDE 22 /* [0..2] F, [3..5] T, [6] sum e, [7] sum e*p, [8..13] argmax F,T, [14] #argmax, \
+                             [15..20] argmin F,T, [21] #argmin                                              */
+#define COV_POSE_ACC 8    /* cov_pose_fused: [0] sum m, [1..3] F, [4..6] T, [7] unused                      */
+
+/* Camera / mask constants shared by every coverage entry point.
+ * ref: src/model.py:13-47 (get_dist_mask, get_fov_mask), src/model.py:93-94 (eps, pc_clip_limits). */
+typedef struct cov_camera {
+    float img_width;  /* pairs with u = h0/(h2+eps)  (1232 in src/tools.py:321) */
+    float img_height; /* pairs with v = h1/(h2+eps)  (1616)                     */
+    float min_dist;   /* Gaussian distance mask: mu = (min+max)/2, sigma = (max-min)/2 */
+    float max_dist;
+    float eps;        /* 1e-6 in the reference */
+} cov_camera;
+
+int cov_version(void);
+const char* cov_last_error(void);
+/* Number of SMs of the current device and bytes of opt-in shared memory per block (0 on failure). */
+int cov_device_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * ModelPose: obs_j = dist_mask * fov_mask [* weight_j];  sum = sum_j obs_j; d(sum)/d(pose).
+ * ref: src/model.py:98-127 (ModelPose.forward/criterion), :50-57 (to_camera_frame).
+ * One pass over the cloud: 12 B/point read (+4 B weight) + 4 B/point written.
+ *   xyz_dev      (n,3) fp32              weight_dev  (n) fp32 or NULL (hpr mask / upstream grad)
+ *   trans_dev    3 fp32                  quat_dev    4 fp32 (w,x,y,z)       K_dev 9 fp32 row-major
+ *   obs_dev      (n) fp32 out or NULL    acc_dev     COV_POSE_ACC doubles out (this shard's sums)
+ * ------------------------------------------------------------------------------------------ */
+size_t cov_pose_workspace_bytes(int64_t n);
+int cov_pose_fused(const float* xyz_dev, int64_t n, const float* weight_dev, const float* trans_dev,
+                   const float* quat_dev, const float* K_dev, const cov_camera* cam, float* obs_dev,
+                   double* acc_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+/* O(1) epilogue on the (all-reduced) accumulators:
+ * out_dev[0] = sum, out_dev[1..3] = d sum/d trans, out_dev[4..7] = d sum/d quat (raw, unnormalised). */
+int cov_pose_epilogue(const double* acc_dev, const float* trans_dev, const float* quat_dev, float* out_dev,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * ModelTraj visibility term over W evaluated poses (the caller applies the wps_step selection).
+ * ref: src/model.py:200-242 (ModelTraj.forward), :244-246 (criterion 'vis').
+ * Pass A  cov_traj_minmax : per-pose min_j m_jw / max_j m_jw              (12 B/point)
+ *         -> all-reduce MIN / MAX across ranks when the cloud is sharded
+ * Pass B  cov_traj_fused  : rewards_j = sigmoid(sum_w logit(clip(p_jw))) and the shard-additive
+ *         gradient accumulators (COV_ACC_STRIDE doubles per pose + 1 trailing sum of rewards)
+ *         (12 B/point read + 4 B/point written)
+ *         -> all-reduce SUM across ranks
+ * Epilogue cov_traj_epilogue: mean reward and d(mean)/d(poses, quats).
+ *   poses_dev (W,3) fp32, quats_dev (W,4) fp32, minmax_dev 2*W fp32: [0,W) minima, [W,2W) maxima
+ *   upstream_dev: NULL (gradient of mean(rewards)) or (n) fp32 d(loss)/d(rewards_j)
+ * ------------------------------------------------------------------------------------------ */
+int cov_traj_max_poses(void);
+size_t cov_traj_workspace_bytes(int64_t n, int n_poses);
+int cov_traj_minmax(const float* xyz_dev, int64_t n, const float* poses_dev, const float* quats_dev, int n_poses,
+                    const float* K_dev, const cov_camera* cam, float* minmax_dev, void* stream);
+int cov_traj_fused(const float* xyz_dev, int64_t n, const float* poses_dev, const float* quats_dev, int n_poses,
+                   const float* K_dev, const cov_camera* cam, const float* minmax_dev, const float* upstream_dev,
+                   float* rewards_dev, double* acc_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+/* out_dev: [0] mean reward, then (W,3) d/d poses, then (W,4) d/d quats  (1 + 7*W floats).
+ * With upstream_mode != 0 the gradients are those of sum_j upstream_j * rewards_j (no 1/N). */
+int cov_traj_epilogue(const double* acc_dev, const float* minmax_dev, const float* quats_dev, int n_poses,
+                      int64_t n_total, int upstream_mode, float* out_dev, void* stream);
+
+/* Forward-only candidate sweep: n_traj trajectories x poses_per_traj poses each, sharing one cloud.
+ * ref: no reference implementation (BASELINE config 5); semantics = ModelTraj.forward per trajectory
+ * with every pose evaluated.  sum_rewards_dev[t] += sum_j rewards_j(t) over this shard (doubles,
+ * zero it first); minmax_dev is (2, n_traj*poses_per_traj) produced by cov_traj_minmax. */
+int cov_sweep_rewards(const float* xyz_dev, int64_t n, const float* poses_dev, const float* quats_dev, int n_traj,
+                      int poses_per_traj, const float* K_dev, const cov_camera* cam, const float* minmax_dev,
+                      double* sum_rewards_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Binary frustum cull.  ref: src/tools.py:176-187 (get_cam_frustum_pts), src/model.py:34-39.
+ *   xyz_dev (n,3) camera-frame points (row-major; the Python wrapper accepts the reference's 3xN).
+ *   dist_mask_dev, fov_mask_dev: (n) uint8 out;  idx_dev: (n) int32 out, first *count entries valid,
+ *   ascending;  count_dev: int64 out.
+ * ------------------------------------------------------------------------------------------ */
+size_t cov_cull_workspace_bytes(int64_t n);
+int cov_frustum_cull(const float* xyz_dev, int64_t n, const float* K_dev, float img_width, float img_height,
+                     float min_dist, float max_dist, uint8_t* dist_mask_dev, uint8_t* fov_mask_dev,
+                     int32_t* idx_dev, int64_t* count_dev, void* workspace_dev, size_t workspace_bytes,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Katz hidden-point removal.  ref: src/tools.py:38-53 (sphericalFlip), :56-64 (convexHull),
+ * :67-85 (hidden_pts_removal).
+ *   cov_hpr_flip: fp32, every operation rounded in the reference's order; radius_dev (1 fp32) out.
+ *   cov_hpr_hull: vertex set of conv(flipped U {0}) with exact decisions; writes vertex_mask (n) uint8
+ *   (1 = hull vertex), origin_is_vertex (1 int32) and uncertified (1 int32: points whose
+ *   floating-point certificate failed and were decided by the exact fallback).
+ * ------------------------------------------------------------------------------------------ */
+int cov_hpr_flip(const float* xyz_dev, int64_t n, float scale /* 10**param */, float* flipped_dev,
+                 float* radius_dev, void* stream);
+size_t cov_hpr_hull_workspace_bytes(int64_t n);
+int cov_hpr_hull(const float* flipped_dev, int64_t n, uint8_t* vertex_mask_dev, int32_t* info_dev,
+                 void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* FP32 FMA / MUFU.EX2 throughput probes used by bench.py for the roofline denominators.
+ * Each runs `iters` dependent-chain iterations on a full grid and writes a checksum; the caller
+ * times them with CUDA events.  Returns the number of FMA (or ex2) operations issued. */
+int64_t cov_probe_fma(int iters, float* sink_dev, void* stream);
+int64_t cov_probe_ex2(int iters, float* sink_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COVERAGE_B200_H */

@@ -126,3 +126,31 @@ def test_sample_known_answers():
     assert int(t["out_wps_step"]) == 2
     assert abs(float(t["out_loss"]) - 6.954090595) < 1e-6
     assert abs(float(t["out_rewards"].mean()) - 0.5291025043) < 1e-7
+
+
+@pytest.mark.parametrize("name", ["traj_box", "traj_compact"])
+def test_torch_port_matches_reference(name):
+    """oracle/torch_port.py (the CPU baseline bench.py times) reproduces the reference's numbers."""
+    import torch
+    from oracle import torch_port
+    g = load_golden(name)
+    step = int(g["out_wps_step"])
+    K = torch.from_numpy(orc.K_DEFAULT.copy())
+    poses, quats = torch.from_numpy(g["in_poses"][::step].copy()), torch.from_numpy(g["in_quats"][::step].copy())
+    vis, gp, gq = torch_port.traj_step(torch.from_numpy(g["in_points"]), poses, quats, K, IMG_W, IMG_H)
+    assert rel_err(vis.item(), g["out_vis"]) < 1e-6
+    assert rel_err(gp.numpy(), g["out_gv_poses"][::step]) < 1e-5
+    assert rel_err(gq.numpy(), g["out_gv_quats"][::step]) < 1e-5
+
+
+def test_torch_port_pose_matches_reference(sample_inputs):
+    import torch
+    from oracle import torch_port
+    g = load_golden("pose_sample")
+    t = torch.from_numpy(g["in_trans"]).requires_grad_(True)
+    q = torch.from_numpy(g["in_quat"]).requires_grad_(True)
+    loss, obs = torch_port.pose_loss(torch.from_numpy(sample_inputs["pts"]), t, q, torch.from_numpy(orc.K_DEFAULT.copy()),
+                                     IMG_W, IMG_H)
+    loss.backward()
+    assert rel_err(loss.item(), g["out_loss"]) < 1e-6 and rel_err(obs.detach().numpy(), g["out_obs"]) < 1e-6
+    assert rel_err(t.grad.numpy(), g["out_g_trans"]) < 1e-5 and rel_err(q.grad.numpy(), g["out_g_quat"]) < 1e-5

@@ -1,0 +1,78 @@
+"""ctypes binding of libcovb200.so (C ABI: include/coverage_b200.h).
+
+The library is built in-tree by `csrc/build.sh` (or `__graft_entry__.build()`); it is never
+pip-installed.  Loading is lazy so that importing the package works on a box without the
+build, but every op calls `lib()` and therefore fails loudly when the library is missing.
+"""
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcovb200.so")
+_lock = threading.Lock()
+_lib = None
+
+ACC_STRIDE = 22   # COV_ACC_STRIDE
+POSE_ACC = 8      # COV_POSE_ACC
+
+
+class Camera(C.Structure):
+    """struct cov_camera."""
+    _fields_ = [("img_width", C.c_float), ("img_height", C.c_float), ("min_dist", C.c_float),
+                ("max_dist", C.c_float), ("eps", C.c_float)]
+
+
+_vp, _i64, _int, _f, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_size_t
+_cam = C.POINTER(Camera)
+
+# name -> (restype, argtypes); must list every symbol include/coverage_b200.h declares
+PROTOTYPES = {
+    "cov_version": (_int, []),
+    "cov_last_error": (C.c_char_p, []),
+    "cov_device_sm_count": (_int, []),
+    "cov_pose_workspace_bytes": (_sz, [_i64]),
+    "cov_pose_fused": (_int, [_vp, _i64, _vp, _vp, _vp, _vp, _cam, _vp, _vp, _vp, _sz, _vp]),
+    "cov_pose_epilogue": (_int, [_vp, _vp, _vp, _vp, _vp]),
+    "cov_traj_max_poses": (_int, []),
+    "cov_traj_workspace_bytes": (_sz, [_i64, _int]),
+    "cov_traj_minmax": (_int, [_vp, _i64, _vp, _vp, _int, _vp, _cam, _vp, _vp]),
+    "cov_traj_fused": (_int, [_vp, _i64, _vp, _vp, _int, _vp, _cam, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "cov_traj_epilogue": (_int, [_vp, _vp, _vp, _int, _i64, _int, _vp, _vp]),
+    "cov_sweep_rewards": (_int, [_vp, _i64, _vp, _vp, _int, _int, _vp, _cam, _vp, _vp, _vp]),
+    "cov_cull_workspace_bytes": (_sz, [_i64]),
+    "cov_frustum_cull": (_int, [_vp, _i64, _vp, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "cov_hpr_flip": (_int, [_vp, _i64, _f, _vp, _vp, _vp]),
+    "cov_hpr_hull_workspace_bytes": (_sz, [_i64]),
+    "cov_hpr_hull": (_int, [_vp, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "cov_probe_fma": (_i64, [_int, _vp, _vp]),
+    "cov_probe_ex2": (_i64, [_int, _vp, _vp]),
+}
+
+
+def lib():
+    """The loaded library; raises RuntimeError if it has not been built."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        f"{LIB_PATH} not found: build it with trajectory_optimization_b200/csrc/build.sh "
+                        "(there is no CPU or PyTorch fallback for the coverage ops)")
+                handle = C.CDLL(LIB_PATH)
+                for name, (res, args) in PROTOTYPES.items():
+                    fn = getattr(handle, name)
+                    fn.restype, fn.argtypes = res, args
+                _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().cov_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def camera(img_width, img_height, min_dist, max_dist, eps):
+    return Camera(float(img_width), float(img_height), float(min_dist), float(max_dist), float(eps))

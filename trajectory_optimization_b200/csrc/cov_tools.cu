@@ -1,0 +1,173 @@
+// cov_tools.cu — binary frustum cull with ordered stream compaction, and the fp32 spherical flip.
+//
+// Cull (reference src/tools.py:176-187, src/model.py:34-39): h = K p evaluated as the fma chain
+// k0*x, +k1*y, +k2*z; u = h0/h2, v = h1/h2 with IEEE division; strict comparisons.  Index set and
+// order are exactly those of torch's boolean-mask gather.  Three small kernels: flags + per-block
+// counts, scan of the block counts, ordered scatter.  24 B/point.
+//
+// Flip (reference src/tools.py:38-53): n = sqrtf(fma(z,z,fma(y,y,x*x))) (= torch CPU linalg.norm),
+// R = max n * 10^param, f = (2*((R-n)*p))/n + p with every operation rounded to fp32 in that order.
+#include "cov_common.cuh"
+#include "../../include/coverage_b200.h"
+
+namespace {
+
+constexpr int kCullBlock = 256;
+
+__device__ __forceinline__ void cull_tests(const float* __restrict__ xyz, int64_t j, const float* k, float wlim,
+                                           float hlim, float min_d, float max_d, bool& dm, bool& fm) {
+    const float x = xyz[j * 3], y = xyz[j * 3 + 1], z = xyz[j * 3 + 2];
+    dm = (z > min_d) && (z < max_d);
+    const float h0 = __fmaf_rn(k[2], z, __fmaf_rn(k[1], y, __fmul_rn(k[0], x)));
+    const float h1 = __fmaf_rn(k[5], z, __fmaf_rn(k[4], y, __fmul_rn(k[3], x)));
+    const float h2 = __fmaf_rn(k[8], z, __fmaf_rn(k[7], y, __fmul_rn(k[6], x)));
+    const float u = __fdiv_rn(h0, h2), v = __fdiv_rn(h1, h2);
+    fm = (h2 > 0.f) && (u > 1.f) && (u < wlim) && (v > 1.f) && (v < hlim);
+}
+
+__global__ void __launch_bounds__(kCullBlock)
+cull_flags_kernel(const float* __restrict__ xyz, int64_t n, const float* __restrict__ K9, float wlim, float hlim,
+                  float min_d, float max_d, uint8_t* __restrict__ dmask, uint8_t* __restrict__ fmask,
+                  int* __restrict__ block_counts) {
+    __shared__ float k[9];
+    if (threadIdx.x < 9) k[threadIdx.x] = K9[threadIdx.x];
+    __syncthreads();
+    const int64_t j = (int64_t)blockIdx.x * kCullBlock + threadIdx.x;
+    bool dm = false, fm = false;
+    if (j < n) {
+        cull_tests(xyz, j, k, wlim, hlim, min_d, max_d, dm, fm);
+        dmask[j] = dm;
+        fmask[j] = fm;
+    }
+    const int c = __syncthreads_count(dm && fm);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = c;
+}
+
+// exclusive scan of block_counts in place (one block); total -> count_out
+__global__ void __launch_bounds__(1024) cull_scan_kernel(int* __restrict__ block_counts, int64_t nblocks,
+                                                          int64_t* __restrict__ count_out) {
+    __shared__ long long sh[1024];
+    const int t = threadIdx.x;
+    const int64_t per = (nblocks + 1023) / 1024;
+    const int64_t lo = (int64_t)t * per, hi = (lo + per < nblocks) ? lo + per : nblocks;
+    long long s = 0;
+    for (int64_t i = lo; i < hi; ++i) s += block_counts[i];
+    sh[t] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan
+        long long v = (t >= o) ? sh[t - o] : 0;
+        __syncthreads();
+        sh[t] += v;
+        __syncthreads();
+    }
+    long long run = sh[t] - s;
+    for (int64_t i = lo; i < hi; ++i) {
+        const int c = block_counts[i];
+        block_counts[i] = (int)run;  // < 2^31 points kept per call (idx is int32)
+        run += c;
+    }
+    if (t == 1023) *count_out = sh[1023];
+}
+
+__global__ void __launch_bounds__(kCullBlock)
+cull_scatter_kernel(const uint8_t* __restrict__ dmask, const uint8_t* __restrict__ fmask, int64_t n,
+                    const int* __restrict__ block_offsets, int32_t* __restrict__ idx) {
+    __shared__ int warp_off[kCullBlock / 32];
+    const int64_t j = (int64_t)blockIdx.x * kCullBlock + threadIdx.x;
+    const bool keep = (j < n) && dmask[j] && fmask[j];
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) warp_off[warp] = __popc(bal);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int i = 0; i < kCullBlock / 32; ++i) {
+            const int c = warp_off[i];
+            warp_off[i] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    if (keep) idx[block_offsets[blockIdx.x] + warp_off[warp] + __popc(bal & ((1u << lane) - 1u))] = (int32_t)j;
+}
+
+__device__ __forceinline__ float flip_norm(float x, float y, float z) {
+    return __fsqrt_rn(__fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x))));
+}
+
+__global__ void __launch_bounds__(256) flip_maxnorm_kernel(const float* __restrict__ xyz, int64_t n,
+                                                            unsigned* __restrict__ max_bits) {
+    float mx = 0.f;
+    for (int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x; j < n; j += (int64_t)gridDim.x * 256)
+        mx = fmaxf(mx, flip_norm(xyz[j * 3], xyz[j * 3 + 1], xyz[j * 3 + 2]));
+    const unsigned w = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));
+    if ((threadIdx.x & 31) == 0) atomicMax(max_bits, w);
+}
+
+__global__ void __launch_bounds__(256) flip_apply_kernel(const float* __restrict__ xyz, int64_t n, float scale,
+                                                          float* __restrict__ radius_io, float* __restrict__ out) {
+    const float radius = __fmul_rn(radius_io[1], scale);  // radius_io[1] = max norm, [0] = radius (written below)
+    for (int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x; j < n; j += (int64_t)gridDim.x * 256) {
+        const float p[3] = {xyz[j * 3], xyz[j * 3 + 1], xyz[j * 3 + 2]};
+        const float nr = flip_norm(p[0], p[1], p[2]);
+        const float rn = __fsub_rn(radius, nr);
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            out[j * 3 + c] = __fadd_rn(__fdiv_rn(__fmul_rn(2.f, __fmul_rn(rn, p[c])), nr), p[c]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) radius_io[0] = radius;
+}
+
+}  // namespace
+
+extern "C" size_t cov_cull_workspace_bytes(int64_t n) {
+    const int64_t nb = (n + kCullBlock - 1) / kCullBlock + 1;
+    return (size_t)nb * sizeof(int);
+}
+
+extern "C" int cov_frustum_cull(const float* xyz, int64_t n, const float* K, float img_width, float img_height,
+                                float min_dist, float max_dist, uint8_t* dmask, uint8_t* fmask, int32_t* idx,
+                                int64_t* count, void* ws, size_t ws_bytes, void* stream) {
+    if (n < 0 || !K || !count || (n > 0 && (!xyz || !dmask || !fmask || !idx || !ws))) {
+        cov_set_error("cov_frustum_cull: null pointer or negative n");
+        return COV_ERR_ARG;
+    }
+    if (n >= (int64_t)1 << 31) {
+        cov_set_error("cov_frustum_cull: n >= 2^31 not supported (int32 indices)");
+        return COV_ERR_UNSUPPORTED;
+    }
+    if (ws_bytes < cov_cull_workspace_bytes(n)) {
+        cov_set_error("cov_frustum_cull: workspace too small");
+        return COV_ERR_WORKSPACE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0) {
+        cudaMemsetAsync(count, 0, sizeof(int64_t), s);
+        return cov_check_launch("cov_frustum_cull");
+    }
+    const int64_t nb = (n + kCullBlock - 1) / kCullBlock;
+    int* counts = (int*)ws;
+    // the comparisons `u < img_width - 1` are against the fp32 value of the Python float (exact for integers)
+    cull_flags_kernel<<<(unsigned)nb, kCullBlock, 0, s>>>(xyz, n, K, (float)((double)img_width - 1.0),
+                                                         (float)((double)img_height - 1.0), min_dist, max_dist, dmask,
+                                                         fmask, counts);
+    cull_scan_kernel<<<1, 1024, 0, s>>>(counts, nb, count);
+    cull_scatter_kernel<<<(unsigned)nb, kCullBlock, 0, s>>>(dmask, fmask, n, counts, idx);
+    return cov_check_launch("cov_frustum_cull");
+}
+
+extern "C" int cov_hpr_flip(const float* xyz, int64_t n, float scale, float* flipped, float* radius, void* stream) {
+    if (n <= 0 || !xyz || !flipped || !radius) {
+        cov_set_error("cov_hpr_flip: null pointer or empty cloud");
+        return COV_ERR_ARG;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    // radius[0] = R (out), radius[1] = max norm scratch
+    cudaMemsetAsync(radius, 0, 2 * sizeof(float), s);
+    int64_t nb = (n + 255) / 256;
+    const int64_t cap = (int64_t)cov_sm_count_cached() * 8;
+    if (nb > cap) nb = cap;
+    flip_maxnorm_kernel<<<(unsigned)nb, 256, 0, s>>>(xyz, n, reinterpret_cast<unsigned*>(radius + 1));
+    flip_apply_kernel<<<(unsigned)nb, 256, 0, s>>>(xyz, n, scale, radius, flipped);
+    return cov_check_launch("cov_hpr_flip");
+}

@@ -1,0 +1,465 @@
+// cov_traj.cu — ModelTraj visibility term, fused forward+backward (reference src/model.py:200-246).
+//
+// Data layout: the cloud stays in HBM as row-major (N,3) fp32 and is streamed once per pass;
+// the W pose rows (t, R mu1, P = K R^T, normalisers) live in shared memory as 5 float4 each and are
+// read with broadcast LDS.128; per-point state (log-odds sum) lives in registers.
+//
+// Pass A (cov_traj_minmax_kernel): per pose min_j m and max_j m.  Thread-local fmin/fmax over the
+//   thread's points, one integer REDUX per warp (m >= 0, so the float order is the uint order), one
+//   shared-memory atomic per warp and pose, one global atomic per block and pose.  Deterministic.
+// Pass B (cov_traj_fused_kernel), per tile of 256*PPT points:
+//   phase 1  every (point, pose): m, gate (m - a >= b/2  <=>  p >= 0.5, exact), warp ballot of the
+//            gate stored as a pose-major bit matrix in shared memory; gated lanes add their log-odds
+//            to the point's running sum in pose order (same order as the reference loop).
+//            rewards_j = sigmoid(L_j) is written, G_j = r_j (1 - r_j) kept in shared memory.
+//   phase 2  the bit matrix is walked pose-major: a lane owns (pose, row segment), pops its set bits,
+//            re-evaluates m and dm/dy for that pair and accumulates the 8 weighted sums in registers —
+//            no atomics, fixed order.  Segments of a pose are combined with xor-shuffles and added to
+//            the block's per-pose accumulators in shared memory by one owner lane.
+//   Block accumulators go to a [block][W][8] fp32 slab; a small kernel adds the slabs in fp64.
+//   The arg-max / arg-min tie sets of the normalisation backward are rare (one point per pose unless
+//   the minimum underflowed to 0, in which case their gradient is exactly negligible and skipped) and
+//   go straight to the fp64 accumulator with atomics.
+#include "cov_common.cuh"
+#include "../../include/coverage_b200.h"
+
+namespace {
+
+constexpr int kWarps = COV_THREADS / 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+__host__ __device__ constexpr int tile_points(int ppt) { return COV_THREADS * ppt; }
+__host__ __device__ constexpr int bit_words(int ppt) { return kWarps * ppt; }         // ballot words per pose
+__host__ __device__ constexpr int bit_stride(int ppt) { return bit_words(ppt) + 1; }  // +1: conflict-free pose-major walk
+
+size_t minmax_smem_bytes(int W) { return (size_t)W * (COV_ROW_F4 * sizeof(float4) + 2 * sizeof(unsigned)); }
+size_t fused_smem_bytes(int W, int ppt) {
+    return (size_t)W * COV_ROW_F4 * sizeof(float4) + (size_t)W * bit_stride(ppt) * sizeof(unsigned) +
+           (size_t)tile_points(ppt) * 4 * sizeof(float) + (size_t)W * 8 * sizeof(float);
+}
+
+// Unweighted dm/dy and dm/dy x y of one (point, pose) into a tie-set accumulator (7 doubles).
+__device__ __noinline__ void tie_accumulate(float x, float y, float z, const float4* row, CovConst C, double* dst) {
+    CovEval ev;
+    const float m = cov_vis<true>(x, y, z, row[0], row[1], row[2], row[3], C, &ev);
+    float gx, gy, gz;
+    cov_vis_grad(m, ev, row[1], row[2], row[3], C, gx, gy, gz);
+    atomicAdd(dst + 0, (double)gx);
+    atomicAdd(dst + 1, (double)gy);
+    atomicAdd(dst + 2, (double)gz);
+    atomicAdd(dst + 3, (double)(gy * ev.yz - gz * ev.yy));
+    atomicAdd(dst + 4, (double)(gz * ev.yx - gx * ev.yz));
+    atomicAdd(dst + 5, (double)(gx * ev.yy - gy * ev.yx));
+    atomicAdd(dst + 6, 1.0);
+}
+
+template <int PPT>
+__global__ void __launch_bounds__(COV_THREADS, 2)
+cov_traj_minmax_kernel(const float* __restrict__ xyz, int64_t n, const float* __restrict__ poses,
+                       const float* __restrict__ quats, int W, const float* __restrict__ K9, CovConst C,
+                       unsigned* __restrict__ gmin, unsigned* __restrict__ gmax) {
+    extern __shared__ float4 smem4[];
+    float4* ptab = smem4;
+    unsigned* smin = reinterpret_cast<unsigned*>(ptab + (size_t)W * COV_ROW_F4);
+    unsigned* smax = smin + W;
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int w = tid; w < W; w += COV_THREADS) {
+        cov_pose_row(poses + 3 * w, quats + 4 * w, K9, C.mu, ptab + (size_t)w * COV_ROW_F4);
+        smin[w] = 0x7f800000u;
+        smax[w] = 0u;
+    }
+    __syncthreads();
+    constexpr int T = tile_points(PPT);
+    const int64_t ntiles = (n + T - 1) / T;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        float px[PPT], py[PPT], pz[PPT];
+#pragma unroll
+        for (int s = 0; s < PPT; ++s) {
+            int64_t j = tile * T + s * COV_THREADS + tid;
+            j = j < n ? j : n - 1;  // a duplicate cannot change a min or a max
+            px[s] = __ldg(xyz + j * 3);
+            py[s] = __ldg(xyz + j * 3 + 1);
+            pz[s] = __ldg(xyz + j * 3 + 2);
+        }
+        for (int w = 0; w < W; ++w) {
+            const float4* row = ptab + (size_t)w * COV_ROW_F4;
+            const float4 v0 = row[0], v1 = row[1], v2 = row[2], v3 = row[3];
+            float mn = __uint_as_float(0x7f800000u), mx = 0.f;
+#pragma unroll
+            for (int s = 0; s < PPT; ++s) {
+                const float m = cov_vis<false>(px[s], py[s], pz[s], v0, v1, v2, v3, C, nullptr);
+                mn = fminf(mn, m);
+                mx = fmaxf(mx, m);
+            }
+            const unsigned umn = __reduce_min_sync(kFull, __float_as_uint(mn));
+            const unsigned umx = __reduce_max_sync(kFull, __float_as_uint(mx));
+            if (lane == 0) {
+                atomicMin(smin + w, umn);
+                atomicMax(smax + w, umx);
+            }
+        }
+    }
+    __syncthreads();
+    for (int w = tid; w < W; w += COV_THREADS) {
+        atomicMin(gmin + w, smin[w]);
+        atomicMax(gmax + w, smax[w]);
+    }
+}
+
+__global__ void cov_minmax_init_kernel(unsigned* gmin, unsigned* gmax, int W) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < W) {
+        gmin[w] = 0x7f800000u;
+        gmax[w] = 0u;
+    }
+}
+
+template <int PPT, bool HAS_UP>
+__global__ void __launch_bounds__(COV_THREADS, 2)
+cov_traj_fused_kernel(const float* __restrict__ xyz, int64_t n, const float* __restrict__ poses,
+                      const float* __restrict__ quats, int W, const float* __restrict__ K9, CovConst C,
+                      const float* __restrict__ minmax, const float* __restrict__ upstream,
+                      float* __restrict__ rewards, float* __restrict__ partials, double* __restrict__ sumr_partials,
+                      double* __restrict__ acc, int seg_log2) {
+    constexpr int T = tile_points(PPT);
+    constexpr int NW = bit_words(PPT);
+    constexpr int RS = bit_stride(PPT);
+    extern __shared__ float4 smem4[];
+    float4* ptab = smem4;
+    unsigned* bits = reinterpret_cast<unsigned*>(ptab + (size_t)W * COV_ROW_F4);
+    float* xs = reinterpret_cast<float*>(bits + (size_t)W * RS);
+    float* ys = xs + T;
+    float* zs = ys + T;
+    float* Gs = zs + T;
+    float* accs = Gs + T;
+    __shared__ double red[kWarps];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int w = tid; w < W; w += COV_THREADS) {
+        float4* row = ptab + (size_t)w * COV_ROW_F4;
+        cov_pose_row(poses + 3 * w, quats + 4 * w, K9, C.mu, row);
+        const float a = minmax[w];
+        const float b = __fsub_rn(minmax[W + w], a);
+        row[3].w = a;
+        row[4] = make_float4(0.5f * b, b, __frcp_rn(b), 0.f);
+    }
+    for (int i = tid; i < W * 8; i += COV_THREADS) accs[i] = 0.f;
+    __syncthreads();
+
+    double sum_r = 0.0;
+    const int64_t ntiles = (n + T - 1) / T;
+    const int nseg = 1 << seg_log2;       // lanes that share one pose row in phase 2
+    const int wps = NW >> seg_log2;       // ballot words per lane
+    const int ntask = W << seg_log2;
+
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        // ------------------------------ phase 1: every (point, pose) ------------------------------
+        float px[PPT], py[PPT], pz[PPT], L[PPT];
+        bool valid[PPT];
+#pragma unroll
+        for (int s = 0; s < PPT; ++s) {
+            int64_t j = tile * T + s * COV_THREADS + tid;
+            valid[s] = j < n;
+            j = valid[s] ? j : n - 1;
+            px[s] = __ldg(xyz + j * 3);
+            py[s] = __ldg(xyz + j * 3 + 1);
+            pz[s] = __ldg(xyz + j * 3 + 2);
+            xs[s * COV_THREADS + tid] = px[s];
+            ys[s * COV_THREADS + tid] = py[s];
+            zs[s * COV_THREADS + tid] = pz[s];
+            L[s] = 0.f;
+        }
+        for (int w = 0; w < W; ++w) {
+            const float4* row = ptab + (size_t)w * COV_ROW_F4;
+            const float4 v0 = row[0], v1 = row[1], v2 = row[2], v3 = row[3], v4 = row[4];
+            unsigned* brow = bits + (size_t)w * RS + warp * PPT;
+#pragma unroll
+            for (int s = 0; s < PPT; ++s) {
+                const float m = cov_vis<false>(px[s], py[s], pz[s], v0, v1, v2, v3, C, nullptr);
+                const float d = __fsub_rn(m, v3.w);
+                const bool act = valid[s] && (d >= v4.x);
+                const unsigned bal = __ballot_sync(kFull, act);
+                if (lane == 0) brow[s] = bal;
+                if (bal != 0u) {
+                    if (act) {
+                        const float p = __fmul_rn(d, v4.z);
+                        const float qc = fminf(p, C.hi);
+                        L[s] += COV_LN2_F * cov_lg2(qc * cov_rcp(1.f - qc));
+                        if (d == v4.y) tie_accumulate(px[s], py[s], pz[s], row, C, acc + (size_t)w * COV_ACC_STRIDE + 8);
+                    }
+                }
+                if (v3.w > 0.f) {  // block-uniform: only when the minimum did not underflow to 0
+                    if (valid[s] && m == v3.w)
+                        tie_accumulate(px[s], py[s], pz[s], row, C, acc + (size_t)w * COV_ACC_STRIDE + 15);
+                }
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < PPT; ++s) {
+            const float r = 1.f / (1.f + expf(-L[s]));
+            float g = r * (1.f - r);
+            if (valid[s]) {
+                const int64_t j = tile * T + s * COV_THREADS + tid;
+                rewards[j] = r;
+                sum_r += (double)r;
+                if (HAS_UP) g *= upstream[j];
+            }
+            Gs[s * COV_THREADS + tid] = g;
+        }
+        __syncthreads();
+        // ------------------------------ phase 2: gated pairs, pose-major ------------------------------
+        for (int base = 0; base < ntask; base += COV_THREADS) {
+            const int task = base + tid;
+            const bool live = task < ntask;
+            const int w = live ? (task >> seg_log2) : 0;
+            const int seg = task & (nseg - 1);
+            const float4* row = ptab + (size_t)w * COV_ROW_F4;
+            const float4 v0 = row[0], v1 = row[1], v2 = row[2], v3 = row[3], v4 = row[4];
+            const unsigned* brow = bits + (size_t)w * RS;
+            int k = seg * wps;
+            const int kend = live ? k + wps : k;
+            unsigned word = live ? brow[k] : 0u;
+            float f0 = 0.f, f1 = 0.f, f2 = 0.f, t0 = 0.f, t1 = 0.f, t2 = 0.f, se = 0.f, sep = 0.f;
+            while (true) {
+                while (word == 0u && k + 1 < kend) word = brow[++k];
+                if (!__any_sync(kFull, word != 0u)) break;
+                if (word != 0u) {
+                    const int bit = __ffs(word) - 1;
+                    word &= word - 1;
+                    const int local = (k % PPT) * COV_THREADS + (k / PPT) * 32 + bit;
+                    CovEval ev;
+                    const float m = cov_vis<true>(xs[local], ys[local], zs[local], v0, v1, v2, v3, C, &ev);
+                    const float d = __fsub_rn(m, v3.w);
+                    const float p = __fdiv_rn(d, v4.y);
+                    if (p <= C.hi) {  // clamp backward gate (inclusive); p >= 0.5 holds for every set bit
+                        float gx, gy, gz;
+                        cov_vis_grad(m, ev, v1, v2, v3, C, gx, gy, gz);
+                        const float e = Gs[local] / (p * (1.f - p));
+                        const float om = e * v4.z;
+                        f0 += om * gx; f1 += om * gy; f2 += om * gz;
+                        t0 += om * (gy * ev.yz - gz * ev.yy);
+                        t1 += om * (gz * ev.yx - gx * ev.yz);
+                        t2 += om * (gx * ev.yy - gy * ev.yx);
+                        se += e;
+                        sep += e * p;
+                    }
+                }
+            }
+            for (int o = 1; o < nseg; o <<= 1) {
+                f0 += __shfl_xor_sync(kFull, f0, o); f1 += __shfl_xor_sync(kFull, f1, o);
+                f2 += __shfl_xor_sync(kFull, f2, o); t0 += __shfl_xor_sync(kFull, t0, o);
+                t1 += __shfl_xor_sync(kFull, t1, o); t2 += __shfl_xor_sync(kFull, t2, o);
+                se += __shfl_xor_sync(kFull, se, o); sep += __shfl_xor_sync(kFull, sep, o);
+            }
+            if (live && seg == 0) {
+                float* a8 = accs + (size_t)w * 8;
+                a8[0] += f0; a8[1] += f1; a8[2] += f2; a8[3] += t0;
+                a8[4] += t1; a8[5] += t2; a8[6] += se; a8[7] += sep;
+            }
+        }
+        __syncthreads();
+    }
+    float* slab = partials + (size_t)blockIdx.x * W * 8;
+    for (int i = tid; i < W * 8; i += COV_THREADS) slab[i] = accs[i];
+    const double ws = cov_warp_sum(sum_r);
+    if (lane == 0) red[warp] = ws;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int i = 0; i < kWarps; ++i) t += red[i];
+        sumr_partials[blockIdx.x] = t;
+    }
+}
+
+// acc[w][0..7] = sum over blocks of the fp32 slabs (fp64, fixed order); acc[W*STRIDE] = sum of rewards.
+__global__ void cov_traj_reduce_kernel(const float* __restrict__ partials, const double* __restrict__ sumr_partials,
+                                       int nblocks, int W, double* __restrict__ acc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < W * 8) {
+        double s = 0.0;
+        for (int b = 0; b < nblocks; ++b) s += (double)partials[(size_t)b * W * 8 + i];
+        acc[(size_t)(i >> 3) * COV_ACC_STRIDE + (i & 7)] = s;
+    }
+    if (i == 0) {
+        double s = 0.0;
+        for (int b = 0; b < nblocks; ++b) s += sumr_partials[b];
+        acc[(size_t)W * COV_ACC_STRIDE] = s;
+    }
+}
+
+// fold the min/max-path terms in and map (F, T) to (d/dt, d/dq~).
+__global__ void cov_traj_epilogue_kernel(const double* __restrict__ acc, const float* __restrict__ minmax,
+                                         const float* __restrict__ quats, int W, double n_total, int upstream_mode,
+                                         float* __restrict__ out) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w == 0) out[0] = (float)(acc[(size_t)W * COV_ACC_STRIDE] / n_total);
+    if (w >= W) return;
+    const double* A = acc + (size_t)w * COV_ACC_STRIDE;
+    const float a = minmax[w];
+    const double b = (double)__fsub_rn(minmax[W + w], a);
+    const double dLdb = -A[7] / b;
+    const double dLda = -A[6] / b - dLdb;
+    double F[3] = {A[0], A[1], A[2]}, Tq[3] = {A[3], A[4], A[5]};
+    if (A[14] > 0.0) {
+        const double c = dLdb / A[14];
+        for (int k = 0; k < 3; ++k) { F[k] += c * A[8 + k]; Tq[k] += c * A[11 + k]; }
+    }
+    if (A[21] > 0.0) {
+        const double c = dLda / A[21];
+        for (int k = 0; k < 3; ++k) { F[k] += c * A[15 + k]; Tq[k] += c * A[18 + k]; }
+    }
+    const double c0 = upstream_mode ? 1.0 : 1.0 / n_total;
+    double qw = quats[4 * w], qx = quats[4 * w + 1], qy = quats[4 * w + 2], qz = quats[4 * w + 3];
+    double qn = sqrt(qw * qw + qx * qx + qy * qy + qz * qz);
+    qn = qn > 1e-12 ? qn : 1e-12;
+    qw /= qn; qx /= qn; qy /= qn; qz /= qn;
+    float* gp = out + 1 + 3 * w;
+    float* gq = out + 1 + 3 * W + 4 * w;
+    for (int k = 0; k < 3; ++k) gp[k] = (float)(-c0 * F[k]);
+    const double s = 2.0 * c0 / qn;
+    gq[0] = (float)(s * (-Tq[0] * qx - Tq[1] * qy - Tq[2] * qz));
+    gq[1] = (float)(s * (Tq[0] * qw + Tq[1] * qz - Tq[2] * qy));
+    gq[2] = (float)(s * (Tq[1] * qw - Tq[0] * qz + Tq[2] * qx));
+    gq[3] = (float)(s * (Tq[2] * qw + Tq[0] * qy - Tq[1] * qx));
+}
+
+constexpr size_t kSmemCap = 227 * 1024 - 64;  // opt-in shared memory per block on sm_100, minus static use
+
+int pick_ppt(int64_t n, int W, bool fused) {
+    const int sms = cov_sm_count_cached();
+    const int cand[3] = {4, 2, 1};
+    for (int i = 0; i < 3; ++i) {
+        const int ppt = cand[i];
+        const size_t sm = fused ? fused_smem_bytes(W, ppt) : minmax_smem_bytes(W);
+        if (sm > kSmemCap) continue;
+        const int64_t ntiles = (n + tile_points(ppt) - 1) / tile_points(ppt);
+        if (ntiles >= 2 * (int64_t)sms || ppt == 1) return ppt;
+    }
+    return 0;
+}
+
+template <typename Kern>
+int grid_for(Kern kern, size_t smem, int64_t ntiles) {
+    int per_sm = 0;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, COV_THREADS, smem) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    int64_t g = (int64_t)per_sm * cov_sm_count_cached();
+    if (g > ntiles) g = ntiles;
+    if (g > COV_MAX_GRID) g = COV_MAX_GRID;
+    return g < 1 ? 1 : (int)g;
+}
+
+int check_traj_args(const char* who, const float* xyz, int64_t n, const float* poses, const float* quats, int W,
+                    const float* K, const cov_camera* cam) {
+    if (!xyz || n <= 0 || !poses || !quats || W <= 0 || !K || !cam) {
+        cov_set_error("%s: null pointer, empty cloud or no poses (n=%lld, W=%d)", who, (long long)n, W);
+        return COV_ERR_ARG;
+    }
+    if (W > cov_traj_max_poses()) {
+        cov_set_error("%s: %d poses exceed the shared-memory pose table (max %d)", who, W, cov_traj_max_poses());
+        return COV_ERR_UNSUPPORTED;
+    }
+    return COV_OK;
+}
+
+}  // namespace
+
+extern "C" int cov_traj_max_poses(void) {
+    int w = 1;
+    while (fused_smem_bytes(w + 1, 1) <= kSmemCap) ++w;
+    return w;
+}
+
+extern "C" size_t cov_traj_workspace_bytes(int64_t n, int n_poses) {
+    (void)n;
+    if (n_poses < 1) n_poses = 1;
+    return (size_t)COV_MAX_GRID * ((size_t)n_poses * 8 * sizeof(float) + sizeof(double));
+}
+
+extern "C" int cov_traj_minmax(const float* xyz, int64_t n, const float* poses, const float* quats, int W,
+                               const float* K, const cov_camera* cam, float* minmax, void* stream) {
+    int rc = check_traj_args("cov_traj_minmax", xyz, n, poses, quats, W, K, cam);
+    if (rc) return rc;
+    if (!minmax) {
+        cov_set_error("cov_traj_minmax: null minmax");
+        return COV_ERR_ARG;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const CovConst C = cov_make_const(cam);
+    unsigned* gmin = reinterpret_cast<unsigned*>(minmax);
+    unsigned* gmax = gmin + W;
+    cov_minmax_init_kernel<<<(W + 255) / 256, 256, 0, s>>>(gmin, gmax, W);
+    const int ppt = pick_ppt(n, W, false);
+    const size_t smem = minmax_smem_bytes(W);
+    const int64_t ntiles = (n + tile_points(ppt) - 1) / tile_points(ppt);
+#define LAUNCH_MM(P)                                                                                          \
+    {                                                                                                         \
+        const int grid = grid_for(cov_traj_minmax_kernel<P>, smem, ntiles);                                   \
+        cov_traj_minmax_kernel<P><<<grid, COV_THREADS, smem, s>>>(xyz, n, poses, quats, W, K, C, gmin, gmax); \
+    }
+    if (ppt == 4) LAUNCH_MM(4) else if (ppt == 2) LAUNCH_MM(2) else LAUNCH_MM(1)
+#undef LAUNCH_MM
+    return cov_check_launch("cov_traj_minmax");
+}
+
+extern "C" int cov_traj_fused(const float* xyz, int64_t n, const float* poses, const float* quats, int W,
+                              const float* K, const cov_camera* cam, const float* minmax, const float* upstream,
+                              float* rewards, double* acc, void* ws, size_t ws_bytes, void* stream) {
+    int rc = check_traj_args("cov_traj_fused", xyz, n, poses, quats, W, K, cam);
+    if (rc) return rc;
+    if (!minmax || !rewards || !acc || !ws) {
+        cov_set_error("cov_traj_fused: null minmax/rewards/acc/workspace");
+        return COV_ERR_ARG;
+    }
+    if (ws_bytes < cov_traj_workspace_bytes(n, W)) {
+        cov_set_error("cov_traj_fused: workspace %zu < %zu bytes", ws_bytes, cov_traj_workspace_bytes(n, W));
+        return COV_ERR_WORKSPACE;
+    }
+    if (((uintptr_t)ws) & 15) {
+        cov_set_error("cov_traj_fused: workspace must be 16-byte aligned");
+        return COV_ERR_ALIGN;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const CovConst C = cov_make_const(cam);
+    const int ppt = pick_ppt(n, W, true);
+    if (ppt == 0) {
+        cov_set_error("cov_traj_fused: %d poses do not fit in shared memory", W);
+        return COV_ERR_UNSUPPORTED;
+    }
+    const size_t smem = fused_smem_bytes(W, ppt);
+    const int64_t ntiles = (n + tile_points(ppt) - 1) / tile_points(ppt);
+    // phase-2 parallelism: split each pose row over 2^seg_log2 lanes until there are >= 2 tasks per thread
+    int seg_log2 = 0;
+    while ((W << seg_log2) < 2 * COV_THREADS && (2 << seg_log2) <= bit_words(ppt) && seg_log2 < 5) ++seg_log2;
+    double* sumr = reinterpret_cast<double*>(ws);
+    float* partials = reinterpret_cast<float*>(sumr + COV_MAX_GRID);
+    cudaMemsetAsync(acc, 0, ((size_t)W * COV_ACC_STRIDE + 1) * sizeof(double), s);
+    int grid = 1;
+#define LAUNCH_F(P, U)                                                                                          \
+    {                                                                                                           \
+        grid = grid_for(cov_traj_fused_kernel<P, U>, smem, ntiles);                                             \
+        cov_traj_fused_kernel<P, U><<<grid, COV_THREADS, smem, s>>>(xyz, n, poses, quats, W, K, C, minmax,      \
+                                                                    upstream, rewards, partials, sumr, acc,     \
+                                                                    seg_log2);                                  \
+    }
+    if (upstream) {
+        if (ppt == 4) LAUNCH_F(4, true) else if (ppt == 2) LAUNCH_F(2, true) else LAUNCH_F(1, true)
+    } else {
+        if (ppt == 4) LAUNCH_F(4, false) else if (ppt == 2) LAUNCH_F(2, false) else LAUNCH_F(1, false)
+    }
+#undef LAUNCH_F
+    cov_traj_reduce_kernel<<<(W * 8 + 255) / 256, 256, 0, s>>>(partials, sumr, grid, W, acc);
+    return cov_check_launch("cov_traj_fused");
+}
+
+extern "C" int cov_traj_epilogue(const double* acc, const float* minmax, const float* quats, int W, int64_t n_total,
+                                 int upstream_mode, float* out, void* stream) {
+    if (!acc || !minmax || !quats || !out || W <= 0 || n_total <= 0) {
+        cov_set_error("cov_traj_epilogue: bad argument");
+        return COV_ERR_ARG;
+    }
+    cov_traj_epilogue_kernel<<<(W + 127) / 128, 128, 0, (cudaStream_t)stream>>>(acc, minmax, quats, W, (double)n_total,
+                                                                               upstream_mode, out);
+    return cov_check_launch("cov_traj_epilogue");
+}

@@ -1,0 +1,274 @@
+"""torch.autograd.Function wrappers over the C ABI (include/coverage_b200.h).
+
+PyTorch is plumbing here: it owns device memory, streams and (when the cloud is sharded over
+ranks) the NCCL communicator.  Every numeric result comes from libcovb200.so.
+
+Sharded use: each rank passes ITS slice of the cloud plus a `group`; the per-pose normalisers
+are all-reduced with MIN/MAX, the accumulators with SUM (a few KB), so every rank ends up with
+the same scalar and the same pose gradients, while per-point outputs stay sharded.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dev_f32(t, device=None, what="tensor"):
+    """fp32, contiguous, on a CUDA device, 16-byte aligned (clones only when it has to)."""
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{what} must be a torch.Tensor")
+    if device is not None and t.device != device:
+        t = t.to(device)
+    if not t.is_cuda:
+        raise RuntimeError(f"{what} is on {t.device}: the coverage ops are CUDA-only (no CPU fallback)")
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    if not t.is_contiguous():
+        t = t.contiguous()
+    if t.data_ptr() % 16:
+        t = t.clone()
+    return t
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr() if t is not None else 0)
+
+
+def _all_reduce(t, op, group):
+    if group is not None:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=op, group=group)
+
+
+def _reduce_ops():
+    import torch.distributed as dist
+    return dist.ReduceOp.MIN, dist.ReduceOp.MAX, dist.ReduceOp.SUM
+
+
+class CoveragePoseFn(torch.autograd.Function):
+    """obs_j = dist_mask*fov_mask[*weight_j], total = sum_j obs_j (reference src/model.py:98-127)."""
+
+    @staticmethod
+    def forward(ctx, points, trans, quat, K, cam, weight, group):
+        L = _lib.lib()
+        dev = points.device
+        pts = _dev_f32(points, what="points")
+        t = _dev_f32(trans, dev, "trans").reshape(3)
+        q = _dev_f32(quat, dev, "quat").reshape(4)
+        Kd = _dev_f32(K, dev, "intrins").reshape(9)
+        w = None if weight is None else _dev_f32(weight, dev, "weight").reshape(-1)
+        n = pts.shape[0]
+        obs = torch.empty(n, dtype=torch.float32, device=dev)
+        out = CoveragePoseFn._run(L, pts, t, q, Kd, cam, w, obs, group)
+        ctx.cam, ctx.group = cam, group
+        ctx.shapes = (trans.shape, quat.shape)
+        ctx.save_for_backward(pts, t, q, Kd, w, out)
+        ctx.set_materialize_grads(False)
+        return obs, out[0].clone()
+
+    @staticmethod
+    def _run(L, pts, t, q, Kd, cam, w, obs, group):
+        dev = pts.device
+        n = pts.shape[0]
+        acc = torch.empty(_lib.POSE_ACC, dtype=torch.float64, device=dev)
+        ws_bytes = L.cov_pose_workspace_bytes(n)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _lib.check(L.cov_pose_fused(_ptr(pts), n, _ptr(w), _ptr(t), _ptr(q), _ptr(Kd), ctypes.byref(cam), _ptr(obs),
+                                    _ptr(acc), _ptr(ws), ws_bytes, _stream()), "cov_pose_fused")
+        if group is not None:
+            _all_reduce(acc, _reduce_ops()[2], group)
+        out = torch.empty(8, dtype=torch.float32, device=dev)
+        _lib.check(L.cov_pose_epilogue(_ptr(acc), _ptr(t), _ptr(q), _ptr(out), _stream()), "cov_pose_epilogue")
+        return out
+
+    @staticmethod
+    def backward(ctx, g_obs, g_total):
+        pts, t, q, Kd, w, out = ctx.saved_tensors
+        g_t = g_q = None
+        if g_total is not None:
+            g_t = g_total * out[1:4]
+            g_q = g_total * out[4:8]
+        if g_obs is not None:
+            # someone differentiated through the per-point vector: one more pass with
+            # weight_j = upstream_j [* weight_j]
+            up = _dev_f32(g_obs, pts.device, "grad_obs").reshape(-1)
+            if w is not None:
+                up = up * w
+            o2 = CoveragePoseFn._run(_lib.lib(), pts, t, q, Kd, ctx.cam, up, None, ctx.group)
+            g_t = o2[1:4] if g_t is None else g_t + o2[1:4]
+            g_q = o2[4:8] if g_q is None else g_q + o2[4:8]
+        ts, qs = ctx.shapes
+        return (None, None if g_t is None else g_t.reshape(ts), None if g_q is None else g_q.reshape(qs),
+                None, None, None, None)
+
+
+class CoverageTrajFn(torch.autograd.Function):
+    """rewards_j = sigmoid(sum_w logit(clip(normalised m_jw))), mean = mean_j rewards_j
+    over the poses given (reference src/model.py:217-237, :246)."""
+
+    @staticmethod
+    def forward(ctx, points, poses, quats, K, cam, n_total, group):
+        L = _lib.lib()
+        dev = points.device
+        pts = _dev_f32(points, what="points")
+        P = _dev_f32(poses, dev, "poses").reshape(-1, 3)
+        Q = _dev_f32(quats, dev, "quats").reshape(-1, 4)
+        Kd = _dev_f32(K, dev, "intrins").reshape(9)
+        W, n = P.shape[0], pts.shape[0]
+        if Q.shape[0] != W:
+            raise ValueError("poses and quats disagree on the number of waypoints")
+        n_total = int(n if n_total is None else n_total)
+        minmax = torch.empty(2 * W, dtype=torch.float32, device=dev)
+        _lib.check(L.cov_traj_minmax(_ptr(pts), n, _ptr(P), _ptr(Q), W, _ptr(Kd), ctypes.byref(cam), _ptr(minmax),
+                                     _stream()), "cov_traj_minmax")
+        if group is not None:
+            mn, mx, _ = _reduce_ops()
+            _all_reduce(minmax[:W], mn, group)
+            _all_reduce(minmax[W:], mx, group)
+        rewards = torch.empty(n, dtype=torch.float32, device=dev)
+        out = CoverageTrajFn._run(L, pts, P, Q, Kd, cam, minmax, None, rewards, n_total, group)
+        ctx.cam, ctx.group, ctx.n_total = cam, group, n_total
+        ctx.shapes = (poses.shape, quats.shape)
+        ctx.save_for_backward(pts, P, Q, Kd, minmax, out)
+        ctx.set_materialize_grads(False)
+        return rewards, out[0].clone()
+
+    @staticmethod
+    def _run(L, pts, P, Q, Kd, cam, minmax, upstream, rewards, n_total, group):
+        dev = pts.device
+        W, n = P.shape[0], pts.shape[0]
+        acc = torch.empty(W * _lib.ACC_STRIDE + 1, dtype=torch.float64, device=dev)
+        ws_bytes = L.cov_traj_workspace_bytes(n, W)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _lib.check(L.cov_traj_fused(_ptr(pts), n, _ptr(P), _ptr(Q), W, _ptr(Kd), ctypes.byref(cam), _ptr(minmax),
+                                    _ptr(upstream), _ptr(rewards), _ptr(acc), _ptr(ws), ws_bytes, _stream()),
+                   "cov_traj_fused")
+        if group is not None:
+            _all_reduce(acc, _reduce_ops()[2], group)
+        out = torch.empty(1 + 7 * W, dtype=torch.float32, device=dev)
+        _lib.check(L.cov_traj_epilogue(_ptr(acc), _ptr(minmax), _ptr(Q), W, n_total, 0 if upstream is None else 1,
+                                       _ptr(out), _stream()), "cov_traj_epilogue")
+        return out
+
+    @staticmethod
+    def backward(ctx, g_rewards, g_mean):
+        pts, P, Q, Kd, minmax, out = ctx.saved_tensors
+        W = P.shape[0]
+        g_p = g_q = None
+        if g_mean is not None:
+            g_p = g_mean * out[1:1 + 3 * W]
+            g_q = g_mean * out[1 + 3 * W:]
+        if g_rewards is not None:
+            up = _dev_f32(g_rewards, pts.device, "grad_rewards").reshape(-1)
+            scratch = torch.empty(pts.shape[0], dtype=torch.float32, device=pts.device)
+            o2 = CoverageTrajFn._run(_lib.lib(), pts, P, Q, Kd, ctx.cam, minmax, up, scratch, ctx.n_total, ctx.group)
+            g_p = o2[1:1 + 3 * W] if g_p is None else g_p + o2[1:1 + 3 * W]
+            g_q = o2[1 + 3 * W:] if g_q is None else g_q + o2[1 + 3 * W:]
+        ps, qs = ctx.shapes
+        return (None, None if g_p is None else g_p.reshape(ps), None if g_q is None else g_q.reshape(qs),
+                None, None, None, None)
+
+
+def coverage_pose(points, trans, quat, intrins, img_width, img_height, min_dist=1.0, max_dist=5.0, eps=1e-6,
+                  weight=None, group=None):
+    """Fused ModelPose objective.  Returns (observations (N,), total = sum(observations));
+    differentiable w.r.t. trans (.., 3) and quat (.., 4) (w, x, y, z)."""
+    cam = _lib.camera(img_width, img_height, min_dist, max_dist, eps)
+    return CoveragePoseFn.apply(points, trans, quat, intrins, cam, weight, group)
+
+
+def coverage_traj(points, poses, quats, intrins, img_width, img_height, min_dist=1.0, max_dist=5.0, eps=1e-6,
+                  n_total=None, group=None):
+    """Fused ModelTraj visibility term over the W poses given.  Returns (rewards (N,), mean(rewards))."""
+    cam = _lib.camera(img_width, img_height, min_dist, max_dist, eps)
+    return CoverageTrajFn.apply(points, poses, quats, intrins, cam, n_total, group)
+
+
+@torch.no_grad()
+def sweep_rewards(points, poses, quats, intrins, img_width, img_height, min_dist=1.0, max_dist=5.0, eps=1e-6,
+                  n_total=None, group=None):
+    """Forward-only mean reward of many candidate trajectories: poses (T, P, 3), quats (T, P, 4) -> (T,) fp64."""
+    L = _lib.lib()
+    pts = _dev_f32(points, what="points")
+    dev = pts.device
+    T, Pn = poses.shape[0], poses.shape[1]
+    P = _dev_f32(poses, dev, "poses").reshape(-1, 3)
+    Q = _dev_f32(quats, dev, "quats").reshape(-1, 4)
+    Kd = _dev_f32(intrins, dev, "intrins").reshape(9)
+    cam = _lib.camera(img_width, img_height, min_dist, max_dist, eps)
+    W, n = T * Pn, pts.shape[0]
+    minmax = torch.empty(2 * W, dtype=torch.float32, device=dev)
+    chunk = L.cov_traj_max_poses()
+    for w0 in range(0, W, chunk):  # pass A reuses the trajectory kernel, one pose-table-full at a time
+        w1 = min(W, w0 + chunk)
+        mm = torch.empty(2 * (w1 - w0), dtype=torch.float32, device=dev)
+        _lib.check(L.cov_traj_minmax(_ptr(pts), n, _ptr(P[w0:w1]), _ptr(Q[w0:w1]), w1 - w0, _ptr(Kd),
+                                     ctypes.byref(cam), _ptr(mm), _stream()), "cov_traj_minmax")
+        minmax[w0:w1] = mm[:w1 - w0]
+        minmax[W + w0:W + w1] = mm[w1 - w0:]
+    if group is not None:
+        mn, mx, _ = _reduce_ops()
+        _all_reduce(minmax[:W], mn, group)
+        _all_reduce(minmax[W:], mx, group)
+    sums = torch.zeros(T, dtype=torch.float64, device=dev)
+    _lib.check(L.cov_sweep_rewards(_ptr(pts), n, _ptr(P), _ptr(Q), T, Pn, _ptr(Kd), ctypes.byref(cam), _ptr(minmax),
+                                   _ptr(sums), _stream()), "cov_sweep_rewards")
+    if group is not None:
+        _all_reduce(sums, _reduce_ops()[2], group)
+    return sums / float(n if n_total is None else n_total)
+
+
+@torch.no_grad()
+def frustum_cull(points_nx3, intrins, img_width, img_height, min_dist=1.0, max_dist=10.0):
+    """Binary frustum test + ordered compaction (reference src/tools.py:176-187).
+    Returns (idx int64 (M,), dist_mask bool (N,), fov_mask bool (N,))."""
+    L = _lib.lib()
+    pts = _dev_f32(points_nx3, what="points")
+    dev = pts.device
+    Kd = _dev_f32(intrins, dev, "intrins")[:3, :3].contiguous().reshape(9)
+    n = pts.shape[0]
+    dm = torch.empty(n, dtype=torch.uint8, device=dev)
+    fm = torch.empty(n, dtype=torch.uint8, device=dev)
+    idx = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    ws_bytes = L.cov_cull_workspace_bytes(n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    _lib.check(L.cov_frustum_cull(_ptr(pts), n, _ptr(Kd), float(img_width), float(img_height), float(min_dist),
+                                  float(max_dist), _ptr(dm), _ptr(fm), _ptr(idx), _ptr(cnt), _ptr(ws), ws_bytes,
+                                  _stream()), "cov_frustum_cull")
+    m = int(cnt.item())
+    return idx[:m].long(), dm.bool(), fm.bool()
+
+
+@torch.no_grad()
+def spherical_flip(points, param):
+    """Bit-exact fp32 spherical flip (reference src/tools.py:38-53). Returns (flipped (N,3), radius 0-dim)."""
+    L = _lib.lib()
+    pts = _dev_f32(points, what="points")
+    n = pts.shape[0]
+    out = torch.empty_like(pts)
+    rad = torch.empty(2, dtype=torch.float32, device=pts.device)
+    _lib.check(L.cov_hpr_flip(_ptr(pts), n, float(10.0 ** param), _ptr(out), _ptr(rad), _stream()), "cov_hpr_flip")
+    return out, rad[0]
+
+
+@torch.no_grad()
+def hpr_hull_mask(flipped):
+    """Vertex mask of conv(flipped U {origin}) (reference src/tools.py:56-64 + the vertex set of :79).
+    Returns (mask uint8 (N,), origin_is_vertex bool, n_exact_fallback int)."""
+    L = _lib.lib()
+    f = _dev_f32(flipped, what="flipped points")
+    n = f.shape[0]
+    mask = torch.empty(n, dtype=torch.uint8, device=f.device)
+    info = torch.zeros(4, dtype=torch.int32, device=f.device)
+    ws_bytes = L.cov_hpr_hull_workspace_bytes(n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=f.device)
+    _lib.check(L.cov_hpr_hull(_ptr(f), n, _ptr(mask), _ptr(info), _ptr(ws), ws_bytes, _stream()), "cov_hpr_hull")
+    info_h = info.tolist()
+    return mask, bool(info_h[0]), int(info_h[1])
