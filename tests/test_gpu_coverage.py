@@ -56,9 +56,9 @@ def test_model_pose_matches_reference(name, dev, mod, sample_inputs):
     loss.backward()
     for sfx in ("", "64"):
         assert rel_err(loss.item(), g["out_loss" + sfx]) < TOL
-        assert rel_err(m.observations.cpu().numpy(), g["out_obs" + sfx]) < TOL
-        assert rel_err(m.trans.grad.cpu().numpy(), g["out_g_trans" + sfx]) < TOL
-        assert rel_err(m.quat.grad.cpu().numpy(), g["out_g_quat" + sfx]) < TOL
+        assert rel_err(m.observations.detach().cpu().numpy(), g["out_obs" + sfx]) < TOL
+        assert rel_err(m.trans.grad.detach().cpu().numpy(), g["out_g_trans" + sfx]) < TOL
+        assert rel_err(m.quat.grad.detach().cpu().numpy(), g["out_g_quat" + sfx]) < TOL
     assert m.observations.shape == (len(pts),) and m.trans.grad.shape == (1, 3) and m.quat.grad.shape == (1, 4)
 
 
@@ -79,11 +79,11 @@ def test_model_traj_matches_reference(name, dev, mod, sample_inputs):
     assert float(m.loss["l2"]) == 0.0 and float(m.loss["length"]) == 0.0
     for sfx in ("", "64"):
         assert rel_err(float(m.loss["vis"]), g["out_vis" + sfx]) < TOL
-        assert rel_err(m.rewards.cpu().numpy(), g["out_rewards" + sfx]) < TOL
-        assert rel_err(gv[0].cpu().numpy(), g["out_gv_poses" + sfx]) < TOL
-        assert rel_err(gv[1].cpu().numpy(), g["out_gv_quats" + sfx]) < TOL
-    assert rel_err(m.poses.grad.cpu().numpy(), g["out_g_poses"]) < TOL
-    assert rel_err(m.quats.grad.cpu().numpy(), g["out_g_quats"]) < TOL
+        assert rel_err(m.rewards.detach().cpu().numpy(), g["out_rewards" + sfx]) < TOL
+        assert rel_err(gv[0].detach().cpu().numpy(), g["out_gv_poses" + sfx]) < TOL
+        assert rel_err(gv[1].detach().cpu().numpy(), g["out_gv_quats" + sfx]) < TOL
+    assert rel_err(m.poses.grad.detach().cpu().numpy(), g["out_g_poses"]) < TOL
+    assert rel_err(m.quats.grad.detach().cpu().numpy(), g["out_g_quats"]) < TOL
     step = int(g["out_wps_step"])
     if step > 1:  # skipped waypoints carry no visibility gradient (src/model.py:217)
         assert float(gv[1][1::step].abs().max()) == 0.0
@@ -117,9 +117,9 @@ def test_traj_matches_oracle_on_seeded_clouds(n, W, ragged, dev, mod):
     vis.backward()
     ref = orc.traj_objective(pts, poses, quats, K_np, IMG_W, IMG_H, dtype=np.float64)
     assert rel_err(vis.item(), ref["vis"]) < TOL
-    assert rel_err(rewards.cpu().numpy(), ref["rewards"]) < TOL
-    assert rel_err(P.grad.cpu().numpy(), ref["g_poses"]) < TOL
-    assert rel_err(Q.grad.cpu().numpy(), ref["g_quats"]) < TOL
+    assert rel_err(rewards.detach().cpu().numpy(), ref["rewards"]) < TOL
+    assert rel_err(P.grad.detach().cpu().numpy(), ref["g_poses"]) < TOL
+    assert rel_err(Q.grad.detach().cpu().numpy(), ref["g_quats"]) < TOL
 
 
 def test_pose_matches_oracle_large_and_ragged(dev, mod):
@@ -135,10 +135,10 @@ def test_pose_matches_oracle_large_and_ragged(dev, mod):
         obs, total = ops.coverage_pose(torch.from_numpy(pts).to(dev), T, Q, K, Wd, Hd)
         (1.0 / (total + 1e-6)).backward()
         ref = orc.pose_objective(pts, t, q, K_np, IMG_W, IMG_H, dtype=np.float64)
-        assert rel_err(obs.cpu().numpy(), ref["obs"]) < TOL
+        assert rel_err(obs.detach().cpu().numpy(), ref["obs"]) < TOL
         assert rel_err(total.item(), ref["sum"]) < TOL
-        assert rel_err(T.grad.cpu().numpy().ravel(), ref["g_trans"]) < TOL
-        assert rel_err(Q.grad.cpu().numpy().ravel(), ref["g_quat"]) < TOL
+        assert rel_err(T.grad.detach().cpu().numpy().ravel(), ref["g_trans"]) < TOL
+        assert rel_err(Q.grad.detach().cpu().numpy().ravel(), ref["g_quat"]) < TOL
 
 
 def test_general_backward_through_per_point_outputs(dev, mod):
@@ -152,15 +152,15 @@ def test_general_backward_through_per_point_outputs(dev, mod):
     rewards, mean = ops.coverage_traj(pts, P, Q, K, W, H)
     g_fused = torch.autograd.grad(mean, [P, Q], retain_graph=True)
     g_gen = torch.autograd.grad(rewards.mean(), [P, Q])
-    assert rel_err(g_gen[0].cpu().numpy(), g_fused[0].cpu().numpy()) < 1e-5
-    assert rel_err(g_gen[1].cpu().numpy(), g_fused[1].cpu().numpy()) < 1e-5
+    assert rel_err(g_gen[0].detach().cpu().numpy(), g_fused[0].detach().cpu().numpy()) < 1e-5
+    assert rel_err(g_gen[1].detach().cpu().numpy(), g_fused[1].detach().cpu().numpy()) < 1e-5
     g2 = load_golden("pose_synth2")
     T = torch.from_numpy(g2["in_trans"]).to(dev).requires_grad_(True)
     Qp = torch.from_numpy(g2["in_quat"]).to(dev).requires_grad_(True)
     obs, total = ops.coverage_pose(torch.from_numpy(g2["in_points"]).to(dev), T, Qp, K, W, H)
     a = torch.autograd.grad(total, [T, Qp], retain_graph=True)
     b = torch.autograd.grad(obs.sum(), [T, Qp])
-    assert rel_err(b[0].cpu().numpy(), a[0].cpu().numpy()) < 1e-5 and rel_err(b[1].cpu().numpy(), a[1].cpu().numpy()) < 1e-5
+    assert rel_err(b[0].detach().cpu().numpy(), a[0].detach().cpu().numpy()) < 1e-5 and rel_err(b[1].detach().cpu().numpy(), a[1].detach().cpu().numpy()) < 1e-5
 
 
 def test_sharded_accumulators_equal_whole_cloud(dev, mod):
@@ -216,8 +216,8 @@ def test_sharded_accumulators_equal_whole_cloud(dev, mod):
                "epilogue")
     assert torch.equal(torch.cat(rew), rewards)  # per-point results do not depend on the sharding
     assert rel_err(out[0].item(), mean.item()) < 1e-6
-    assert rel_err(out[1:1 + 3 * W].cpu().numpy(), gp.reshape(-1).cpu().numpy()) < 1e-5
-    assert rel_err(out[1 + 3 * W:].cpu().numpy(), gq.reshape(-1).cpu().numpy()) < 1e-5
+    assert rel_err(out[1:1 + 3 * W].detach().cpu().numpy(), gp.reshape(-1).detach().cpu().numpy()) < 1e-5
+    assert rel_err(out[1 + 3 * W:].detach().cpu().numpy(), gq.reshape(-1).detach().cpu().numpy()) < 1e-5
     # run-to-run determinism of the whole pipeline (fixed-order reductions)
     rewards2, mean2 = ops.coverage_traj(pts, Pg, Qg, K, Wd, Hd)
     gp2, gq2 = torch.autograd.grad(mean2, [Pg, Qg])

@@ -156,6 +156,7 @@ cov_traj_fused_kernel(const float* __restrict__ xyz, int64_t n, const float* __r
         // ------------------------------ phase 1: every (point, pose) ------------------------------
         float px[PPT], py[PPT], pz[PPT], L[PPT];
         bool valid[PPT];
+        unsigned vmask[PPT];
 #pragma unroll
         for (int s = 0; s < PPT; ++s) {
             int64_t j = tile * T + s * COV_THREADS + tid;
@@ -168,30 +169,46 @@ cov_traj_fused_kernel(const float* __restrict__ xyz, int64_t n, const float* __r
             ys[s * COV_THREADS + tid] = py[s];
             zs[s * COV_THREADS + tid] = pz[s];
             L[s] = 0.f;
+            vmask[s] = __ballot_sync(kFull, valid[s]);
         }
         for (int w = 0; w < W; ++w) {
             const float4* row = ptab + (size_t)w * COV_ROW_F4;
             const float4 v0 = row[0], v1 = row[1], v2 = row[2], v3 = row[3], v4 = row[4];
-            unsigned* brow = bits + (size_t)w * RS + warp * PPT;
+            // straight-line evaluation of the thread's PPT points (independent chains -> ILP), votes afterwards
+            float m[PPT], d[PPT];
+            unsigned bal[PPT];
+            unsigned any = 0u;
 #pragma unroll
             for (int s = 0; s < PPT; ++s) {
-                const float m = cov_vis<false>(px[s], py[s], pz[s], v0, v1, v2, v3, C, nullptr);
-                const float d = __fsub_rn(m, v3.w);
-                const bool act = valid[s] && (d >= v4.x);
-                const unsigned bal = __ballot_sync(kFull, act);
-                if (lane == 0) brow[s] = bal;
-                if (bal != 0u) {
-                    if (act) {
-                        const float p = __fmul_rn(d, v4.z);
+                m[s] = cov_vis<false>(px[s], py[s], pz[s], v0, v1, v2, v3, C, nullptr);
+                d[s] = __fsub_rn(m[s], v3.w);
+            }
+#pragma unroll
+            for (int s = 0; s < PPT; ++s) {
+                bal[s] = __ballot_sync(kFull, d[s] >= v4.x) & vmask[s];
+                any |= bal[s];
+            }
+            if (lane == 0) {
+                unsigned* brow = bits + (size_t)w * RS + warp * PPT;
+#pragma unroll
+                for (int s = 0; s < PPT; ++s) brow[s] = bal[s];
+            }
+            if (any != 0u) {  // warp-uniform; ~1 % of (warp, pose) iterations on a random cloud
+#pragma unroll
+                for (int s = 0; s < PPT; ++s) {
+                    if ((bal[s] >> lane) & 1u) {
+                        const float p = __fmul_rn(d[s], v4.z);
                         const float qc = fminf(p, C.hi);
                         L[s] += COV_LN2_F * cov_lg2(qc * cov_rcp(1.f - qc));
-                        if (d == v4.y) tie_accumulate(px[s], py[s], pz[s], row, C, acc + (size_t)w * COV_ACC_STRIDE + 8);
+                        if (d[s] == v4.y) tie_accumulate(px[s], py[s], pz[s], row, C, acc + (size_t)w * COV_ACC_STRIDE + 8);
                     }
                 }
-                if (v3.w > 0.f) {  // block-uniform: only when the minimum did not underflow to 0
-                    if (valid[s] && m == v3.w)
+            }
+            if (v3.w > 0.f) {  // block-uniform: only when the minimum did not underflow to 0
+#pragma unroll
+                for (int s = 0; s < PPT; ++s)
+                    if (((vmask[s] >> lane) & 1u) && m[s] == v3.w)
                         tie_accumulate(px[s], py[s], pz[s], row, C, acc + (size_t)w * COV_ACC_STRIDE + 15);
-                }
             }
         }
 #pragma unroll
