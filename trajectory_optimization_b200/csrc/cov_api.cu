@@ -29,11 +29,14 @@ CovConst cov_make_const(const cov_camera* cam) {
     const double mu = ((double)cam->min_dist + (double)cam->max_dist) / 2.0;
     const double sigma = ((double)cam->max_dist - (double)cam->min_dist) / 2.0;
     const double log2e = 1.4426950408889634;
+    const double rkf = std::sqrt(0.5 * log2e);
     C.eps = cam->eps;
     C.kd = (float)(0.5 * log2e / (sigma * sigma));
-    C.kf = (float)(0.5 * log2e);
-    C.inv_w = (float)(1.0 / (double)cam->img_width);
-    C.inv_h = (float)(1.0 / (double)cam->img_height);
+    C.zk = (float)(-log2e);
+    C.zc = (float)(log2e * (double)cam->eps);
+    C.c0 = (float)(-0.5 * rkf);
+    C.cw = (float)(rkf / (double)cam->img_width);
+    C.ch = (float)(rkf / (double)cam->img_height);
     C.inv_s2 = (float)(1.0 / (sigma * sigma));
     C.mu = (float)mu;
     C.hi = (float)(1.0 - (double)cam->eps);

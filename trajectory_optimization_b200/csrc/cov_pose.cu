@@ -19,15 +19,16 @@ __device__ __forceinline__ void pose_point(float x, float y, float z, float wgt,
     CovEval ev;
     float m = cov_vis<true>(x, y, z, row[0], row[1], row[2], row[3], C, &ev);
     float gx, gy, gz;
-    cov_vis_grad(m, ev, row[1], row[2], row[3], C, gx, gy, gz);
+    cov_vis_grad(m, ev, row[0], row[1], row[2], C, gx, gy, gz);
     m = m > 0.f ? m : 0.f;  // also drops the NaN of the measure-zero h2 == -eps case
     m *= wgt; gx *= wgt; gy *= wgt; gz *= wgt;
+    const float yx = x - row[5].x, yy = y - row[5].y, yz = z - row[5].z;  // lever arm about the camera centre
     obs = m;
     S.m += m;
     S.fx += gx; S.fy += gy; S.fz += gz;
-    S.tx += gy * ev.yz - gz * ev.yy;   // (g x y)_x
-    S.ty += gz * ev.yx - gx * ev.yz;
-    S.tz += gx * ev.yy - gy * ev.yx;
+    S.tx += gy * yz - gz * yy;   // (g x y)_x
+    S.ty += gz * yx - gx * yz;
+    S.tz += gx * yy - gy * yx;
 }
 
 template <bool HAS_W, bool HAS_OBS>
@@ -37,7 +38,7 @@ cov_pose_kernel(const float* __restrict__ xyz, int64_t n, const float* __restric
                 CovConst C, float* __restrict__ obs, float* __restrict__ partials) {
     __shared__ float4 row[COV_ROW_F4];
     __shared__ float red[COV_THREADS / 32][8];
-    if (threadIdx.x == 0) cov_pose_row(trans, quat, K9, C.mu, row);
+    if (threadIdx.x == 0) cov_pose_row(trans, quat, K9, C, row);
     __syncthreads();
 
     PoseSums S = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};

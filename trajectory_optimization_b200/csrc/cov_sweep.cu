@@ -31,11 +31,12 @@ cov_sweep_kernel(const float* __restrict__ xyz, int64_t n, const float* __restri
     const int tid = threadIdx.x, lane = tid & 31;
     for (int w = tid; w < W; w += COV_THREADS) {
         float4* row = ptab + (size_t)w * COV_ROW_F4;
-        cov_pose_row(poses + 3 * w, quats + 4 * w, K9, C.mu, row);
+        cov_pose_row(poses + 3 * w, quats + 4 * w, K9, C, row);
         const float a = mins[w];
         const float b = __fsub_rn(maxs[w], a);
-        row[3].w = a;
-        row[4] = make_float4(0.5f * b, b, __frcp_rn(b), 0.f);
+        const float hb = 0.5f * b;
+        row[3].w = (a + hb) * (1.f - 9.5367431640625e-07f);  // conservative gate threshold
+        row[4] = make_float4(hb, b, __frcp_rn(b), a);
     }
     for (int t = tid; t < n_traj; t += COV_THREADS) ssum[t] = 0.0;
     __syncthreads();
@@ -49,9 +50,9 @@ cov_sweep_kernel(const float* __restrict__ xyz, int64_t n, const float* __restri
             int64_t j = tile * T + s * COV_THREADS + tid;
             valid[s] = j < n;
             j = valid[s] ? j : n - 1;
-            px[s] = __ldg(xyz + j * 3);
-            py[s] = __ldg(xyz + j * 3 + 1);
-            pz[s] = __ldg(xyz + j * 3 + 2);
+            px[s] = valid[s] ? __ldg(xyz + j * 3) : 3.0e18f;  // past the end: m = 0 exactly, never gated
+            py[s] = valid[s] ? __ldg(xyz + j * 3 + 1) : 3.0e18f;
+            pz[s] = valid[s] ? __ldg(xyz + j * 3 + 2) : 3.0e18f;
         }
         for (int t = 0; t < n_traj; ++t) {
             float L[PPT];
@@ -59,14 +60,19 @@ cov_sweep_kernel(const float* __restrict__ xyz, int64_t n, const float* __restri
             for (int s = 0; s < PPT; ++s) L[s] = 0.f;
             for (int i = 0; i < per_traj; ++i) {
                 const float4* row = ptab + (size_t)(t * per_traj + i) * COV_ROW_F4;
-                const float4 v0 = row[0], v1 = row[1], v2 = row[2], v3 = row[3], v4 = row[4];
+                const float4 v0 = row[0], v1 = row[1], v2 = row[2], v3 = row[3];
+                float m[PPT];
 #pragma unroll
-                for (int s = 0; s < PPT; ++s) {
-                    const float m = cov_vis<false>(px[s], py[s], pz[s], v0, v1, v2, v3, C, nullptr);
-                    const float d = __fsub_rn(m, v3.w);
-                    const bool act = d >= v4.x;
-                    if (__any_sync(kFull, act)) {
-                        if (act) {
+                for (int s = 0; s < PPT; ++s) m[s] = cov_vis<false>(px[s], py[s], pz[s], v0, v1, v2, v3, C, nullptr);
+                float mmax = m[0];
+#pragma unroll
+                for (int s = 1; s < PPT; ++s) mmax = fmaxf(mmax, m[s]);
+                if (__any_sync(kFull, mmax >= v3.w)) {
+                    const float4 v4 = row[4];
+#pragma unroll
+                    for (int s = 0; s < PPT; ++s) {
+                        const float d = __fsub_rn(m[s], v4.w);
+                        if (d >= v4.x) {
                             const float qc = fminf(__fmul_rn(d, v4.z), C.hi);
                             L[s] += COV_LN2_F * cov_lg2(qc * cov_rcp(1.f - qc));
                         }

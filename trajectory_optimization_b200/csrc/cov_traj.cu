@@ -30,7 +30,7 @@ constexpr unsigned kFull = 0xffffffffu;
 
 __host__ __device__ constexpr int tile_points(int ppt) { return COV_THREADS * ppt; }
 __host__ __device__ constexpr int bit_words(int ppt) { return kWarps * ppt; }         // ballot words per pose
-__host__ __device__ constexpr int bit_stride(int ppt) { return bit_words(ppt) + 1; }  // +1: conflict-free pose-major walk
+__host__ __device__ constexpr int bit_stride(int ppt) { return bit_words(ppt) + 4; }  // rows stay 16-byte aligned
 
 size_t minmax_smem_bytes(int W) { return (size_t)W * (COV_ROW_F4 * sizeof(float4) + 2 * sizeof(unsigned)); }
 size_t fused_smem_bytes(int W, int ppt) {
@@ -43,13 +43,14 @@ __device__ __noinline__ void tie_accumulate(float x, float y, float z, const flo
     CovEval ev;
     const float m = cov_vis<true>(x, y, z, row[0], row[1], row[2], row[3], C, &ev);
     float gx, gy, gz;
-    cov_vis_grad(m, ev, row[1], row[2], row[3], C, gx, gy, gz);
+    cov_vis_grad(m, ev, row[0], row[1], row[2], C, gx, gy, gz);
+    const float yx = x - row[5].x, yy = y - row[5].y, yz = z - row[5].z;
     atomicAdd(dst + 0, (double)gx);
     atomicAdd(dst + 1, (double)gy);
     atomicAdd(dst + 2, (double)gz);
-    atomicAdd(dst + 3, (double)(gy * ev.yz - gz * ev.yy));
-    atomicAdd(dst + 4, (double)(gz * ev.yx - gx * ev.yz));
-    atomicAdd(dst + 5, (double)(gx * ev.yy - gy * ev.yx));
+    atomicAdd(dst + 3, (double)(gy * yz - gz * yy));
+    atomicAdd(dst + 4, (double)(gz * yx - gx * yz));
+    atomicAdd(dst + 5, (double)(gx * yy - gy * yx));
     atomicAdd(dst + 6, 1.0);
 }
 
@@ -64,7 +65,7 @@ cov_traj_minmax_kernel(const float* __restrict__ xyz, int64_t n, const float* __
     unsigned* smax = smin + W;
     const int tid = threadIdx.x, lane = tid & 31;
     for (int w = tid; w < W; w += COV_THREADS) {
-        cov_pose_row(poses + 3 * w, quats + 4 * w, K9, C.mu, ptab + (size_t)w * COV_ROW_F4);
+        cov_pose_row(poses + 3 * w, quats + 4 * w, K9, C, ptab + (size_t)w * COV_ROW_F4);
         smin[w] = 0x7f800000u;
         smax[w] = 0u;
     }
@@ -81,21 +82,36 @@ cov_traj_minmax_kernel(const float* __restrict__ xyz, int64_t n, const float* __
             py[s] = __ldg(xyz + j * 3 + 1);
             pz[s] = __ldg(xyz + j * 3 + 2);
         }
-        for (int w = 0; w < W; ++w) {
-            const float4* row = ptab + (size_t)w * COV_ROW_F4;
-            const float4 v0 = row[0], v1 = row[1], v2 = row[2], v3 = row[3];
-            float mn = __uint_as_float(0x7f800000u), mx = 0.f;
+        for (int w0 = 0; w0 < W; w0 += 32) {
+            // lane i keeps the warp-wide min/max of pose w0+i in registers; one shared atomic per 32 poses
+            unsigned keep_mn = 0x7f800000u, keep_mx = 0u;
+            const int wn = (W - w0 < 32) ? (W - w0) : 32;
+            for (int i = 0; i < wn; ++i) {
+                const float4* row = ptab + (size_t)(w0 + i) * COV_ROW_F4;
+                const float4 v0 = row[0], v1 = row[1], v2 = row[2], v3 = row[3];
+                float m[PPT];
 #pragma unroll
-            for (int s = 0; s < PPT; ++s) {
-                const float m = cov_vis<false>(px[s], py[s], pz[s], v0, v1, v2, v3, C, nullptr);
-                mn = fminf(mn, m);
-                mx = fmaxf(mx, m);
+                for (int s = 0; s < PPT; ++s) m[s] = cov_vis<false>(px[s], py[s], pz[s], v0, v1, v2, v3, C, nullptr);
+                float mn = m[0], mx = m[0];
+#pragma unroll
+                for (int s = 1; s + 1 < PPT; s += 2) {
+                    mn = fminf(mn, fminf(m[s], m[s + 1]));
+                    mx = fmaxf(mx, fmaxf(m[s], m[s + 1]));
+                }
+                if ((PPT & 1) == 0) {
+                    mn = fminf(mn, m[PPT - 1]);
+                    mx = fmaxf(mx, m[PPT - 1]);
+                }
+                const unsigned umn = __reduce_min_sync(kFull, __float_as_uint(mn));
+                const unsigned umx = __reduce_max_sync(kFull, __float_as_uint(mx));
+                if (lane == i) {
+                    keep_mn = umn;
+                    keep_mx = umx;
+                }
             }
-            const unsigned umn = __reduce_min_sync(kFull, __float_as_uint(mn));
-            const unsigned umx = __reduce_max_sync(kFull, __float_as_uint(mx));
-            if (lane == 0) {
-                atomicMin(smin + w, umn);
-                atomicMax(smax + w, umx);
+            if (lane < wn) {
+                atomicMin(smin + w0 + lane, keep_mn);
+                atomicMax(smax + w0 + lane, keep_mx);
             }
         }
     }
@@ -133,15 +149,20 @@ cov_traj_fused_kernel(const float* __restrict__ xyz, int64_t n, const float* __r
     float* Gs = zs + T;
     float* accs = Gs + T;
     __shared__ double red[kWarps];
+    __shared__ int amin_pos;  // some pose has min_j m > 0: its arg-min points carry gradient
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) amin_pos = 0;
+    __syncthreads();
     for (int w = tid; w < W; w += COV_THREADS) {
         float4* row = ptab + (size_t)w * COV_ROW_F4;
-        cov_pose_row(poses + 3 * w, quats + 4 * w, K9, C.mu, row);
+        cov_pose_row(poses + 3 * w, quats + 4 * w, K9, C, row);
         const float a = minmax[w];
         const float b = __fsub_rn(minmax[W + w], a);
-        row[3].w = a;
-        row[4] = make_float4(0.5f * b, b, __frcp_rn(b), 0.f);
+        const float hb = 0.5f * b;
+        row[3].w = (a + hb) * (1.f - 9.5367431640625e-07f);  // conservative gate threshold (exact test in the rare path)
+        row[4] = make_float4(hb, b, __frcp_rn(b), a);
+        if (a > 0.f) amin_pos = 1;  // benign race: every writer stores 1
     }
     for (int i = tid; i < W * 8; i += COV_THREADS) accs[i] = 0.f;
     __syncthreads();
@@ -156,59 +177,62 @@ cov_traj_fused_kernel(const float* __restrict__ xyz, int64_t n, const float* __r
         // ------------------------------ phase 1: every (point, pose) ------------------------------
         float px[PPT], py[PPT], pz[PPT], L[PPT];
         bool valid[PPT];
-        unsigned vmask[PPT];
 #pragma unroll
         for (int s = 0; s < PPT; ++s) {
-            int64_t j = tile * T + s * COV_THREADS + tid;
+            const int64_t j = tile * T + s * COV_THREADS + tid;
             valid[s] = j < n;
-            j = valid[s] ? j : n - 1;
-            px[s] = __ldg(xyz + j * 3);
-            py[s] = __ldg(xyz + j * 3 + 1);
-            pz[s] = __ldg(xyz + j * 3 + 2);
+            // a point past the end sits 3e18 m away: m = 0 exactly, never gated, never a tie
+            px[s] = valid[s] ? __ldg(xyz + j * 3) : 3.0e18f;
+            py[s] = valid[s] ? __ldg(xyz + j * 3 + 1) : 3.0e18f;
+            pz[s] = valid[s] ? __ldg(xyz + j * 3 + 2) : 3.0e18f;
             xs[s * COV_THREADS + tid] = px[s];
             ys[s * COV_THREADS + tid] = py[s];
             zs[s * COV_THREADS + tid] = pz[s];
             L[s] = 0.f;
-            vmask[s] = __ballot_sync(kFull, valid[s]);
         }
+        const bool check_amin = amin_pos != 0;
         for (int w = 0; w < W; ++w) {
             const float4* row = ptab + (size_t)w * COV_ROW_F4;
-            const float4 v0 = row[0], v1 = row[1], v2 = row[2], v3 = row[3], v4 = row[4];
-            // straight-line evaluation of the thread's PPT points (independent chains -> ILP), votes afterwards
-            float m[PPT], d[PPT];
+            const float4 v0 = row[0], v1 = row[1], v2 = row[2], v3 = row[3];
+            // straight-line evaluation of the thread's PPT points (independent chains -> ILP), one vote per pose
+            float m[PPT];
+#pragma unroll
+            for (int s = 0; s < PPT; ++s) m[s] = cov_vis<false>(px[s], py[s], pz[s], v0, v1, v2, v3, C, nullptr);
+            float mmax = m[0];
+#pragma unroll
+            for (int s = 1; s + 1 < PPT; s += 2) mmax = fmaxf(mmax, fmaxf(m[s], m[s + 1]));
+            if ((PPT & 1) == 0) mmax = fmaxf(mmax, m[PPT - 1]);
             unsigned bal[PPT];
-            unsigned any = 0u;
 #pragma unroll
-            for (int s = 0; s < PPT; ++s) {
-                m[s] = cov_vis<false>(px[s], py[s], pz[s], v0, v1, v2, v3, C, nullptr);
-                d[s] = __fsub_rn(m[s], v3.w);
-            }
-#pragma unroll
-            for (int s = 0; s < PPT; ++s) {
-                bal[s] = __ballot_sync(kFull, d[s] >= v4.x) & vmask[s];
-                any |= bal[s];
-            }
-            if (lane == 0) {
-                unsigned* brow = bits + (size_t)w * RS + warp * PPT;
-#pragma unroll
-                for (int s = 0; s < PPT; ++s) brow[s] = bal[s];
-            }
-            if (any != 0u) {  // warp-uniform; ~1 % of (warp, pose) iterations on a random cloud
+            for (int s = 0; s < PPT; ++s) bal[s] = 0u;
+            if (__any_sync(kFull, mmax >= v3.w)) {  // warp-uniform; a few % of (warp, pose) iterations
+                const float4 v4 = row[4];
 #pragma unroll
                 for (int s = 0; s < PPT; ++s) {
-                    if ((bal[s] >> lane) & 1u) {
-                        const float p = __fmul_rn(d[s], v4.z);
+                    const float d = __fsub_rn(m[s], v4.w);
+                    const bool act = d >= v4.x;  // exactly p >= 0.5
+                    bal[s] = __ballot_sync(kFull, act);
+                    if (act) {
+                        const float p = __fmul_rn(d, v4.z);
                         const float qc = fminf(p, C.hi);
                         L[s] += COV_LN2_F * cov_lg2(qc * cov_rcp(1.f - qc));
-                        if (d[s] == v4.y) tie_accumulate(px[s], py[s], pz[s], row, C, acc + (size_t)w * COV_ACC_STRIDE + 8);
+                        if (d == v4.y) tie_accumulate(px[s], py[s], pz[s], row, C, acc + (size_t)w * COV_ACC_STRIDE + 8);
                     }
                 }
             }
-            if (v3.w > 0.f) {  // block-uniform: only when the minimum did not underflow to 0
+            if (lane == 0) {
+                unsigned* brow = bits + (size_t)w * RS + warp * PPT;
+                if (PPT == 4) *reinterpret_cast<uint4*>(brow) = make_uint4(bal[0], bal[1 % PPT], bal[2 % PPT], bal[3 % PPT]);
+                else if (PPT == 2) *reinterpret_cast<uint2*>(brow) = make_uint2(bal[0], bal[1 % PPT]);
+                else brow[0] = bal[0];
+            }
+            if (check_amin) {  // block-uniform; only compact clouds whose minimum did not underflow to 0
+                const float a = row[4].w;
+                if (a > 0.f) {
 #pragma unroll
-                for (int s = 0; s < PPT; ++s)
-                    if (((vmask[s] >> lane) & 1u) && m[s] == v3.w)
-                        tie_accumulate(px[s], py[s], pz[s], row, C, acc + (size_t)w * COV_ACC_STRIDE + 15);
+                    for (int s = 0; s < PPT; ++s)
+                        if (m[s] == a) tie_accumulate(px[s], py[s], pz[s], row, C, acc + (size_t)w * COV_ACC_STRIDE + 15);
+                }
             }
         }
 #pragma unroll
@@ -231,7 +255,7 @@ cov_traj_fused_kernel(const float* __restrict__ xyz, int64_t n, const float* __r
             const int w = live ? (task >> seg_log2) : 0;
             const int seg = task & (nseg - 1);
             const float4* row = ptab + (size_t)w * COV_ROW_F4;
-            const float4 v0 = row[0], v1 = row[1], v2 = row[2], v3 = row[3], v4 = row[4];
+            const float4 v0 = row[0], v1 = row[1], v2 = row[2], v3 = row[3], v4 = row[4], v5 = row[5];
             const unsigned* brow = bits + (size_t)w * RS;
             int k = seg * wps;
             const int kend = live ? k + wps : k;
@@ -245,18 +269,20 @@ cov_traj_fused_kernel(const float* __restrict__ xyz, int64_t n, const float* __r
                     word &= word - 1;
                     const int local = (k % PPT) * COV_THREADS + (k / PPT) * 32 + bit;
                     CovEval ev;
-                    const float m = cov_vis<true>(xs[local], ys[local], zs[local], v0, v1, v2, v3, C, &ev);
-                    const float d = __fsub_rn(m, v3.w);
+                    const float x = xs[local], y = ys[local], z = zs[local];
+                    const float m = cov_vis<true>(x, y, z, v0, v1, v2, v3, C, &ev);
+                    const float d = __fsub_rn(m, v4.w);
                     const float p = __fdiv_rn(d, v4.y);
                     if (p <= C.hi) {  // clamp backward gate (inclusive); p >= 0.5 holds for every set bit
                         float gx, gy, gz;
-                        cov_vis_grad(m, ev, v1, v2, v3, C, gx, gy, gz);
+                        cov_vis_grad(m, ev, v0, v1, v2, C, gx, gy, gz);
+                        const float yx = x - v5.x, yy = y - v5.y, yz = z - v5.z;
                         const float e = Gs[local] / (p * (1.f - p));
                         const float om = e * v4.z;
                         f0 += om * gx; f1 += om * gy; f2 += om * gz;
-                        t0 += om * (gy * ev.yz - gz * ev.yy);
-                        t1 += om * (gz * ev.yx - gx * ev.yz);
-                        t2 += om * (gx * ev.yy - gy * ev.yx);
+                        t0 += om * (gy * yz - gz * yy);
+                        t1 += om * (gz * yx - gx * yz);
+                        t2 += om * (gx * yy - gy * yx);
                         se += e;
                         sep += e * p;
                     }
@@ -340,7 +366,7 @@ __global__ void cov_traj_epilogue_kernel(const double* __restrict__ acc, const f
     gq[3] = (float)(s * (Tq[2] * qw + Tq[0] * qy - Tq[1] * qx));
 }
 
-constexpr size_t kSmemCap = 227 * 1024 - 64;  // opt-in shared memory per block on sm_100, minus static use
+constexpr size_t kSmemCap = 227 * 1024 - 256;  // opt-in shared memory per block on sm_100, minus static use
 
 int pick_ppt(int64_t n, int W, bool fused) {
     const int sms = cov_sm_count_cached();
@@ -407,7 +433,8 @@ extern "C" int cov_traj_minmax(const float* xyz, int64_t n, const float* poses, 
     unsigned* gmin = reinterpret_cast<unsigned*>(minmax);
     unsigned* gmax = gmin + W;
     cov_minmax_init_kernel<<<(W + 255) / 256, 256, 0, s>>>(gmin, gmax, W);
-    const int ppt = pick_ppt(n, W, false);
+    int ppt = pick_ppt(n, W, false);
+    if (ppt == 4 && (n + tile_points(8) - 1) / tile_points(8) >= 4 * (int64_t)cov_sm_count_cached()) ppt = 8;
     const size_t smem = minmax_smem_bytes(W);
     const int64_t ntiles = (n + tile_points(ppt) - 1) / tile_points(ppt);
 #define LAUNCH_MM(P)                                                                                          \
@@ -415,7 +442,7 @@ extern "C" int cov_traj_minmax(const float* xyz, int64_t n, const float* poses, 
         const int grid = grid_for(cov_traj_minmax_kernel<P>, smem, ntiles);                                   \
         cov_traj_minmax_kernel<P><<<grid, COV_THREADS, smem, s>>>(xyz, n, poses, quats, W, K, C, gmin, gmax); \
     }
-    if (ppt == 4) LAUNCH_MM(4) else if (ppt == 2) LAUNCH_MM(2) else LAUNCH_MM(1)
+    if (ppt == 8) LAUNCH_MM(8) else if (ppt == 4) LAUNCH_MM(4) else if (ppt == 2) LAUNCH_MM(2) else LAUNCH_MM(1)
 #undef LAUNCH_MM
     return cov_check_launch("cov_traj_minmax");
 }
