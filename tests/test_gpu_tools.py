@@ -62,3 +62,61 @@ def test_flip_bit_exact_vs_oracle_1m(dev, tools):
     f = tools.sphericalFlip(torch.from_numpy(pts).to(dev), dev, 2)
     ref, _, _ = orc.spherical_flip(pts, 2)
     assert np.array_equal(f.detach().cpu().numpy().view(np.uint32), ref.view(np.uint32))
+
+
+HPR_CASES = ["hpr_shell", "hpr_shell_small", "hpr_halfspace", "hpr_sample"]
+
+
+@pytest.mark.parametrize("name", HPR_CASES)
+def test_hidden_pts_removal_index_sets_bit_exact(name, dev, tools):
+    """Visible-point index sets equal the reference's (Qhull) on the recorded fixtures, incl. the vertices[:-1] quirk."""
+    g = load_golden(name)
+    pts = torch.from_numpy(g["in_points"]).to(dev)
+    vis, mask = tools.hidden_pts_removal(pts, dev, int(g["in_R_param"]))
+    assert mask.dtype == torch.float32 and mask.shape == (len(pts),)
+    idx = torch.nonzero(mask).reshape(-1).cpu().numpy()
+    assert np.array_equal(idx, g["out_idx"])
+    if "out_visible" in g:
+        assert np.array_equal(vis.cpu().numpy(), g["out_visible"])
+    hull = tools.convexHull(tools.sphericalFlip(pts, dev, 2), dev)
+    assert hull.n_exact_fallback == 0  # every decision carried an fp64 certificate
+    origin_is_vertex = name == "hpr_halfspace"
+    assert (hull.vertices[-1] == len(pts)) == origin_is_vertex
+    assert np.array_equal(hull.vertices[:-1], g["out_idx"])
+
+
+@pytest.mark.parametrize("kind,n", [("shell", 1_000_000), ("halfspace", 300_000), ("tiny", 5), ("tiny", 64)])
+def test_hidden_pts_removal_matches_oracle(kind, n, dev, tools):
+    """BASELINE config 2 (1M-point shell cloud, camera inside) and a half-space cloud (origin is a hull vertex)."""
+    gen = np.random.default_rng(1)
+    if kind == "halfspace":
+        pts = (gen.random((n, 3)) * np.array([20, 20, 4]) + np.array([-10, -10, 2])).astype(np.float32)
+    else:
+        d = gen.standard_normal((n, 3))
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        pts = (d * gen.uniform(2, 8, (n, 1))).astype(np.float32)
+    ref_idx, ref_mask = orc.hidden_pts_removal(pts, 2)
+    vis, mask = tools.hidden_pts_removal(torch.from_numpy(pts).to(dev), dev, 2)
+    assert np.array_equal(torch.nonzero(mask).reshape(-1).cpu().numpy(), ref_idx)
+    assert np.array_equal(vis.cpu().numpy(), pts[ref_idx])
+
+
+def test_model_pose_hpr_branch(dev, tools):
+    """ModelPose.forward(hpr=True) multiplies the observations by the occlusion mask of the untransformed cloud
+    (reference src/model.py:112-115)."""
+    from trajectory_optimization_b200 import model
+    g = load_golden("hpr_shell")
+    pts = torch.from_numpy(g["in_points"]).to(dev)
+    K, W, H = tools.load_intrinsics(dev)
+    m = model.ModelPose(pts, torch.tensor([[0.1, 0.2, 0.0]]), torch.tensor([[1.0, 0.0, 0.0, 0.0]]), K, W, H, device=dev)
+    loss_hpr = m(hpr=True)
+    obs_hpr = m.observations.detach().clone()
+    loss_hpr.backward()
+    m2 = model.ModelPose(pts, torch.tensor([[0.1, 0.2, 0.0]]), torch.tensor([[1.0, 0.0, 0.0, 0.0]]), K, W, H, device=dev)
+    m2()
+    mask = torch.zeros(len(pts), device=dev)
+    mask[torch.from_numpy(g["out_idx"]).to(dev)] = 1
+    assert torch.equal(obs_hpr, (m2.observations.detach() * mask))
+    ref = orc.pose_objective(g["in_points"], [0.1, 0.2, 0.0], [1.0, 0, 0, 0], K_np, IMG_W, IMG_H, weight=mask.cpu().numpy())
+    assert abs(loss_hpr.item() - float(ref["loss"])) / float(ref["loss"]) < 1e-4
+    assert np.abs(m.trans.grad.cpu().numpy().ravel() - ref["g_trans"]).max() / np.abs(ref["g_trans"]).max() < 1e-4

@@ -20,6 +20,8 @@
 //   The arg-max / arg-min tie sets of the normalisation backward are rare (one point per pose unless
 //   the minimum underflowed to 0, in which case their gradient is exactly negligible and skipped) and
 //   go straight to the fp64 accumulator with atomics.
+#include <cstdlib>
+
 #include "cov_common.cuh"
 #include "../../include/coverage_b200.h"
 
@@ -39,7 +41,9 @@ size_t fused_smem_bytes(int W, int ppt) {
 }
 
 // Unweighted dm/dy and dm/dy x y of one (point, pose) into a tie-set accumulator (7 doubles).
-__device__ __noinline__ void tie_accumulate(float x, float y, float z, const float4* row, CovConst C, double* dst) {
+__device__ __noinline__ void tie_accumulate(float x, float y, float z, const float4* row, CovConst C, double* acc,
+                                            int slot) {
+    double* dst = acc + slot;
     CovEval ev;
     const float m = cov_vis<true>(x, y, z, row[0], row[1], row[2], row[3], C, &ev);
     float gx, gy, gz;
@@ -54,8 +58,8 @@ __device__ __noinline__ void tie_accumulate(float x, float y, float z, const flo
     atomicAdd(dst + 6, 1.0);
 }
 
-template <int PPT>
-__global__ void __launch_bounds__(COV_THREADS, 2)
+template <int PPT, int MINB, int U>
+__global__ void __launch_bounds__(COV_THREADS, MINB)
 cov_traj_minmax_kernel(const float* __restrict__ xyz, int64_t n, const float* __restrict__ poses,
                        const float* __restrict__ quats, int W, const float* __restrict__ K9, CovConst C,
                        unsigned* __restrict__ gmin, unsigned* __restrict__ gmax) {
@@ -86,27 +90,37 @@ cov_traj_minmax_kernel(const float* __restrict__ xyz, int64_t n, const float* __
             // lane i keeps the warp-wide min/max of pose w0+i in registers; one shared atomic per 32 poses
             unsigned keep_mn = 0x7f800000u, keep_mx = 0u;
             const int wn = (W - w0 < 32) ? (W - w0) : 32;
-            for (int i = 0; i < wn; ++i) {
-                const float4* row = ptab + (size_t)(w0 + i) * COV_ROW_F4;
-                const float4 v0 = row[0], v1 = row[1], v2 = row[2], v3 = row[3];
-                float m[PPT];
+            for (int i = 0; i < wn; i += U) {
+                float mn[U], mx[U];
+                int wi[U];
 #pragma unroll
-                for (int s = 0; s < PPT; ++s) m[s] = cov_vis<false>(px[s], py[s], pz[s], v0, v1, v2, v3, C, nullptr);
-                float mn = m[0], mx = m[0];
+                for (int u = 0; u < U; ++u) {  // U poses in flight: U*PPT independent evaluation chains
+                    wi[u] = (i + u < wn) ? (i + u) : (wn - 1);  // odd remainder: re-evaluate the last pose (harmless)
+                    const float4* row = ptab + (size_t)(w0 + wi[u]) * COV_ROW_F4;
+                    const float4 v0 = row[0], v1 = row[1], v2 = row[2], v3 = row[3];
+                    float m[PPT];
 #pragma unroll
-                for (int s = 1; s + 1 < PPT; s += 2) {
-                    mn = fminf(mn, fminf(m[s], m[s + 1]));
-                    mx = fmaxf(mx, fmaxf(m[s], m[s + 1]));
+                    for (int s = 0; s < PPT; ++s) m[s] = cov_vis<false>(px[s], py[s], pz[s], v0, v1, v2, v3, C, nullptr);
+                    mn[u] = m[0];
+                    mx[u] = m[0];
+#pragma unroll
+                    for (int s = 1; s + 1 < PPT; s += 2) {
+                        mn[u] = fminf(mn[u], fminf(m[s], m[s + 1]));
+                        mx[u] = fmaxf(mx[u], fmaxf(m[s], m[s + 1]));
+                    }
+                    if ((PPT & 1) == 0) {
+                        mn[u] = fminf(mn[u], m[PPT - 1]);
+                        mx[u] = fmaxf(mx[u], m[PPT - 1]);
+                    }
                 }
-                if ((PPT & 1) == 0) {
-                    mn = fminf(mn, m[PPT - 1]);
-                    mx = fmaxf(mx, m[PPT - 1]);
-                }
-                const unsigned umn = __reduce_min_sync(kFull, __float_as_uint(mn));
-                const unsigned umx = __reduce_max_sync(kFull, __float_as_uint(mx));
-                if (lane == i) {
-                    keep_mn = umn;
-                    keep_mx = umx;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const unsigned umn = __reduce_min_sync(kFull, __float_as_uint(mn[u]));
+                    const unsigned umx = __reduce_max_sync(kFull, __float_as_uint(mx[u]));
+                    if (lane == wi[u]) {
+                        keep_mn = umn;
+                        keep_mx = umx;
+                    }
                 }
             }
             if (lane < wn) {
@@ -130,7 +144,65 @@ __global__ void cov_minmax_init_kernel(unsigned* gmin, unsigned* gmax, int W) {
     }
 }
 
-template <int PPT, bool HAS_UP>
+// Phase-1 body of the fused pass for U consecutive poses starting at w (U*PPT independent chains).
+template <int PPT, int U, bool AMIN>
+__device__ __forceinline__ void fused_pose_iter(int w, const float4* __restrict__ ptab, unsigned* __restrict__ bits_warp,
+                                                int RS, const float (&px)[PPT], const float (&py)[PPT],
+                                                const float (&pz)[PPT], float (&L)[PPT], const CovConst& C,
+                                                double* __restrict__ acc, int lane) {
+    float m[U][PPT];
+    float mmax[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const float4* row = ptab + (size_t)(w + u) * COV_ROW_F4;
+        const float4 v0 = row[0], v1 = row[1], v2 = row[2], v3 = row[3];
+#pragma unroll
+        for (int s = 0; s < PPT; ++s) m[u][s] = cov_vis<false>(px[s], py[s], pz[s], v0, v1, v2, v3, C, nullptr);
+        mmax[u] = m[u][0];
+#pragma unroll
+        for (int s = 1; s + 1 < PPT; s += 2) mmax[u] = fmaxf(mmax[u], fmaxf(m[u][s], m[u][s + 1]));
+        if ((PPT & 1) == 0) mmax[u] = fmaxf(mmax[u], m[u][PPT - 1]);
+        mmax[u] -= v3.w;  // >= 0  <=>  some point of this lane may pass the gate (conservative threshold)
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const float4* row = ptab + (size_t)(w + u) * COV_ROW_F4;
+        unsigned bal[PPT];
+#pragma unroll
+        for (int s = 0; s < PPT; ++s) bal[s] = 0u;
+        if (__any_sync(kFull, mmax[u] >= 0.f)) {  // warp-uniform; a few % of (warp, pose) iterations
+            const float4 v4 = row[4];
+#pragma unroll
+            for (int s = 0; s < PPT; ++s) {
+                const float d = __fsub_rn(m[u][s], v4.w);
+                const bool act = d >= v4.x;  // exactly p >= 0.5
+                bal[s] = __ballot_sync(kFull, act);
+                if (act) {
+                    const float p = __fmul_rn(d, v4.z);
+                    const float qc = fminf(p, C.hi);
+                    L[s] += COV_LN2_F * cov_lg2(qc * cov_rcp(1.f - qc));
+                    if (d == v4.y) tie_accumulate(px[s], py[s], pz[s], row, C, acc, (w + u) * COV_ACC_STRIDE + 8);
+                }
+            }
+        }
+        if (lane == 0) {
+            unsigned* brow = bits_warp + (size_t)(w + u) * RS;
+            if (PPT == 4) *reinterpret_cast<uint4*>(brow) = make_uint4(bal[0], bal[1 % PPT], bal[2 % PPT], bal[3 % PPT]);
+            else if (PPT == 2) *reinterpret_cast<uint2*>(brow) = make_uint2(bal[0], bal[1 % PPT]);
+            else brow[0] = bal[0];
+        }
+        if (AMIN) {  // only compact clouds whose minimum did not underflow to 0 (block-uniform choice of the loop)
+            const float a = row[4].w;
+            if (a > 0.f) {
+#pragma unroll
+                for (int s = 0; s < PPT; ++s)
+                    if (m[u][s] == a) tie_accumulate(px[s], py[s], pz[s], row, C, acc, (w + u) * COV_ACC_STRIDE + 15);
+            }
+        }
+    }
+}
+
+template <int PPT, bool HAS_UP, int U>
 __global__ void __launch_bounds__(COV_THREADS, 2)
 cov_traj_fused_kernel(const float* __restrict__ xyz, int64_t n, const float* __restrict__ poses,
                       const float* __restrict__ quats, int W, const float* __restrict__ K9, CovConst C,
@@ -191,48 +263,14 @@ cov_traj_fused_kernel(const float* __restrict__ xyz, int64_t n, const float* __r
             L[s] = 0.f;
         }
         const bool check_amin = amin_pos != 0;
-        for (int w = 0; w < W; ++w) {
-            const float4* row = ptab + (size_t)w * COV_ROW_F4;
-            const float4 v0 = row[0], v1 = row[1], v2 = row[2], v3 = row[3];
-            // straight-line evaluation of the thread's PPT points (independent chains -> ILP), one vote per pose
-            float m[PPT];
-#pragma unroll
-            for (int s = 0; s < PPT; ++s) m[s] = cov_vis<false>(px[s], py[s], pz[s], v0, v1, v2, v3, C, nullptr);
-            float mmax = m[0];
-#pragma unroll
-            for (int s = 1; s + 1 < PPT; s += 2) mmax = fmaxf(mmax, fmaxf(m[s], m[s + 1]));
-            if ((PPT & 1) == 0) mmax = fmaxf(mmax, m[PPT - 1]);
-            unsigned bal[PPT];
-#pragma unroll
-            for (int s = 0; s < PPT; ++s) bal[s] = 0u;
-            if (__any_sync(kFull, mmax >= v3.w)) {  // warp-uniform; a few % of (warp, pose) iterations
-                const float4 v4 = row[4];
-#pragma unroll
-                for (int s = 0; s < PPT; ++s) {
-                    const float d = __fsub_rn(m[s], v4.w);
-                    const bool act = d >= v4.x;  // exactly p >= 0.5
-                    bal[s] = __ballot_sync(kFull, act);
-                    if (act) {
-                        const float p = __fmul_rn(d, v4.z);
-                        const float qc = fminf(p, C.hi);
-                        L[s] += COV_LN2_F * cov_lg2(qc * cov_rcp(1.f - qc));
-                        if (d == v4.y) tie_accumulate(px[s], py[s], pz[s], row, C, acc + (size_t)w * COV_ACC_STRIDE + 8);
-                    }
-                }
-            }
-            if (lane == 0) {
-                unsigned* brow = bits + (size_t)w * RS + warp * PPT;
-                if (PPT == 4) *reinterpret_cast<uint4*>(brow) = make_uint4(bal[0], bal[1 % PPT], bal[2 % PPT], bal[3 % PPT]);
-                else if (PPT == 2) *reinterpret_cast<uint2*>(brow) = make_uint2(bal[0], bal[1 % PPT]);
-                else brow[0] = bal[0];
-            }
-            if (check_amin) {  // block-uniform; only compact clouds whose minimum did not underflow to 0
-                const float a = row[4].w;
-                if (a > 0.f) {
-#pragma unroll
-                    for (int s = 0; s < PPT; ++s)
-                        if (m[s] == a) tie_accumulate(px[s], py[s], pz[s], row, C, acc + (size_t)w * COV_ACC_STRIDE + 15);
-                }
+        {
+            unsigned* bits_warp = bits + warp * PPT;
+            int w = 0;
+            if (!check_amin) {
+                for (; w + U <= W; w += U) fused_pose_iter<PPT, U, false>(w, ptab, bits_warp, RS, px, py, pz, L, C, acc, lane);
+                for (; w < W; ++w) fused_pose_iter<PPT, 1, false>(w, ptab, bits_warp, RS, px, py, pz, L, C, acc, lane);
+            } else {
+                for (; w < W; ++w) fused_pose_iter<PPT, 1, true>(w, ptab, bits_warp, RS, px, py, pz, L, C, acc, lane);
             }
         }
 #pragma unroll
@@ -366,7 +404,13 @@ __global__ void cov_traj_epilogue_kernel(const double* __restrict__ acc, const f
     gq[3] = (float)(s * (Tq[2] * qw + Tq[0] * qy - Tq[1] * qx));
 }
 
-constexpr size_t kSmemCap = 227 * 1024 - 256;  // opt-in shared memory per block on sm_100, minus static use
+constexpr size_t kSmemCap = 227 * 1024 - 256;
+
+// development-only kernel-variant switch (COV_DEV_* environment variables); 0 = shipped configuration
+int dev_variant(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}  // opt-in shared memory per block on sm_100, minus static use
 
 int pick_ppt(int64_t n, int W, bool fused) {
     const int sms = cov_sm_count_cached();
@@ -436,13 +480,22 @@ extern "C" int cov_traj_minmax(const float* xyz, int64_t n, const float* poses, 
     int ppt = pick_ppt(n, W, false);
     if (ppt == 4 && (n + tile_points(8) - 1) / tile_points(8) >= 4 * (int64_t)cov_sm_count_cached()) ppt = 8;
     const size_t smem = minmax_smem_bytes(W);
-    const int64_t ntiles = (n + tile_points(ppt) - 1) / tile_points(ppt);
-#define LAUNCH_MM(P)                                                                                          \
-    {                                                                                                         \
-        const int grid = grid_for(cov_traj_minmax_kernel<P>, smem, ntiles);                                   \
-        cov_traj_minmax_kernel<P><<<grid, COV_THREADS, smem, s>>>(xyz, n, poses, quats, W, K, C, gmin, gmax); \
+    const int mm_variant = dev_variant("COV_DEV_MM", 0);
+    const int eff_ppt = (ppt == 8) ? ((mm_variant == 0 || mm_variant == 4) ? 8 : (mm_variant == 5 ? 2 : 4)) : (ppt >= 4 ? 4 : ppt);
+    const int64_t ntiles = (n + tile_points(eff_ppt) - 1) / tile_points(eff_ppt);
+#define LAUNCH_MM(P, B, U)                                                                                          \
+    {                                                                                                               \
+        const int grid = grid_for(cov_traj_minmax_kernel<P, B, U>, smem, ntiles);                                   \
+        cov_traj_minmax_kernel<P, B, U><<<grid, COV_THREADS, smem, s>>>(xyz, n, poses, quats, W, K, C, gmin, gmax); \
     }
-    if (ppt == 8) LAUNCH_MM(8) else if (ppt == 4) LAUNCH_MM(4) else if (ppt == 2) LAUNCH_MM(2) else LAUNCH_MM(1)
+    const int variant = dev_variant("COV_DEV_MM", 0);
+    if (ppt == 8 && variant == 0) LAUNCH_MM(8, 2, 2)
+    else if (ppt == 8 && variant == 1) LAUNCH_MM(4, 3, 1)
+    else if (ppt == 8 && variant == 2) LAUNCH_MM(4, 2, 2)
+    else if (ppt == 8 && variant == 3) LAUNCH_MM(4, 3, 2)
+    else if (ppt == 8 && variant == 4) LAUNCH_MM(8, 2, 1)
+    else if (ppt == 8 && variant == 5) LAUNCH_MM(2, 3, 4)
+    else if (ppt >= 4) LAUNCH_MM(4, 2, 1) else if (ppt == 2) LAUNCH_MM(2, 2, 1) else LAUNCH_MM(1, 2, 1)
 #undef LAUNCH_MM
     return cov_check_launch("cov_traj_minmax");
 }
@@ -466,7 +519,9 @@ extern "C" int cov_traj_fused(const float* xyz, int64_t n, const float* poses, c
     }
     cudaStream_t s = (cudaStream_t)stream;
     const CovConst C = cov_make_const(cam);
-    const int ppt = pick_ppt(n, W, true);
+    int ppt = pick_ppt(n, W, true);
+    const int fvariant = dev_variant("COV_DEV_F", 0);
+    if (ppt == 4 && (fvariant == 2 || fvariant == 3)) ppt = 2;
     if (ppt == 0) {
         cov_set_error("cov_traj_fused: %d poses do not fit in shared memory", W);
         return COV_ERR_UNSUPPORTED;
@@ -480,17 +535,20 @@ extern "C" int cov_traj_fused(const float* xyz, int64_t n, const float* poses, c
     float* partials = reinterpret_cast<float*>(sumr + COV_MAX_GRID);
     cudaMemsetAsync(acc, 0, ((size_t)W * COV_ACC_STRIDE + 1) * sizeof(double), s);
     int grid = 1;
-#define LAUNCH_F(P, U)                                                                                          \
+#define LAUNCH_F(P, UP, U)                                                                                      \
     {                                                                                                           \
-        grid = grid_for(cov_traj_fused_kernel<P, U>, smem, ntiles);                                             \
-        cov_traj_fused_kernel<P, U><<<grid, COV_THREADS, smem, s>>>(xyz, n, poses, quats, W, K, C, minmax,      \
-                                                                    upstream, rewards, partials, sumr, acc,     \
-                                                                    seg_log2);                                  \
+        grid = grid_for(cov_traj_fused_kernel<P, UP, U>, smem, ntiles);                                         \
+        cov_traj_fused_kernel<P, UP, U><<<grid, COV_THREADS, smem, s>>>(xyz, n, poses, quats, W, K, C, minmax,  \
+                                                                        upstream, rewards, partials, sumr, acc, \
+                                                                        seg_log2);                              \
     }
     if (upstream) {
-        if (ppt == 4) LAUNCH_F(4, true) else if (ppt == 2) LAUNCH_F(2, true) else LAUNCH_F(1, true)
+        if (ppt == 4) LAUNCH_F(4, true, 1) else if (ppt == 2) LAUNCH_F(2, true, 1) else LAUNCH_F(1, true, 1)
     } else {
-        if (ppt == 4) LAUNCH_F(4, false) else if (ppt == 2) LAUNCH_F(2, false) else LAUNCH_F(1, false)
+        if (ppt == 4 && fvariant == 1) LAUNCH_F(4, false, 2)
+        else if (ppt == 2 && fvariant == 2) LAUNCH_F(2, false, 2)
+        else if (ppt == 2 && fvariant == 3) LAUNCH_F(2, false, 4)
+        else if (ppt == 4) LAUNCH_F(4, false, 1) else if (ppt == 2) LAUNCH_F(2, false, 1) else LAUNCH_F(1, false, 1)
     }
 #undef LAUNCH_F
     cov_traj_reduce_kernel<<<(W * 8 + 255) / 256, 256, 0, s>>>(partials, sumr, grid, W, acc);
