@@ -51,21 +51,73 @@ def _reduce_ops():
     return dist.ReduceOp.MIN, dist.ReduceOp.MAX, dist.ReduceOp.SUM
 
 
+class CudaBackend:
+    """The five C-ABI calls of the coverage path on device tensors.  `ops._BACKEND` is the only instance the
+    product uses; the N>1 CPU tests swap in a stand-in with the same methods to exercise the collective
+    plumbing below over gloo."""
+
+    def prepare(self, t, device=None, what="tensor"):
+        return _dev_f32(t, device, what)
+
+    def pose_fused(self, pts, t, q, Kd, cam, w, obs):
+        L = _lib.lib()
+        n = pts.shape[0]
+        acc = torch.empty(_lib.POSE_ACC, dtype=torch.float64, device=pts.device)
+        ws_bytes = L.cov_pose_workspace_bytes(n)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=pts.device)
+        _lib.check(L.cov_pose_fused(_ptr(pts), n, _ptr(w), _ptr(t), _ptr(q), _ptr(Kd), ctypes.byref(cam), _ptr(obs),
+                                    _ptr(acc), _ptr(ws), ws_bytes, _stream()), "cov_pose_fused")
+        return acc
+
+    def pose_epilogue(self, acc, t, q):
+        out = torch.empty(8, dtype=torch.float32, device=acc.device)
+        _lib.check(_lib.lib().cov_pose_epilogue(_ptr(acc), _ptr(t), _ptr(q), _ptr(out), _stream()), "cov_pose_epilogue")
+        return out
+
+    def traj_minmax(self, pts, P, Q, Kd, cam):
+        W = P.shape[0]
+        minmax = torch.empty(2 * W, dtype=torch.float32, device=pts.device)
+        _lib.check(_lib.lib().cov_traj_minmax(_ptr(pts), pts.shape[0], _ptr(P), _ptr(Q), W, _ptr(Kd), ctypes.byref(cam),
+                                              _ptr(minmax), _stream()), "cov_traj_minmax")
+        return minmax
+
+    def traj_fused(self, pts, P, Q, Kd, cam, minmax, upstream, rewards):
+        L = _lib.lib()
+        W, n = P.shape[0], pts.shape[0]
+        acc = torch.empty(W * _lib.ACC_STRIDE + 1, dtype=torch.float64, device=pts.device)
+        ws_bytes = L.cov_traj_workspace_bytes(n, W)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=pts.device)
+        _lib.check(L.cov_traj_fused(_ptr(pts), n, _ptr(P), _ptr(Q), W, _ptr(Kd), ctypes.byref(cam), _ptr(minmax),
+                                    _ptr(upstream), _ptr(rewards), _ptr(acc), _ptr(ws), ws_bytes, _stream()),
+                   "cov_traj_fused")
+        return acc
+
+    def traj_epilogue(self, acc, minmax, Q, n_total, upstream_mode):
+        W = Q.shape[0]
+        out = torch.empty(1 + 7 * W, dtype=torch.float32, device=acc.device)
+        _lib.check(_lib.lib().cov_traj_epilogue(_ptr(acc), _ptr(minmax), _ptr(Q), W, n_total, upstream_mode, _ptr(out),
+                                                _stream()), "cov_traj_epilogue")
+        return out
+
+
+_BACKEND = CudaBackend()
+
+
 class CoveragePoseFn(torch.autograd.Function):
     """obs_j = dist_mask*fov_mask[*weight_j], total = sum_j obs_j (reference src/model.py:98-127)."""
 
     @staticmethod
     def forward(ctx, points, trans, quat, K, cam, weight, group):
-        L = _lib.lib()
+        B = _BACKEND
         dev = points.device
-        pts = _dev_f32(points, what="points")
-        t = _dev_f32(trans, dev, "trans").reshape(3)
-        q = _dev_f32(quat, dev, "quat").reshape(4)
-        Kd = _dev_f32(K, dev, "intrins").reshape(9)
-        w = None if weight is None else _dev_f32(weight, dev, "weight").reshape(-1)
+        pts = B.prepare(points, what="points")
+        t = B.prepare(trans, dev, "trans").reshape(3)
+        q = B.prepare(quat, dev, "quat").reshape(4)
+        Kd = B.prepare(K, dev, "intrins").reshape(9)
+        w = None if weight is None else B.prepare(weight, dev, "weight").reshape(-1)
         n = pts.shape[0]
         obs = torch.empty(n, dtype=torch.float32, device=dev)
-        out = CoveragePoseFn._run(L, pts, t, q, Kd, cam, w, obs, group)
+        out = CoveragePoseFn._run(pts, t, q, Kd, cam, w, obs, group)
         ctx.cam, ctx.group = cam, group
         ctx.shapes = (trans.shape, quat.shape)
         ctx.save_for_backward(pts, t, q, Kd, w, out)
@@ -73,19 +125,11 @@ class CoveragePoseFn(torch.autograd.Function):
         return obs, out[0].clone()
 
     @staticmethod
-    def _run(L, pts, t, q, Kd, cam, w, obs, group):
-        dev = pts.device
-        n = pts.shape[0]
-        acc = torch.empty(_lib.POSE_ACC, dtype=torch.float64, device=dev)
-        ws_bytes = L.cov_pose_workspace_bytes(n)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        _lib.check(L.cov_pose_fused(_ptr(pts), n, _ptr(w), _ptr(t), _ptr(q), _ptr(Kd), ctypes.byref(cam), _ptr(obs),
-                                    _ptr(acc), _ptr(ws), ws_bytes, _stream()), "cov_pose_fused")
+    def _run(pts, t, q, Kd, cam, w, obs, group):
+        acc = _BACKEND.pose_fused(pts, t, q, Kd, cam, w, obs)   # this shard's sums (8 doubles)
         if group is not None:
             _all_reduce(acc, _reduce_ops()[2], group)
-        out = torch.empty(8, dtype=torch.float32, device=dev)
-        _lib.check(L.cov_pose_epilogue(_ptr(acc), _ptr(t), _ptr(q), _ptr(out), _stream()), "cov_pose_epilogue")
-        return out
+        return _BACKEND.pose_epilogue(acc, t, q)
 
     @staticmethod
     def backward(ctx, g_obs, g_total):
@@ -97,10 +141,10 @@ class CoveragePoseFn(torch.autograd.Function):
         if g_obs is not None:
             # someone differentiated through the per-point vector: one more pass with
             # weight_j = upstream_j [* weight_j]
-            up = _dev_f32(g_obs, pts.device, "grad_obs").reshape(-1)
+            up = _BACKEND.prepare(g_obs, pts.device, "grad_obs").reshape(-1)
             if w is not None:
                 up = up * w
-            o2 = CoveragePoseFn._run(_lib.lib(), pts, t, q, Kd, ctx.cam, up, None, ctx.group)
+            o2 = CoveragePoseFn._run(pts, t, q, Kd, ctx.cam, up, None, ctx.group)
             g_t = o2[1:4] if g_t is None else g_t + o2[1:4]
             g_q = o2[4:8] if g_q is None else g_q + o2[4:8]
         ts, qs = ctx.shapes
@@ -114,25 +158,23 @@ class CoverageTrajFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, points, poses, quats, K, cam, n_total, group):
-        L = _lib.lib()
+        B = _BACKEND
         dev = points.device
-        pts = _dev_f32(points, what="points")
-        P = _dev_f32(poses, dev, "poses").reshape(-1, 3)
-        Q = _dev_f32(quats, dev, "quats").reshape(-1, 4)
-        Kd = _dev_f32(K, dev, "intrins").reshape(9)
+        pts = B.prepare(points, what="points")
+        P = B.prepare(poses, dev, "poses").reshape(-1, 3)
+        Q = B.prepare(quats, dev, "quats").reshape(-1, 4)
+        Kd = B.prepare(K, dev, "intrins").reshape(9)
         W, n = P.shape[0], pts.shape[0]
         if Q.shape[0] != W:
             raise ValueError("poses and quats disagree on the number of waypoints")
         n_total = int(n if n_total is None else n_total)
-        minmax = torch.empty(2 * W, dtype=torch.float32, device=dev)
-        _lib.check(L.cov_traj_minmax(_ptr(pts), n, _ptr(P), _ptr(Q), W, _ptr(Kd), ctypes.byref(cam), _ptr(minmax),
-                                     _stream()), "cov_traj_minmax")
-        if group is not None:
+        minmax = B.traj_minmax(pts, P, Q, Kd, cam)          # pass A on this shard
+        if group is not None:                                # global normalisers: W minima, W maxima
             mn, mx, _ = _reduce_ops()
             _all_reduce(minmax[:W], mn, group)
             _all_reduce(minmax[W:], mx, group)
         rewards = torch.empty(n, dtype=torch.float32, device=dev)
-        out = CoverageTrajFn._run(L, pts, P, Q, Kd, cam, minmax, None, rewards, n_total, group)
+        out = CoverageTrajFn._run(pts, P, Q, Kd, cam, minmax, None, rewards, n_total, group)
         ctx.cam, ctx.group, ctx.n_total = cam, group, n_total
         ctx.shapes = (poses.shape, quats.shape)
         ctx.save_for_backward(pts, P, Q, Kd, minmax, out)
@@ -140,21 +182,11 @@ class CoverageTrajFn(torch.autograd.Function):
         return rewards, out[0].clone()
 
     @staticmethod
-    def _run(L, pts, P, Q, Kd, cam, minmax, upstream, rewards, n_total, group):
-        dev = pts.device
-        W, n = P.shape[0], pts.shape[0]
-        acc = torch.empty(W * _lib.ACC_STRIDE + 1, dtype=torch.float64, device=dev)
-        ws_bytes = L.cov_traj_workspace_bytes(n, W)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        _lib.check(L.cov_traj_fused(_ptr(pts), n, _ptr(P), _ptr(Q), W, _ptr(Kd), ctypes.byref(cam), _ptr(minmax),
-                                    _ptr(upstream), _ptr(rewards), _ptr(acc), _ptr(ws), ws_bytes, _stream()),
-                   "cov_traj_fused")
+    def _run(pts, P, Q, Kd, cam, minmax, upstream, rewards, n_total, group):
+        acc = _BACKEND.traj_fused(pts, P, Q, Kd, cam, minmax, upstream, rewards)   # pass B: W*22+1 doubles
         if group is not None:
             _all_reduce(acc, _reduce_ops()[2], group)
-        out = torch.empty(1 + 7 * W, dtype=torch.float32, device=dev)
-        _lib.check(L.cov_traj_epilogue(_ptr(acc), _ptr(minmax), _ptr(Q), W, n_total, 0 if upstream is None else 1,
-                                       _ptr(out), _stream()), "cov_traj_epilogue")
-        return out
+        return _BACKEND.traj_epilogue(acc, minmax, Q, n_total, 0 if upstream is None else 1)
 
     @staticmethod
     def backward(ctx, g_rewards, g_mean):
@@ -165,9 +197,9 @@ class CoverageTrajFn(torch.autograd.Function):
             g_p = g_mean * out[1:1 + 3 * W]
             g_q = g_mean * out[1 + 3 * W:]
         if g_rewards is not None:
-            up = _dev_f32(g_rewards, pts.device, "grad_rewards").reshape(-1)
+            up = _BACKEND.prepare(g_rewards, pts.device, "grad_rewards").reshape(-1)
             scratch = torch.empty(pts.shape[0], dtype=torch.float32, device=pts.device)
-            o2 = CoverageTrajFn._run(_lib.lib(), pts, P, Q, Kd, ctx.cam, minmax, up, scratch, ctx.n_total, ctx.group)
+            o2 = CoverageTrajFn._run(pts, P, Q, Kd, ctx.cam, minmax, up, scratch, ctx.n_total, ctx.group)
             g_p = o2[1:1 + 3 * W] if g_p is None else g_p + o2[1:1 + 3 * W]
             g_q = o2[1 + 3 * W:] if g_q is None else g_q + o2[1 + 3 * W:]
         ps, qs = ctx.shapes
