@@ -119,10 +119,11 @@ int cov_frustum_cull(const float* xyz_dev, int64_t n, const float* K_dev, float 
 /* ------------------------------------------------------------------------------------------
  * Katz hidden-point removal.  ref: src/tools.py:38-53 (sphericalFlip), :56-64 (convexHull),
  * :67-85 (hidden_pts_removal).
- *   cov_hpr_flip: fp32, every operation rounded in the reference's order; radius_dev (1 fp32) out.
- *   cov_hpr_hull: vertex set of conv(flipped U {0}) with exact decisions; writes vertex_mask (n) uint8
- *   (1 = hull vertex), origin_is_vertex (1 int32) and uncertified (1 int32: points whose
- *   floating-point certificate failed and were decided by the exact fallback).
+ *   cov_hpr_flip: fp32, every operation rounded in the reference's order; radius_dev is 2 fp32:
+ *   [0] = R = max|p| * scale (out), [1] = max|p| (scratch/out).
+ *   cov_hpr_hull: vertex set of conv(flipped U {0}); writes vertex_mask (n) uint8 (1 = hull vertex) and
+ *   info_dev (4 int32): [0] origin is a hull vertex, [1] number of decisions whose fp64 certificate could
+ *   not be validated (0 on non-degenerate input), [2] number of vertices among the n points, [3] GJK iterations.
  * ------------------------------------------------------------------------------------------ */
 int cov_hpr_flip(const float* xyz_dev, int64_t n, float scale /* 10**param */, float* flipped_dev,
                  float* radius_dev, void* stream);

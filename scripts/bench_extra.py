@@ -1,0 +1,106 @@
+#!/usr/bin/env python
+"""Secondary measurements for the other BASELINE configs (one GPU), written as JSON lines:
+  c1  single-camera pose optimisation, 100k points: opt-step latency (zero_grad + fwd + bwd + Adam), plus the
+      ModelPose kernel at 1e8 points against the HBM roofline;
+  c3  5-camera trajectory evaluation, 20 waypoints, 10M points (fwd+bwd evals/s);
+  c5  candidate sweep sample: 64 of the 1024 trajectories x 32 waypoints on a 50M-point cloud (fwd evals/s).
+c2 (HPR) is scripts/hpr_bench.py.  Not the driver's bench; numbers are quoted in DESIGN.md/profiles."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from trajectory_optimization_b200 import model, multicam, ops, tools  # noqa: E402
+
+dev = torch.device("cuda:0")
+K, iw, ih = tools.load_intrinsics(dev)
+peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+HBM = float(peaks.get("hbm_gbs", 6650.0))
+
+
+def events(fn, reps):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def box(n, seed):
+    g = torch.Generator(device=dev).manual_seed(seed)
+    lo, hi = torch.tensor(bench.BOX_LO, device=dev), torch.tensor(bench.BOX_HI, device=dev)
+    return torch.rand(n, 3, generator=g, device=dev) * (hi - lo) + lo
+
+
+# ---- c1: pose optimisation step latency at 100k points ----
+pts = box(100_000, 0)
+m = model.ModelPose(pts, torch.tensor([[6.0, 2.0, 0.0]]), torch.tensor([[0.92, 0.0, 0.0, 0.39]]), K, iw, ih, device=dev)
+opt = torch.optim.Adam([{"params": [m.trans], "lr": 0.02}, {"params": [m.quat], "lr": 0.02}])
+
+
+def pose_step():
+    opt.zero_grad()
+    loss = m()
+    loss.backward()
+    opt.step()
+
+
+ms = events(pose_step, 200)
+t0 = time.perf_counter()
+for _ in range(200):
+    pose_step()
+torch.cuda.synchronize()
+wall = (time.perf_counter() - t0) / 200 * 1e3
+print(json.dumps({"config": "c1: ModelPose opt step (zero_grad+fwd+bwd+Adam), 100k points", "gpu_ms_per_step": ms,
+                  "wall_ms_per_step": wall, "evals_per_s": 1e5 / (wall * 1e-3)}), flush=True)
+# ModelPose kernel alone at 1e8 points vs HBM
+big = box(100_000_000, 1)
+T = torch.tensor([[6.0, 2.0, 0.0]], device=dev, requires_grad=True)
+Q = torch.tensor([[0.92, 0.0, 0.0, 0.39]], device=dev, requires_grad=True)
+ms = events(lambda: ops.coverage_pose(big, T, Q, K, iw, ih), 10)
+print(json.dumps({"config": "ModelPose fused fwd+bwd, 1e8 points", "ms": ms, "evals_per_s": 1e8 / (ms * 1e-3),
+                  "hbm_GBps_algorithmic_16B_per_point": 1.6e9 / (ms * 1e-3) / 1e9, "hbm_frac_of_measured_peak": 1.6 / (ms * 1e-3) / HBM}),
+      flush=True)
+del big
+
+# ---- c3: 20 waypoints x 5 cams, 10M points, fwd+bwd ----
+pts = box(10_000_000, 2)
+rig = multicam.ring_rig(5)
+body = bench.body_waypoints(20, 12.0).to(dev).requires_grad_(True)
+
+
+def traj_step():
+    body.grad = None
+    t, q = multicam.camera_poses_from_body(body, rig)
+    rewards, mean = ops.coverage_traj(pts, t.reshape(-1, 3), q.reshape(-1, 4), K, iw, ih)
+    (1.0 / (mean + 1e-6)).backward()
+
+
+ms = events(traj_step, 20)
+print(json.dumps({"config": "c3: 20 waypoints x 5 cams, 10M points, fwd+bwd", "ms_per_step": ms,
+                  "evals_per_s": 1e7 * 100 / (ms * 1e-3)}), flush=True)
+
+# ---- c5 sample: 64 trajectories x 32 waypoints (single camera per waypoint), 50M points, forward only ----
+pts = box(50_000_000, 3)
+gen = np.random.default_rng(2)
+base = bench.body_waypoints(32, 20.0).numpy()
+Tn = 64
+poses = np.repeat(base[None, :, :3], Tn, 0) + gen.normal(0, 1.0, (Tn, 1, 3)) * np.array([1, 1, 0])
+yaw = base[None, :, 3] + gen.normal(0, 0.2, (Tn, 32))
+quats = np.stack([np.cos(yaw / 2), 0 * yaw, 0 * yaw, np.sin(yaw / 2)], -1)
+P, Qs = torch.tensor(poses, dtype=torch.float32, device=dev), torch.tensor(quats, dtype=torch.float32, device=dev)
+ms = events(lambda: ops.sweep_rewards(pts, P, Qs, K, iw, ih), 3)
+pairs = 5e7 * Tn * 32
+print(json.dumps({"config": "c5 sample: 64 of 1024 trajectories x 32 waypoints, 50M points, forward only (2 passes)",
+                  "ms": ms, "pairs_per_s": pairs / (ms * 1e-3), "extrapolated_full_c5_s": ms * 1e-3 * 1024 / Tn}), flush=True)
