@@ -131,6 +131,16 @@ size_t cov_hpr_hull_workspace_bytes(int64_t n);
 int cov_hpr_hull(const float* flipped_dev, int64_t n, uint8_t* vertex_mask_dev, int32_t* info_dev,
                  void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* Exact pruning of (point, pose) pairs in cov_traj_minmax / cov_traj_fused (default on): a pair whose distance
+ * Gaussian alone bounds m below what could matter (the running maximum in pass A once a zero minimum has been
+ * seen; half the normalised range in pass B) is skipped after 6 instructions; results are bit-identical to
+ * the dense evaluation.  Process-wide switch, meant for A/B measurements.  cov_stats copies four counters to
+ * the host (this call synchronises): [0] pass-B warp-iterations, [1] fully evaluated ones, [2],[3] same for
+ * pass A; reset != 0 clears them. */
+void cov_set_pruning(int enabled);
+int cov_get_pruning(void);
+int cov_stats(int reset, unsigned long long* out4_host);
+
 /* FP32 FMA / MUFU.EX2 throughput probes used by bench.py for the roofline denominators.
  * Each runs `iters` dependent-chain iterations on a full grid and writes a checksum; the caller
  * times them with CUDA events.  Returns the number of FMA (or ex2) operations issued. */

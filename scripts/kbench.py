@@ -53,6 +53,25 @@ def timeit(fn, reps=5):
     return e0.elapsed_time(e1) / reps
 
 
+import ctypes as C
+stats = (C.c_ulonglong * 4)()
+L.cov_set_pruning(1)
+L.cov_stats(1, None)
+ms_a = timeit(pass_a)
+mm_p = minmax.clone()
+ms_b = timeit(pass_b)
+acc_p, rew_p = acc.clone(), rewards.clone()
+L.cov_stats(1, stats)
+print(f"pruned: pass A {ms_a:.3f} ms, pass B {ms_b:.3f} ms  -> {n * W / (ms_a + ms_b) / 1e6:.1f} G evals/s (dense-equivalent); "
+      f"full-evaluated warp-iterations: pass B {stats[1] / max(stats[0], 1):.3f}, pass A {stats[3] / max(stats[2], 1):.3f}", flush=True)
+L.cov_set_pruning(0)
+ms_a = timeit(pass_a)
+same_mm = torch.equal(minmax, mm_p)
+ms_b = timeit(pass_b)
+print(f"dense : pass A {ms_a:.3f} ms, pass B {ms_b:.3f} ms  -> {n * W / (ms_a + ms_b) / 1e6:.1f} G evals/s; "
+      f"pruned==dense: minmax {same_mm} rewards {torch.equal(rewards, rew_p)} acc {torch.equal(acc, acc_p)}", flush=True)
+if len(sys.argv) <= 2:
+    sys.exit(0)
 ref_mm = ref_acc = ref_rew = None
 for v in range(6):
     os.environ["COV_DEV_MM"] = str(v)

@@ -44,7 +44,7 @@ int main(int argc, char** argv) {
         int cert[3];
         const int rc = hull_classify_point(g, k, cert);
         counts[rc]++;
-        mask[hull_float_as_int(sorted[k].w)] = (rc == HULL_EXTREME || rc == HULL_OVERFLOW || rc == HULL_EXTREME_UNCERT) ? 1 : 0;
+        mask[hull_float_as_int(sorted[k].w)] = (rc == HULL_EXTREME || rc == HULL_EXTREME_UNCERT) ? 1 : 0;  // an LP that ran away (OVERFLOW) had no feasible region in reach
     }
     // origin: GJK with a sequential support search
     HullSimplex S;

@@ -259,3 +259,30 @@ def test_errors_are_loud(dev, mod):
     obs, total = ops.coverage_pose(base[1:], torch.zeros(1, 3, device=dev), torch.tensor([[1.0, 0, 0, 0]], device=dev),
                                    K, Wd, Hd)
     assert obs.shape == (100,)
+
+
+def test_pruned_evaluation_is_bit_identical_to_dense(dev, mod):
+    """The bound-based pruning of (point, pose) pairs must not change a single bit of any output."""
+    from trajectory_optimization_b200 import _lib
+    model, tools, ops = mod
+    L = _lib.lib()
+    gen = np.random.default_rng(5)
+    pts = torch.from_numpy(_box(gen, 3_000_017)).to(dev)
+    poses, yaw = _s_curve(33, 14.0)
+    quats = np.stack([np.cos(yaw / 2), 0 * yaw, 0 * yaw, np.sin(yaw / 2)], 1).astype(np.float32)
+    quats += gen.normal(0, 0.2, quats.shape).astype(np.float32)
+    K, Wd, Hd = tools.load_intrinsics(dev)
+    outs = []
+    try:
+        for mode in (1, 0):
+            L.cov_set_pruning(mode)
+            P = torch.from_numpy(poses).to(dev).requires_grad_(True)
+            Q = torch.from_numpy(quats).to(dev).requires_grad_(True)
+            rewards, mean = ops.coverage_traj(pts, P, Q, K, Wd, Hd)
+            gp, gq = torch.autograd.grad(mean, [P, Q])
+            outs.append((rewards, mean, gp, gq))
+    finally:
+        L.cov_set_pruning(1)
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    assert float((outs[0][0] != 0.5).float().mean()) > 1e-4  # the case does exercise gated pairs

@@ -56,6 +56,29 @@ int cov_sm_count_cached() {
     return sms;
 }
 
+// Exact bound-based pruning of (point, pose) pairs (cov_traj.cu); process-wide switch for A/B measurements.
+static int g_pruning = 1;
+int cov_pruning_enabled() { return g_pruning; }
+extern "C" void cov_set_pruning(int enabled) { g_pruning = enabled ? 1 : 0; }
+extern "C" int cov_get_pruning(void) { return g_pruning; }
+
+// Work counters (development / benchmark reporting only): [0] pass-B warp-iterations, [1] of which fully
+// evaluated, [2] pass-A warp-iterations, [3] of which fully evaluated.
+__device__ unsigned long long g_cov_stats[4];
+unsigned long long* cov_stats_device_ptr() {
+    unsigned long long* p = nullptr;
+    cudaGetSymbolAddress((void**)&p, g_cov_stats);
+    return p;
+}
+extern "C" int cov_stats(int reset, unsigned long long* out4_host) {
+    unsigned long long* p = cov_stats_device_ptr();
+    if (!p) return COV_ERR_CUDA;
+    if (out4_host && cudaMemcpy(out4_host, p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return COV_ERR_CUDA;
+    if (reset && cudaMemset(p, 0, 4 * sizeof(unsigned long long)) != cudaSuccess) return COV_ERR_CUDA;
+    return COV_OK;
+}
+
 extern "C" int cov_version(void) { return 100; }
 extern "C" const char* cov_last_error(void) { return g_err; }
 extern "C" int cov_device_sm_count(void) {

@@ -93,6 +93,13 @@ __device__ inline void cov_pose_row(const float* __restrict__ t3, const float* _
     row[5] = make_float4(t3[0], t3[1], t3[2], 0.f);
 }
 
+// |x - td|^2 exactly as cov_vis computes it (same three instructions per component), for the pruning
+// pre-filter:  m = s * 2^-(kd q2 + ...) <= 2^-(kd q2) * (1 + 1.3e-5)   (s <= 1 up to the rcp rounding).
+__device__ __forceinline__ float cov_q2(float x, float y, float z, const float4& v3) {
+    const float ex = __fsub_rn(x, v3.x), ey = __fsub_rn(y, v3.y), ez = __fsub_rn(z, v3.z);
+    return __fmaf_rn(ez, ez, __fmaf_rn(ey, ey, __fmul_rn(ex, ex)));
+}
+
 struct CovEval {  // intermediates the gradient needs
     float ex, ey, ez, zi, s, e2z, du, dv;
 };
@@ -153,3 +160,5 @@ void cov_set_error(const char* fmt, ...);
 int cov_check_launch(const char* what);
 CovConst cov_make_const(const struct cov_camera* cam);
 int cov_sm_count_cached();
+int cov_pruning_enabled();
+unsigned long long* cov_stats_device_ptr();

@@ -139,7 +139,7 @@ hull_classify_kernel(int G, const int* __restrict__ cell_start, const float4* __
     g.rho_max = __longlong_as_double((long long)*rho_max_bits);
     int cert[3];
     const int rc = hull_classify_point(g, k, cert);
-    const bool vertex = (rc == HULL_EXTREME || rc == HULL_EXTREME_UNCERT || rc == HULL_OVERFLOW);
+    const bool vertex = (rc == HULL_EXTREME || rc == HULL_EXTREME_UNCERT);  // OVERFLOW: the LP ran away, no feasible region in reach
     mask[__float_as_int(sorted[k].w)] = vertex ? 1 : 0;
     if (rc != HULL_EXTREME && rc != HULL_INSIDE) atomicAdd(info + 1, 1);  // decided by the LP but not certified in fp64
     if (vertex) atomicAdd(info + 2, 1);

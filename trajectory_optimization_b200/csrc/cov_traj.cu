@@ -34,7 +34,7 @@ __host__ __device__ constexpr int tile_points(int ppt) { return COV_THREADS * pp
 __host__ __device__ constexpr int bit_words(int ppt) { return kWarps * ppt; }         // ballot words per pose
 __host__ __device__ constexpr int bit_stride(int ppt) { return bit_words(ppt) + 4; }  // rows stay 16-byte aligned
 
-size_t minmax_smem_bytes(int W) { return (size_t)W * (COV_ROW_F4 * sizeof(float4) + 2 * sizeof(unsigned)); }
+size_t minmax_smem_bytes(int W) { return (size_t)W * (COV_ROW_F4 * sizeof(float4) + 3 * sizeof(unsigned)); }
 size_t fused_smem_bytes(int W, int ppt) {
     return (size_t)W * COV_ROW_F4 * sizeof(float4) + (size_t)W * bit_stride(ppt) * sizeof(unsigned) +
            (size_t)tile_points(ppt) * 4 * sizeof(float) + (size_t)W * 8 * sizeof(float);
@@ -58,20 +58,28 @@ __device__ __noinline__ void tie_accumulate(float x, float y, float z, const flo
     atomicAdd(dst + 6, 1.0);
 }
 
-template <int PPT, int MINB, int U>
+// PRUNE: once this block has seen m == 0 for a pose (so the global minimum is 0), a warp skips the evaluation of
+// its points for that pose when none of them can reach the block's running maximum:
+//   m <= 2^-(kd q2) (1+1.3e-5)  and  q2 > qcap = (-log2(max) + 1e-4)/kd  =>  m < max.
+// Skipped pairs can change neither the minimum (already 0, and m >= 0) nor the maximum: results are identical.
+template <int PPT, int MINB, int U, bool PRUNE>
 __global__ void __launch_bounds__(COV_THREADS, MINB)
 cov_traj_minmax_kernel(const float* __restrict__ xyz, int64_t n, const float* __restrict__ poses,
                        const float* __restrict__ quats, int W, const float* __restrict__ K9, CovConst C,
-                       unsigned* __restrict__ gmin, unsigned* __restrict__ gmax) {
+                       unsigned* __restrict__ gmin, unsigned* __restrict__ gmax, unsigned long long* __restrict__ stats) {
     extern __shared__ float4 smem4[];
     float4* ptab = smem4;
     unsigned* smin = reinterpret_cast<unsigned*>(ptab + (size_t)W * COV_ROW_F4);
     unsigned* smax = smin + W;
+    float* sqcap = reinterpret_cast<float*>(smax + W);
     const int tid = threadIdx.x, lane = tid & 31;
+    const float inv_kd = 1.f / C.kd;
+    unsigned n_iter = 0, n_full = 0;
     for (int w = tid; w < W; w += COV_THREADS) {
         cov_pose_row(poses + 3 * w, quats + 4 * w, K9, C, ptab + (size_t)w * COV_ROW_F4);
         smin[w] = 0x7f800000u;
         smax[w] = 0u;
+        sqcap[w] = __uint_as_float(0x7f800000u);  // +inf: evaluate everything until a zero minimum is known
     }
     __syncthreads();
     constexpr int T = tile_points(PPT);
@@ -97,7 +105,18 @@ cov_traj_minmax_kernel(const float* __restrict__ xyz, int64_t n, const float* __
                 for (int u = 0; u < U; ++u) {  // U poses in flight: U*PPT independent evaluation chains
                     wi[u] = (i + u < wn) ? (i + u) : (wn - 1);  // odd remainder: re-evaluate the last pose (harmless)
                     const float4* row = ptab + (size_t)(w0 + wi[u]) * COV_ROW_F4;
-                    const float4 v0 = row[0], v1 = row[1], v2 = row[2], v3 = row[3];
+                    const float4 v3 = row[3];
+                    mn[u] = __uint_as_float(0x7f800000u);  // neutral elements when the pose is skipped
+                    mx[u] = 0.f;
+                    if (PRUNE) {
+                        float qmin = cov_q2(px[0], py[0], pz[0], v3);
+#pragma unroll
+                        for (int s = 1; s < PPT; ++s) qmin = fminf(qmin, cov_q2(px[s], py[s], pz[s], v3));
+                        ++n_iter;
+                        if (!__any_sync(kFull, qmin <= sqcap[w0 + wi[u]])) continue;
+                        ++n_full;
+                    }
+                    const float4 v0 = row[0], v1 = row[1], v2 = row[2];
                     float m[PPT];
 #pragma unroll
                     for (int s = 0; s < PPT; ++s) m[s] = cov_vis<false>(px[s], py[s], pz[s], v0, v1, v2, v3, C, nullptr);
@@ -126,6 +145,12 @@ cov_traj_minmax_kernel(const float* __restrict__ xyz, int64_t n, const float* __
             if (lane < wn) {
                 atomicMin(smin + w0 + lane, keep_mn);
                 atomicMax(smax + w0 + lane, keep_mx);
+                if (PRUNE) {
+                    // stale values are only ever larger (the maximum grows), i.e. conservative
+                    const unsigned bmn = smin[w0 + lane], bmx = smax[w0 + lane];
+                    if (bmn == 0u && bmx != 0u)
+                        sqcap[w0 + lane] = (1e-4f - __log2f(__uint_as_float(bmx))) * inv_kd * 1.000001f;
+                }
             }
         }
     }
@@ -133,6 +158,10 @@ cov_traj_minmax_kernel(const float* __restrict__ xyz, int64_t n, const float* __
     for (int w = tid; w < W; w += COV_THREADS) {
         atomicMin(gmin + w, smin[w]);
         atomicMax(gmax + w, smax[w]);
+    }
+    if (PRUNE && lane == 0) {
+        atomicAdd(stats + 2, (unsigned long long)n_iter);
+        atomicAdd(stats + 3, (unsigned long long)n_full);
     }
 }
 
@@ -145,7 +174,7 @@ __global__ void cov_minmax_init_kernel(unsigned* gmin, unsigned* gmax, int W) {
 }
 
 // Phase-1 body of the fused pass for U consecutive poses starting at w (U*PPT independent chains).
-template <int PPT, int U, bool AMIN>
+template <int PPT, int U, bool AMIN, bool THR5>
 __device__ __forceinline__ void fused_pose_iter(int w, const float4* __restrict__ ptab, unsigned* __restrict__ bits_warp,
                                                 int RS, const float (&px)[PPT], const float (&py)[PPT],
                                                 const float (&pz)[PPT], float (&L)[PPT], const CovConst& C,
@@ -162,7 +191,8 @@ __device__ __forceinline__ void fused_pose_iter(int w, const float4* __restrict_
 #pragma unroll
         for (int s = 1; s + 1 < PPT; s += 2) mmax[u] = fmaxf(mmax[u], fmaxf(m[u][s], m[u][s + 1]));
         if ((PPT & 1) == 0) mmax[u] = fmaxf(mmax[u], m[u][PPT - 1]);
-        mmax[u] -= v3.w;  // >= 0  <=>  some point of this lane may pass the gate (conservative threshold)
+        // >= 0  <=>  some point of this lane may pass the gate (conservative threshold; lives in v5.w when pruning)
+        mmax[u] -= THR5 ? row[5].w : v3.w;
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -202,13 +232,32 @@ __device__ __forceinline__ void fused_pose_iter(int w, const float4* __restrict_
     }
 }
 
-template <int PPT, bool HAS_UP, int U>
+// Pruned phase-1 body: v3.w holds qthr = (-log2(thr) + 1e-4)/kd; a pair with q2 > qthr has
+// m <= 2^-(kd q2)(1+1.3e-5) < thr, so it is neither gated nor the arg-max.  The warp runs the exact body only when
+// one of its 32*PPT points passes; the bit matrix was zeroed at the start of the tile.
+template <int PPT>
+__device__ __forceinline__ void fused_pose_iter_pruned(int w, const float4* __restrict__ ptab,
+                                                       unsigned* __restrict__ bits_warp, int RS, const float (&px)[PPT],
+                                                       const float (&py)[PPT], const float (&pz)[PPT], float (&L)[PPT],
+                                                       const CovConst& C, double* __restrict__ acc, int lane,
+                                                       unsigned& n_full) {
+    const float4 v3 = ptab[(size_t)w * COV_ROW_F4 + 3];
+    float qmin = cov_q2(px[0], py[0], pz[0], v3);
+#pragma unroll
+    for (int s = 1; s < PPT; ++s) qmin = fminf(qmin, cov_q2(px[s], py[s], pz[s], v3));
+    if (__any_sync(kFull, qmin <= v3.w)) {
+        ++n_full;
+        fused_pose_iter<PPT, 1, false, true>(w, ptab, bits_warp, RS, px, py, pz, L, C, acc, lane);
+    }
+}
+
+template <int PPT, bool HAS_UP, int U, bool PRUNE>
 __global__ void __launch_bounds__(COV_THREADS, 2)
 cov_traj_fused_kernel(const float* __restrict__ xyz, int64_t n, const float* __restrict__ poses,
                       const float* __restrict__ quats, int W, const float* __restrict__ K9, CovConst C,
                       const float* __restrict__ minmax, const float* __restrict__ upstream,
                       float* __restrict__ rewards, float* __restrict__ partials, double* __restrict__ sumr_partials,
-                      double* __restrict__ acc, int seg_log2) {
+                      double* __restrict__ acc, int seg_log2, unsigned long long* __restrict__ stats) {
     constexpr int T = tile_points(PPT);
     constexpr int NW = bit_words(PPT);
     constexpr int RS = bit_stride(PPT);
@@ -232,7 +281,11 @@ cov_traj_fused_kernel(const float* __restrict__ xyz, int64_t n, const float* __r
         const float a = minmax[w];
         const float b = __fsub_rn(minmax[W + w], a);
         const float hb = 0.5f * b;
-        row[3].w = (a + hb) * (1.f - 9.5367431640625e-07f);  // conservative gate threshold (exact test in the rare path)
+        const float thr = (a + hb) * (1.f - 9.5367431640625e-07f);  // conservative gate threshold (exact test in the rare path)
+        row[5].w = thr;
+        // pruning: q2 above this cannot reach thr (thr <= 0 or NaN: never prune)
+        const float qthr = (thr > 0.f) ? (float)((1e-4 - log2((double)thr)) / (double)C.kd * 1.000001) : __uint_as_float(0x7f800000u);
+        row[3].w = PRUNE ? qthr : thr;
         row[4] = make_float4(hb, b, __frcp_rn(b), a);
         if (a > 0.f) amin_pos = 1;  // benign race: every writer stores 1
     }
@@ -240,6 +293,7 @@ cov_traj_fused_kernel(const float* __restrict__ xyz, int64_t n, const float* __r
     __syncthreads();
 
     double sum_r = 0.0;
+    unsigned n_iter = 0, n_full = 0;
     const int64_t ntiles = (n + T - 1) / T;
     const int nseg = 1 << seg_log2;       // lanes that share one pose row in phase 2
     const int wps = NW >> seg_log2;       // ballot words per lane
@@ -266,11 +320,20 @@ cov_traj_fused_kernel(const float* __restrict__ xyz, int64_t n, const float* __r
         {
             unsigned* bits_warp = bits + warp * PPT;
             int w = 0;
-            if (!check_amin) {
-                for (; w + U <= W; w += U) fused_pose_iter<PPT, U, false>(w, ptab, bits_warp, RS, px, py, pz, L, C, acc, lane);
-                for (; w < W; ++w) fused_pose_iter<PPT, 1, false>(w, ptab, bits_warp, RS, px, py, pz, L, C, acc, lane);
+            if (check_amin) {  // arg-min points carry gradient: every pair must be looked at
+                for (; w < W; ++w) fused_pose_iter<PPT, 1, true, PRUNE>(w, ptab, bits_warp, RS, px, py, pz, L, C, acc, lane);
+            } else if (PRUNE) {
+                for (int wz = lane; wz < W; wz += 32) {  // this warp's columns of the gate bit matrix start at zero
+                    unsigned* brow = bits_warp + (size_t)wz * RS;
+#pragma unroll
+                    for (int s = 0; s < PPT; ++s) brow[s] = 0u;
+                }
+                __syncwarp();
+                for (; w < W; ++w) fused_pose_iter_pruned<PPT>(w, ptab, bits_warp, RS, px, py, pz, L, C, acc, lane, n_full);
+                n_iter += W;
             } else {
-                for (; w < W; ++w) fused_pose_iter<PPT, 1, true>(w, ptab, bits_warp, RS, px, py, pz, L, C, acc, lane);
+                for (; w + U <= W; w += U) fused_pose_iter<PPT, U, false, false>(w, ptab, bits_warp, RS, px, py, pz, L, C, acc, lane);
+                for (; w < W; ++w) fused_pose_iter<PPT, 1, false, false>(w, ptab, bits_warp, RS, px, py, pz, L, C, acc, lane);
             }
         }
 #pragma unroll
@@ -349,6 +412,10 @@ cov_traj_fused_kernel(const float* __restrict__ xyz, int64_t n, const float* __r
         double t = 0.0;
         for (int i = 0; i < kWarps; ++i) t += red[i];
         sumr_partials[blockIdx.x] = t;
+    }
+    if (PRUNE && lane == 0) {
+        atomicAdd(stats + 0, (unsigned long long)n_iter);
+        atomicAdd(stats + 1, (unsigned long long)n_full);
     }
 }
 
@@ -483,11 +550,20 @@ extern "C" int cov_traj_minmax(const float* xyz, int64_t n, const float* poses, 
     const int mm_variant = dev_variant("COV_DEV_MM", 0);
     const int eff_ppt = (ppt == 8) ? ((mm_variant == 0 || mm_variant == 4) ? 8 : (mm_variant == 5 ? 2 : 4)) : (ppt >= 4 ? 4 : ppt);
     const int64_t ntiles = (n + tile_points(eff_ppt) - 1) / tile_points(eff_ppt);
-#define LAUNCH_MM(P, B, U)                                                                                          \
-    {                                                                                                               \
-        const int grid = grid_for(cov_traj_minmax_kernel<P, B, U>, smem, ntiles);                                   \
-        cov_traj_minmax_kernel<P, B, U><<<grid, COV_THREADS, smem, s>>>(xyz, n, poses, quats, W, K, C, gmin, gmax); \
+#define LAUNCH_MM(P, B, U)                                                                                        \
+    {                                                                                                             \
+        if (prune) {                                                                                              \
+            const int grid = grid_for(cov_traj_minmax_kernel<P, B, 1, true>, smem, ntiles);                       \
+            cov_traj_minmax_kernel<P, B, 1, true><<<grid, COV_THREADS, smem, s>>>(xyz, n, poses, quats, W, K, C,  \
+                                                                                  gmin, gmax, stats);             \
+        } else {                                                                                                  \
+            const int grid = grid_for(cov_traj_minmax_kernel<P, B, U, false>, smem, ntiles);                      \
+            cov_traj_minmax_kernel<P, B, U, false><<<grid, COV_THREADS, smem, s>>>(xyz, n, poses, quats, W, K, C, \
+                                                                                   gmin, gmax, stats);            \
+        }                                                                                                         \
     }
+    const bool prune = cov_pruning_enabled() != 0;
+    unsigned long long* stats = cov_stats_device_ptr();
     const int variant = dev_variant("COV_DEV_MM", 0);
     if (ppt == 8 && variant == 0) LAUNCH_MM(8, 2, 2)
     else if (ppt == 8 && variant == 1) LAUNCH_MM(4, 3, 1)
@@ -535,13 +611,20 @@ extern "C" int cov_traj_fused(const float* xyz, int64_t n, const float* poses, c
     float* partials = reinterpret_cast<float*>(sumr + COV_MAX_GRID);
     cudaMemsetAsync(acc, 0, ((size_t)W * COV_ACC_STRIDE + 1) * sizeof(double), s);
     int grid = 1;
-#define LAUNCH_F(P, UP, U)                                                                                      \
-    {                                                                                                           \
-        grid = grid_for(cov_traj_fused_kernel<P, UP, U>, smem, ntiles);                                         \
-        cov_traj_fused_kernel<P, UP, U><<<grid, COV_THREADS, smem, s>>>(xyz, n, poses, quats, W, K, C, minmax,  \
-                                                                        upstream, rewards, partials, sumr, acc, \
-                                                                        seg_log2);                              \
+#define LAUNCH_F(P, UP, U)                                                                                        \
+    {                                                                                                             \
+        if (prune) {                                                                                              \
+            grid = grid_for(cov_traj_fused_kernel<P, UP, 1, true>, smem, ntiles);                                 \
+            cov_traj_fused_kernel<P, UP, 1, true><<<grid, COV_THREADS, smem, s>>>(                                \
+                xyz, n, poses, quats, W, K, C, minmax, upstream, rewards, partials, sumr, acc, seg_log2, stats);  \
+        } else {                                                                                                  \
+            grid = grid_for(cov_traj_fused_kernel<P, UP, U, false>, smem, ntiles);                                \
+            cov_traj_fused_kernel<P, UP, U, false><<<grid, COV_THREADS, smem, s>>>(                               \
+                xyz, n, poses, quats, W, K, C, minmax, upstream, rewards, partials, sumr, acc, seg_log2, stats);  \
+        }                                                                                                         \
     }
+    const bool prune = cov_pruning_enabled() != 0;
+    unsigned long long* stats = cov_stats_device_ptr();
     if (upstream) {
         if (ppt == 4) LAUNCH_F(4, true, 1) else if (ppt == 2) LAUNCH_F(2, true, 1) else LAUNCH_F(1, true, 1)
     } else {

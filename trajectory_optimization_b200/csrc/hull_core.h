@@ -31,18 +31,21 @@
 #define HULL_HD inline
 #endif
 
-#define HULL_MAX_ACTIVE 32
-#define HULL_EPS 4.0e-12      /* relative shrink of every half-plane (>> 129 * 2^-50) */
-#define HULL_TILT_MAX 64.0    /* the rounding margin of the half-planes is valid for |alpha|,|beta| <= this (89.1 deg) */
-#define HULL_BOX 1.0e6        /* LP bounding box; a solution beyond HULL_TILT_MAX is reported as uncertified */
+#define HULL_MAX_ACTIVE 64
+#define HULL_EPS 4.0e-15      /* half-planes are shrunk by HULL_EPS (1 + 2 tilt) |d|_1: ~4x the fp64 rounding of n.d */
+#define HULL_TILT_NEAR 1.0    /* first attempt: |alpha|,|beta| <= 1 (tilt below 55 degrees), tight rounding margin */
+#define HULL_TILT_MAX 64.0    /* second attempt (silhouette points): tilt below 89.1 degrees */
+#define HULL_BOX 1.0e6        /* bounding box of the LP itself */
 
-enum { HULL_UNDECIDED = 0, HULL_EXTREME = 1, HULL_INSIDE = 2, HULL_INSIDE_UNCERT = 3, HULL_OVERFLOW = 4, HULL_EXTREME_UNCERT = 5 };
+enum { HULL_UNDECIDED = 0, HULL_EXTREME = 1, HULL_INSIDE = 2, HULL_INSIDE_UNCERT = 3, HULL_OVERFLOW = 4, HULL_EXTREME_UNCERT = 5,
+       HULL_NOCHANGE = 6 };
 
 struct HullFrame {  // local frame of the point under test
     double p[3], rho, u[3], e1[3], e2[3];
 };
 
 struct HullLP {
+    double tilt;                    // box |alpha|,|beta| <= tilt the rounding margin was computed for
     double x0, x1;                  // current least-tilt feasible (alpha, beta)
     int n;                          // active constraints
     int cert[3];                    // on infeasibility: candidate ids of the blocking constraints
@@ -66,18 +69,20 @@ HULL_HD void hull_frame_init(HullFrame& F, double px, double py, double pz) {
     F.e2[2] = F.u[0] * F.e1[1] - F.u[1] * F.e1[0];
 }
 
-HULL_HD void hull_lp_init(HullLP& L) {
+HULL_HD void hull_lp_init(HullLP& L, double tilt) {
+    L.tilt = tilt;
     L.x0 = 0.0; L.x1 = 0.0; L.n = 0;
     L.cert[0] = L.cert[1] = L.cert[2] = -1;
 }
 
 // Half-plane of candidate s in the frame of p, shrunk by the rounding margin.
-HULL_HD void hull_constraint(const HullFrame& F, double sx, double sy, double sz, double& a, double& b, double& c) {
+HULL_HD void hull_constraint(const HullFrame& F, double tilt, double sx, double sy, double sz, double& a, double& b,
+                             double& c) {
     const double dx = F.p[0] - sx, dy = F.p[1] - sy, dz = F.p[2] - sz;
     a = F.e1[0] * dx + F.e1[1] * dy + F.e1[2] * dz;
     b = F.e2[0] * dx + F.e2[1] * dy + F.e2[2] * dz;
     c = F.u[0] * dx + F.u[1] * dy + F.u[2] * dz;
-    c -= HULL_EPS * (fabs(dx) + fabs(dy) + fabs(dz)) * (1.0 + 2.0 * HULL_TILT_MAX);
+    c -= HULL_EPS * (fabs(dx) + fabs(dy) + fabs(dz)) * (1.0 + 2.0 * tilt);
 }
 
 // Violated beyond evaluation noise?  The half-planes are shrunk by HULL_EPS >> this tolerance, so a constraint
@@ -85,12 +90,14 @@ HULL_HD void hull_constraint(const HullFrame& F, double sx, double sy, double sz
 // being re-added when the optimum sits on its boundary line.
 HULL_HD bool hull_violated(const HullLP& L, double a, double b, double c) {
     const double v = a * L.x0 + b * L.x1 + c;
-    return v < -1.0e-13 * (fabs(a * L.x0) + fabs(b * L.x1) + fabs(c));
+    return v < -1.0e-15 * (fabs(a * L.x0) + fabs(b * L.x1) + fabs(c));
 }
 
 // Add a violated half-plane (a,b,c) [candidate id cid].  Returns HULL_UNDECIDED (new optimum stored),
 // HULL_INSIDE (active set infeasible, L.cert filled) or HULL_OVERFLOW (active set full / tilt box hit).
 HULL_HD int hull_lp_add(HullLP& L, double a, double b, double c, int cid) {
+    for (int k = 0; k < L.n; ++k)
+        if (L.id[k] == cid) return HULL_NOCHANGE;  // already active: the residual is evaluation noise of the optimum
     const double nn = a * a + b * b;
     if (!(nn > 0.0)) {  // degenerate direction: constraint is c >= 0 for every (alpha,beta) and it is violated
         L.cert[0] = cid; L.cert[1] = cid; L.cert[2] = cid;
@@ -103,7 +110,8 @@ HULL_HD int hull_lp_add(HullLP& L, double a, double b, double c, int cid) {
         int m = 0;
         for (int k = 0; k < L.n; ++k) {
             const double v = L.a[k] * L.x0 + L.b[k] * L.x1 + L.c[k];
-            if (v <= 1.0e-9 * (fabs(L.a[k] * L.x0) + fabs(L.b[k] * L.x1) + fabs(L.c[k]))) {
+            // binding ones, plus the most recent third (the ones most likely to block the next move)
+            if (k >= L.n - HULL_MAX_ACTIVE / 3 || v <= 1.0e-9 * (fabs(L.a[k] * L.x0) + fabs(L.b[k] * L.x1) + fabs(L.c[k]))) {
                 L.a[m] = L.a[k]; L.b[m] = L.b[k]; L.c[m] = L.c[k]; L.id[m] = L.id[k]; ++m;
             }
         }
@@ -115,7 +123,8 @@ HULL_HD int hull_lp_add(HullLP& L, double a, double b, double c, int cid) {
     const double q0 = -c * a * inv, q1 = -c * b * inv, t0 = -b * rn, t1 = a * rn;
     double lo = -1e300, hi = 1e300;
     int ilo = -1, ihi = -1;
-    // bounding box |x|,|y| <= HULL_BOX (ids -2: not a proof of infeasibility)
+    // LP bounding box (ids -2: hitting it is not a proof of infeasibility -> HULL_OVERFLOW).  It is much wider than
+    // the tilt the rounding margin covers; a solution beyond L.tilt is re-done with the wider margin by the caller.
     const double bx[4][3] = {{1, 0, HULL_BOX}, {-1, 0, HULL_BOX}, {0, 1, HULL_BOX}, {0, -1, HULL_BOX}};
     for (int k = 0; k < 4 + L.n; ++k) {
         double ai, bi, ci;
@@ -215,9 +224,10 @@ HULL_HD int hull_sweep_cell(const HullGrid& g, int cell, int self, const HullFra
         if (k == self) continue;
         const float4 s = g.sorted[k];
         double a, bb, c;
-        hull_constraint(F, (double)s.x, (double)s.y, (double)s.z, a, bb, c);
+        hull_constraint(F, L.tilt, (double)s.x, (double)s.y, (double)s.z, a, bb, c);
         if (hull_violated(L, a, bb, c)) {
             const int rc = hull_lp_add(L, a, bb, c, k);
+            if (rc == HULL_NOCHANGE) continue;
             if (rc != HULL_UNDECIDED) return rc;
             changed = true;
         }
@@ -228,12 +238,12 @@ HULL_HD int hull_sweep_cell(const HullGrid& g, int cell, int self, const HullFra
 #define HULL_R_NEAR 6
 
 // Classify sorted point `self`.  cert_out receives the three sorted-array ids of an INSIDE certificate.
-HULL_HD int hull_classify_point(const HullGrid& g, int self, int* cert_out) {
+HULL_HD int hull_classify_attempt(const HullGrid& g, int self, double tilt, int* cert_out) {
     const float4 ps = g.sorted[self];
     HullFrame F;
     hull_frame_init(F, (double)ps.x, (double)ps.y, (double)ps.z);
     HullLP L;
-    hull_lp_init(L);
+    hull_lp_init(L, tilt);
     const int G = g.G;
     const int cx = hull_cell_coord(F.u[0], G), cy = hull_cell_coord(F.u[1], G), cz = hull_cell_coord(F.u[2], G);
     int clean = -1;  // every voxel within Chebyshev radius `clean` has been swept without moving the LP
@@ -284,7 +294,7 @@ HULL_HD int hull_classify_point(const HullGrid& g, int self, int* cert_out) {
         }
         if (rc == HULL_UNDECIDED && !changed) rc = HULL_EXTREME;
     }
-    if (rc == HULL_EXTREME && (fabs(L.x0) > HULL_TILT_MAX || fabs(L.x1) > HULL_TILT_MAX)) rc = HULL_EXTREME_UNCERT;
+    if (rc == HULL_EXTREME && (fabs(L.x0) > L.tilt || fabs(L.x1) > L.tilt)) rc = HULL_EXTREME_UNCERT;  // margin not valid
     if (rc == HULL_INSIDE) {
         cert_out[0] = L.cert[0]; cert_out[1] = L.cert[1]; cert_out[2] = L.cert[2];
         const float4 s1 = g.sorted[L.cert[0]], s2 = g.sorted[L.cert[1]], s3 = g.sorted[L.cert[2]];
@@ -293,6 +303,13 @@ HULL_HD int hull_classify_point(const HullGrid& g, int self, int* cert_out) {
             !hull_certify_inside(F.p, a1, a2, a3))
             rc = HULL_INSIDE_UNCERT;
     }
+    return rc;
+}
+
+// Two attempts: a tight tilt box (and rounding margin) that settles everything but silhouette points, then the wide one.
+HULL_HD int hull_classify_point(const HullGrid& g, int self, int* cert_out) {
+    int rc = hull_classify_attempt(g, self, HULL_TILT_NEAR, cert_out);
+    if (rc == HULL_EXTREME_UNCERT || rc == HULL_OVERFLOW) rc = hull_classify_attempt(g, self, HULL_TILT_MAX, cert_out);
     return rc;
 }
 
