@@ -41,7 +41,11 @@ def pass_b():
                "fused")
 
 
-def timeit(fn, reps=5):
+REPS = int(os.environ.get("KBENCH_REPS", "5"))
+
+
+def timeit(fn, reps=None):
+    reps = REPS if reps is None else reps
     fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
