@@ -320,7 +320,7 @@ def main():
 
     def pass_b():
         _lib.check(L.cov_traj_fused(pts.data_ptr(), n_local, P.data_ptr(), Q.data_ptr(), W, K.data_ptr(),
-                                    ctypes.byref(cam), minmax.data_ptr(), None, rewards.data_ptr(), acc.data_ptr(),
+                                    ctypes.byref(cam), minmax.data_ptr(), None, None, rewards.data_ptr(), acc.data_ptr(),
                                     ws.data_ptr(), wsb, stream), "cov_traj_fused")
 
     pass_a()
@@ -329,7 +329,7 @@ def main():
         dist.all_reduce(minmax[W:], op=dist.ReduceOp.MAX)
     pass_b()
     reps = max(3, min(args.steps, 10))
-    stats = (ctypes.c_ulonglong * 4)()
+    stats = (ctypes.c_ulonglong * 8)()
     L.cov_stats(1, None)
     ms_a = timed(pass_a, reps) / reps
     ms_b = timed(pass_b, reps) / reps

@@ -83,6 +83,8 @@ int cov_pose_epilogue(const double* acc_dev, const float* trans_dev, const float
  * Epilogue cov_traj_epilogue: mean reward and d(mean)/d(poses, quats).
  *   poses_dev (W,3) fp32, quats_dev (W,4) fp32, minmax_dev 2*W fp32: [0,W) minima, [W,2W) maxima
  *   upstream_dev: NULL (gradient of mean(rewards)) or (n) fp32 d(loss)/d(rewards_j)
+ *   reward_index_dev: NULL, or (n) int32: point j of xyz_dev is point reward_index_dev[j] of the caller's cloud
+ *   (the permutation cov_spatial_sort returns); rewards_dev and upstream_dev are then indexed in the caller's order.
  * ------------------------------------------------------------------------------------------ */
 int cov_traj_max_poses(void);
 size_t cov_traj_workspace_bytes(int64_t n, int n_poses);
@@ -90,7 +92,8 @@ int cov_traj_minmax(const float* xyz_dev, int64_t n, const float* poses_dev, con
                     const float* K_dev, const cov_camera* cam, float* minmax_dev, void* stream);
 int cov_traj_fused(const float* xyz_dev, int64_t n, const float* poses_dev, const float* quats_dev, int n_poses,
                    const float* K_dev, const cov_camera* cam, const float* minmax_dev, const float* upstream_dev,
-                   float* rewards_dev, double* acc_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+                   const int32_t* reward_index_dev, float* rewards_dev, double* acc_dev, void* workspace_dev,
+                   size_t workspace_bytes, void* stream);
 /* out_dev: [0] mean reward, then (W,3) d/d poses, then (W,4) d/d quats  (1 + 7*W floats).
  * With upstream_mode != 0 the gradients are those of sum_j upstream_j * rewards_j (no 1/N). */
 int cov_traj_epilogue(const double* acc_dev, const float* minmax_dev, const float* quats_dev, int n_poses,
@@ -103,6 +106,22 @@ int cov_traj_epilogue(const double* acc_dev, const float* minmax_dev, const floa
 int cov_sweep_rewards(const float* xyz_dev, int64_t n, const float* poses_dev, const float* quats_dev, int n_traj,
                       int poses_per_traj, const float* K_dev, const cov_camera* cam, const float* minmax_dev,
                       double* sum_rewards_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Multi-camera front end: n_body waypoints (x, y, z, yaw) x n_cams fixed extrinsics -> camera poses in the layout
+ * cov_traj_* / cov_sweep_rewards take (pose index = body*n_cams + cam), and the chain rule back.
+ * ref: no reference implementation (BASELINE north_star item 3); the camera rig is the tf extrinsics of
+ * src/pc_processor.py:33-39,161-165; the reference's optimisable parameters are the outputs (src/model.py:170-171).
+ *   body_dev (n_body,4) fp32;  rig_dev (n_cams,7) fp32: unit quaternion q_body_cam (w,x,y,z), lever arm t_body_cam
+ *   q_world_cam = q_z(yaw) (x) q_body_cam,  t_world_cam = xyz + R_z(yaw) t_body_cam
+ *   backward: g_poses_dev (n_body*n_cams,3) and/or g_quats_dev (n_body*n_cams,4) (either may be NULL) ->
+ *   g_body_dev (n_body,4) = scale * d/d(x,y,z,yaw).
+ * ------------------------------------------------------------------------------------------ */
+int cov_rig_poses(const float* body_dev, int n_body, const float* rig_dev, int n_cams, float* poses_dev,
+                  float* quats_dev, void* stream);
+int cov_rig_poses_backward(const float* body_dev, int n_body, const float* rig_dev, int n_cams,
+                           const float* g_poses_dev, const float* g_quats_dev, float scale, float* g_body_dev,
+                           void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Binary frustum cull.  ref: src/tools.py:176-187 (get_cam_frustum_pts), src/model.py:34-39.
@@ -132,14 +151,26 @@ int cov_hpr_hull(const float* flipped_dev, int64_t n, uint8_t* vertex_mask_dev, 
                  void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* Exact pruning of (point, pose) pairs in cov_traj_minmax / cov_traj_fused (default on): a pair whose distance
- * Gaussian alone bounds m below what could matter (the running maximum in pass A once a zero minimum has been
- * seen; half the normalised range in pass B) is skipped after 6 instructions; results are bit-identical to
- * the dense evaluation.  Process-wide switch, meant for A/B measurements.  cov_stats copies four counters to
- * the host (this call synchronises): [0] pass-B warp-iterations, [1] fully evaluated ones, [2],[3] same for
- * pass A; reset != 0 clears them. */
+ * Gaussian alone bounds m below what could matter (the largest m seen so far in pass A once a zero minimum is
+ * known; half the normalised range in pass B) is skipped: per tile of 1024-2048 consecutive points the block tests
+ * every pose against the tile's bounding box, each warp re-tests against the box of its own 128-256 points, then
+ * per point.  Results are bit-identical to the dense evaluation on ANY point order; the saving grows with the
+ * spatial coherence of consecutive points (cov_spatial_sort below).  Process-wide switch, meant for A/B
+ * measurements.  cov_stats copies eight counters of (warp, pose) pairs to the host (this call synchronises):
+ * [0] pass B all pairs, [1] fully evaluated, [2],[3] same for pass A, [4]/[5] pass B/A pairs that ran the
+ * per-point pre-filter, [6]/[7] pass B/A pairs that survived the tile-level test; reset != 0 clears them. */
 void cov_set_pruning(int enabled);
 int cov_get_pruning(void);
-int cov_stats(int reset, unsigned long long* out4_host);
+int cov_stats(int reset, unsigned long long* out8_host);
+
+/* Spatial (Morton) ordering of a cloud, done once per cloud (the reference hands the optimiser one fixed cloud:
+ * src/trajectory_optimization.py:83-96, src/model.py:164), so that consecutive points are close in space and the
+ * tile-level pruning above applies.  Keys are 30-bit Morton codes of the points quantised to a cubic grid of
+ * 1024 cells along the longest extent of the bounding box; the sort is stable, hence deterministic.
+ *   xyz_sorted_dev (n,3) fp32 out;  perm_dev (n) int32 out: xyz_sorted[j] = xyz[perm[j]]  (n < 2^31). */
+size_t cov_spatial_sort_workspace_bytes(int64_t n);
+int cov_spatial_sort(const float* xyz_dev, int64_t n, float* xyz_sorted_dev, int32_t* perm_dev, void* workspace_dev,
+                     size_t workspace_bytes, void* stream);
 
 /* FP32 FMA / MUFU.EX2 throughput probes used by bench.py for the roofline denominators.
  * Each runs `iters` dependent-chain iterations on a full grid and writes a checksum; the caller

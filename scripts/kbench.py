@@ -1,6 +1,9 @@
 #!/usr/bin/env python
-"""Development micro-benchmark: time cov_traj_minmax / cov_traj_fused kernel variants (COV_DEV_* switches)
-on the bench.py workload at a reduced cloud size.  Not part of the product or the reported numbers."""
+"""Development micro-benchmark: times cov_traj_minmax / cov_traj_fused on the bench.py workload at a chosen cloud
+size — dense, pruned on the unsorted cloud, pruned on the Morton-sorted cloud — and checks that the three give
+bit-identical normalisers and rewards.  Not part of the product or the reported numbers.
+
+usage: kbench.py [n_points] [variants]"""
 import ctypes
 import os
 import sys
@@ -10,12 +13,12 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
-from trajectory_optimization_b200 import _lib, multicam, tools  # noqa: E402
+from trajectory_optimization_b200 import _lib, multicam, ops, tools  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 25_600_000
 dev = torch.device("cuda:0")
 L = _lib.lib()
-pts = bench.make_cloud_shard(n, 0, 1, dev)
+pts_raw = bench.make_cloud_shard(n, 0, 1, dev)
 K, iw, ih = tools.load_intrinsics(dev)
 rig = multicam.ring_rig(5)
 t, q = multicam.camera_poses_from_body(bench.body_waypoints().to(dev), rig)
@@ -28,20 +31,22 @@ rewards = torch.empty(n, device=dev)
 wsb = L.cov_traj_workspace_bytes(n, W)
 ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
 stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+REPS = int(os.environ.get("KBENCH_REPS", "5"))
+
+state = {"pts": pts_raw, "perm": None}
 
 
 def pass_a():
-    _lib.check(L.cov_traj_minmax(pts.data_ptr(), n, P.data_ptr(), Q.data_ptr(), W, K.data_ptr(), ctypes.byref(cam),
+    p = state["pts"]
+    _lib.check(L.cov_traj_minmax(p.data_ptr(), n, P.data_ptr(), Q.data_ptr(), W, K.data_ptr(), ctypes.byref(cam),
                                  minmax.data_ptr(), stream), "minmax")
 
 
 def pass_b():
-    _lib.check(L.cov_traj_fused(pts.data_ptr(), n, P.data_ptr(), Q.data_ptr(), W, K.data_ptr(), ctypes.byref(cam),
-                                minmax.data_ptr(), None, rewards.data_ptr(), acc.data_ptr(), ws.data_ptr(), wsb, stream),
-               "fused")
-
-
-REPS = int(os.environ.get("KBENCH_REPS", "5"))
+    p, perm = state["pts"], state["perm"]
+    _lib.check(L.cov_traj_fused(p.data_ptr(), n, P.data_ptr(), Q.data_ptr(), W, K.data_ptr(), ctypes.byref(cam),
+                                minmax.data_ptr(), None, None if perm is None else perm.data_ptr(), rewards.data_ptr(),
+                                acc.data_ptr(), ws.data_ptr(), wsb, stream), "fused")
 
 
 def timeit(fn, reps=None):
@@ -57,25 +62,53 @@ def timeit(fn, reps=None):
     return e0.elapsed_time(e1) / reps
 
 
-import ctypes as C
-stats = (C.c_ulonglong * 4)()
-L.cov_set_pruning(1)
-L.cov_stats(1, None)
-ms_a = timeit(pass_a)
-mm_p = minmax.clone()
-ms_b = timeit(pass_b)
-acc_p, rew_p = acc.clone(), rewards.clone()
-L.cov_stats(1, stats)
-print(f"pruned: pass A {ms_a:.3f} ms, pass B {ms_b:.3f} ms  -> {n * W / (ms_a + ms_b) / 1e6:.1f} G evals/s (dense-equivalent); "
-      f"full-evaluated warp-iterations: pass B {stats[1] / max(stats[0], 1):.3f}, pass A {stats[3] / max(stats[2], 1):.3f}", flush=True)
+def run(label):
+    stats = (ctypes.c_ulonglong * 8)()
+    L.cov_stats(1, None)
+    ms_a = timeit(pass_a)
+    mm = minmax.clone()
+    ms_b = timeit(pass_b)
+    L.cov_stats(1, stats)
+    s = list(stats)
+    fr = lambda a, b: a / max(b, 1)  # noqa: E731
+    print(f"{label:14s}: pass A {ms_a:8.3f} ms, pass B {ms_b:8.3f} ms -> {n * W / (ms_a + ms_b) / 1e6:9.1f} G evals/s "
+          f"(dense-equivalent) | B: tile-listed {fr(s[6], s[0]):.4f} prefiltered {fr(s[4], s[0]):.4f} full {fr(s[1], s[0]):.4f}"
+          f" | A: tile-listed {fr(s[7], s[2]):.4f} prefiltered {fr(s[5], s[2]):.4f} full {fr(s[3], s[2]):.4f}", flush=True)
+    return mm, rewards.clone(), acc.clone()
+
+
 L.cov_set_pruning(0)
-ms_a = timeit(pass_a)
-same_mm = torch.equal(minmax, mm_p)
-ms_b = timeit(pass_b)
-print(f"dense : pass A {ms_a:.3f} ms, pass B {ms_b:.3f} ms  -> {n * W / (ms_a + ms_b) / 1e6:.1f} G evals/s; "
-      f"pruned==dense: minmax {same_mm} rewards {torch.equal(rewards, rew_p)} acc {torch.equal(acc, acc_p)}", flush=True)
+mm_d, rew_d, acc_d = run("dense")
+L.cov_set_pruning(1)
+mm_u, rew_u, acc_u = run("pruned/unsorted")
+print(f"   == dense: minmax {torch.equal(mm_u, mm_d)} rewards {torch.equal(rew_u, rew_d)} acc {torch.equal(acc_u, acc_d)} "
+      f"acc_rel {float(((acc_u - acc_d).abs().max() / acc_d.abs().max()).item()):.2e}", flush=True)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+ops.spatial_sort(pts_raw)
+e0.record()
+sorted_pts, perm = ops.spatial_sort(pts_raw)
+e1.record()
+torch.cuda.synchronize()
+print(f"spatial sort of {n} points: {e0.elapsed_time(e1):.3f} ms; sorted == gather: "
+      f"{torch.equal(sorted_pts, pts_raw[perm.long()])}; perm is a permutation: "
+      f"{bool((torch.sort(perm.long()).values == torch.arange(n, device=dev)).all().item())}", flush=True)
+state["pts"], state["perm"] = sorted_pts, perm
+mm_s, rew_s, acc_s = run("pruned/sorted")
+print(f"   == dense: minmax {torch.equal(mm_s, mm_d)} rewards {torch.equal(rew_s, rew_d)} "
+      f"acc_rel {float(((acc_s - acc_d).abs().max() / acc_d.abs().max()).item()):.2e} "
+      f"sum_r_rel {abs(float(acc_s[-1] - acc_d[-1])) / float(acc_d[-1]):.2e}", flush=True)
+mm_s2, rew_s2, acc_s2 = run("pruned/sorted")
+print(f"   run-to-run: minmax {torch.equal(mm_s2, mm_s)} rewards {torch.equal(rew_s2, rew_s)} acc {torch.equal(acc_s2, acc_s)}", flush=True)
+L.cov_set_pruning(0)
+mm_ds, rew_ds, acc_ds = run("dense/sorted")
+print(f"   sorted pruned == sorted dense: minmax {torch.equal(mm_s, mm_ds)} rewards {torch.equal(rew_s, rew_ds)} "
+      f"acc {torch.equal(acc_s, acc_ds)}", flush=True)
+L.cov_set_pruning(1)
 if len(sys.argv) <= 2:
     sys.exit(0)
+state["pts"], state["perm"] = pts_raw, None
+L.cov_set_pruning(0)
 ref_mm = ref_acc = ref_rew = None
 for v in range(6):
     os.environ["COV_DEV_MM"] = str(v)

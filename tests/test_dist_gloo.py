@@ -64,7 +64,7 @@ class OracleBackend:
         # fp64 so that the stand-in's second pass can find its arg-min/arg-max by exact comparison
         return torch.tensor([m.min() for m in mm] + [m.max() for m in mm], dtype=torch.float64)
 
-    def traj_fused(self, pts, P, Q, Kd, cam, minmax, upstream, rewards):
+    def traj_fused(self, pts, P, Q, Kd, cam, minmax, upstream, rewards, reward_index=None):
         W, hi = len(P), float(np.float32(1.0 - cam.eps))
         acc, L, keep = np.zeros(W * ACC + 1), np.zeros(len(pts)), []
         for w in range(W):

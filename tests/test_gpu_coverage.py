@@ -207,7 +207,7 @@ def test_sharded_accumulators_equal_whole_cloud(dev, mod):
         wsb = L.cov_traj_workspace_bytes(s.shape[0], W)
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
         _lib.check(L.cov_traj_fused(s.data_ptr(), s.shape[0], P.data_ptr(), Q.data_ptr(), W, K.data_ptr(),
-                                    ctypes.byref(cam), minmax.data_ptr(), None, r.data_ptr(), a.data_ptr(),
+                                    ctypes.byref(cam), minmax.data_ptr(), None, None, r.data_ptr(), a.data_ptr(),
                                     ws.data_ptr(), wsb, stream), "fused")
         acc += a
         rew.append(r)
@@ -283,6 +283,107 @@ def test_pruned_evaluation_is_bit_identical_to_dense(dev, mod):
             outs.append((rewards, mean, gp, gq))
     finally:
         L.cov_set_pruning(1)
-    for a, b in zip(*outs):
-        assert torch.equal(a, b)
-    assert float((outs[0][0] != 0.5).float().mean()) > 1e-4  # the case does exercise gated pairs
+    (r1, m1, gp1, gq1), (r0, m0, gp0, gq0) = outs
+    assert torch.equal(r1, r0) and torch.equal(m1, m0)           # per-point outputs and their mean: every bit
+    # the gradient accumulators see the same addends in a different fp32 summation order
+    assert rel_err(gp1.cpu().numpy(), gp0.cpu().numpy()) < 2e-6 and rel_err(gq1.cpu().numpy(), gq0.cpu().numpy()) < 2e-6
+    assert float((r1 != 0.5).float().mean()) > 1e-4  # the case does exercise gated pairs
+
+
+def test_spatial_sort_is_a_stable_morton_permutation(dev, mod):
+    model, tools, ops = mod
+    gen = np.random.default_rng(3)
+    for n in (1, 5, 1000, 250_007):
+        pts_np = _box(gen, n)
+        if n >= 1000:
+            pts_np[10] = pts_np[500]  # duplicate points keep their input order (stable sort)
+        pts = torch.from_numpy(pts_np).to(dev)
+        out, perm = ops.spatial_sort(pts)
+        assert perm.dtype == torch.int32 and out.shape == pts.shape
+        assert torch.equal(torch.sort(perm.long()).values, torch.arange(n, device=dev))
+        assert torch.equal(out, pts[perm.long()])
+        # restate the key on the host: 10 bits per axis on a cubic grid over the bounding box, z-y-x interleave
+        lo = pts_np.min(0)
+        ext = np.float32((pts_np.max(0) - lo).max())
+        scale = np.float32(1023.999) / ext if ext > 0 else np.float32(0)
+        cell = np.clip(((pts_np - lo) * scale), 0, 1023).astype(np.uint32)
+        key = np.zeros(n, np.uint64)
+        for b in range(10):
+            for a in range(3):
+                key |= ((cell[:, a].astype(np.uint64) >> b) & 1) << (3 * b + a)
+        order = np.argsort(key, kind="stable")
+        assert np.array_equal(order, perm.cpu().numpy())
+
+
+def test_model_traj_sorted_cloud_equals_caller_order(dev, mod):
+    """ModelTraj on its Morton-ordered copy returns rewards in the caller's point order, bit-identical to the
+    evaluation of the cloud as given, and the same objective and gradients."""
+    model, tools, ops = mod
+    gen = np.random.default_rng(8)
+    pts = torch.from_numpy(_box(gen, 700_003))
+    poses, yaw = _s_curve(24, 12.0)
+    quats = np.stack([np.cos(yaw / 2), 0 * yaw, 0 * yaw, np.sin(yaw / 2)], 1).astype(np.float32)
+    quats += gen.normal(0, 0.1, quats.shape).astype(np.float32)
+    K, Wd, Hd = tools.load_intrinsics(dev)
+    res = []
+    for flag in (True, False):
+        m = model.ModelTraj(pts, torch.from_numpy(poses), torch.from_numpy(quats), K, Wd, Hd, device=dev, spatial_sort=flag)
+        loss = m(vis_wps_dist=0.0)
+        loss.backward()
+        res.append((m.rewards.detach().clone(), loss.detach().clone(), m.poses.grad.clone(), m.quats.grad.clone()))
+    (r1, l1, gp1, gq1), (r0, l0, gp0, gq0) = res
+    assert torch.equal(r1, r0)
+    assert rel_err(l1.item(), l0.item()) < 1e-6
+    assert rel_err(gp1.cpu().numpy(), gp0.cpu().numpy()) < 5e-6 and rel_err(gq1.cpu().numpy(), gq0.cpu().numpy()) < 5e-6
+    # differentiating through the per-point vector (upstream gradient in the caller's order) also goes through the permutation
+    m = model.ModelTraj(pts, torch.from_numpy(poses), torch.from_numpy(quats), K, Wd, Hd, device=dev)
+    m(vis_wps_dist=0.0)
+    wgt = torch.linspace(0.5, 1.5, pts.shape[0], device=dev)
+    ga = torch.autograd.grad((m.rewards * wgt).sum(), [m.poses, m.quats])
+    m0 = model.ModelTraj(pts, torch.from_numpy(poses), torch.from_numpy(quats), K, Wd, Hd, device=dev, spatial_sort=False)
+    m0(vis_wps_dist=0.0)
+    gb = torch.autograd.grad((m0.rewards * wgt).sum(), [m0.poses, m0.quats])
+    assert rel_err(ga[0].cpu().numpy(), gb[0].cpu().numpy()) < 5e-6 and rel_err(ga[1].cpu().numpy(), gb[1].cpu().numpy()) < 5e-6
+
+
+def test_tile_pruning_on_sorted_cloud_is_bit_identical_to_dense(dev, mod):
+    """Where the tile-level pruning actually bites (a Morton-ordered cloud): normalisers, rewards and their mean
+    must not change by a bit against the dense evaluation; compact-cloud poses (min > 0) are never pruned."""
+    import ctypes
+    from trajectory_optimization_b200 import _lib
+    model, tools, ops = mod
+    L = _lib.lib()
+    gen = np.random.default_rng(21)
+    K, Wd, Hd = tools.load_intrinsics(dev)
+    cam = _lib.camera(Wd, Hd, 1.0, 5.0, 1e-6)
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for n, compact in ((2_000_003, False), (300_001, True)):
+        if compact:  # cloud in front of every camera and within a few metres: min_j m > 0 for all poses
+            pts_np = _box(gen, n, (1.0, 1.0, 1.5), (4.0, 4.0, 4.5))
+            poses = (gen.random((12, 3), dtype=np.float32) * 0.6 - 0.3).astype(np.float32)
+            quats = (np.array([1.0, 0, 0, 0]) + gen.normal(0, 0.15, (12, 4))).astype(np.float32)
+        else:
+            pts_np = _box(gen, n)
+            poses, yaw = _s_curve(40, 16.0)
+            quats = np.stack([np.cos(yaw / 2), 0 * yaw, 0 * yaw, np.sin(yaw / 2)], 1).astype(np.float32)
+        pts, perm = ops.spatial_sort(torch.from_numpy(pts_np).to(dev))
+        P, Q = torch.from_numpy(poses).to(dev), torch.from_numpy(quats).to(dev)
+        W = P.shape[0]
+        outs = []
+        try:
+            for mode in (1, 0):
+                L.cov_set_pruning(mode)
+                mm = torch.empty(2 * W, device=dev)
+                _lib.check(L.cov_traj_minmax(pts.data_ptr(), n, P.data_ptr(), Q.data_ptr(), W, K.data_ptr(),
+                                             ctypes.byref(cam), mm.data_ptr(), stream), "minmax")
+                Pg, Qg = P.clone().requires_grad_(True), Q.clone().requires_grad_(True)
+                rewards, mean = ops.coverage_traj(pts, Pg, Qg, K, Wd, Hd, reward_index=perm)
+                gp, gq = torch.autograd.grad(mean, [Pg, Qg])
+                outs.append((mm, rewards, mean, gp, gq))
+        finally:
+            L.cov_set_pruning(1)
+        (mm1, r1, m1, gp1, gq1), (mm0, r0, m0, gp0, gq0) = outs
+        assert torch.equal(mm1, mm0) and torch.equal(r1, r0) and torch.equal(m1, m0)
+        assert rel_err(gp1.cpu().numpy(), gp0.cpu().numpy()) < 2e-6 and rel_err(gq1.cpu().numpy(), gq0.cpu().numpy()) < 2e-6
+        if compact:
+            assert int((mm0[:W] > 0).sum()) >= 6  # most of these poses keep min_j m > 0 (never pruned), a few do not

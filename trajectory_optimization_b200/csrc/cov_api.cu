@@ -62,20 +62,21 @@ int cov_pruning_enabled() { return g_pruning; }
 extern "C" void cov_set_pruning(int enabled) { g_pruning = enabled ? 1 : 0; }
 extern "C" int cov_get_pruning(void) { return g_pruning; }
 
-// Work counters (development / benchmark reporting only): [0] pass-B warp-iterations, [1] of which fully
-// evaluated, [2] pass-A warp-iterations, [3] of which fully evaluated.
-__device__ unsigned long long g_cov_stats[4];
+// Work counters (development / benchmark reporting only), in (warp, pose) pairs: [0] pass B all pairs, [1] fully
+// evaluated, [2] pass A all pairs, [3] fully evaluated, [4]/[5] pass B/A pairs that ran the per-point distance
+// pre-filter, [6]/[7] pass B/A pairs that survived the tile-level box test.
+__device__ unsigned long long g_cov_stats[8];
 unsigned long long* cov_stats_device_ptr() {
     unsigned long long* p = nullptr;
     cudaGetSymbolAddress((void**)&p, g_cov_stats);
     return p;
 }
-extern "C" int cov_stats(int reset, unsigned long long* out4_host) {
+extern "C" int cov_stats(int reset, unsigned long long* out8_host) {
     unsigned long long* p = cov_stats_device_ptr();
     if (!p) return COV_ERR_CUDA;
-    if (out4_host && cudaMemcpy(out4_host, p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess)
+    if (out8_host && cudaMemcpy(out8_host, p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess)
         return COV_ERR_CUDA;
-    if (reset && cudaMemset(p, 0, 4 * sizeof(unsigned long long)) != cudaSuccess) return COV_ERR_CUDA;
+    if (reset && cudaMemset(p, 0, 8 * sizeof(unsigned long long)) != cudaSuccess) return COV_ERR_CUDA;
     return COV_OK;
 }
 

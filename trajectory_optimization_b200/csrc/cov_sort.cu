@@ -1,0 +1,151 @@
+// cov_sort.cu — spatial (Morton) ordering of a point cloud, done once per cloud.
+//
+// The reference builds one ModelTraj per cloud and then iterates the optimiser on it
+// (src/trajectory_optimization.py:83-127, src/model.py:164), so the cloud is constant over hundreds of objective
+// evaluations.  Ordering it along a Z-curve makes every run of consecutive points spatially compact, which is what
+// the tile-level pruning of cov_traj.cu feeds on.  Pipeline (all on the caller's stream, workspace from the caller):
+//   1. bounding box of the cloud           (block reduce + integer atomics on order-preserving keys)
+//   2. 30-bit Morton key per point         (cubic cells: 1024 along the longest extent)
+//   3. stable LSD radix sort of (key, index) pairs — cub::DeviceRadixSort (CUDA toolkit header library; this is
+//      set-up work outside the per-step hot path)
+//   4. gather xyz_sorted[j] = xyz[perm[j]]
+#include <cub/device/device_radix_sort.cuh>
+
+#include "cov_common.cuh"
+#include "../../include/coverage_b200.h"
+
+namespace {
+
+__device__ __forceinline__ unsigned sort_f2ord(float f) {
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float sort_ord2f(unsigned u) {
+    return __uint_as_float((u & 0x80000000u) ? (u ^ 0x80000000u) : ~u);
+}
+
+// box[0..2] = min xyz, box[3..5] = max xyz as order-preserving uints
+__global__ void sort_box_init_kernel(unsigned* box) {
+    if (threadIdx.x < 3) box[threadIdx.x] = 0xffffffffu;
+    else if (threadIdx.x < 6) box[threadIdx.x] = 0u;
+}
+
+__global__ void __launch_bounds__(256) sort_box_kernel(const float* __restrict__ xyz, int64_t n, unsigned* __restrict__ box) {
+    const float inf = __uint_as_float(0x7f800000u);
+    float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float v = __ldg(xyz + j * 3 + k);
+            if (v == v && fabsf(v) != inf) {  // NaN / inf points do not shape the grid (they land in cell 0 or 1023)
+                lo[k] = fminf(lo[k], v);
+                hi[k] = fmaxf(hi[k], v);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const unsigned l = __reduce_min_sync(0xffffffffu, sort_f2ord(lo[k]));
+        const unsigned h = __reduce_max_sync(0xffffffffu, sort_f2ord(hi[k]));
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(box + k, l);
+            atomicMax(box + 3 + k, h);
+        }
+    }
+}
+
+__device__ __forceinline__ unsigned spread10(unsigned v) {  // 10 bits -> every third bit
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+
+__global__ void __launch_bounds__(256) sort_key_kernel(const float* __restrict__ xyz, int64_t n, const unsigned* __restrict__ box,
+                                                       unsigned* __restrict__ keys, int32_t* __restrict__ idx) {
+    const float lx = sort_ord2f(box[0]), ly = sort_ord2f(box[1]), lz = sort_ord2f(box[2]);
+    const float ext = fmaxf(fmaxf(sort_ord2f(box[3]) - lx, sort_ord2f(box[4]) - ly), sort_ord2f(box[5]) - lz);
+    const float scale = (ext > 0.f && ext < __uint_as_float(0x7f800000u)) ? 1023.999f / ext : 0.f;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+        const float x = __ldg(xyz + j * 3), y = __ldg(xyz + j * 3 + 1), z = __ldg(xyz + j * 3 + 2);
+        // fminf/fmaxf drop NaN operands, so a NaN coordinate maps to cell 0
+        const unsigned ix = (unsigned)fminf(fmaxf((x - lx) * scale, 0.f), 1023.f);
+        const unsigned iy = (unsigned)fminf(fmaxf((y - ly) * scale, 0.f), 1023.f);
+        const unsigned iz = (unsigned)fminf(fmaxf((z - lz) * scale, 0.f), 1023.f);
+        keys[j] = spread10(ix) | (spread10(iy) << 1) | (spread10(iz) << 2);
+        idx[j] = (int32_t)j;
+    }
+}
+
+__global__ void __launch_bounds__(256) sort_gather_kernel(const float* __restrict__ xyz, int64_t n, const int32_t* __restrict__ perm,
+                                                          float* __restrict__ out) {
+    // 3 consecutive threads move one point, so the writes are fully coalesced
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 3 * n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t j = i / 3;
+        const int k = (int)(i - 3 * j);
+        out[i] = __ldg(xyz + (int64_t)perm[j] * 3 + k);
+    }
+}
+
+size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+size_t cub_temp_bytes(int64_t n) {
+    size_t bytes = 0;
+    cub::DoubleBuffer<unsigned> k(nullptr, nullptr);
+    cub::DoubleBuffer<int32_t> v(nullptr, nullptr);
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, k, v, (int)n, 0, 30, (cudaStream_t)0);
+    return bytes;
+}
+
+}  // namespace
+
+// workspace: [box 256 B][keys A n u32][keys B n u32][idx B n i32][cub temp]
+extern "C" size_t cov_spatial_sort_workspace_bytes(int64_t n) {
+    if (n < 1) n = 1;
+    return 256 + 3 * align256((size_t)n * 4) + align256(cub_temp_bytes(n)) + 256;
+}
+
+extern "C" int cov_spatial_sort(const float* xyz, int64_t n, float* xyz_sorted, int32_t* perm, void* ws, size_t ws_bytes,
+                                void* stream) {
+    if (!xyz || !xyz_sorted || !perm || !ws || n <= 0) {
+        cov_set_error("cov_spatial_sort: null pointer or empty cloud (n=%lld)", (long long)n);
+        return COV_ERR_ARG;
+    }
+    if (n >= ((int64_t)1 << 31)) {
+        cov_set_error("cov_spatial_sort: %lld points exceed the int32 index range", (long long)n);
+        return COV_ERR_UNSUPPORTED;
+    }
+    if (ws_bytes < cov_spatial_sort_workspace_bytes(n)) {
+        cov_set_error("cov_spatial_sort: workspace %zu < %zu bytes", ws_bytes, cov_spatial_sort_workspace_bytes(n));
+        return COV_ERR_WORKSPACE;
+    }
+    if (((uintptr_t)ws) & 255) {
+        cov_set_error("cov_spatial_sort: workspace must be 256-byte aligned");
+        return COV_ERR_ALIGN;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    char* base = reinterpret_cast<char*>(ws);
+    unsigned* box = reinterpret_cast<unsigned*>(base);
+    const size_t col = align256((size_t)n * 4);
+    unsigned* keys_a = reinterpret_cast<unsigned*>(base + 256);
+    unsigned* keys_b = reinterpret_cast<unsigned*>(base + 256 + col);
+    int32_t* idx_b = reinterpret_cast<int32_t*>(base + 256 + 2 * col);
+    void* temp = base + 256 + 3 * col;
+    size_t temp_bytes = cub_temp_bytes(n);
+
+    const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)cov_sm_count_cached() * 16);
+    sort_box_init_kernel<<<1, 32, 0, s>>>(box);
+    sort_box_kernel<<<grid, 256, 0, s>>>(xyz, n, box);
+    sort_key_kernel<<<grid, 256, 0, s>>>(xyz, n, box, keys_a, perm);
+    cub::DoubleBuffer<unsigned> k(keys_a, keys_b);
+    cub::DoubleBuffer<int32_t> v(perm, idx_b);
+    if (cub::DeviceRadixSort::SortPairs(temp, temp_bytes, k, v, (int)n, 0, 30, s) != cudaSuccess)
+        return cov_check_launch("cov_spatial_sort (radix sort)") ? COV_ERR_CUDA : COV_ERR_CUDA;
+    if (v.Current() != perm)
+        cudaMemcpyAsync(perm, v.Current(), (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToDevice, s);
+    const int ggrid = (int)std::min<int64_t>((3 * n + 255) / 256, (int64_t)cov_sm_count_cached() * 32);
+    sort_gather_kernel<<<ggrid, 256, 0, s>>>(xyz, n, perm, xyz_sorted);
+    return cov_check_launch("cov_spatial_sort");
+}

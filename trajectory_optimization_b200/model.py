@@ -154,7 +154,7 @@ def mean_angle_calc(traj_wps, eps=1e-6):
 class ModelTraj(nn.Module):
     def __init__(self, points, wps_poses, wps_quats, intrins, img_width, img_height, min_dist=1.0, max_dist=5.0,
                  smoothness_weight=14.0, traj_length_weight=0.02, device=torch.device("cuda"), group=None,
-                 n_total=None):
+                 n_total=None, spatial_sort=True):
         super().__init__()
         assert wps_poses.dim() == wps_quats.dim()
         assert wps_poses.size()[1] == 3
@@ -178,14 +178,23 @@ class ModelTraj(nn.Module):
         self.traj_length_weight = traj_length_weight
         self.group = group        # torch.distributed group when `points` is this rank's shard
         self.n_total = n_total    # global point count in that case
+        # The cloud is constant over the optimisation (src/trajectory_optimization.py:83-127), so a Morton-ordered
+        # copy is made once; the kernels prune whole tiles of it per pose (bit-identical results) and write
+        # `rewards` back in the order of `self.points`.
+        self.spatial_sort = spatial_sort
         self._mean = None
         self._step_cache = {}
         self._pts32 = None
+        self._perm = None
         self.to(self.device)
 
     def _cloud(self):
         if self._pts32 is None or self._pts32_src is not self.points:
-            self._pts32 = ops._dev_f32(self.points, what="points")
+            pts = ops._dev_f32(self.points, what="points")
+            self._perm = None
+            if self.spatial_sort and pts.shape[0] > 0:
+                pts, self._perm = ops.spatial_sort(pts)
+            self._pts32 = pts
             self._pts32_src = self.points
         return self._pts32
 
@@ -201,9 +210,11 @@ class ModelTraj(nn.Module):
         t0 = time()
         wps_step = self._wps_step(vis_wps_dist)
         # waypoints range(0, N_wps, wps_step) (src/model.py:217); the others get no visibility gradient
-        rewards, mean = ops.coverage_traj(self._cloud(), self.poses[::wps_step], self.quats[::wps_step], self.K,
+        cloud = self._cloud()
+        rewards, mean = ops.coverage_traj(cloud, self.poses[::wps_step], self.quats[::wps_step], self.K,
                                           self.img_width, self.img_height, self.pc_clip_limits[0],
-                                          self.pc_clip_limits[1], self.eps, n_total=self.n_total, group=self.group)
+                                          self.pc_clip_limits[1], self.eps, n_total=self.n_total, group=self.group,
+                                          reward_index=self._perm)
         self.rewards = rewards
         self._mean = mean
         if debug:

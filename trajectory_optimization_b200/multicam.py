@@ -6,9 +6,12 @@ multi-camera setting comes from tf extrinsics of a 5-6 camera rig (src/pc_proces
 Here a rig is a list of (R_body_cam, t_body_cam); the autograd chain from the per-camera gradients
 the kernels return back to the 4 body parameters is handled by torch on (W, 4)-sized tensors.
 """
+import ctypes
 import math
 
 import torch
+
+from . import _lib
 
 # body (x fwd, y left, z up) <- optical (x right, y down, z fwd)
 R_BODY_OPTICAL = torch.tensor([[0.0, 0.0, 1.0], [-1.0, 0.0, 0.0], [0.0, -1.0, 0.0]])
@@ -51,3 +54,51 @@ def camera_poses_from_body(body_xyzyaw, rig):
     Rwc = Rz[..., None, :, :] @ Rbc                              # (...,C,3,3)
     twc = xyz[..., None, :] + (Rz[..., None, :, :] @ tbc[..., None]).squeeze(-1)
     return twc, matrix_to_quat_wxyz(Rwc)
+
+
+def rig_tensor(rig, device):
+    """(C,7) fp32 device tensor [q_body_cam (w,x,y,z), t_body_cam] for the fused front end."""
+    R = torch.stack([r for r, _ in rig]).double()
+    q = matrix_to_quat_wxyz(R)
+    q = q / q.norm(dim=-1, keepdim=True)
+    t = torch.stack([torch.as_tensor(t) for _, t in rig]).double()
+    return torch.cat([q, t], -1).float().contiguous().to(device)
+
+
+class RigPosesFn(torch.autograd.Function):
+    """camera_poses_from_body as two O(W) CUDA launches (cov_rig_poses / cov_rig_poses_backward)."""
+
+    @staticmethod
+    def forward(ctx, body, rig7):
+        if not body.is_cuda:
+            raise RuntimeError("RigPosesFn is CUDA-only (use camera_poses_from_body for CPU tensors)")
+        b = body.detach().contiguous().float()
+        B, C = b.shape[0], rig7.shape[0]
+        poses = torch.empty(B * C, 3, dtype=torch.float32, device=b.device)
+        quats = torch.empty(B * C, 4, dtype=torch.float32, device=b.device)
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(_lib.lib().cov_rig_poses(b.data_ptr(), B, rig7.data_ptr(), C, poses.data_ptr(), quats.data_ptr(), stream),
+                   "cov_rig_poses")
+        ctx.save_for_backward(b, rig7)
+        ctx.set_materialize_grads(False)
+        return poses, quats
+
+    @staticmethod
+    def backward(ctx, g_poses, g_quats):
+        b, rig7 = ctx.saved_tensors
+        if g_poses is None and g_quats is None:
+            return None, None
+        gp = None if g_poses is None else g_poses.contiguous().float()
+        gq = None if g_quats is None else g_quats.contiguous().float()
+        out = torch.empty_like(b)
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(_lib.lib().cov_rig_poses_backward(b.data_ptr(), b.shape[0], rig7.data_ptr(), rig7.shape[0],
+                                                     0 if gp is None else gp.data_ptr(), 0 if gq is None else gq.data_ptr(),
+                                                     1.0, out.data_ptr(), stream), "cov_rig_poses_backward")
+        return out, None
+
+
+def camera_poses_fused(body_xyzyaw, rig7):
+    """body (B,4) CUDA tensor, rig7 from `rig_tensor` -> (poses (B*C,3), quats (B*C,4)), differentiable in body.
+    Same map as `camera_poses_from_body` up to the sign of each quaternion (which no consumer depends on)."""
+    return RigPosesFn.apply(body_xyzyaw, rig7)

@@ -81,14 +81,15 @@ class CudaBackend:
                                               _ptr(minmax), _stream()), "cov_traj_minmax")
         return minmax
 
-    def traj_fused(self, pts, P, Q, Kd, cam, minmax, upstream, rewards):
+    def traj_fused(self, pts, P, Q, Kd, cam, minmax, upstream, rewards, reward_index=None):
         L = _lib.lib()
         W, n = P.shape[0], pts.shape[0]
         acc = torch.empty(W * _lib.ACC_STRIDE + 1, dtype=torch.float64, device=pts.device)
         ws_bytes = L.cov_traj_workspace_bytes(n, W)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=pts.device)
         _lib.check(L.cov_traj_fused(_ptr(pts), n, _ptr(P), _ptr(Q), W, _ptr(Kd), ctypes.byref(cam), _ptr(minmax),
-                                    _ptr(upstream), _ptr(rewards), _ptr(acc), _ptr(ws), ws_bytes, _stream()),
+                                    _ptr(upstream), _ptr(reward_index), _ptr(rewards), _ptr(acc), _ptr(ws), ws_bytes,
+                                    _stream()),
                    "cov_traj_fused")
         return acc
 
@@ -157,10 +158,13 @@ class CoverageTrajFn(torch.autograd.Function):
     over the poses given (reference src/model.py:217-237, :246)."""
 
     @staticmethod
-    def forward(ctx, points, poses, quats, K, cam, n_total, group):
+    def forward(ctx, points, poses, quats, K, cam, n_total, group, reward_index=None):
         B = _BACKEND
         dev = points.device
         pts = B.prepare(points, what="points")
+        if reward_index is not None and (reward_index.dtype != torch.int32 or reward_index.shape[0] != pts.shape[0]
+                                         or reward_index.device != dev or not reward_index.is_contiguous()):
+            raise ValueError("reward_index must be a contiguous int32 tensor with one entry per point, on the cloud's device")
         P = B.prepare(poses, dev, "poses").reshape(-1, 3)
         Q = B.prepare(quats, dev, "quats").reshape(-1, 4)
         Kd = B.prepare(K, dev, "intrins").reshape(9)
@@ -174,16 +178,16 @@ class CoverageTrajFn(torch.autograd.Function):
             _all_reduce(minmax[:W], mn, group)
             _all_reduce(minmax[W:], mx, group)
         rewards = torch.empty(n, dtype=torch.float32, device=dev)
-        out = CoverageTrajFn._run(pts, P, Q, Kd, cam, minmax, None, rewards, n_total, group)
-        ctx.cam, ctx.group, ctx.n_total = cam, group, n_total
+        out = CoverageTrajFn._run(pts, P, Q, Kd, cam, minmax, None, rewards, n_total, group, reward_index)
+        ctx.cam, ctx.group, ctx.n_total, ctx.reward_index = cam, group, n_total, reward_index
         ctx.shapes = (poses.shape, quats.shape)
         ctx.save_for_backward(pts, P, Q, Kd, minmax, out)
         ctx.set_materialize_grads(False)
         return rewards, out[0].clone()
 
     @staticmethod
-    def _run(pts, P, Q, Kd, cam, minmax, upstream, rewards, n_total, group):
-        acc = _BACKEND.traj_fused(pts, P, Q, Kd, cam, minmax, upstream, rewards)   # pass B: W*22+1 doubles
+    def _run(pts, P, Q, Kd, cam, minmax, upstream, rewards, n_total, group, reward_index=None):
+        acc = _BACKEND.traj_fused(pts, P, Q, Kd, cam, minmax, upstream, rewards, reward_index)   # pass B: W*22+1 doubles
         if group is not None:
             _all_reduce(acc, _reduce_ops()[2], group)
         return _BACKEND.traj_epilogue(acc, minmax, Q, n_total, 0 if upstream is None else 1)
@@ -199,12 +203,13 @@ class CoverageTrajFn(torch.autograd.Function):
         if g_rewards is not None:
             up = _BACKEND.prepare(g_rewards, pts.device, "grad_rewards").reshape(-1)
             scratch = torch.empty(pts.shape[0], dtype=torch.float32, device=pts.device)
-            o2 = CoverageTrajFn._run(pts, P, Q, Kd, ctx.cam, minmax, up, scratch, ctx.n_total, ctx.group)
+            o2 = CoverageTrajFn._run(pts, P, Q, Kd, ctx.cam, minmax, up, scratch, ctx.n_total, ctx.group,
+                                     ctx.reward_index)
             g_p = o2[1:1 + 3 * W] if g_p is None else g_p + o2[1:1 + 3 * W]
             g_q = o2[1 + 3 * W:] if g_q is None else g_q + o2[1 + 3 * W:]
         ps, qs = ctx.shapes
         return (None, None if g_p is None else g_p.reshape(ps), None if g_q is None else g_q.reshape(qs),
-                None, None, None, None)
+                None, None, None, None, None)
 
 
 def coverage_pose(points, trans, quat, intrins, img_width, img_height, min_dist=1.0, max_dist=5.0, eps=1e-6,
@@ -216,10 +221,30 @@ def coverage_pose(points, trans, quat, intrins, img_width, img_height, min_dist=
 
 
 def coverage_traj(points, poses, quats, intrins, img_width, img_height, min_dist=1.0, max_dist=5.0, eps=1e-6,
-                  n_total=None, group=None):
-    """Fused ModelTraj visibility term over the W poses given.  Returns (rewards (N,), mean(rewards))."""
+                  n_total=None, group=None, reward_index=None):
+    """Fused ModelTraj visibility term over the W poses given.  Returns (rewards (N,), mean(rewards)).
+    `reward_index` (int32, from `spatial_sort`): `points` is a reordered copy of the caller's cloud and
+    rewards come back in the caller's order."""
     cam = _lib.camera(img_width, img_height, min_dist, max_dist, eps)
-    return CoverageTrajFn.apply(points, poses, quats, intrins, cam, n_total, group)
+    return CoverageTrajFn.apply(points, poses, quats, intrins, cam, n_total, group, reward_index)
+
+
+@torch.no_grad()
+def spatial_sort(points):
+    """Morton-order copy of a cloud, made once per cloud (see include/coverage_b200.h: cov_spatial_sort).
+    Returns (sorted (N,3) fp32, perm (N,) int32) with sorted[j] = points[perm[j]]."""
+    L = _lib.lib()
+    pts = _dev_f32(points, what="points")
+    n = pts.shape[0]
+    out = torch.empty_like(pts)
+    perm = torch.empty(n, dtype=torch.int32, device=pts.device)
+    if n == 0:
+        return out, perm
+    ws_bytes = L.cov_spatial_sort_workspace_bytes(n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=pts.device)
+    _lib.check(L.cov_spatial_sort(_ptr(pts), n, _ptr(out), _ptr(perm), _ptr(ws), ws_bytes, _stream()),
+               "cov_spatial_sort")
+    return out, perm
 
 
 @torch.no_grad()
