@@ -215,10 +215,11 @@ def main():
 
     rig7 = multicam.rig_tensor(rig, dev)
 
-    def step(points, perm):
+    def step(points, perm, boxes):
         body.grad = None
         t, q = multicam.camera_poses_fused(body, rig7)          # (x, y, z, yaw) x rig -> 320 camera poses
-        rewards, mean = ops.coverage_traj(points, t, q, K, img_w, img_h, n_total=n_total, group=group, reward_index=perm)
+        rewards, mean = ops.coverage_traj(points, t, q, K, img_w, img_h, n_total=n_total, group=group, reward_index=perm,
+                                          boxes=boxes)
         loss = 1.0 / (mean + 1e-6)
         loss.backward()
         return loss
@@ -250,23 +251,25 @@ def main():
     pts_sorted, perm = ops.spatial_sort(pts)
     ev0.record()
     pts_sorted, perm = ops.spatial_sort(pts)
+    boxes = ops.tile_boxes(pts_sorted)
     ev1.record()
     torch.cuda.synchronize()
     ms_sort = ev0.elapsed_time(ev1)
+    boxes = ops.tile_boxes(pts_sorted)
     for _ in range(args.warmup):
-        step(pts_sorted, perm)
+        step(pts_sorted, perm, boxes)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_total = timed(lambda: step(pts_sorted, perm), args.steps)
+    ms_total = timed(lambda: step(pts_sorted, perm, boxes), args.steps)
     clocks = sampler.stop() if rank == 0 else None
     value = n_total * W * args.steps / (ms_total * 1e-3)
     # same step with pruning switched off: every (point, pose) pair fully evaluated (bit-identical rewards)
     L.cov_set_pruning(0)
     for _ in range(2):
-        step(pts_sorted, perm)
+        step(pts_sorted, perm, boxes)
     dense_steps = max(2, min(args.steps, 5))
-    ms_dense = timed(lambda: step(pts_sorted, perm), dense_steps) / dense_steps
+    ms_dense = timed(lambda: step(pts_sorted, perm, boxes), dense_steps) / dense_steps
     L.cov_set_pruning(1)
 
     # ---- end to end: host (pinned) inputs in, loss + gradients out, every step ----
@@ -301,7 +304,7 @@ def main():
             body.copy_(host_body, non_blocking=True)
         sorted_cur, perm_cur = ops.spatial_sort(bufs[cur])
         free[cur].record(main)
-        loss = step(sorted_cur, perm_cur)
+        loss = step(sorted_cur, perm_cur, ops.tile_boxes(sorted_cur))
         host_out[:1].copy_(loss.detach().reshape(1), non_blocking=True)
         host_out[1:].copy_(body.grad.reshape(-1), non_blocking=True)
         main.synchronize()
@@ -318,6 +321,7 @@ def main():
     pts = bufs[0]
     del bufs, host_pts
     pts_sorted, perm = ops.spatial_sort(pts)
+    boxes = ops.tile_boxes(pts_sorted)
 
     # ---- per-call timing for the roofline (pass A = cov_traj_minmax, pass B = cov_traj_fused) ----
     import ctypes
@@ -334,12 +338,13 @@ def main():
 
     def pass_a():
         _lib.check(L.cov_traj_minmax(pts_sorted.data_ptr(), n_local, P.data_ptr(), Q.data_ptr(), W, K.data_ptr(),
-                                     ctypes.byref(cam), minmax.data_ptr(), stream), "cov_traj_minmax")
+                                     ctypes.byref(cam), boxes.data_ptr(), minmax.data_ptr(), ws.data_ptr(), wsb, stream),
+                   "cov_traj_minmax")
 
     def pass_b():
         _lib.check(L.cov_traj_fused(pts_sorted.data_ptr(), n_local, P.data_ptr(), Q.data_ptr(), W, K.data_ptr(),
-                                    ctypes.byref(cam), minmax.data_ptr(), None, perm.data_ptr(), rewards.data_ptr(),
-                                    acc.data_ptr(), ws.data_ptr(), wsb, stream), "cov_traj_fused")
+                                    ctypes.byref(cam), boxes.data_ptr(), minmax.data_ptr(), None, perm.data_ptr(),
+                                    rewards.data_ptr(), acc.data_ptr(), ws.data_ptr(), wsb, stream), "cov_traj_fused")
 
     def global_minmax():
         pass_a()

@@ -88,12 +88,16 @@ int cov_pose_epilogue(const double* acc_dev, const float* trans_dev, const float
  * ------------------------------------------------------------------------------------------ */
 int cov_traj_max_poses(void);
 size_t cov_traj_workspace_bytes(int64_t n, int n_poses);
+/* boxes_dev: NULL, or the bounding boxes cov_tile_boxes made for this cloud (built once per cloud; with NULL the
+ * pruned kernels rebuild them into the workspace on every call).  workspace_dev: cov_traj_workspace_bytes(n, n_poses)
+ * bytes, 256-byte aligned, shared by both calls. */
 int cov_traj_minmax(const float* xyz_dev, int64_t n, const float* poses_dev, const float* quats_dev, int n_poses,
-                    const float* K_dev, const cov_camera* cam, float* minmax_dev, void* stream);
+                    const float* K_dev, const cov_camera* cam, const float* boxes_dev, float* minmax_dev,
+                    void* workspace_dev, size_t workspace_bytes, void* stream);
 int cov_traj_fused(const float* xyz_dev, int64_t n, const float* poses_dev, const float* quats_dev, int n_poses,
-                   const float* K_dev, const cov_camera* cam, const float* minmax_dev, const float* upstream_dev,
-                   const int32_t* reward_index_dev, float* rewards_dev, double* acc_dev, void* workspace_dev,
-                   size_t workspace_bytes, void* stream);
+                   const float* K_dev, const cov_camera* cam, const float* boxes_dev, const float* minmax_dev,
+                   const float* upstream_dev, const int32_t* reward_index_dev, float* rewards_dev, double* acc_dev,
+                   void* workspace_dev, size_t workspace_bytes, void* stream);
 /* out_dev: [0] mean reward, then (W,3) d/d poses, then (W,4) d/d quats  (1 + 7*W floats).
  * With upstream_mode != 0 the gradients are those of sum_j upstream_j * rewards_j (no 1/N). */
 int cov_traj_epilogue(const double* acc_dev, const float* minmax_dev, const float* quats_dev, int n_poses,
@@ -151,14 +155,16 @@ int cov_hpr_hull(const float* flipped_dev, int64_t n, uint8_t* vertex_mask_dev, 
                  void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* Exact pruning of (point, pose) pairs in cov_traj_minmax / cov_traj_fused (default on): a pair whose distance
- * Gaussian alone bounds m below what could matter (the largest m seen so far in pass A once a zero minimum is
- * known; half the normalised range in pass B) is skipped: per tile of 1024-2048 consecutive points the block tests
- * every pose against the tile's bounding box, each warp re-tests against the box of its own 128-256 points, then
- * per point.  Results are bit-identical to the dense evaluation on ANY point order; the saving grows with the
- * spatial coherence of consecutive points (cov_spatial_sort below).  Process-wide switch, meant for A/B
- * measurements.  cov_stats copies eight counters of (warp, pose) pairs to the host (this call synchronises):
- * [0] pass B all pairs, [1] fully evaluated, [2],[3] same for pass A, [4]/[5] pass B/A pairs that ran the
- * per-point pre-filter, [6]/[7] pass B/A pairs that survived the tile-level test; reset != 0 clears them. */
+ * Gaussian alone bounds m below what could matter (a sampled lower bound of the maximum in pass A once a zero
+ * minimum is known; the gate threshold in pass B) is never evaluated.  Pipeline per call: cull (one warp per tile of
+ * 256-2048 consecutive points: union of the tile's boxes against every pose) -> ascending work list of the tiles
+ * with a non-empty pose mask -> persistent evaluation kernel over the work list (tile, boxes and mask arrive by TMA;
+ * each warp re-tests against the box of its own points, then per point).  Normalisers and rewards are bit-identical
+ * to the dense evaluation on ANY point order; the saving grows with the spatial coherence of consecutive points
+ * (cov_spatial_sort below).  Process-wide switch, meant for A/B measurements.  cov_stats copies eight counters of
+ * (warp, pose) pairs to the host (this call synchronises): [0] pass B all pairs, [1] fully evaluated, [2],[3] same
+ * for pass A, [4]/[5] pass B/A pairs that ran the per-point pre-filter, [6]/[7] pass B/A pairs listed by the cull;
+ * reset != 0 clears them. */
 void cov_set_pruning(int enabled);
 int cov_get_pruning(void);
 int cov_stats(int reset, unsigned long long* out8_host);
@@ -169,6 +175,12 @@ int cov_stats(int reset, unsigned long long* out8_host);
  * 1024 cells along the longest extent of the bounding box; the sort is stable, hence deterministic.
  *   xyz_sorted_dev (n,3) fp32 out;  perm_dev (n) int32 out: xyz_sorted[j] = xyz[perm[j]]  (n < 2^31). */
 size_t cov_spatial_sort_workspace_bytes(int64_t n);
+/* Bounding boxes of runs of COV_BOX_POINTS consecutive points of a cloud (any order; tight after cov_spatial_sort):
+ * boxes_dev receives cov_tile_boxes_count(n) boxes of 8 fp32 each, (lo.xyz, 0, hi.xyz, 0); boxes past the end of the
+ * cloud are empty (+inf, -inf).  16-byte aligned. */
+#define COV_BOX_POINTS 128
+int64_t cov_tile_boxes_count(int64_t n);
+int cov_tile_boxes(const float* xyz_dev, int64_t n, float* boxes_dev, void* stream);
 int cov_spatial_sort(const float* xyz_dev, int64_t n, float* xyz_sorted_dev, int32_t* perm_dev, void* workspace_dev,
                      size_t workspace_bytes, void* stream);
 

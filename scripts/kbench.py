@@ -3,7 +3,7 @@
 size — dense, pruned on the unsorted cloud, pruned on the Morton-sorted cloud — and checks that the three give
 bit-identical normalisers and rewards.  Not part of the product or the reported numbers.
 
-usage: kbench.py [n_points] [variants]"""
+usage: kbench.py [n_points]"""
 import ctypes
 import os
 import sys
@@ -33,18 +33,20 @@ ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
 stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 REPS = int(os.environ.get("KBENCH_REPS", "5"))
 
-state = {"pts": pts_raw, "perm": None}
+state = {"pts": pts_raw, "perm": None, "boxes": None}
 
 
 def pass_a():
     p = state["pts"]
     _lib.check(L.cov_traj_minmax(p.data_ptr(), n, P.data_ptr(), Q.data_ptr(), W, K.data_ptr(), ctypes.byref(cam),
-                                 minmax.data_ptr(), stream), "minmax")
+                                 state["boxes"].data_ptr() if state["boxes"] is not None else None, minmax.data_ptr(),
+                                 ws.data_ptr(), wsb, stream), "minmax")
 
 
 def pass_b():
     p, perm = state["pts"], state["perm"]
     _lib.check(L.cov_traj_fused(p.data_ptr(), n, P.data_ptr(), Q.data_ptr(), W, K.data_ptr(), ctypes.byref(cam),
+                                state["boxes"].data_ptr() if state["boxes"] is not None else None,
                                 minmax.data_ptr(), None, None if perm is None else perm.data_ptr(), rewards.data_ptr(),
                                 acc.data_ptr(), ws.data_ptr(), wsb, stream), "fused")
 
@@ -93,7 +95,7 @@ torch.cuda.synchronize()
 print(f"spatial sort of {n} points: {e0.elapsed_time(e1):.3f} ms; sorted == gather: "
       f"{torch.equal(sorted_pts, pts_raw[perm.long()])}; perm is a permutation: "
       f"{bool((torch.sort(perm.long()).values == torch.arange(n, device=dev)).all().item())}", flush=True)
-state["pts"], state["perm"] = sorted_pts, perm
+state["pts"], state["perm"], state["boxes"] = sorted_pts, perm, ops.tile_boxes(sorted_pts)
 mm_s, rew_s, acc_s = run("pruned/sorted")
 print(f"   == dense: minmax {torch.equal(mm_s, mm_d)} rewards {torch.equal(rew_s, rew_d)} "
       f"acc_rel {float(((acc_s - acc_d).abs().max() / acc_d.abs().max()).item()):.2e} "
@@ -105,24 +107,3 @@ mm_ds, rew_ds, acc_ds = run("dense/sorted")
 print(f"   sorted pruned == sorted dense: minmax {torch.equal(mm_s, mm_ds)} rewards {torch.equal(rew_s, rew_ds)} "
       f"acc {torch.equal(acc_s, acc_ds)}", flush=True)
 L.cov_set_pruning(1)
-if len(sys.argv) <= 2:
-    sys.exit(0)
-state["pts"], state["perm"] = pts_raw, None
-L.cov_set_pruning(0)
-ref_mm = ref_acc = ref_rew = None
-for v in range(6):
-    os.environ["COV_DEV_MM"] = str(v)
-    ms = timeit(pass_a)
-    if ref_mm is None:
-        ref_mm = minmax.clone()
-    print(f"minmax variant {v}: {ms:8.3f} ms  {n * W / ms / 1e6:8.1f} G evals/s  same={torch.equal(minmax, ref_mm)}", flush=True)
-os.environ["COV_DEV_MM"] = "0"
-pass_a()
-for v in range(4):
-    os.environ["COV_DEV_F"] = str(v)
-    ms = timeit(pass_b)
-    if ref_acc is None:
-        ref_acc, ref_rew = acc.clone(), rewards.clone()
-    err = float(((acc - ref_acc).abs().max() / ref_acc.abs().max()).item())
-    print(f"fused  variant {v}: {ms:8.3f} ms  {n * W / ms / 1e6:8.1f} G evals/s  rewards_same={torch.equal(rewards, ref_rew)} acc_rel={err:.2e}",
-          flush=True)

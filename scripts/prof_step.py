@@ -17,6 +17,7 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 dev = torch.device("cuda:0")
 L = _lib.lib()
 pts, perm = ops.spatial_sort(bench.make_cloud_shard(n, 0, 1, dev))
+boxes = ops.tile_boxes(pts)
 K, iw, ih = tools.load_intrinsics(dev)
 t, q = multicam.camera_poses_from_body(bench.body_waypoints().to(dev), multicam.ring_rig(5))
 P, Q = t.reshape(-1, 3).contiguous(), q.reshape(-1, 4).contiguous()
@@ -30,9 +31,9 @@ ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
 stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 for _ in range(reps):
     _lib.check(L.cov_traj_minmax(pts.data_ptr(), n, P.data_ptr(), Q.data_ptr(), W, K.data_ptr(), ctypes.byref(cam),
-                                 minmax.data_ptr(), stream), "minmax")
+                                 boxes.data_ptr(), minmax.data_ptr(), ws.data_ptr(), wsb, stream), "minmax")
     _lib.check(L.cov_traj_fused(pts.data_ptr(), n, P.data_ptr(), Q.data_ptr(), W, K.data_ptr(), ctypes.byref(cam),
-                                minmax.data_ptr(), None, perm.data_ptr(), rewards.data_ptr(), acc.data_ptr(),
+                                boxes.data_ptr(), minmax.data_ptr(), None, perm.data_ptr(), rewards.data_ptr(), acc.data_ptr(),
                                 ws.data_ptr(), wsb, stream), "fused")
 torch.cuda.synchronize()
 print("mean reward", float(acc[-1]) / n)

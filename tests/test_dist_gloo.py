@@ -59,12 +59,15 @@ class OracleBackend:
         a = acc.numpy()
         return torch.tensor(np.concatenate([[a[0]], -a[1:4], self._quat_grad(a[4:7], q)]), dtype=torch.float32)
 
-    def traj_minmax(self, pts, P, Q, Kd, cam):
+    def traj_workspace(self, pts, W):
+        return None
+
+    def traj_minmax(self, pts, P, Q, Kd, cam, boxes=None, ws=None):
         mm = [self._vis(pts, P[w], Q[w], Kd, cam)[0] for w in range(len(P))]
         # fp64 so that the stand-in's second pass can find its arg-min/arg-max by exact comparison
         return torch.tensor([m.min() for m in mm] + [m.max() for m in mm], dtype=torch.float64)
 
-    def traj_fused(self, pts, P, Q, Kd, cam, minmax, upstream, rewards, reward_index=None):
+    def traj_fused(self, pts, P, Q, Kd, cam, minmax, upstream, rewards, reward_index=None, boxes=None, ws=None):
         W, hi = len(P), float(np.float32(1.0 - cam.eps))
         acc, L, keep = np.zeros(W * ACC + 1), np.zeros(len(pts)), []
         for w in range(W):

@@ -195,8 +195,10 @@ def test_sharded_accumulators_equal_whole_cloud(dev, mod):
     mm = []
     for s in shards:
         t = torch.empty(2 * W, device=dev)
+        wsb = L.cov_traj_workspace_bytes(s.shape[0], W)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
         _lib.check(L.cov_traj_minmax(s.data_ptr(), s.shape[0], P.data_ptr(), Q.data_ptr(), W, K.data_ptr(),
-                                     ctypes.byref(cam), t.data_ptr(), stream), "minmax")
+                                     ctypes.byref(cam), None, t.data_ptr(), ws.data_ptr(), wsb, stream), "minmax")
         mm.append(t)
     minmax = torch.cat([torch.minimum(mm[0][:W], mm[1][:W]), torch.maximum(mm[0][W:], mm[1][W:])])
     acc = torch.zeros(W * _lib.ACC_STRIDE + 1, dtype=torch.float64, device=dev)
@@ -207,7 +209,7 @@ def test_sharded_accumulators_equal_whole_cloud(dev, mod):
         wsb = L.cov_traj_workspace_bytes(s.shape[0], W)
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
         _lib.check(L.cov_traj_fused(s.data_ptr(), s.shape[0], P.data_ptr(), Q.data_ptr(), W, K.data_ptr(),
-                                    ctypes.byref(cam), minmax.data_ptr(), None, None, r.data_ptr(), a.data_ptr(),
+                                    ctypes.byref(cam), None, minmax.data_ptr(), None, None, r.data_ptr(), a.data_ptr(),
                                     ws.data_ptr(), wsb, stream), "fused")
         acc += a
         rew.append(r)
@@ -367,6 +369,7 @@ def test_tile_pruning_on_sorted_cloud_is_bit_identical_to_dense(dev, mod):
             poses, yaw = _s_curve(40, 16.0)
             quats = np.stack([np.cos(yaw / 2), 0 * yaw, 0 * yaw, np.sin(yaw / 2)], 1).astype(np.float32)
         pts, perm = ops.spatial_sort(torch.from_numpy(pts_np).to(dev))
+        boxes = ops.tile_boxes(pts)
         P, Q = torch.from_numpy(poses).to(dev), torch.from_numpy(quats).to(dev)
         W = P.shape[0]
         outs = []
@@ -374,10 +377,13 @@ def test_tile_pruning_on_sorted_cloud_is_bit_identical_to_dense(dev, mod):
             for mode in (1, 0):
                 L.cov_set_pruning(mode)
                 mm = torch.empty(2 * W, device=dev)
+                wsb = L.cov_traj_workspace_bytes(n, W)
+                ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
                 _lib.check(L.cov_traj_minmax(pts.data_ptr(), n, P.data_ptr(), Q.data_ptr(), W, K.data_ptr(),
-                                             ctypes.byref(cam), mm.data_ptr(), stream), "minmax")
+                                             ctypes.byref(cam), boxes.data_ptr(), mm.data_ptr(), ws.data_ptr(), wsb,
+                                             stream), "minmax")
                 Pg, Qg = P.clone().requires_grad_(True), Q.clone().requires_grad_(True)
-                rewards, mean = ops.coverage_traj(pts, Pg, Qg, K, Wd, Hd, reward_index=perm)
+                rewards, mean = ops.coverage_traj(pts, Pg, Qg, K, Wd, Hd, reward_index=perm, boxes=boxes)
                 gp, gq = torch.autograd.grad(mean, [Pg, Qg])
                 outs.append((mm, rewards, mean, gp, gq))
         finally:

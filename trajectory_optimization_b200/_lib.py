@@ -36,8 +36,8 @@ PROTOTYPES = {
     "cov_pose_epilogue": (_int, [_vp, _vp, _vp, _vp, _vp]),
     "cov_traj_max_poses": (_int, []),
     "cov_traj_workspace_bytes": (_sz, [_i64, _int]),
-    "cov_traj_minmax": (_int, [_vp, _i64, _vp, _vp, _int, _vp, _cam, _vp, _vp]),
-    "cov_traj_fused": (_int, [_vp, _i64, _vp, _vp, _int, _vp, _cam, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "cov_traj_minmax": (_int, [_vp, _i64, _vp, _vp, _int, _vp, _cam, _vp, _vp, _vp, _sz, _vp]),
+    "cov_traj_fused": (_int, [_vp, _i64, _vp, _vp, _int, _vp, _cam, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "cov_traj_epilogue": (_int, [_vp, _vp, _vp, _int, _i64, _int, _vp, _vp]),
     "cov_sweep_rewards": (_int, [_vp, _i64, _vp, _vp, _int, _int, _vp, _cam, _vp, _vp, _vp]),
     "cov_rig_poses": (_int, [_vp, _int, _vp, _int, _vp, _vp, _vp]),
@@ -52,6 +52,8 @@ PROTOTYPES = {
     "cov_stats": (_int, [_int, _vp]),
     "cov_spatial_sort_workspace_bytes": (_sz, [_i64]),
     "cov_spatial_sort": (_int, [_vp, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "cov_tile_boxes_count": (_i64, [_i64]),
+    "cov_tile_boxes": (_int, [_vp, _i64, _vp, _vp]),
     "cov_probe_fma": (_i64, [_int, _vp, _vp]),
     "cov_probe_ex2": (_i64, [_int, _vp, _vp]),
 }

@@ -1,25 +1,41 @@
 // cov_traj.cu — ModelTraj visibility term, fused forward+backward (reference src/model.py:200-246).
 //
-// Data layout: the cloud stays in HBM as row-major (N,3) fp32 and is streamed once per pass;
-// the W pose rows (t, R mu1, P = K R^T, normalisers) live in shared memory as 5 float4 each and are
-// read with broadcast LDS.128; per-point state (log-odds sum) lives in registers.
+// Data layout: the cloud stays in HBM as row-major (N,3) fp32; the W pose rows (constants of cov_common.cuh) live
+// in shared memory as 6 float4 each and are read with broadcast LDS.128; per-point state lives in registers.
 //
-// Pass A (cov_traj_minmax_kernel): per pose min_j m and max_j m.  Thread-local fmin/fmax over the
-//   thread's points, one integer REDUX per warp (m >= 0, so the float order is the uint order), one
-//   shared-memory atomic per warp and pose, one global atomic per block and pose.  Deterministic.
-// Pass B (cov_traj_fused_kernel), per tile of 256*PPT points:
-//   phase 1  every (point, pose): m, gate (m - a >= b/2  <=>  p >= 0.5, exact), warp ballot of the
-//            gate stored as a pose-major bit matrix in shared memory; gated lanes add their log-odds
-//            to the point's running sum in pose order (same order as the reference loop).
-//            rewards_j = sigmoid(L_j) is written, G_j = r_j (1 - r_j) kept in shared memory.
-//   phase 2  the bit matrix is walked pose-major: a lane owns (pose, row segment), pops its set bits,
-//            re-evaluates m and dm/dy for that pair and accumulates the 8 weighted sums in registers —
-//            no atomics, fixed order.  Segments of a pose are combined with xor-shuffles and added to
-//            the block's per-pose accumulators in shared memory by one owner lane.
-//   Block accumulators go to a [block][W][8] fp32 slab; a small kernel adds the slabs in fp64.
-//   The arg-max / arg-min tie sets of the normalisation backward are rare (one point per pose unless
-//   the minimum underflowed to 0, in which case their gradient is exactly negligible and skipped) and
-//   go straight to the fp64 accumulator with atomics.
+// Two passes per objective evaluation (the min/max normalisation of src/model.py:226-227 needs the extrema first):
+//   pass A  cov_traj_minmax   per pose min_j m and max_j m
+//   pass B  cov_traj_fused    rewards_j = sigmoid(sum_w logit(clip(p_jw))) + the gradient accumulators
+//
+// Each pass exists in two forms that give bit-identical normalisers and rewards:
+//
+// DENSE (cov_set_pruning(0)): every (point, pose) pair is evaluated.  FP32-issue bound.
+//   pass A: thread-local fmin/fmax over the thread's points, one integer REDUX per warp (m >= 0, so the float order
+//           is the uint order), one shared atomic per warp and 32 poses, one global atomic per block and pose.
+//   pass B, per tile of 256*PPT points:
+//     phase 1  every pair: m, gate (m - a >= b/2  <=>  p >= 0.5, exact), warp ballot of the gate into a pose-major
+//              bit matrix in shared memory; gated lanes add their log-odds to the point's running sum in pose order.
+//     phase 2  the bit matrix is walked pose-major: a lane owns (pose, row segment), pops its set bits, re-evaluates
+//              m and dm/dx for that pair and accumulates the 8 weighted sums in registers — no atomics, fixed order.
+//
+// PRUNED (default): cull -> compact -> evaluate, on boxes of 128 consecutive points (cov_tile_boxes; tight when the
+//   cloud is Morton-ordered by cov_spatial_sort, valid for any order).  A pair whose distance Gaussian alone bounds m
+//   below what can matter is never evaluated:  m <= 2^-(kd q2)(1+1.3e-5)  and  q2 >= box bound > qcap  =>  m < bound.
+//     pass A: bound = a lower bound of max_j m from a strided sample of the cloud (seed launch), valid once the
+//             minimum is known to be exactly 0 (skipped points have m >= 0);
+//     pass B: bound = the conservative gate threshold (a + b/2)(1 - 2^-20): a pair below it is neither gated nor
+//             the arg-max, adds logit(1/2) = 0 to the log-odds sum and nothing to the gradient.
+//   cov_cull_kernel      one warp per tile: union of the tile's boxes against every pose -> per-tile pose bit mask
+//   cov_worklist_kernel  ascending list of the tiles with a non-empty mask (single block scan: deterministic)
+//   *_tiles_kernel       persistent blocks walk the work list; tile points, boxes and mask arrive together through a
+//                        double-buffered TMA bulk copy (one mbarrier per buffer); a warp evaluates a listed pose only
+//                        if its own 128-point box and then one of its points pass the same test.
+//   Tiles that are not listed are never read: their rewards are the pre-filled 1/2 (exact), their sum is 0.5 * count.
+//
+// Block accumulators go to a [block][W][8] fp32 slab; a small kernel adds the slabs in fp64 in a fixed order.
+// The arg-max / arg-min tie sets of the normalisation backward are rare (one point per pose unless the minimum
+// underflowed to 0, in which case their gradient is exactly negligible and skipped) and go straight to the fp64
+// accumulator with atomics.
 #include <algorithm>
 #include <cstdlib>
 
@@ -30,28 +46,33 @@ namespace {
 
 constexpr int kWarps = COV_THREADS / 32;
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kMaskWords = 64;  // active-pose bit mask: covers cov_traj_max_poses() <= 2048
+constexpr int kMaskWords = 64;   // pose bit mask of a tile: covers cov_traj_max_poses() <= 2048
+constexpr int kBoxPts = COV_BOX_POINTS;  // points per precomputed bounding box
 
 __host__ __device__ constexpr int tile_points(int ppt) { return COV_THREADS * ppt; }
 __host__ __device__ constexpr int bit_words(int ppt) { return kWarps * ppt; }         // ballot words per pose
-__host__ __device__ constexpr int bit_stride(int ppt) { return bit_words(ppt) + 4; }  // rows stay 16-byte aligned
+__host__ __device__ constexpr int bit_stride(int ppt) { return bit_words(ppt) + 4; }  // dense rows: padded, 16-byte aligned
+__host__ __device__ constexpr int tile_boxes(int ppt) { return tile_points(ppt) / kBoxPts; }
+__host__ __device__ inline int mask_stride_words(int W) { return (((W + 31) >> 5) + 3) & ~3; }  // 16-byte multiple
+// one staged tile of the pruned kernels: points | boxes | pose mask (all 16-byte multiples, buffer 128-byte multiple)
+__host__ __device__ constexpr int stage_floats(int ppt) { return tile_points(ppt) * 3 + tile_boxes(ppt) * 8 + kMaskWords; }
 
-size_t minmax_smem_bytes(int W) { return (size_t)W * (COV_ROW_F4 * sizeof(float4) + 3 * sizeof(unsigned)); }
-// pruned pass A: pose table + block min/max/cap, then the 128-byte aligned double buffer of raw tiles [2][T*3]
-__host__ __device__ inline int minmax_tiles_raw_offset_floats(int W) {
+size_t minmax_smem_bytes(int W) { return (size_t)W * (COV_ROW_F4 * sizeof(float4) + 2 * sizeof(unsigned)); }
+__host__ __device__ inline int minmax_tiles_stage_offset_floats(int W) {
     return (int)((((size_t)W * (COV_ROW_F4 * 16 + 12) + 127) & ~(size_t)127) / 4);
 }
 size_t minmax_tiles_smem_bytes(int W, int ppt) {
-    return (size_t)minmax_tiles_raw_offset_floats(W) * 4 + 2 * (size_t)tile_points(ppt) * 12;
+    return (size_t)minmax_tiles_stage_offset_floats(W) * 4 + 2 * (size_t)stage_floats(ppt) * 4;
 }
-// fused pass: pose table, then (128-byte aligned) the tile buffer(s), G_j, gate bits, accumulators, active-pose list
-__host__ __device__ inline int fused_raw_offset_floats(int W) {
+// fused pass: pose table, then (128-byte aligned) the tile stage(s), G_j, gate bits, accumulators, gated-pose list
+__host__ __device__ inline int fused_stage_offset_floats(int W) {
     return (int)((((size_t)W * COV_ROW_F4 * 16 + 127) & ~(size_t)127) / 4);
 }
 size_t fused_smem_bytes(int W, int ppt, bool prune) {
     const size_t rs = prune ? bit_words(ppt) : bit_stride(ppt);
-    return (size_t)fused_raw_offset_floats(W) * 4 + (size_t)(prune ? 2 : 1) * tile_points(ppt) * 12 +
-           (size_t)tile_points(ppt) * 4 + (size_t)W * rs * sizeof(unsigned) + (size_t)W * 8 * sizeof(float) +
+    const size_t stage = prune ? 2 * (size_t)stage_floats(ppt) * 4 : (size_t)tile_points(ppt) * 12;
+    return (size_t)fused_stage_offset_floats(W) * 4 + stage + (size_t)tile_points(ppt) * 4 +
+           (size_t)W * rs * sizeof(unsigned) + (size_t)W * 8 * sizeof(float) +
            (prune ? (((size_t)W * sizeof(unsigned short) + 15) & ~(size_t)15) : 0);
 }
 
@@ -73,7 +94,7 @@ __device__ __noinline__ void tie_accumulate(float x, float y, float z, const flo
     atomicAdd(dst + 6, 1.0);
 }
 
-// ---- tile-level pruning helpers -------------------------------------------------------------------------------
+// ---- pruning helpers ------------------------------------------------------------------------------------------
 // Order-preserving float <-> uint map (so one integer REDUX gives a float min or max of either sign).
 __device__ __forceinline__ unsigned f2ord(float f) {
     const unsigned u = __float_as_uint(f);
@@ -83,68 +104,37 @@ __device__ __forceinline__ float ord2f(unsigned u) {
     return __uint_as_float((u & 0x80000000u) ? (u ^ 0x80000000u) : ~u);
 }
 
-// Axis-aligned box of the 32*PPT points a warp holds (identical in every lane).  Points flagged invalid are ignored.
-template <int PPT>
-__device__ __forceinline__ void warp_box(const float (&px)[PPT], const float (&py)[PPT], const float (&pz)[PPT],
-                                         const bool (&valid)[PPT], float3& lo, float3& hi) {
-    const float inf = __uint_as_float(0x7f800000u);
-    float lx = inf, ly = inf, lz = inf, hx = -inf, hy = -inf, hz = -inf;
-#pragma unroll
-    for (int s = 0; s < PPT; ++s) {
-        if (valid[s]) {
-            lx = fminf(lx, px[s]); ly = fminf(ly, py[s]); lz = fminf(lz, pz[s]);
-            hx = fmaxf(hx, px[s]); hy = fmaxf(hy, py[s]); hz = fmaxf(hz, pz[s]);
-        }
-    }
-    lo.x = ord2f(__reduce_min_sync(kFull, f2ord(lx)));
-    lo.y = ord2f(__reduce_min_sync(kFull, f2ord(ly)));
-    lo.z = ord2f(__reduce_min_sync(kFull, f2ord(lz)));
-    hi.x = ord2f(__reduce_max_sync(kFull, f2ord(hx)));
-    hi.y = ord2f(__reduce_max_sync(kFull, f2ord(hy)));
-    hi.z = ord2f(__reduce_max_sync(kFull, f2ord(hz)));
-}
-
 // Lower bound of cov_q2(x, y, z, v3) over every point of the box [lo, hi].  Rounding is monotone, so with the same
 // operation sequence as cov_q2 (fsub, then fmul/fma/fma) the bound holds for the COMPUTED q2 of each point, exactly:
 // |fl(x - td)| >= max(fl(lo - td), fl(td - hi), 0) for lo <= x <= hi.  An empty box (lo = +inf) gives +inf.
-__device__ __forceinline__ float box_q2lb(const float3& lo, const float3& hi, const float4& v3) {
+__device__ __forceinline__ float box_q2lb(const float4& lo, const float4& hi, const float4& v3) {
     const float dx = fmaxf(fmaxf(__fsub_rn(lo.x, v3.x), __fsub_rn(v3.x, hi.x)), 0.f);
     const float dy = fmaxf(fmaxf(__fsub_rn(lo.y, v3.y), __fsub_rn(v3.y, hi.y)), 0.f);
     const float dz = fmaxf(fmaxf(__fsub_rn(lo.z, v3.z), __fsub_rn(v3.z, hi.z)), 0.f);
     return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
 }
-
-// Union of the kWarps warp boxes a block left in shared memory (wbox[warp] = lo.xyz, hi.xyz).
-__device__ __forceinline__ void block_box(const float (*wbox)[8], float3& lo, float3& hi) {
-    lo = make_float3(wbox[0][0], wbox[0][1], wbox[0][2]);
-    hi = make_float3(wbox[0][4], wbox[0][5], wbox[0][6]);
-#pragma unroll
-    for (int i = 1; i < kWarps; ++i) {
-        lo.x = fminf(lo.x, wbox[i][0]); lo.y = fminf(lo.y, wbox[i][1]); lo.z = fminf(lo.z, wbox[i][2]);
-        hi.x = fmaxf(hi.x, wbox[i][4]); hi.y = fmaxf(hi.y, wbox[i][5]); hi.z = fmaxf(hi.z, wbox[i][6]);
-    }
+__device__ __forceinline__ void box_union(float4& lo, float4& hi, const float4& lo2, const float4& hi2) {
+    lo.x = fminf(lo.x, lo2.x); lo.y = fminf(lo.y, lo2.y); lo.z = fminf(lo.z, lo2.z);
+    hi.x = fmaxf(hi.x, hi2.x); hi.y = fmaxf(hi.y, hi2.y); hi.z = fmaxf(hi.z, hi2.z);
+}
+// Pass-A cap on q2 from the extrema seen so far (as uints): +inf (evaluate everything) unless the minimum is known
+// to be exactly 0.  NaN propagates and every test against it evaluates.
+__device__ __forceinline__ float minmax_qcap(unsigned mn, unsigned mx, float inv_kd) {
+    float cap = __uint_as_float(0x7f800000u);
+    if (mn == 0u && mx != 0u) cap = (1e-4f - __log2f(__uint_as_float(mx))) * inv_kd * 1.000001f;
+    return cap;
 }
 
-// Ask the L2 to fetch the points of a tile this block will read next (one thread issues it).
-__device__ __forceinline__ void prefetch_tile_l2(const float* __restrict__ xyz, int64_t n, int64_t tile, int tile_pts) {
-    const int64_t first = tile * tile_pts;
-    if (first >= n) return;
-    int64_t pts = n - first;
-    if (pts > tile_pts) pts = tile_pts;
-    const unsigned bytes = (unsigned)(pts * 12) & ~15u;
-    if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(xyz + first * 3), "r"(bytes) : "memory");
-}
-
-// ---- double-buffered TMA stream of whole tiles (pruned kernels) ------------------------------------------------
-// One elected thread arms an mbarrier with the byte count and issues one cp.async.bulk (global -> shared) per
-// tile; everybody waits on the barrier's phase parity.  Tile k+1 is in flight while tile k is processed.
+// ---- TMA bulk copies (global -> shared) completing on an mbarrier ------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_copy(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_u32(dst_smem)),
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
@@ -164,34 +154,36 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         : "memory");
 }
 
-__device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
+// One staged tile: points (unless the tile is the ragged last one), its boxes and its pose mask, on one mbarrier.
+template <int PPT>
+__device__ __forceinline__ void stage_issue(float* stage, unsigned long long* bar, const float* __restrict__ xyz,
+                                            const float4* __restrict__ boxes, const unsigned* __restrict__ amask_g,
+                                            int mask_stride, int64_t tile, int64_t nfull) {
+    constexpr int T = tile_points(PPT);
+    constexpr int NB = tile_boxes(PPT);
+    const bool whole = tile < nfull;
+    mbar_expect_tx(bar, (whole ? T * 12u : 0u) + NB * 32u + (unsigned)mask_stride * 4u);
+    if (whole) tma_copy(stage, xyz + tile * (T * 3), T * 12u, bar);
+    tma_copy(stage + T * 3, boxes + tile * (NB * 2), NB * 32u, bar);
+    tma_copy(stage + T * 3 + NB * 8, amask_g + tile * mask_stride, (unsigned)mask_stride * 4u, bar);
 }
 
-// PRUNE: once this block has seen m == 0 for a pose (so the global minimum is 0), a warp skips the evaluation of
-// its points for that pose when none of them can reach the block's running maximum:
-//   m <= 2^-(kd q2) (1+1.3e-5)  and  q2 > qcap = (-log2(max) + 1e-4)/kd  =>  m < max.
-// Skipped pairs can change neither the minimum (already 0, and m >= 0) nor the maximum: results are identical.
-template <int PPT, int MINB, int U, bool PRUNE>
+// =============================================== pass A, dense ===============================================
+// Also the SEED launch of the pruned pass (point_stride > 1: every point_stride-th point, n = number of samples).
+template <int PPT, int MINB, int U>
 __global__ void __launch_bounds__(COV_THREADS, MINB)
-cov_traj_minmax_kernel(const float* __restrict__ xyz, int64_t n, const float* __restrict__ poses,
+cov_traj_minmax_kernel(const float* __restrict__ xyz, int64_t n, int64_t point_stride, const float* __restrict__ poses,
                        const float* __restrict__ quats, int W, const float* __restrict__ K9, CovConst C,
-                       unsigned* __restrict__ gmin, unsigned* __restrict__ gmax, unsigned long long* __restrict__ stats) {
+                       unsigned* __restrict__ gmin, unsigned* __restrict__ gmax) {
     extern __shared__ float4 smem4[];
     float4* ptab = smem4;
     unsigned* smin = reinterpret_cast<unsigned*>(ptab + (size_t)W * COV_ROW_F4);
     unsigned* smax = smin + W;
-    float* sqcap = reinterpret_cast<float*>(smax + W);
     const int tid = threadIdx.x, lane = tid & 31;
-    const float inv_kd = 1.f / C.kd;
-    unsigned n_iter = 0, n_full = 0;
     for (int w = tid; w < W; w += COV_THREADS) {
         cov_pose_row(poses + 3 * w, quats + 4 * w, K9, C, ptab + (size_t)w * COV_ROW_F4);
         smin[w] = 0x7f800000u;
         smax[w] = 0u;
-        sqcap[w] = __uint_as_float(0x7f800000u);  // +inf: evaluate everything until a zero minimum is known
     }
     __syncthreads();
     constexpr int T = tile_points(PPT);
@@ -201,7 +193,7 @@ cov_traj_minmax_kernel(const float* __restrict__ xyz, int64_t n, const float* __
 #pragma unroll
         for (int s = 0; s < PPT; ++s) {
             int64_t j = tile * T + s * COV_THREADS + tid;
-            j = j < n ? j : n - 1;  // a duplicate cannot change a min or a max
+            j = (j < n ? j : n - 1) * point_stride;  // a duplicate cannot change a min or a max
             px[s] = __ldg(xyz + j * 3);
             py[s] = __ldg(xyz + j * 3 + 1);
             pz[s] = __ldg(xyz + j * 3 + 2);
@@ -217,18 +209,7 @@ cov_traj_minmax_kernel(const float* __restrict__ xyz, int64_t n, const float* __
                 for (int u = 0; u < U; ++u) {  // U poses in flight: U*PPT independent evaluation chains
                     wi[u] = (i + u < wn) ? (i + u) : (wn - 1);  // odd remainder: re-evaluate the last pose (harmless)
                     const float4* row = ptab + (size_t)(w0 + wi[u]) * COV_ROW_F4;
-                    const float4 v3 = row[3];
-                    mn[u] = __uint_as_float(0x7f800000u);  // neutral elements when the pose is skipped
-                    mx[u] = 0.f;
-                    if (PRUNE) {
-                        float qmin = cov_q2(px[0], py[0], pz[0], v3);
-#pragma unroll
-                        for (int s = 1; s < PPT; ++s) qmin = fminf(qmin, cov_q2(px[s], py[s], pz[s], v3));
-                        ++n_iter;
-                        if (!__any_sync(kFull, qmin <= sqcap[w0 + wi[u]])) continue;
-                        ++n_full;
-                    }
-                    const float4 v0 = row[0], v1 = row[1], v2 = row[2];
+                    const float4 v0 = row[0], v1 = row[1], v2 = row[2], v3 = row[3];
                     float m[PPT];
 #pragma unroll
                     for (int s = 0; s < PPT; ++s) m[s] = cov_vis<false>(px[s], py[s], pz[s], v0, v1, v2, v3, C, nullptr);
@@ -257,12 +238,6 @@ cov_traj_minmax_kernel(const float* __restrict__ xyz, int64_t n, const float* __
             if (lane < wn) {
                 atomicMin(smin + w0 + lane, keep_mn);
                 atomicMax(smax + w0 + lane, keep_mx);
-                if (PRUNE) {
-                    // stale values are only ever larger (the maximum grows), i.e. conservative
-                    const unsigned bmn = smin[w0 + lane], bmx = smax[w0 + lane];
-                    if (bmn == 0u && bmx != 0u)
-                        sqcap[w0 + lane] = (1e-4f - __log2f(__uint_as_float(bmx))) * inv_kd * 1.000001f;
-                }
             }
         }
     }
@@ -271,79 +246,214 @@ cov_traj_minmax_kernel(const float* __restrict__ xyz, int64_t n, const float* __
         atomicMin(gmin + w, smin[w]);
         atomicMax(gmax + w, smax[w]);
     }
-    if (PRUNE && lane == 0) {
-        atomicAdd(stats + 2, (unsigned long long)n_iter);
-        atomicAdd(stats + 3, (unsigned long long)n_full);
+}
+
+__global__ void __launch_bounds__(256) cov_fill_kernel(float* __restrict__ dst, int64_t n, float v) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+        if (i + 4 <= n && ((reinterpret_cast<uintptr_t>(dst + i) & 15) == 0)) {
+            *reinterpret_cast<float4*>(dst + i) = make_float4(v, v, v, v);
+        } else {
+            for (int64_t k = i; k < n && k < i + 4; ++k) dst[k] = v;
+        }
     }
 }
 
-// Pass A with tile-level pruning (the product default).  Works on any point order and pays off when consecutive
-// points are spatially close (cov_spatial_sort): per tile the block builds the bounding boxes of its warps' points,
-// tests every pose against the block box (thread-parallel, 1 pose per thread and round) and keeps a bit mask of
-// the poses that can still matter; each warp then walks that mask, re-tests against its own box, runs the per-lane
-// distance pre-filter and only then the full evaluation.
-// A pose can be skipped for a set of points when (i) its global minimum is already known to be exactly 0 (skipped
-// points have m >= 0, so they cannot lower it) and (ii) every skipped point has m < the largest m seen so far:
-//   m <= 2^-(kd q2) (1 + 1.3e-5),  q2 >= box bound > qcap = (1e-4 - log2(max_seen)) / kd   =>   m < max_seen.
-// "Seen so far" is global: blocks publish their per-pose min/max to gmin/gmax after every tile and read them
-// (relaxed loads, L2) before the next one; stale values are only looser.  Tiles are visited in a golden-ratio
-// stride so the first rounds sample the whole cloud and the bounds tighten early.  min/max stay exact.
+__global__ void cov_minmax_init_kernel(unsigned* gmin, unsigned* gmax, int W) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < W) {
+        gmin[w] = 0x7f800000u;
+        gmax[w] = 0u;
+    }
+}
+
+// ============================================ pruned passes: set-up ============================================
+// Pose table in global memory, built once per call (the pruned kernels copy it to shared memory).  With `minmax`
+// (pass B) the rows carry the normalisation constants: v3.w = qthr, v4 = (b/2, b, 1/b, a), v5.w = thr.
+// flags[1] is set when some pose has min_j m > 0.
+__global__ void cov_pose_table_kernel(const float* __restrict__ poses, const float* __restrict__ quats, int W,
+                                      const float* __restrict__ K9, CovConst C, const float* __restrict__ minmax,
+                                      float4* __restrict__ table, int* __restrict__ flags) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= W) return;
+    float4 row[COV_ROW_F4];
+    cov_pose_row(poses + 3 * w, quats + 4 * w, K9, C, row);
+    if (minmax) {
+        const float a = minmax[w];
+        const float b = __fsub_rn(minmax[W + w], a);
+        const float hb = 0.5f * b;
+        const float thr = (a + hb) * (1.f - 9.5367431640625e-07f);  // conservative gate threshold
+        row[5].w = thr;
+        // q2 above qthr cannot reach thr (thr <= 0 or NaN, or a > 0 — arg-min points carry gradient: never prune)
+        row[3].w = (thr > 0.f && !(a > 0.f)) ? (float)((1e-4 - log2((double)thr)) / (double)C.kd * 1.000001)
+                                             : __uint_as_float(0x7f800000u);
+        row[4] = make_float4(hb, b, __frcp_rn(b), a);
+        if (a > 0.f) atomicOr(flags + 1, 1);
+    }
+#pragma unroll
+    for (int i = 0; i < COV_ROW_F4; ++i) table[(size_t)w * COV_ROW_F4 + i] = row[i];
+}
+
+// Bounding boxes of runs of kBoxPts consecutive points: boxes[2b] = (lo, 0), boxes[2b+1] = (hi, 0); boxes past the
+// end of the cloud are empty (+inf, -inf).  One warp per box.
+__global__ void __launch_bounds__(256) cov_tile_boxes_kernel(const float* __restrict__ xyz, int64_t n, int64_t nboxes,
+                                                             float4* __restrict__ boxes) {
+    const float inf = __uint_as_float(0x7f800000u);
+    const int lane = threadIdx.x & 31;
+    for (int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); b < nboxes; b += (int64_t)gridDim.x * 8) {
+        float lx = inf, ly = inf, lz = inf, hx = -inf, hy = -inf, hz = -inf;
+#pragma unroll
+        for (int s = 0; s < kBoxPts / 32; ++s) {
+            const int64_t j = b * kBoxPts + s * 32 + lane;
+            if (j < n) {
+                const float x = __ldg(xyz + j * 3), y = __ldg(xyz + j * 3 + 1), z = __ldg(xyz + j * 3 + 2);
+                lx = fminf(lx, x); ly = fminf(ly, y); lz = fminf(lz, z);
+                hx = fmaxf(hx, x); hy = fmaxf(hy, y); hz = fmaxf(hz, z);
+            }
+        }
+        const unsigned ulx = __reduce_min_sync(kFull, f2ord(lx)), uly = __reduce_min_sync(kFull, f2ord(ly));
+        const unsigned ulz = __reduce_min_sync(kFull, f2ord(lz)), uhx = __reduce_max_sync(kFull, f2ord(hx));
+        const unsigned uhy = __reduce_max_sync(kFull, f2ord(hy)), uhz = __reduce_max_sync(kFull, f2ord(hz));
+        if (lane == 0) {
+            boxes[2 * b] = make_float4(ord2f(ulx), ord2f(uly), ord2f(ulz), 0.f);
+            boxes[2 * b + 1] = make_float4(ord2f(uhx), ord2f(uhy), ord2f(uhz), 0.f);
+        }
+    }
+}
+
+// Cull: one warp per tile.  mask[tile][c] bit i <=> pose 32c+i can matter for some point of the tile; flags[tile] =
+// the mask is not empty.  Pass A passes gmin/gmax (after the seed launch) and the cap is derived here; pass B
+// reads qthr from the table.
+__global__ void __launch_bounds__(256)
+cov_cull_kernel(const float4* __restrict__ boxes, int boxes_per_tile, int64_t ntiles, const float4* __restrict__ table,
+                int W, const unsigned* __restrict__ gmin, const unsigned* __restrict__ gmax, float inv_kd,
+                unsigned* __restrict__ amask_g, int mask_stride, unsigned char* __restrict__ flags) {
+    extern __shared__ float4 v3s[];
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int w = tid; w < W; w += blockDim.x) {
+        float4 v3 = table[(size_t)w * COV_ROW_F4 + 3];
+        if (gmin) v3.w = minmax_qcap(gmin[w], gmax[w], inv_kd);
+        v3s[w] = v3;
+    }
+    __syncthreads();
+    const float inf = __uint_as_float(0x7f800000u);
+    const int nwords = (W + 31) >> 5;
+    for (int64_t tile = (int64_t)blockIdx.x * 8 + (tid >> 5); tile < ntiles; tile += (int64_t)gridDim.x * 8) {
+        float4 lo = make_float4(inf, inf, inf, 0.f), hi = make_float4(-inf, -inf, -inf, 0.f);
+        if (lane < boxes_per_tile) {
+            lo = boxes[(tile * boxes_per_tile + lane) * 2];
+            hi = boxes[(tile * boxes_per_tile + lane) * 2 + 1];
+        }
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {  // boxes_per_tile <= 16
+            lo.x = fminf(lo.x, __shfl_xor_sync(kFull, lo.x, o)); lo.y = fminf(lo.y, __shfl_xor_sync(kFull, lo.y, o));
+            lo.z = fminf(lo.z, __shfl_xor_sync(kFull, lo.z, o)); hi.x = fmaxf(hi.x, __shfl_xor_sync(kFull, hi.x, o));
+            hi.y = fmaxf(hi.y, __shfl_xor_sync(kFull, hi.y, o)); hi.z = fmaxf(hi.z, __shfl_xor_sync(kFull, hi.z, o));
+        }
+        lo.x = __shfl_sync(kFull, lo.x, 0); lo.y = __shfl_sync(kFull, lo.y, 0); lo.z = __shfl_sync(kFull, lo.z, 0);
+        hi.x = __shfl_sync(kFull, hi.x, 0); hi.y = __shfl_sync(kFull, hi.y, 0); hi.z = __shfl_sync(kFull, hi.z, 0);
+        unsigned any = 0u;
+        for (int c = 0; c < mask_stride; ++c) {
+            const int w = c * 32 + lane;
+            bool active = false;
+            if (c < nwords && w < W) {
+                const float4 v3 = v3s[w];
+                active = !(box_q2lb(lo, hi, v3) > v3.w);  // NaN cap: evaluate
+            }
+            const unsigned bal = __ballot_sync(kFull, active);
+            if (lane == 0) amask_g[tile * mask_stride + c] = bal;
+            any |= bal;
+        }
+        if (lane == 0) flags[tile] = any != 0u;
+    }
+}
+
+// Ascending list of flagged tiles + their count (single block: deterministic order, no atomics).
+__global__ void __launch_bounds__(1024) cov_worklist_kernel(const unsigned char* __restrict__ flags, int64_t ntiles,
+                                                            int* __restrict__ worklist, int* __restrict__ count) {
+    __shared__ int warp_tot[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t chunk = (ntiles + 1023) / 1024;
+    const int64_t lo = (int64_t)tid * chunk, hi = lo + chunk < ntiles ? lo + chunk : ntiles;
+    int c = 0;
+    for (int64_t t = lo; t < hi; ++t) c += flags[t] ? 1 : 0;
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int v = warp_tot[lane], s = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(kFull, s, o);
+            if (lane >= o) s += u;
+        }
+        warp_tot[lane] = s - v;  // exclusive
+        if (lane == 31) *count = s;
+    }
+    __syncthreads();
+    int pos = warp_tot[warp] + incl - c;
+    for (int64_t t = lo; t < hi; ++t)
+        if (flags[t]) worklist[pos++] = (int)t;
+}
+
+// =============================================== pass A, pruned ===============================================
 template <int PPT, int MINB>
 __global__ void __launch_bounds__(COV_THREADS, MINB)
-cov_traj_minmax_tiles_kernel(const float* __restrict__ xyz, int64_t n, const float* __restrict__ poses,
-                             const float* __restrict__ quats, int W, const float* __restrict__ K9, CovConst C,
-                             unsigned* __restrict__ gmin, unsigned* __restrict__ gmax, unsigned long long tile_stride,
-                             unsigned long long* __restrict__ stats) {
+cov_traj_minmax_tiles_kernel(const float* __restrict__ xyz, int64_t n, const float4* __restrict__ table, int W, CovConst C,
+                             unsigned* __restrict__ gmin, unsigned* __restrict__ gmax, const float4* __restrict__ boxes,
+                             const unsigned* __restrict__ amask_g, int mask_stride, const int* __restrict__ worklist,
+                             const int* __restrict__ count_ptr, int64_t ntiles, unsigned long long* __restrict__ stats) {
     constexpr int T = tile_points(PPT);
+    constexpr int NB = tile_boxes(PPT);
+    constexpr int SF = stage_floats(PPT);
+    constexpr int WB = (32 * PPT >= kBoxPts) ? (32 * PPT / kBoxPts) : 1;  // boxes covering one warp's points
     extern __shared__ float4 smem4[];
     float4* ptab = smem4;
     unsigned* smin = reinterpret_cast<unsigned*>(ptab + (size_t)W * COV_ROW_F4);
     unsigned* smax = smin + W;
     float* sqcap = reinterpret_cast<float*>(smax + W);
-    float* raw = reinterpret_cast<float*>(smem4) + minmax_tiles_raw_offset_floats(W);  // [2][T*3], 128-byte aligned
-    __shared__ unsigned amask[kMaskWords];
-    __shared__ float wbox[kWarps][8];
+    float* stage = reinterpret_cast<float*>(smem4) + minmax_tiles_stage_offset_floats(W);  // [2][SF]
     __shared__ __align__(8) unsigned long long mbar[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float inv_kd = 1.f / C.kd;
-    const float inf = __uint_as_float(0x7f800000u);
     unsigned n_box = 0, n_pre = 0, n_full = 0;
-    unsigned long long n_iter = 0;
     if (tid == 0) {
         mbar_init(&mbar[0], 1);
         mbar_init(&mbar[1], 1);
         mbar_fence_init();
     }
+    for (int i = tid; i < W * COV_ROW_F4; i += COV_THREADS) ptab[i] = table[i];
     for (int w = tid; w < W; w += COV_THREADS) {
-        cov_pose_row(poses + 3 * w, quats + 4 * w, K9, C, ptab + (size_t)w * COV_ROW_F4);
         smin[w] = 0x7f800000u;
         smax[w] = 0u;
+        sqcap[w] = minmax_qcap(gmin[w], gmax[w], inv_kd);  // from the seed launch (any later value is tighter and valid)
     }
     __syncthreads();
-    const unsigned long long ntiles = (unsigned long long)((n + T - 1) / T);
+    const int count = *count_ptr;
+    const int64_t nfull = n / T;
     const int nwords = (W + 31) >> 5;
-    const int64_t nfull = n / T;  // tiles [0, nfull) are complete and arrive by TMA; a ragged last tile is loaded by hand
-    unsigned uses0 = 0, uses1 = 0;  // completed TMA phases per buffer (uniform over the block)
-    if (tid == 0 && blockIdx.x < ntiles) {
-        const int64_t t0 = (int64_t)(((unsigned long long)blockIdx.x * tile_stride) % ntiles);
-        if (t0 < nfull) tma_load_1d(raw, xyz + t0 * (T * 3), T * 12, &mbar[0]);
-    }
+    unsigned uses0 = 0, uses1 = 0;
+    if (tid == 0 && (int)blockIdx.x < count)
+        stage_issue<PPT>(stage, &mbar[0], xyz, boxes, amask_g, mask_stride, (int64_t)worklist[blockIdx.x], nfull);
     int buf = 0;
-    for (unsigned long long it = blockIdx.x; it < ntiles; it += gridDim.x, buf ^= 1) {
-        const int64_t tile = (int64_t)((it * tile_stride) % ntiles);
-        if (tid == 0 && it + gridDim.x < ntiles) {  // the other buffer was last read two barriers ago
-            const int64_t tn = (int64_t)(((it + gridDim.x) * tile_stride) % ntiles);
-            if (tn < nfull) tma_load_1d(raw + (buf ^ 1) * (T * 3), xyz + tn * (T * 3), T * 12, &mbar[buf ^ 1]);
-        }
+    for (int i = blockIdx.x; i < count; i += gridDim.x, buf ^= 1) {
+        const int64_t tile = worklist[i];
+        if (tid == 0 && i + (int)gridDim.x < count)  // the other stage was last read before the previous barrier
+            stage_issue<PPT>(stage + (buf ^ 1) * SF, &mbar[buf ^ 1], xyz, boxes, amask_g, mask_stride,
+                             (int64_t)worklist[i + gridDim.x], nfull);
+        if (buf == 0) mbar_wait(&mbar[0], uses0++ & 1u);
+        else mbar_wait(&mbar[1], uses1++ & 1u);
+        const float* st = stage + buf * SF;
         float px[PPT], py[PPT], pz[PPT];
-        bool valid[PPT];
         if (tile < nfull) {
-            if (buf == 0) mbar_wait(&mbar[0], uses0++ & 1u);
-            else mbar_wait(&mbar[1], uses1++ & 1u);
-            const float* src = raw + buf * (T * 3) + (warp * (32 * PPT) + lane) * 3;
+            const float* src = st + (warp * (32 * PPT) + lane) * 3;
 #pragma unroll
             for (int s = 0; s < PPT; ++s) {
-                valid[s] = true;
                 px[s] = src[s * 96];
                 py[s] = src[s * 96 + 1];
                 pz[s] = src[s * 96 + 2];
@@ -353,41 +463,20 @@ cov_traj_minmax_tiles_kernel(const float* __restrict__ xyz, int64_t n, const flo
             for (int s = 0; s < PPT; ++s) {
                 int64_t j = tile * T + warp * (32 * PPT) + s * 32 + lane;
                 j = j < n ? j : n - 1;  // a duplicate cannot change a min or a max
-                valid[s] = true;
                 px[s] = __ldg(xyz + j * 3);
                 py[s] = __ldg(xyz + j * 3 + 1);
                 pz[s] = __ldg(xyz + j * 3 + 2);
             }
         }
-        float3 wlo, whi;
-        warp_box<PPT>(px, py, pz, valid, wlo, whi);
-        if (lane == 0) {
-            wbox[warp][0] = wlo.x; wbox[warp][1] = wlo.y; wbox[warp][2] = wlo.z;
-            wbox[warp][4] = whi.x; wbox[warp][5] = whi.y; wbox[warp][6] = whi.z;
-        }
-        __syncthreads();
-        {
-            float3 blo, bhi;
-            block_box(wbox, blo, bhi);
-            for (int c = warp; c < nwords; c += kWarps) {
-                const int w = c * 32 + lane;
-                bool active = false;
-                if (w < W) {
-                    const unsigned mn = min(ld_relaxed(gmin + w), smin[w]);
-                    const unsigned mx = max(ld_relaxed(gmax + w), smax[w]);
-                    float cap = inf;
-                    if (mn == 0u && mx != 0u) cap = (1e-4f - __log2f(__uint_as_float(mx))) * inv_kd * 1.000001f;
-                    sqcap[w] = cap;
-                    active = !(box_q2lb(blo, bhi, ptab[(size_t)w * COV_ROW_F4 + 3]) > cap);  // NaN cap: evaluate
-                }
-                const unsigned bal = __ballot_sync(kFull, active);
-                if (lane == 0) amask[c] = bal;
-            }
-        }
-        __syncthreads();
-        n_iter += (unsigned long long)W;
+        // box of this warp's points = union of the precomputed boxes that cover them
+        const float4* tb = reinterpret_cast<const float4*>(st + T * 3);
+        const int b0 = (warp * 32 * PPT) / kBoxPts;
+        float4 wlo = tb[2 * b0], whi = tb[2 * b0 + 1];
+#pragma unroll
+        for (int k = 1; k < WB; ++k) box_union(wlo, whi, tb[2 * (b0 + k)], tb[2 * (b0 + k) + 1]);
+        const unsigned* am = reinterpret_cast<const unsigned*>(st + T * 3 + NB * 8);
         for (int c = 0; c < nwords; ++c) {
-            unsigned word = amask[c];
+            unsigned word = am[c];
             while (word) {
                 const int w = c * 32 + __ffs(word) - 1;
                 word &= word - 1;
@@ -420,44 +509,27 @@ cov_traj_minmax_tiles_kernel(const float* __restrict__ xyz, int64_t n, const flo
                 }
             }
         }
-        __syncthreads();
-        for (int w = tid; w < W; w += COV_THREADS) {  // publish what this tile may have changed
-            if ((amask[w >> 5] >> (w & 31)) & 1u) {
-                atomicMin(gmin + w, smin[w]);
-                atomicMax(gmax + w, smax[w]);
-            }
+        __syncthreads();  // every warp is done with this stage before it is refilled
+    }
+    for (int w = tid; w < W; w += COV_THREADS) {
+        if (smax[w] != 0u || smin[w] != 0x7f800000u) {
+            atomicMin(gmin + w, smin[w]);
+            atomicMax(gmax + w, smax[w]);
         }
     }
     if (lane == 0) {
-        atomicAdd(stats + 2, n_iter);
+        if (tid == 0 && blockIdx.x == 0) atomicAdd(stats + 2, (unsigned long long)ntiles * kWarps * W);
         atomicAdd(stats + 3, (unsigned long long)n_full);
         atomicAdd(stats + 5, (unsigned long long)n_pre);
         atomicAdd(stats + 7, (unsigned long long)n_box);
     }
 }
 
-__global__ void __launch_bounds__(256) cov_fill_kernel(float* __restrict__ dst, int64_t n, float v) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
-    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
-        if (i + 4 <= n && ((reinterpret_cast<uintptr_t>(dst + i) & 15) == 0)) {
-            *reinterpret_cast<float4*>(dst + i) = make_float4(v, v, v, v);
-        } else {
-            for (int64_t k = i; k < n && k < i + 4; ++k) dst[k] = v;
-        }
-    }
-}
-
-__global__ void cov_minmax_init_kernel(unsigned* gmin, unsigned* gmax, int W) {
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w < W) {
-        gmin[w] = 0x7f800000u;
-        gmax[w] = 0u;
-    }
-}
-
-// Gate bit matrix addressing.  Row w holds kWarps groups of PPT ballot words (group g = the words of warp g).
+// =================================================== pass B ===================================================
+// Gate bit matrix addressing.  Row w holds kWarps groups of PPT ballot words (group g = the words of warp g; word k
+// of a row covers points [32k, 32k+32) of the tile, since a warp owns 32*PPT consecutive points).
 // Dense kernel: rows are padded by 4 words (conflict-free when lanes walk different rows at the same word).
-// Pruned kernel: rows are unpadded (shared memory goes to the second tile buffer) and group g sits at slot
+// Pruned kernel: rows are unpadded (the shared memory goes to the second tile stage) and group g sits at slot
 // g ^ (w & 7) instead, which spreads the same access pattern over 8 bank groups.
 template <int PPT, bool SWZ>
 __device__ __forceinline__ unsigned* bit_row_group(unsigned* bits, int w, int group) {
@@ -471,12 +543,14 @@ __device__ __forceinline__ unsigned bit_word(const unsigned* bits, int w, int k)
     return bits[(size_t)w * RS + (SWZ ? ((g ^ (w & 7)) * PPT) : g * PPT) + sidx];
 }
 
-// Phase-1 body of the fused pass for U consecutive poses starting at w (U*PPT independent chains).
-template <int PPT, int U, bool AMIN, bool THR5>
+// Phase-1 body for U consecutive poses starting at w (U*PPT independent chains).  TILES = pruned kernel: the
+// conservative threshold lives in v5.w (v3.w holds qthr), bit rows are swizzled, and `gmask` collects the poses
+// that got at least one gated pair in this tile.
+template <int PPT, int U, bool AMIN, bool TILES>
 __device__ __forceinline__ void fused_pose_iter(int w, const float4* __restrict__ ptab, unsigned* __restrict__ bits,
                                                 int warp, const float (&px)[PPT], const float (&py)[PPT],
                                                 const float (&pz)[PPT], float (&L)[PPT], const CovConst& C,
-                                                double* __restrict__ acc, int lane) {
+                                                double* __restrict__ acc, int lane, unsigned* __restrict__ gmask) {
     float m[U][PPT];
     float mmax[U];
 #pragma unroll
@@ -489,8 +563,8 @@ __device__ __forceinline__ void fused_pose_iter(int w, const float4* __restrict_
 #pragma unroll
         for (int s = 1; s + 1 < PPT; s += 2) mmax[u] = fmaxf(mmax[u], fmaxf(m[u][s], m[u][s + 1]));
         if ((PPT & 1) == 0) mmax[u] = fmaxf(mmax[u], m[u][PPT - 1]);
-        // >= 0  <=>  some point of this lane may pass the gate (conservative threshold; lives in v5.w when pruning)
-        mmax[u] -= THR5 ? row[5].w : v3.w;
+        // >= 0  <=>  some point of this lane may pass the gate (conservative threshold)
+        mmax[u] -= TILES ? row[5].w : v3.w;
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -514,10 +588,16 @@ __device__ __forceinline__ void fused_pose_iter(int w, const float4* __restrict_
             }
         }
         if (lane == 0) {
-            unsigned* brow = bit_row_group<PPT, THR5>(bits, w + u, warp);
+            unsigned* brow = bit_row_group<PPT, TILES>(bits, w + u, warp);
             if (PPT == 4) *reinterpret_cast<uint4*>(brow) = make_uint4(bal[0], bal[1 % PPT], bal[2 % PPT], bal[3 % PPT]);
             else if (PPT == 2) *reinterpret_cast<uint2*>(brow) = make_uint2(bal[0], bal[1 % PPT]);
             else brow[0] = bal[0];
+            if (TILES) {
+                unsigned anyb = 0u;
+#pragma unroll
+                for (int s = 0; s < PPT; ++s) anyb |= bal[s];
+                if (anyb) atomicOr(gmask + ((w + u) >> 5), 1u << ((w + u) & 31));
+            }
         }
         if (AMIN) {  // only compact clouds whose minimum did not underflow to 0 (block-uniform choice of the loop)
             const float a = row[4].w;
@@ -530,51 +610,109 @@ __device__ __forceinline__ void fused_pose_iter(int w, const float4* __restrict_
     }
 }
 
-// Pass B.  PRUNE (the product default) adds tile-level pruning: v3.w of a pose row holds
-// qthr = (1e-4 - log2(thr))/kd with thr the conservative gate threshold; a pair with q2 > qthr has
-// m <= 2^-(kd q2)(1+1.3e-5) < thr, so it is neither gated nor the arg-max, contributes logit(1/2) = 0 to the
-// log-odds sum and nothing to the gradient.  Per tile the block keeps the ascending list of poses whose qthr-ball
-// meets the tile's bounding box; a warp runs the exact body for a listed pose only when the ball also meets the
-// warp's own box and one of its 32*PPT points passes the per-point test.  Poses with min_j m > 0 are always
-// listed (their arg-min points carry gradient).  Results are bit-identical to the dense kernel.
-// Point layout of a tile: local = warp*32*PPT + s*32 + lane (a warp owns 32*PPT consecutive points), so ballot
-// word k of a pose row covers points [32k, 32k+32).
-template <int PPT, bool HAS_UP, int U, bool PRUNE>
+// Phase 2: the gated pairs of `nposes2` bit rows (rows alist[0..nposes2) when LIST, else rows 0..nposes2-1), each row
+// split over 2^seg_log2 lanes.  A lane pops its set bits in ascending point order, recomputes m (bit-identical) and
+// dm/dx, and accumulates in registers; segments are combined with xor-shuffles; one owner lane adds into accs.
+template <int PPT, bool TILES>
+__device__ __forceinline__ void fused_phase2(const float4* __restrict__ ptab, const unsigned* __restrict__ bits,
+                                             const float* __restrict__ pt, const float* __restrict__ Gs,
+                                             float* __restrict__ accs, const unsigned short* __restrict__ alist,
+                                             int nposes2, int seg_log2, const CovConst& C, int tid) {
+    constexpr int NW = bit_words(PPT);
+    const int nseg = 1 << seg_log2;       // lanes that share one pose row
+    const int wps = NW >> seg_log2;       // ballot words per lane
+    const int ntask = nposes2 << seg_log2;
+    for (int base = 0; base < ntask; base += COV_THREADS) {
+        const int task = base + tid;
+        const bool live = task < ntask;
+        const int wi = live ? (task >> seg_log2) : 0;
+        const int w = TILES ? (int)alist[wi] : wi;
+        const int seg = task & (nseg - 1);
+        const float4* row = ptab + (size_t)w * COV_ROW_F4;
+        const float4 v0 = row[0], v1 = row[1], v2 = row[2], v3 = row[3], v4 = row[4], v5 = row[5];
+        int k = seg * wps;
+        const int kend = live ? k + wps : k;
+        unsigned word = live ? bit_word<PPT, TILES>(bits, w, k) : 0u;
+        float f0 = 0.f, f1 = 0.f, f2 = 0.f, t0 = 0.f, t1 = 0.f, t2 = 0.f, se = 0.f, sep = 0.f;
+        while (true) {
+            while (word == 0u && k + 1 < kend) word = bit_word<PPT, TILES>(bits, w, ++k);
+            if (!__any_sync(kFull, word != 0u)) break;
+            if (word != 0u) {
+                const int bit = __ffs(word) - 1;
+                word &= word - 1;
+                const int local = k * 32 + bit;
+                CovEval ev;
+                const float x = pt[local * 3], y = pt[local * 3 + 1], z = pt[local * 3 + 2];
+                const float m = cov_vis<true>(x, y, z, v0, v1, v2, v3, C, &ev);
+                const float d = __fsub_rn(m, v4.w);
+                const float p = __fdiv_rn(d, v4.y);
+                if (p <= C.hi) {  // clamp backward gate (inclusive); p >= 0.5 holds for every set bit
+                    float gx, gy, gz;
+                    cov_vis_grad(m, ev, v0, v1, v2, C, gx, gy, gz);
+                    const float yx = x - v5.x, yy = y - v5.y, yz = z - v5.z;
+                    const float e = Gs[local] / (p * (1.f - p));
+                    const float om = e * v4.z;
+                    f0 += om * gx; f1 += om * gy; f2 += om * gz;
+                    t0 += om * (gy * yz - gz * yy);
+                    t1 += om * (gz * yx - gx * yz);
+                    t2 += om * (gx * yy - gy * yx);
+                    se += e;
+                    sep += e * p;
+                }
+            }
+        }
+        for (int o = 1; o < nseg; o <<= 1) {
+            f0 += __shfl_xor_sync(kFull, f0, o); f1 += __shfl_xor_sync(kFull, f1, o);
+            f2 += __shfl_xor_sync(kFull, f2, o); t0 += __shfl_xor_sync(kFull, t0, o);
+            t1 += __shfl_xor_sync(kFull, t1, o); t2 += __shfl_xor_sync(kFull, t2, o);
+            se += __shfl_xor_sync(kFull, se, o); sep += __shfl_xor_sync(kFull, sep, o);
+        }
+        if (live && seg == 0) {
+            float* a8 = accs + (size_t)w * 8;
+            a8[0] += f0; a8[1] += f1; a8[2] += f2; a8[3] += t0;
+            a8[4] += t1; a8[5] += t2; a8[6] += se; a8[7] += sep;
+        }
+    }
+}
+
+__device__ __forceinline__ void fused_block_epilogue(const float* accs, int W, float* __restrict__ partials,
+                                                     double* __restrict__ sumr_partials, double sum_r, double* red,
+                                                     int tid) {
+    float* slab = partials + (size_t)blockIdx.x * W * 8;
+    for (int i = tid; i < W * 8; i += COV_THREADS) slab[i] = accs[i];
+    const double ws = cov_warp_sum(sum_r);
+    if ((tid & 31) == 0) red[tid >> 5] = ws;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int i = 0; i < kWarps; ++i) t += red[i];
+        sumr_partials[blockIdx.x] = t;
+    }
+}
+
+// ---- dense ----
+template <int PPT, bool HAS_UP, int U>
 __global__ void __launch_bounds__(COV_THREADS, 2)
 cov_traj_fused_kernel(const float* __restrict__ xyz, int64_t n, const float* __restrict__ poses,
                       const float* __restrict__ quats, int W, const float* __restrict__ K9, CovConst C,
                       const float* __restrict__ minmax, const float* __restrict__ upstream,
                       const int32_t* __restrict__ out_index, float* __restrict__ rewards,
                       float* __restrict__ partials, double* __restrict__ sumr_partials, double* __restrict__ acc,
-                      int seg_log2_dense, unsigned long long* __restrict__ stats) {
+                      int seg_log2) {
     constexpr int T = tile_points(PPT);
-    constexpr int NW = bit_words(PPT);
-    constexpr int RS = PRUNE ? NW : bit_stride(PPT);
-    // shared memory: pose table | tile buffer 0 (T points, xyz interleaved) | [PRUNE: tile buffer 1] | G_j | gate bits |
-    // block accumulators | [PRUNE: active-pose list]          (tile buffers first: they need 128-byte alignment)
+    constexpr int RS = bit_stride(PPT);
+    // shared memory: pose table | the tile's points (xyz interleaved) | G_j | gate bits | block accumulators
     extern __shared__ float4 smem4[];
     float4* ptab = smem4;
-    float* raw = reinterpret_cast<float*>(smem4) + fused_raw_offset_floats(W);
-    float* Gs = raw + (PRUNE ? 2 : 1) * (T * 3);
+    float* pt = reinterpret_cast<float*>(smem4) + fused_stage_offset_floats(W);
+    float* Gs = pt + T * 3;
     unsigned* bits = reinterpret_cast<unsigned*>(Gs + T);
     float* accs = reinterpret_cast<float*>(bits + (size_t)W * RS);
-    unsigned short* alist = reinterpret_cast<unsigned short*>(accs + (size_t)W * 8);
     __shared__ double red[kWarps];
     __shared__ int amin_pos;  // some pose has min_j m > 0: its arg-min points carry gradient
-    __shared__ unsigned amask[kMaskWords];
-    __shared__ float wbox[kWarps][8];
-    __shared__ int n_active;
-    __shared__ __align__(8) unsigned long long mbar[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) {
-        amin_pos = 0;
-        if (PRUNE) {
-            mbar_init(&mbar[0], 1);
-            mbar_init(&mbar[1], 1);
-            mbar_fence_init();
-        }
-    }
+    if (tid == 0) amin_pos = 0;
     __syncthreads();
     for (int w = tid; w < W; w += COV_THREADS) {
         float4* row = ptab + (size_t)w * COV_ROW_F4;
@@ -582,12 +720,7 @@ cov_traj_fused_kernel(const float* __restrict__ xyz, int64_t n, const float* __r
         const float a = minmax[w];
         const float b = __fsub_rn(minmax[W + w], a);
         const float hb = 0.5f * b;
-        const float thr = (a + hb) * (1.f - 9.5367431640625e-07f);  // conservative gate threshold (exact test in the rare path)
-        row[5].w = thr;
-        // pruning: q2 above this cannot reach thr (thr <= 0 or NaN, or a > 0: never prune)
-        const float qthr = (thr > 0.f && !(a > 0.f)) ? (float)((1e-4 - log2((double)thr)) / (double)C.kd * 1.000001)
-                                                      : __uint_as_float(0x7f800000u);
-        row[3].w = PRUNE ? qthr : thr;
+        row[3].w = (a + hb) * (1.f - 9.5367431640625e-07f);  // conservative gate threshold (exact test in the rare path)
         row[4] = make_float4(hb, b, __frcp_rn(b), a);
         if (a > 0.f) amin_pos = 1;  // benign race: every writer stores 1
     }
@@ -595,30 +728,119 @@ cov_traj_fused_kernel(const float* __restrict__ xyz, int64_t n, const float* __r
     __syncthreads();
 
     double sum_r = 0.0;
-    unsigned long long n_iter = 0;
-    unsigned n_box = 0, n_pre = 0, n_full = 0;
     const int64_t ntiles = (n + T - 1) / T;
-    const int64_t nfull = n / T;  // complete tiles arrive by TMA (PRUNE); a ragged last tile is loaded by hand
-    const int nwords = (W + 31) >> 5;
     const bool check_amin = amin_pos != 0;
-    unsigned uses0 = 0, uses1 = 0;
-    int buf = 0;
-    if (PRUNE && tid == 0 && (int64_t)blockIdx.x < nfull) tma_load_1d(raw, xyz + (int64_t)blockIdx.x * (T * 3), T * 12, &mbar[0]);
-
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        // ------------------------------ phase 1: every (point, pose) that can matter ------------------------------
         float px[PPT], py[PPT], pz[PPT], L[PPT];
         bool valid[PPT];
         const int lbase = warp * (32 * PPT) + lane;
-        float* pt = raw + (PRUNE ? buf : 0) * (T * 3);  // this tile's points in shared memory (phase 2 reads them)
-        if (PRUNE) {
-            // the other buffer was last read in phase 2 of the previous tile, which ended at a barrier
-            if (tid == 0 && tile + gridDim.x < nfull)
-                tma_load_1d(raw + (buf ^ 1) * (T * 3), xyz + (tile + gridDim.x) * (T * 3), T * 12, &mbar[buf ^ 1]);
+#pragma unroll
+        for (int s = 0; s < PPT; ++s) {
+            const int64_t j = tile * T + lbase + s * 32;
+            valid[s] = j < n;
+            // a point past the end sits 3e18 m away: m = 0 exactly, never gated, never a tie
+            px[s] = valid[s] ? __ldg(xyz + j * 3) : 3.0e18f;
+            py[s] = valid[s] ? __ldg(xyz + j * 3 + 1) : 3.0e18f;
+            pz[s] = valid[s] ? __ldg(xyz + j * 3 + 2) : 3.0e18f;
+            pt[(lbase + s * 32) * 3] = px[s];
+            pt[(lbase + s * 32) * 3 + 1] = py[s];
+            pt[(lbase + s * 32) * 3 + 2] = pz[s];
+            L[s] = 0.f;
         }
-        if (PRUNE && tile < nfull) {
-            if (buf == 0) mbar_wait(&mbar[0], uses0++ & 1u);
-            else mbar_wait(&mbar[1], uses1++ & 1u);
+        {
+            int w = 0;
+            if (check_amin) {  // arg-min points carry gradient: every pair must be looked at
+                for (; w < W; ++w) fused_pose_iter<PPT, 1, true, false>(w, ptab, bits, warp, px, py, pz, L, C, acc, lane, nullptr);
+            } else {
+                for (; w + U <= W; w += U) fused_pose_iter<PPT, U, false, false>(w, ptab, bits, warp, px, py, pz, L, C, acc, lane, nullptr);
+                for (; w < W; ++w) fused_pose_iter<PPT, 1, false, false>(w, ptab, bits, warp, px, py, pz, L, C, acc, lane, nullptr);
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < PPT; ++s) {
+            const float r = 1.f / (1.f + expf(-L[s]));
+            float g = r * (1.f - r);
+            if (valid[s]) {
+                const int64_t j = tile * T + lbase + s * 32;
+                const int64_t jo = out_index ? (int64_t)out_index[j] : j;
+                rewards[jo] = r;
+                sum_r += (double)r;
+                if (HAS_UP) g *= upstream[jo];
+            }
+            Gs[lbase + s * 32] = g;
+        }
+        __syncthreads();
+        fused_phase2<PPT, false>(ptab, bits, pt, Gs, accs, nullptr, W, seg_log2, C, tid);
+        __syncthreads();
+    }
+    fused_block_epilogue(accs, W, partials, sumr_partials, sum_r, red, tid);
+}
+
+// ---- pruned: persistent blocks over the work list of tiles with a non-empty pose mask ----
+// sumr_partials receive sum_j (r_j - 1/2) over the listed tiles (the rest is 0.5 * n, added by the reduce kernel);
+// `rewards` was pre-filled with 1/2, only other values are stored.
+template <int PPT, bool HAS_UP>
+__global__ void __launch_bounds__(COV_THREADS, 2)
+cov_traj_fused_tiles_kernel(const float* __restrict__ xyz, int64_t n, const float4* __restrict__ table, int W, CovConst C,
+                            const float* __restrict__ upstream, const int32_t* __restrict__ out_index,
+                            float* __restrict__ rewards, float* __restrict__ partials,
+                            double* __restrict__ sumr_partials, double* __restrict__ acc,
+                            const float4* __restrict__ boxes, const unsigned* __restrict__ amask_g, int mask_stride,
+                            const int* __restrict__ worklist, const int* __restrict__ count_ptr, int64_t ntiles,
+                            unsigned long long* __restrict__ stats) {
+    constexpr int T = tile_points(PPT);
+    constexpr int NW = bit_words(PPT);
+    constexpr int NB = tile_boxes(PPT);
+    constexpr int SF = stage_floats(PPT);
+    constexpr int WB = (32 * PPT >= kBoxPts) ? (32 * PPT / kBoxPts) : 1;
+    // shared memory: pose table | 2 tile stages (points, boxes, pose mask) | G_j | gate bits | block accumulators |
+    // gated-pose list
+    extern __shared__ float4 smem4[];
+    float4* ptab = smem4;
+    float* stage = reinterpret_cast<float*>(smem4) + fused_stage_offset_floats(W);
+    float* Gs = stage + 2 * SF;
+    unsigned* bits = reinterpret_cast<unsigned*>(Gs + T);
+    float* accs = reinterpret_cast<float*>(bits + (size_t)W * NW);
+    unsigned short* alist = reinterpret_cast<unsigned short*>(accs + (size_t)W * 8);
+    __shared__ double red[kWarps];
+    __shared__ unsigned gmask[2][kMaskWords];  // poses with a gated pair in the current / next tile
+    __shared__ __align__(8) unsigned long long mbar[2];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        mbar_fence_init();
+    }
+    for (int i = tid; i < W * COV_ROW_F4; i += COV_THREADS) ptab[i] = table[i];
+    for (int i = tid; i < W * 8; i += COV_THREADS) accs[i] = 0.f;
+    if (tid < 2 * kMaskWords) (&gmask[0][0])[tid] = 0u;
+    const bool check_amin = count_ptr[1] != 0;  // flags[1]: some pose has min_j m > 0
+    __syncthreads();
+
+    double sum_r = 0.0;
+    unsigned n_box = 0, n_pre = 0, n_full = 0;
+    const int count = count_ptr[0];
+    const int64_t nfull = n / T;
+    const int nwords = (W + 31) >> 5;
+    unsigned uses0 = 0, uses1 = 0;
+    if (tid == 0 && (int)blockIdx.x < count)
+        stage_issue<PPT>(stage, &mbar[0], xyz, boxes, amask_g, mask_stride, (int64_t)worklist[blockIdx.x], nfull);
+    int buf = 0;
+    for (int i = blockIdx.x; i < count; i += gridDim.x, buf ^= 1) {
+        const int64_t tile = worklist[i];
+        if (tid == 0 && i + (int)gridDim.x < count)  // the other stage was last read before the previous barrier
+            stage_issue<PPT>(stage + (buf ^ 1) * SF, &mbar[buf ^ 1], xyz, boxes, amask_g, mask_stride,
+                             (int64_t)worklist[i + gridDim.x], nfull);
+        if (buf == 0) mbar_wait(&mbar[0], uses0++ & 1u);
+        else mbar_wait(&mbar[1], uses1++ & 1u);
+        float* pt = stage + buf * SF;  // this tile's points (phase 2 reads them again)
+        unsigned* gm = gmask[buf];
+        // ------------------------------ phase 1: the (point, pose) pairs that can matter ------------------------------
+        float px[PPT], py[PPT], pz[PPT], L[PPT];
+        bool valid[PPT];
+        const int lbase = warp * (32 * PPT) + lane;
+        if (tile < nfull) {
 #pragma unroll
             for (int s = 0; s < PPT; ++s) {
                 valid[s] = true;
@@ -627,7 +849,7 @@ cov_traj_fused_kernel(const float* __restrict__ xyz, int64_t n, const float* __r
                 pz[s] = pt[(lbase + s * 32) * 3 + 2];
                 L[s] = 0.f;
             }
-        } else {
+        } else {  // the ragged last tile (always the last entry of the list): loaded by hand
 #pragma unroll
             for (int s = 0; s < PPT; ++s) {
                 const int64_t j = tile * T + lbase + s * 32;
@@ -642,113 +864,49 @@ cov_traj_fused_kernel(const float* __restrict__ xyz, int64_t n, const float* __r
                 L[s] = 0.f;
             }
         }
-        if (PRUNE) {
-            float3 wlo, whi;
-            warp_box<PPT>(px, py, pz, valid, wlo, whi);
-            if (lane == 0) {
-                wbox[warp][0] = wlo.x; wbox[warp][1] = wlo.y; wbox[warp][2] = wlo.z;
-                wbox[warp][4] = whi.x; wbox[warp][5] = whi.y; wbox[warp][6] = whi.z;
-            }
-            __syncthreads();
-            {
-                float3 blo, bhi;
-                block_box(wbox, blo, bhi);
-                for (int c = warp; c < nwords; c += kWarps) {
-                    const int w = c * 32 + lane;
-                    bool active = false;
-                    if (w < W) {
-                        const float4 v3 = ptab[(size_t)w * COV_ROW_F4 + 3];
-                        active = !(box_q2lb(blo, bhi, v3) > v3.w);
-                    }
-                    const unsigned bal = __ballot_sync(kFull, active);
-                    if (lane == 0) amask[c] = bal;
+        const float4* tb = reinterpret_cast<const float4*>(pt + T * 3);
+        const int b0 = (warp * 32 * PPT) / kBoxPts;
+        float4 wlo = tb[2 * b0], whi = tb[2 * b0 + 1];
+#pragma unroll
+        for (int k = 1; k < WB; ++k) box_union(wlo, whi, tb[2 * (b0 + k)], tb[2 * (b0 + k) + 1]);
+        const unsigned* am = reinterpret_cast<const unsigned*>(pt + T * 3 + NB * 8);
+        for (int c = 0; c < nwords; ++c) {
+            unsigned word = am[c];
+            while (word) {
+                const int w = c * 32 + __ffs(word) - 1;
+                word &= word - 1;
+                const float4 v3 = ptab[(size_t)w * COV_ROW_F4 + 3];
+                ++n_box;
+                bool run = !(box_q2lb(wlo, whi, v3) > v3.w);
+                if (run) {
+                    ++n_pre;
+                    float qmin = cov_q2(px[0], py[0], pz[0], v3);
+#pragma unroll
+                    for (int s = 1; s < PPT; ++s) qmin = fminf(qmin, cov_q2(px[s], py[s], pz[s], v3));
+                    run = __any_sync(kFull, !(qmin > v3.w));
                 }
-            }
-            __syncthreads();
-            n_iter += (unsigned long long)W;
-            {   // nothing listed (every warp reaches the same verdict): rewards are exactly 1/2, no gradient, next tile
-                unsigned anyw = 0u;
-                for (int c = lane; c < nwords; c += 32) anyw |= amask[c];
-                if (!__any_sync(kFull, anyw != 0u)) {
-                    int cnt = 0;
+                if (run) {  // (a row this warp skips is never read: no gated bit of it is reported in gmask)
+                    ++n_full;
+                    if (check_amin) fused_pose_iter<PPT, 1, true, true>(w, ptab, bits, warp, px, py, pz, L, C, acc, lane, gm);
+                    else fused_pose_iter<PPT, 1, false, true>(w, ptab, bits, warp, px, py, pz, L, C, acc, lane, gm);
+                } else if (lane == 0) {  // ... but another warp may report that row: this warp's words must be defined
+                    unsigned* brow = bit_row_group<PPT, true>(bits, w, warp);
 #pragma unroll
-                    for (int s = 0; s < PPT; ++s) cnt += valid[s] ? 1 : 0;
-                    sum_r += 0.5 * (double)cnt;
-                    if (!out_index) {  // (with out_index the caller-order rewards were pre-filled with 1/2)
-#pragma unroll
-                        for (int s = 0; s < PPT; ++s)
-                            if (valid[s]) rewards[tile * T + lbase + s * 32] = 0.5f;
-                    }
-                    buf ^= 1;
-                    continue;
+                    for (int s = 0; s < PPT; ++s) brow[s] = 0u;
                 }
-            }
-            if (warp == 0) {  // ascending list of the tile's active poses for phase 2 (read after the next barrier)
-                int base = 0;
-                for (int c0 = 0; c0 < nwords; c0 += 32) {
-                    const unsigned word = (c0 + lane < nwords) ? amask[c0 + lane] : 0u;
-                    const int cnt = __popc(word);
-                    int incl = cnt;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int t = __shfl_up_sync(kFull, incl, o);
-                        if (lane >= o) incl += t;
-                    }
-                    int pos = base + incl - cnt;
-                    unsigned wv = word;
-                    while (wv) {
-                        alist[pos++] = (unsigned short)((c0 + lane) * 32 + __ffs(wv) - 1);
-                        wv &= wv - 1;
-                    }
-                    base += __shfl_sync(kFull, incl, 31);
-                }
-                if (lane == 0) n_active = base;
-            }
-            for (int c = 0; c < nwords; ++c) {
-                unsigned word = amask[c];
-                while (word) {
-                    const int w = c * 32 + __ffs(word) - 1;
-                    word &= word - 1;
-                    const float4 v3 = ptab[(size_t)w * COV_ROW_F4 + 3];
-                    ++n_box;
-                    bool run = !(box_q2lb(wlo, whi, v3) > v3.w);
-                    if (run) {
-                        ++n_pre;
-                        float qmin = cov_q2(px[0], py[0], pz[0], v3);
-#pragma unroll
-                        for (int s = 1; s < PPT; ++s) qmin = fminf(qmin, cov_q2(px[s], py[s], pz[s], v3));
-                        run = __any_sync(kFull, !(qmin > v3.w));
-                    }
-                    if (run) {
-                        ++n_full;
-                        if (check_amin) fused_pose_iter<PPT, 1, true, true>(w, ptab, bits, warp, px, py, pz, L, C, acc, lane);
-                        else fused_pose_iter<PPT, 1, false, true>(w, ptab, bits, warp, px, py, pz, L, C, acc, lane);
-                    } else if (lane == 0) {  // this warp's words of a listed row must still be defined
-                        unsigned* brow = bit_row_group<PPT, true>(bits, w, warp);
-#pragma unroll
-                        for (int s = 0; s < PPT; ++s) brow[s] = 0u;
-                    }
-                }
-            }
-        } else {
-            int w = 0;
-            if (check_amin) {  // arg-min points carry gradient: every pair must be looked at
-                for (; w < W; ++w) fused_pose_iter<PPT, 1, true, false>(w, ptab, bits, warp, px, py, pz, L, C, acc, lane);
-            } else {
-                for (; w + U <= W; w += U) fused_pose_iter<PPT, U, false, false>(w, ptab, bits, warp, px, py, pz, L, C, acc, lane);
-                for (; w < W; ++w) fused_pose_iter<PPT, 1, false, false>(w, ptab, bits, warp, px, py, pz, L, C, acc, lane);
             }
         }
 #pragma unroll
         for (int s = 0; s < PPT; ++s) {
-            const float r = 1.f / (1.f + expf(-L[s]));
-            float g = r * (1.f - r);
+            float r = 0.5f, g = 0.25f;  // exactly what the formulas below give for L = 0
+            if (L[s] != 0.f) {
+                r = 1.f / (1.f + expf(-L[s]));
+                g = r * (1.f - r);
+            }
             if (valid[s]) {
                 const int64_t j = tile * T + lbase + s * 32;
-                sum_r += (double)r;
-                // pruned + out_index: the caller-order rewards were pre-filled with 1/2 (what every ungated point gets,
-                // exactly), so only the others are scattered
-                const bool store = !(PRUNE && out_index) || r != 0.5f;
+                sum_r += (double)(r - 0.5f);
+                const bool store = r != 0.5f;
                 int64_t jo = j;
                 if (out_index && (store || HAS_UP)) jo = (int64_t)out_index[j];
                 if (store) rewards[jo] = r;
@@ -756,92 +914,49 @@ cov_traj_fused_kernel(const float* __restrict__ xyz, int64_t n, const float* __r
             }
             Gs[lbase + s * 32] = g;
         }
-        __syncthreads();
-        // ------------------------------ phase 2: gated pairs, pose-major ------------------------------
-        const int nposes2 = PRUNE ? n_active : W;
-        int seg_log2 = seg_log2_dense;
-        if (PRUNE) {  // split each listed pose row over 2^seg_log2 lanes until there are >= 2 tasks per thread
-            seg_log2 = 0;
-            while ((nposes2 << seg_log2) < 2 * COV_THREADS && (2 << seg_log2) <= NW && seg_log2 < 5) ++seg_log2;
+        __syncthreads();  // bits, G_j, gmask complete
+        // every warp derives the same ascending list of gated poses (identical stores to alist: no barrier needed)
+        int n2 = 0;
+        for (int c0 = 0; c0 < nwords; c0 += 32) {
+            const unsigned word = (c0 + lane < nwords) ? gm[c0 + lane] : 0u;
+            const int cnt = __popc(word);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(kFull, incl, o);
+                if (lane >= o) incl += t;
+            }
+            int pos = n2 + incl - cnt;
+            unsigned wv = word;
+            while (wv) {
+                alist[pos++] = (unsigned short)((c0 + lane) * 32 + __ffs(wv) - 1);
+                wv &= wv - 1;
+            }
+            n2 += __shfl_sync(kFull, incl, 31);
         }
-        const int nseg = 1 << seg_log2;       // lanes that share one pose row
-        const int wps = NW >> seg_log2;       // ballot words per lane
-        const int ntask = nposes2 << seg_log2;
-        for (int base = 0; base < ntask; base += COV_THREADS) {
-            const int task = base + tid;
-            const bool live = task < ntask;
-            const int wi = live ? (task >> seg_log2) : 0;
-            const int w = PRUNE ? (int)alist[wi] : wi;
-            const int seg = task & (nseg - 1);
-            const float4* row = ptab + (size_t)w * COV_ROW_F4;
-            const float4 v0 = row[0], v1 = row[1], v2 = row[2], v3 = row[3], v4 = row[4], v5 = row[5];
-            int k = seg * wps;
-            const int kend = live ? k + wps : k;
-            unsigned word = live ? bit_word<PPT, PRUNE>(bits, w, k) : 0u;
-            float f0 = 0.f, f1 = 0.f, f2 = 0.f, t0 = 0.f, t1 = 0.f, t2 = 0.f, se = 0.f, sep = 0.f;
-            while (true) {
-                while (word == 0u && k + 1 < kend) word = bit_word<PPT, PRUNE>(bits, w, ++k);
-                if (!__any_sync(kFull, word != 0u)) break;
-                if (word != 0u) {
-                    const int bit = __ffs(word) - 1;
-                    word &= word - 1;
-                    const int local = k * 32 + bit;
-                    CovEval ev;
-                    const float x = pt[local * 3], y = pt[local * 3 + 1], z = pt[local * 3 + 2];
-                    const float m = cov_vis<true>(x, y, z, v0, v1, v2, v3, C, &ev);
-                    const float d = __fsub_rn(m, v4.w);
-                    const float p = __fdiv_rn(d, v4.y);
-                    if (p <= C.hi) {  // clamp backward gate (inclusive); p >= 0.5 holds for every set bit
-                        float gx, gy, gz;
-                        cov_vis_grad(m, ev, v0, v1, v2, C, gx, gy, gz);
-                        const float yx = x - v5.x, yy = y - v5.y, yz = z - v5.z;
-                        const float e = Gs[local] / (p * (1.f - p));
-                        const float om = e * v4.z;
-                        f0 += om * gx; f1 += om * gy; f2 += om * gz;
-                        t0 += om * (gy * yz - gz * yy);
-                        t1 += om * (gz * yx - gx * yz);
-                        t2 += om * (gx * yy - gy * yx);
-                        se += e;
-                        sep += e * p;
-                    }
-                }
-            }
-            for (int o = 1; o < nseg; o <<= 1) {
-                f0 += __shfl_xor_sync(kFull, f0, o); f1 += __shfl_xor_sync(kFull, f1, o);
-                f2 += __shfl_xor_sync(kFull, f2, o); t0 += __shfl_xor_sync(kFull, t0, o);
-                t1 += __shfl_xor_sync(kFull, t1, o); t2 += __shfl_xor_sync(kFull, t2, o);
-                se += __shfl_xor_sync(kFull, se, o); sep += __shfl_xor_sync(kFull, sep, o);
-            }
-            if (live && seg == 0) {
-                float* a8 = accs + (size_t)w * 8;
-                a8[0] += f0; a8[1] += f1; a8[2] += f2; a8[3] += t0;
-                a8[4] += t1; a8[5] += t2; a8[6] += se; a8[7] += sep;
-            }
+        __syncwarp();
+        if (tid < kMaskWords) gmask[buf ^ 1][tid] = 0u;  // next tile's mask: its writers come after the barrier below
+        if (n2 > 0) {
+            // split each listed row over 2^seg_log2 lanes until there are >= 2 tasks per thread
+            int seg_log2 = 0;
+            while ((n2 << seg_log2) < 2 * COV_THREADS && (2 << seg_log2) <= NW && seg_log2 < 5) ++seg_log2;
+            fused_phase2<PPT, true>(ptab, bits, pt, Gs, accs, alist, n2, seg_log2, C, tid);
         }
-        __syncthreads();
-        buf ^= 1;
+        __syncthreads();  // stage, bits, G_j, alist and gmask[buf] may be reused
     }
-    float* slab = partials + (size_t)blockIdx.x * W * 8;
-    for (int i = tid; i < W * 8; i += COV_THREADS) slab[i] = accs[i];
-    const double ws = cov_warp_sum(sum_r);
-    if (lane == 0) red[warp] = ws;
-    __syncthreads();
-    if (tid == 0) {
-        double t = 0.0;
-        for (int i = 0; i < kWarps; ++i) t += red[i];
-        sumr_partials[blockIdx.x] = t;
-    }
-    if (PRUNE && lane == 0) {
-        atomicAdd(stats + 0, n_iter);
+    fused_block_epilogue(accs, W, partials, sumr_partials, sum_r, red, tid);
+    if (lane == 0) {
+        if (tid == 0 && blockIdx.x == 0) atomicAdd(stats + 0, (unsigned long long)ntiles * kWarps * W);
         atomicAdd(stats + 1, (unsigned long long)n_full);
         atomicAdd(stats + 4, (unsigned long long)n_pre);
         atomicAdd(stats + 6, (unsigned long long)n_box);
     }
 }
 
-// acc[w][0..7] = sum over blocks of the fp32 slabs (fp64, fixed order); acc[W*STRIDE] = sum of rewards.
+// acc[w][0..7] = sum over blocks of the fp32 slabs (fp64, fixed order); acc[W*STRIDE] = base + sum of the blocks'
+// reward sums (base = 0.5 * n for the pruned kernel, whose blocks sum r - 1/2 over the listed tiles only).
 __global__ void cov_traj_reduce_kernel(const float* __restrict__ partials, const double* __restrict__ sumr_partials,
-                                       int nblocks, int W, double* __restrict__ acc) {
+                                       int nblocks, int W, double base, double* __restrict__ acc) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < W * 8) {
         double s = 0.0;
@@ -851,7 +966,7 @@ __global__ void cov_traj_reduce_kernel(const float* __restrict__ partials, const
     if (i == 0) {
         double s = 0.0;
         for (int b = 0; b < nblocks; ++b) s += sumr_partials[b];
-        acc[(size_t)W * COV_ACC_STRIDE] = s;
+        acc[(size_t)W * COV_ACC_STRIDE] = base + s;
     }
 }
 
@@ -891,13 +1006,10 @@ __global__ void cov_traj_epilogue_kernel(const double* __restrict__ acc, const f
     gq[3] = (float)(s * (Tq[2] * qw + Tq[0] * qy - Tq[1] * qx));
 }
 
-constexpr size_t kSmemCap = 227 * 1024 - 256;
-
-// development-only kernel-variant switch (COV_DEV_* environment variables); 0 = shipped configuration
-int dev_variant(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return v ? atoi(v) : dflt;
-}  // opt-in shared memory per block on sm_100, minus static use
+// ==================================================== host ====================================================
+constexpr size_t kSmemCap = 227 * 1024 - 1024;  // opt-in shared memory per block on sm_100, minus static use
+constexpr int64_t kSeedSamples = 65536;          // pruned pass A: size of the strided sample that seeds the bounds
+constexpr int64_t kDenseBelow = 4 * kSeedSamples;  // clouds this small go straight to the dense pass A
 
 int pick_ppt(int64_t n, int W, bool fused, bool prune) {
     const int sms = cov_sm_count_cached();
@@ -925,22 +1037,42 @@ int grid_for(Kern kern, size_t smem, int64_t ntiles) {
     return g < 1 ? 1 : (int)g;
 }
 
-// Tile visiting order of the pruned pass A: it -> (it * stride) mod ntiles with stride ~ ntiles/phi, coprime to
-// ntiles, so any run of consecutive `it` is spread evenly over the (spatially sorted) cloud.
-unsigned long long golden_stride(unsigned long long ntiles) {
-    if (ntiles < 3) return 1;
-    auto gcd = [](unsigned long long a, unsigned long long b) {
-        while (b) { const unsigned long long t = a % b; a = b; b = t; }
-        return a;
-    };
-    unsigned long long s = (unsigned long long)((double)ntiles * 0.6180339887498949);
-    if (s < 1) s = 1;
-    while (gcd(s, ntiles) != 1) ++s;
-    return s % ntiles ? s % ntiles : 1;
+size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+int64_t boxes_padded(int64_t n) { return ((n + 2047) / 2048) * (2048 / kBoxPts); }
+
+// Workspace of both passes (every region 256-byte aligned):
+//   [reward-sum partials][accumulator slabs][pose table][ints: count, amin flag][work list][tile flags][tile masks][boxes]
+struct TrajWorkspace {
+    double* sumr;
+    float* partials;
+    float4* table;
+    int* ints;
+    int* worklist;
+    unsigned char* flags;
+    unsigned* amask;
+    float4* boxes;
+    size_t bytes;
+};
+TrajWorkspace carve_workspace(void* ws, int64_t n, int W) {
+    const int64_t nt = (n + 255) / 256;  // tiles at the smallest tile size
+    char* p = reinterpret_cast<char*>(ws);
+    size_t off = 0;
+    TrajWorkspace t;
+    auto take = [&](size_t bytes) { char* q = p + off; off += align256(bytes); return q; };
+    t.sumr = reinterpret_cast<double*>(take(COV_MAX_GRID * sizeof(double)));
+    t.partials = reinterpret_cast<float*>(take((size_t)COV_MAX_GRID * W * 8 * sizeof(float)));
+    t.table = reinterpret_cast<float4*>(take((size_t)W * COV_ROW_F4 * sizeof(float4)));
+    t.ints = reinterpret_cast<int*>(take(256));
+    t.worklist = reinterpret_cast<int*>(take((size_t)nt * sizeof(int)));
+    t.flags = reinterpret_cast<unsigned char*>(take((size_t)nt));
+    t.amask = reinterpret_cast<unsigned*>(take((size_t)nt * mask_stride_words(W) * sizeof(unsigned)));
+    t.boxes = reinterpret_cast<float4*>(take((size_t)boxes_padded(n) * 2 * sizeof(float4)));
+    t.bytes = off;
+    return t;
 }
 
 int check_traj_args(const char* who, const float* xyz, int64_t n, const float* poses, const float* quats, int W,
-                    const float* K, const cov_camera* cam) {
+                    const float* K, const cov_camera* cam, const void* ws, size_t ws_bytes) {
     if (!xyz || n <= 0 || !poses || !quats || W <= 0 || !K || !cam) {
         cov_set_error("%s: null pointer, empty cloud or no poses (n=%lld, W=%d)", who, (long long)n, W);
         return COV_ERR_ARG;
@@ -949,137 +1081,211 @@ int check_traj_args(const char* who, const float* xyz, int64_t n, const float* p
         cov_set_error("%s: %d poses exceed the shared-memory pose table (max %d)", who, W, cov_traj_max_poses());
         return COV_ERR_UNSUPPORTED;
     }
+    if (n >= ((int64_t)1 << 31) * 256) {
+        cov_set_error("%s: %lld points exceed the int32 tile index range", who, (long long)n);
+        return COV_ERR_UNSUPPORTED;
+    }
+    if (!ws) {
+        cov_set_error("%s: null workspace", who);
+        return COV_ERR_ARG;
+    }
+    if (ws_bytes < cov_traj_workspace_bytes(n, W)) {
+        cov_set_error("%s: workspace %zu < %zu bytes", who, ws_bytes, cov_traj_workspace_bytes(n, W));
+        return COV_ERR_WORKSPACE;
+    }
+    if ((((uintptr_t)ws) & 255) || (((uintptr_t)xyz) & 15)) {
+        cov_set_error("%s: workspace must be 256-byte aligned and the cloud 16-byte aligned", who);
+        return COV_ERR_ALIGN;
+    }
     return COV_OK;
+}
+
+// boxes for this call: the caller's (cov_tile_boxes, once per cloud) or built into the workspace now
+const float4* boxes_for_call(const float* xyz, int64_t n, const float* boxes_dev, const TrajWorkspace& t, cudaStream_t s) {
+    if (boxes_dev) return reinterpret_cast<const float4*>(boxes_dev);
+    const int64_t nb = boxes_padded(n);
+    const int grid = (int)std::min<int64_t>((nb + 7) / 8, (int64_t)cov_sm_count_cached() * 16);
+    cov_tile_boxes_kernel<<<grid, 256, 0, s>>>(xyz, n, nb, t.boxes);
+    return t.boxes;
+}
+
+void launch_cull(const float4* boxes, int ppt, int64_t ntiles, const TrajWorkspace& t, int W, const unsigned* gmin,
+                 const unsigned* gmax, float inv_kd, cudaStream_t s) {
+    const int grid = (int)std::min<int64_t>((ntiles + 7) / 8, (int64_t)cov_sm_count_cached() * 8);
+    cov_cull_kernel<<<grid, 256, (size_t)W * sizeof(float4), s>>>(boxes, tile_boxes(ppt), ntiles, t.table, W, gmin, gmax,
+                                                                 inv_kd, t.amask, mask_stride_words(W), t.flags);
+    cov_worklist_kernel<<<1, 1024, 0, s>>>(t.flags, ntiles, t.worklist, t.ints);
 }
 
 }  // namespace
 
 extern "C" int cov_traj_max_poses(void) {
     int w = 1;
-    while (fused_smem_bytes(w + 1, 1, false) <= kSmemCap && fused_smem_bytes(w + 1, 1, true) <= kSmemCap) ++w;
+    while (w < 32 * kMaskWords && fused_smem_bytes(w + 1, 1, false) <= kSmemCap && fused_smem_bytes(w + 1, 1, true) <= kSmemCap &&
+           minmax_tiles_smem_bytes(w + 1, 1) <= kSmemCap && (size_t)(w + 1) * sizeof(float4) <= 48 * 1024)
+        ++w;
     return w;
 }
 
 extern "C" size_t cov_traj_workspace_bytes(int64_t n, int n_poses) {
-    (void)n;
+    if (n < 1) n = 1;
     if (n_poses < 1) n_poses = 1;
-    return (size_t)COV_MAX_GRID * ((size_t)n_poses * 8 * sizeof(float) + sizeof(double));
+    return carve_workspace(nullptr, n, n_poses).bytes;
+}
+
+extern "C" int64_t cov_tile_boxes_count(int64_t n) { return n > 0 ? boxes_padded(n) : 0; }
+
+extern "C" int cov_tile_boxes(const float* xyz, int64_t n, float* boxes, void* stream) {
+    if (!xyz || !boxes || n <= 0) {
+        cov_set_error("cov_tile_boxes: null pointer or empty cloud (n=%lld)", (long long)n);
+        return COV_ERR_ARG;
+    }
+    if (((uintptr_t)boxes) & 15) {
+        cov_set_error("cov_tile_boxes: boxes must be 16-byte aligned");
+        return COV_ERR_ALIGN;
+    }
+    const int64_t nb = boxes_padded(n);
+    const int grid = (int)std::min<int64_t>((nb + 7) / 8, (int64_t)cov_sm_count_cached() * 16);
+    cov_tile_boxes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(xyz, n, nb, reinterpret_cast<float4*>(boxes));
+    return cov_check_launch("cov_tile_boxes");
 }
 
 extern "C" int cov_traj_minmax(const float* xyz, int64_t n, const float* poses, const float* quats, int W,
-                               const float* K, const cov_camera* cam, float* minmax, void* stream) {
-    int rc = check_traj_args("cov_traj_minmax", xyz, n, poses, quats, W, K, cam);
+                               const float* K, const cov_camera* cam, const float* boxes_dev, float* minmax, void* ws,
+                               size_t ws_bytes, void* stream) {
+    int rc = check_traj_args("cov_traj_minmax", xyz, n, poses, quats, W, K, cam, ws, ws_bytes);
     if (rc) return rc;
     if (!minmax) {
         cov_set_error("cov_traj_minmax: null minmax");
         return COV_ERR_ARG;
+    }
+    if (boxes_dev && (((uintptr_t)boxes_dev) & 15)) {
+        cov_set_error("cov_traj_minmax: boxes must be 16-byte aligned");
+        return COV_ERR_ALIGN;
     }
     cudaStream_t s = (cudaStream_t)stream;
     const CovConst C = cov_make_const(cam);
     unsigned* gmin = reinterpret_cast<unsigned*>(minmax);
     unsigned* gmax = gmin + W;
     cov_minmax_init_kernel<<<(W + 255) / 256, 256, 0, s>>>(gmin, gmax, W);
-    const bool prune = cov_pruning_enabled() != 0;
+    const bool prune = cov_pruning_enabled() != 0 && n >= kDenseBelow;
     int ppt = pick_ppt(n, W, false, prune);
     if (ppt == 4 && (n + tile_points(8) - 1) / tile_points(8) >= 4 * (int64_t)cov_sm_count_cached() &&
         (!prune || minmax_tiles_smem_bytes(W, 8) <= kSmemCap))
         ppt = 8;
-    const size_t smem = minmax_smem_bytes(W);
-    const int mm_variant = dev_variant("COV_DEV_MM", 0);
-    const int eff_ppt = (ppt == 8) ? ((mm_variant == 0 || mm_variant == 4) ? 8 : (mm_variant == 5 ? 2 : 4)) : (ppt >= 4 ? 4 : ppt);
-    const int64_t ntiles = (n + tile_points(eff_ppt) - 1) / tile_points(eff_ppt);
-#define LAUNCH_MM(P, B, U)                                                                                        \
-    {                                                                                                             \
-        if (prune) {                                                                                              \
-            const size_t smem_t = minmax_tiles_smem_bytes(W, P);                                                  \
-            const int grid = grid_for(cov_traj_minmax_tiles_kernel<P, B>, smem_t, ntiles);                        \
-            cov_traj_minmax_tiles_kernel<P, B><<<grid, COV_THREADS, smem_t, s>>>(                                 \
-                xyz, n, poses, quats, W, K, C, gmin, gmax, golden_stride((unsigned long long)ntiles), stats);     \
-        } else {                                                                                                  \
-            const int grid = grid_for(cov_traj_minmax_kernel<P, B, U, false>, smem, ntiles);                      \
-            cov_traj_minmax_kernel<P, B, U, false><<<grid, COV_THREADS, smem, s>>>(xyz, n, poses, quats, W, K, C, \
-                                                                                   gmin, gmax, stats);            \
-        }                                                                                                         \
+    if (ppt == 0) {
+        cov_set_error("cov_traj_minmax: %d poses do not fit in shared memory", W);
+        return COV_ERR_UNSUPPORTED;
     }
+    const size_t smem = minmax_smem_bytes(W);
+    const int64_t ntiles = (n + tile_points(ppt) - 1) / tile_points(ppt);
+#define LAUNCH_DENSE(P, B, U, NPTS, STRIDE)                                                                           \
+    {                                                                                                                 \
+        const int64_t nt_ = ((NPTS) + tile_points(P) - 1) / tile_points(P);                                           \
+        const int grid = grid_for(cov_traj_minmax_kernel<P, B, U>, smem, nt_);                                        \
+        cov_traj_minmax_kernel<P, B, U><<<grid, COV_THREADS, smem, s>>>(xyz, NPTS, STRIDE, poses, quats, W, K, C, gmin, \
+                                                                        gmax);                                        \
+    }
+    if (!prune) {
+        if (ppt == 8) LAUNCH_DENSE(8, 2, 2, n, 1)
+        else if (ppt == 4) LAUNCH_DENSE(4, 2, 1, n, 1)
+        else if (ppt == 2) LAUNCH_DENSE(2, 2, 1, n, 1)
+        else LAUNCH_DENSE(1, 2, 1, n, 1)
+        return cov_check_launch("cov_traj_minmax");
+    }
+    // pruned: seed the bounds on a strided sample, cull tiles against them, evaluate the listed tiles
+    const TrajWorkspace t = carve_workspace(ws, n, W);
+    const float4* boxes = boxes_for_call(xyz, n, boxes_dev, t, s);
+    const int64_t stride = (n + kSeedSamples - 1) / kSeedSamples;
+    const int64_t nsamples = (n + stride - 1) / stride;
+    LAUNCH_DENSE(1, 2, 1, nsamples, stride)
+#undef LAUNCH_DENSE
+    cov_pose_table_kernel<<<(W + 127) / 128, 128, 0, s>>>(poses, quats, W, K, C, nullptr, t.table, t.ints);
+    launch_cull(boxes, ppt, ntiles, t, W, gmin, gmax, 1.f / C.kd, s);
     unsigned long long* stats = cov_stats_device_ptr();
-    const int variant = dev_variant("COV_DEV_MM", 0);
-    if (ppt == 8 && variant == 0) LAUNCH_MM(8, 2, 2)
-    else if (ppt == 8 && variant == 1) LAUNCH_MM(4, 3, 1)
-    else if (ppt == 8 && variant == 2) LAUNCH_MM(4, 2, 2)
-    else if (ppt == 8 && variant == 3) LAUNCH_MM(4, 3, 2)
-    else if (ppt == 8 && variant == 4) LAUNCH_MM(8, 2, 1)
-    else if (ppt == 8 && variant == 5) LAUNCH_MM(2, 3, 4)
-    else if (ppt >= 4) LAUNCH_MM(4, 2, 1) else if (ppt == 2) LAUNCH_MM(2, 2, 1) else LAUNCH_MM(1, 2, 1)
-#undef LAUNCH_MM
+#define LAUNCH_TILES(P)                                                                                             \
+    {                                                                                                               \
+        const size_t smem_t = minmax_tiles_smem_bytes(W, P);                                                        \
+        const int grid = grid_for(cov_traj_minmax_tiles_kernel<P, 2>, smem_t, ntiles);                              \
+        cov_traj_minmax_tiles_kernel<P, 2><<<grid, COV_THREADS, smem_t, s>>>(                                       \
+            xyz, n, t.table, W, C, gmin, gmax, boxes, t.amask, mask_stride_words(W), t.worklist, t.ints, ntiles, stats); \
+    }
+    if (ppt == 8) LAUNCH_TILES(8) else if (ppt == 4) LAUNCH_TILES(4) else if (ppt == 2) LAUNCH_TILES(2) else LAUNCH_TILES(1)
+#undef LAUNCH_TILES
     return cov_check_launch("cov_traj_minmax");
 }
 
 extern "C" int cov_traj_fused(const float* xyz, int64_t n, const float* poses, const float* quats, int W,
-                              const float* K, const cov_camera* cam, const float* minmax, const float* upstream,
-                              const int32_t* reward_index, float* rewards, double* acc, void* ws, size_t ws_bytes,
-                              void* stream) {
-    int rc = check_traj_args("cov_traj_fused", xyz, n, poses, quats, W, K, cam);
+                              const float* K, const cov_camera* cam, const float* boxes_dev, const float* minmax,
+                              const float* upstream, const int32_t* reward_index, float* rewards, double* acc, void* ws,
+                              size_t ws_bytes, void* stream) {
+    int rc = check_traj_args("cov_traj_fused", xyz, n, poses, quats, W, K, cam, ws, ws_bytes);
     if (rc) return rc;
-    if (!minmax || !rewards || !acc || !ws) {
-        cov_set_error("cov_traj_fused: null minmax/rewards/acc/workspace");
+    if (!minmax || !rewards || !acc) {
+        cov_set_error("cov_traj_fused: null minmax/rewards/acc");
         return COV_ERR_ARG;
     }
-    if (ws_bytes < cov_traj_workspace_bytes(n, W)) {
-        cov_set_error("cov_traj_fused: workspace %zu < %zu bytes", ws_bytes, cov_traj_workspace_bytes(n, W));
-        return COV_ERR_WORKSPACE;
-    }
-    if (((uintptr_t)ws) & 15) {
-        cov_set_error("cov_traj_fused: workspace must be 16-byte aligned");
+    if (boxes_dev && (((uintptr_t)boxes_dev) & 15)) {
+        cov_set_error("cov_traj_fused: boxes must be 16-byte aligned");
         return COV_ERR_ALIGN;
     }
     cudaStream_t s = (cudaStream_t)stream;
     const CovConst C = cov_make_const(cam);
     const bool prune = cov_pruning_enabled() != 0;
-    int ppt = pick_ppt(n, W, true, prune);
-    const int fvariant = dev_variant("COV_DEV_F", 0);
-    if (ppt == 4 && (fvariant == 2 || fvariant == 3)) ppt = 2;
+    const int ppt = pick_ppt(n, W, true, prune);
     if (ppt == 0) {
         cov_set_error("cov_traj_fused: %d poses do not fit in shared memory", W);
         return COV_ERR_UNSUPPORTED;
     }
     const size_t smem = fused_smem_bytes(W, ppt, prune);
     const int64_t ntiles = (n + tile_points(ppt) - 1) / tile_points(ppt);
-    // phase-2 parallelism: split each pose row over 2^seg_log2 lanes until there are >= 2 tasks per thread
-    int seg_log2 = 0;
-    while ((W << seg_log2) < 2 * COV_THREADS && (2 << seg_log2) <= bit_words(ppt) && seg_log2 < 5) ++seg_log2;
-    double* sumr = reinterpret_cast<double*>(ws);
-    float* partials = reinterpret_cast<float*>(sumr + COV_MAX_GRID);
+    const TrajWorkspace t = carve_workspace(ws, n, W);
     cudaMemsetAsync(acc, 0, ((size_t)W * COV_ACC_STRIDE + 1) * sizeof(double), s);
-    if (reward_index && prune) {  // the pruned kernel scatters only rewards != 1/2
+    int grid = 1;
+    if (!prune) {
+        // phase-2 parallelism: split each pose row over 2^seg_log2 lanes until there are >= 2 tasks per thread
+        int seg_log2 = 0;
+        while ((W << seg_log2) < 2 * COV_THREADS && (2 << seg_log2) <= bit_words(ppt) && seg_log2 < 5) ++seg_log2;
+#define LAUNCH_F(P, UP)                                                                                           \
+    {                                                                                                             \
+        grid = grid_for(cov_traj_fused_kernel<P, UP, 1>, smem, ntiles);                                           \
+        cov_traj_fused_kernel<P, UP, 1><<<grid, COV_THREADS, smem, s>>>(xyz, n, poses, quats, W, K, C, minmax,    \
+                                                                        upstream, reward_index, rewards, t.partials, \
+                                                                        t.sumr, acc, seg_log2);                   \
+    }
+        if (upstream) {
+            if (ppt == 4) LAUNCH_F(4, true) else if (ppt == 2) LAUNCH_F(2, true) else LAUNCH_F(1, true)
+        } else {
+            if (ppt == 4) LAUNCH_F(4, false) else if (ppt == 2) LAUNCH_F(2, false) else LAUNCH_F(1, false)
+        }
+#undef LAUNCH_F
+        cov_traj_reduce_kernel<<<(W * 8 + 255) / 256, 256, 0, s>>>(t.partials, t.sumr, grid, W, 0.0, acc);
+        return cov_check_launch("cov_traj_fused");
+    }
+    // pruned: rewards start at 1/2; cull tiles against the gate thresholds; evaluate the listed tiles
+    const float4* boxes = boxes_for_call(xyz, n, boxes_dev, t, s);
+    cudaMemsetAsync(t.ints, 0, 256, s);
+    cov_pose_table_kernel<<<(W + 127) / 128, 128, 0, s>>>(poses, quats, W, K, C, minmax, t.table, t.ints);
+    {
         const int fgrid = (int)std::min<int64_t>((n + 1023) / 1024, (int64_t)cov_sm_count_cached() * 16);
         cov_fill_kernel<<<fgrid, 256, 0, s>>>(rewards, n, 0.5f);
     }
-    int grid = 1;
-#define LAUNCH_F(P, UP, U)                                                                                        \
-    {                                                                                                             \
-        if (prune) {                                                                                              \
-            grid = grid_for(cov_traj_fused_kernel<P, UP, 1, true>, smem, ntiles);                                 \
-            cov_traj_fused_kernel<P, UP, 1, true><<<grid, COV_THREADS, smem, s>>>(                                \
-                xyz, n, poses, quats, W, K, C, minmax, upstream, reward_index, rewards, partials, sumr, acc, seg_log2,  \
-                stats);  \
-        } else {                                                                                                  \
-            grid = grid_for(cov_traj_fused_kernel<P, UP, U, false>, smem, ntiles);                                \
-            cov_traj_fused_kernel<P, UP, U, false><<<grid, COV_THREADS, smem, s>>>(                               \
-                xyz, n, poses, quats, W, K, C, minmax, upstream, reward_index, rewards, partials, sumr, acc, seg_log2,  \
-                stats);  \
-        }                                                                                                         \
-    }
+    launch_cull(boxes, ppt, ntiles, t, W, nullptr, nullptr, 0.f, s);
     unsigned long long* stats = cov_stats_device_ptr();
-    if (upstream) {
-        if (ppt == 4) LAUNCH_F(4, true, 1) else if (ppt == 2) LAUNCH_F(2, true, 1) else LAUNCH_F(1, true, 1)
-    } else {
-        if (ppt == 4 && fvariant == 1) LAUNCH_F(4, false, 2)
-        else if (ppt == 2 && fvariant == 2) LAUNCH_F(2, false, 2)
-        else if (ppt == 2 && fvariant == 3) LAUNCH_F(2, false, 4)
-        else if (ppt == 4) LAUNCH_F(4, false, 1) else if (ppt == 2) LAUNCH_F(2, false, 1) else LAUNCH_F(1, false, 1)
+#define LAUNCH_FT(P, UP)                                                                                          \
+    {                                                                                                             \
+        grid = grid_for(cov_traj_fused_tiles_kernel<P, UP>, smem, ntiles);                                        \
+        cov_traj_fused_tiles_kernel<P, UP><<<grid, COV_THREADS, smem, s>>>(                                       \
+            xyz, n, t.table, W, C, upstream, reward_index, rewards, t.partials, t.sumr, acc, boxes, t.amask,      \
+            mask_stride_words(W), t.worklist, t.ints, ntiles, stats);                                             \
     }
-#undef LAUNCH_F
-    cov_traj_reduce_kernel<<<(W * 8 + 255) / 256, 256, 0, s>>>(partials, sumr, grid, W, acc);
+    if (upstream) {
+        if (ppt == 4) LAUNCH_FT(4, true) else if (ppt == 2) LAUNCH_FT(2, true) else LAUNCH_FT(1, true)
+    } else {
+        if (ppt == 4) LAUNCH_FT(4, false) else if (ppt == 2) LAUNCH_FT(2, false) else LAUNCH_FT(1, false)
+    }
+#undef LAUNCH_FT
+    cov_traj_reduce_kernel<<<(W * 8 + 255) / 256, 256, 0, s>>>(t.partials, t.sumr, grid, W, 0.5 * (double)n, acc);
     return cov_check_launch("cov_traj_fused");
 }
 

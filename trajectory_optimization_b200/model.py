@@ -186,6 +186,7 @@ class ModelTraj(nn.Module):
         self._step_cache = {}
         self._pts32 = None
         self._perm = None
+        self._boxes = None
         self.to(self.device)
 
     def _cloud(self):
@@ -194,6 +195,7 @@ class ModelTraj(nn.Module):
             self._perm = None
             if self.spatial_sort and pts.shape[0] > 0:
                 pts, self._perm = ops.spatial_sort(pts)
+            self._boxes = ops.tile_boxes(pts)
             self._pts32 = pts
             self._pts32_src = self.points
         return self._pts32
@@ -214,7 +216,7 @@ class ModelTraj(nn.Module):
         rewards, mean = ops.coverage_traj(cloud, self.poses[::wps_step], self.quats[::wps_step], self.K,
                                           self.img_width, self.img_height, self.pc_clip_limits[0],
                                           self.pc_clip_limits[1], self.eps, n_total=self.n_total, group=self.group,
-                                          reward_index=self._perm)
+                                          reward_index=self._perm, boxes=self._boxes)
         self.rewards = rewards
         self._mean = mean
         if debug:

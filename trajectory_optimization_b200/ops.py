@@ -74,22 +74,27 @@ class CudaBackend:
         _lib.check(_lib.lib().cov_pose_epilogue(_ptr(acc), _ptr(t), _ptr(q), _ptr(out), _stream()), "cov_pose_epilogue")
         return out
 
-    def traj_minmax(self, pts, P, Q, Kd, cam):
+    def traj_workspace(self, pts, W):
+        ws_bytes = _lib.lib().cov_traj_workspace_bytes(pts.shape[0], W)
+        return torch.empty(ws_bytes, dtype=torch.uint8, device=pts.device)
+
+    def traj_minmax(self, pts, P, Q, Kd, cam, boxes=None, ws=None):
         W = P.shape[0]
         minmax = torch.empty(2 * W, dtype=torch.float32, device=pts.device)
+        ws = self.traj_workspace(pts, W) if ws is None else ws
         _lib.check(_lib.lib().cov_traj_minmax(_ptr(pts), pts.shape[0], _ptr(P), _ptr(Q), W, _ptr(Kd), ctypes.byref(cam),
-                                              _ptr(minmax), _stream()), "cov_traj_minmax")
+                                              _ptr(boxes), _ptr(minmax), _ptr(ws), ws.numel(), _stream()),
+                   "cov_traj_minmax")
         return minmax
 
-    def traj_fused(self, pts, P, Q, Kd, cam, minmax, upstream, rewards, reward_index=None):
+    def traj_fused(self, pts, P, Q, Kd, cam, minmax, upstream, rewards, reward_index=None, boxes=None, ws=None):
         L = _lib.lib()
         W, n = P.shape[0], pts.shape[0]
         acc = torch.empty(W * _lib.ACC_STRIDE + 1, dtype=torch.float64, device=pts.device)
-        ws_bytes = L.cov_traj_workspace_bytes(n, W)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=pts.device)
-        _lib.check(L.cov_traj_fused(_ptr(pts), n, _ptr(P), _ptr(Q), W, _ptr(Kd), ctypes.byref(cam), _ptr(minmax),
-                                    _ptr(upstream), _ptr(reward_index), _ptr(rewards), _ptr(acc), _ptr(ws), ws_bytes,
-                                    _stream()),
+        ws = self.traj_workspace(pts, W) if ws is None else ws
+        _lib.check(L.cov_traj_fused(_ptr(pts), n, _ptr(P), _ptr(Q), W, _ptr(Kd), ctypes.byref(cam), _ptr(boxes),
+                                    _ptr(minmax), _ptr(upstream), _ptr(reward_index), _ptr(rewards), _ptr(acc), _ptr(ws),
+                                    ws.numel(), _stream()),
                    "cov_traj_fused")
         return acc
 
@@ -158,7 +163,7 @@ class CoverageTrajFn(torch.autograd.Function):
     over the poses given (reference src/model.py:217-237, :246)."""
 
     @staticmethod
-    def forward(ctx, points, poses, quats, K, cam, n_total, group, reward_index=None):
+    def forward(ctx, points, poses, quats, K, cam, n_total, group, reward_index=None, boxes=None):
         B = _BACKEND
         dev = points.device
         pts = B.prepare(points, what="points")
@@ -172,22 +177,23 @@ class CoverageTrajFn(torch.autograd.Function):
         if Q.shape[0] != W:
             raise ValueError("poses and quats disagree on the number of waypoints")
         n_total = int(n if n_total is None else n_total)
-        minmax = B.traj_minmax(pts, P, Q, Kd, cam)          # pass A on this shard
+        ws = B.traj_workspace(pts, W)                        # shared by both passes (and the upstream backward)
+        minmax = B.traj_minmax(pts, P, Q, Kd, cam, boxes, ws)   # pass A on this shard
         if group is not None:                                # global normalisers: W minima, W maxima
             mn, mx, _ = _reduce_ops()
             _all_reduce(minmax[:W], mn, group)
             _all_reduce(minmax[W:], mx, group)
         rewards = torch.empty(n, dtype=torch.float32, device=dev)
-        out = CoverageTrajFn._run(pts, P, Q, Kd, cam, minmax, None, rewards, n_total, group, reward_index)
-        ctx.cam, ctx.group, ctx.n_total, ctx.reward_index = cam, group, n_total, reward_index
+        out = CoverageTrajFn._run(pts, P, Q, Kd, cam, minmax, None, rewards, n_total, group, reward_index, boxes, ws)
+        ctx.cam, ctx.group, ctx.n_total, ctx.reward_index, ctx.boxes = cam, group, n_total, reward_index, boxes
         ctx.shapes = (poses.shape, quats.shape)
         ctx.save_for_backward(pts, P, Q, Kd, minmax, out)
         ctx.set_materialize_grads(False)
         return rewards, out[0].clone()
 
     @staticmethod
-    def _run(pts, P, Q, Kd, cam, minmax, upstream, rewards, n_total, group, reward_index=None):
-        acc = _BACKEND.traj_fused(pts, P, Q, Kd, cam, minmax, upstream, rewards, reward_index)   # pass B: W*22+1 doubles
+    def _run(pts, P, Q, Kd, cam, minmax, upstream, rewards, n_total, group, reward_index=None, boxes=None, ws=None):
+        acc = _BACKEND.traj_fused(pts, P, Q, Kd, cam, minmax, upstream, rewards, reward_index, boxes, ws)   # pass B
         if group is not None:
             _all_reduce(acc, _reduce_ops()[2], group)
         return _BACKEND.traj_epilogue(acc, minmax, Q, n_total, 0 if upstream is None else 1)
@@ -204,12 +210,12 @@ class CoverageTrajFn(torch.autograd.Function):
             up = _BACKEND.prepare(g_rewards, pts.device, "grad_rewards").reshape(-1)
             scratch = torch.empty(pts.shape[0], dtype=torch.float32, device=pts.device)
             o2 = CoverageTrajFn._run(pts, P, Q, Kd, ctx.cam, minmax, up, scratch, ctx.n_total, ctx.group,
-                                     ctx.reward_index)
+                                     ctx.reward_index, ctx.boxes)
             g_p = o2[1:1 + 3 * W] if g_p is None else g_p + o2[1:1 + 3 * W]
             g_q = o2[1 + 3 * W:] if g_q is None else g_q + o2[1 + 3 * W:]
         ps, qs = ctx.shapes
         return (None, None if g_p is None else g_p.reshape(ps), None if g_q is None else g_q.reshape(qs),
-                None, None, None, None, None)
+                None, None, None, None, None, None)
 
 
 def coverage_pose(points, trans, quat, intrins, img_width, img_height, min_dist=1.0, max_dist=5.0, eps=1e-6,
@@ -221,12 +227,25 @@ def coverage_pose(points, trans, quat, intrins, img_width, img_height, min_dist=
 
 
 def coverage_traj(points, poses, quats, intrins, img_width, img_height, min_dist=1.0, max_dist=5.0, eps=1e-6,
-                  n_total=None, group=None, reward_index=None):
+                  n_total=None, group=None, reward_index=None, boxes=None):
     """Fused ModelTraj visibility term over the W poses given.  Returns (rewards (N,), mean(rewards)).
     `reward_index` (int32, from `spatial_sort`): `points` is a reordered copy of the caller's cloud and
-    rewards come back in the caller's order."""
+    rewards come back in the caller's order.  `boxes` (from `tile_boxes(points)`): built once per cloud so the
+    pruned kernels do not rebuild them on every call."""
     cam = _lib.camera(img_width, img_height, min_dist, max_dist, eps)
-    return CoverageTrajFn.apply(points, poses, quats, intrins, cam, n_total, group, reward_index)
+    return CoverageTrajFn.apply(points, poses, quats, intrins, cam, n_total, group, reward_index, boxes)
+
+
+@torch.no_grad()
+def tile_boxes(points):
+    """Bounding boxes of runs of 128 consecutive points (include/coverage_b200.h: cov_tile_boxes), (nb, 8) fp32."""
+    L = _lib.lib()
+    pts = _dev_f32(points, what="points")
+    n = pts.shape[0]
+    boxes = torch.empty(max(int(L.cov_tile_boxes_count(n)), 1), 8, dtype=torch.float32, device=pts.device)
+    if n > 0:
+        _lib.check(L.cov_tile_boxes(_ptr(pts), n, _ptr(boxes), _stream()), "cov_tile_boxes")
+    return boxes
 
 
 @torch.no_grad()
@@ -249,7 +268,7 @@ def spatial_sort(points):
 
 @torch.no_grad()
 def sweep_rewards(points, poses, quats, intrins, img_width, img_height, min_dist=1.0, max_dist=5.0, eps=1e-6,
-                  n_total=None, group=None):
+                  n_total=None, group=None, boxes=None):
     """Forward-only mean reward of many candidate trajectories: poses (T, P, 3), quats (T, P, 4) -> (T,) fp64."""
     L = _lib.lib()
     pts = _dev_f32(points, what="points")
@@ -262,11 +281,15 @@ def sweep_rewards(points, poses, quats, intrins, img_width, img_height, min_dist
     W, n = T * Pn, pts.shape[0]
     minmax = torch.empty(2 * W, dtype=torch.float32, device=dev)
     chunk = L.cov_traj_max_poses()
+    boxes = tile_boxes(pts) if boxes is None else boxes
+    ws_bytes = L.cov_traj_workspace_bytes(n, min(W, chunk))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     for w0 in range(0, W, chunk):  # pass A reuses the trajectory kernel, one pose-table-full at a time
         w1 = min(W, w0 + chunk)
         mm = torch.empty(2 * (w1 - w0), dtype=torch.float32, device=dev)
         _lib.check(L.cov_traj_minmax(_ptr(pts), n, _ptr(P[w0:w1]), _ptr(Q[w0:w1]), w1 - w0, _ptr(Kd),
-                                     ctypes.byref(cam), _ptr(mm), _stream()), "cov_traj_minmax")
+                                     ctypes.byref(cam), _ptr(boxes), _ptr(mm), _ptr(ws), ws_bytes, _stream()),
+                   "cov_traj_minmax")
         minmax[w0:w1] = mm[:w1 - w0]
         minmax[W + w0:W + w1] = mm[w1 - w0:]
     if group is not None:
