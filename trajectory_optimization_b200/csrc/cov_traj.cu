@@ -69,11 +69,11 @@ __host__ __device__ inline int fused_stage_offset_floats(int W) {
     return (int)((((size_t)W * COV_ROW_F4 * 16 + 127) & ~(size_t)127) / 4);
 }
 size_t fused_smem_bytes(int W, int ppt, bool prune) {
-    const size_t rs = prune ? bit_words(ppt) : bit_stride(ppt);
-    const size_t stage = prune ? 2 * (size_t)stage_floats(ppt) * 4 : (size_t)tile_points(ppt) * 12;
-    return (size_t)fused_stage_offset_floats(W) * 4 + stage + (size_t)tile_points(ppt) * 4 +
-           (size_t)W * rs * sizeof(unsigned) + (size_t)W * 8 * sizeof(float) +
-           (prune ? (((size_t)W * sizeof(unsigned short) + 15) & ~(size_t)15) : 0);
+    if (prune)  // pose table | 2 tile stages | block accumulators
+        return (size_t)fused_stage_offset_floats(W) * 4 + 2 * (size_t)stage_floats(ppt) * 4 + (size_t)W * 8 * sizeof(float);
+    // pose table | tile points | G_j | gate bits | block accumulators
+    return (size_t)fused_stage_offset_floats(W) * 4 + (size_t)tile_points(ppt) * 12 + (size_t)tile_points(ppt) * 4 +
+           (size_t)W * bit_stride(ppt) * sizeof(unsigned) + (size_t)W * 8 * sizeof(float);
 }
 
 // Unweighted dm/dy and dm/dy x y of one (point, pose) into a tie-set accumulator (7 doubles).
@@ -327,7 +327,8 @@ __global__ void __launch_bounds__(256) cov_tile_boxes_kernel(const float* __rest
 __global__ void __launch_bounds__(256)
 cov_cull_kernel(const float4* __restrict__ boxes, int boxes_per_tile, int64_t ntiles, const float4* __restrict__ table,
                 int W, const unsigned* __restrict__ gmin, const unsigned* __restrict__ gmax, float inv_kd,
-                unsigned* __restrict__ amask_g, int mask_stride, unsigned char* __restrict__ flags) {
+                unsigned* __restrict__ amask_g, int mask_stride, unsigned char* __restrict__ flags,
+                unsigned long long* __restrict__ listed_pairs) {
     extern __shared__ float4 v3s[];
     const int tid = threadIdx.x, lane = tid & 31;
     for (int w = tid; w < W; w += blockDim.x) {
@@ -338,6 +339,7 @@ cov_cull_kernel(const float4* __restrict__ boxes, int boxes_per_tile, int64_t nt
     __syncthreads();
     const float inf = __uint_as_float(0x7f800000u);
     const int nwords = (W + 31) >> 5;
+    unsigned long long npairs = 0;
     for (int64_t tile = (int64_t)blockIdx.x * 8 + (tid >> 5); tile < ntiles; tile += (int64_t)gridDim.x * 8) {
         float4 lo = make_float4(inf, inf, inf, 0.f), hi = make_float4(-inf, -inf, -inf, 0.f);
         if (lane < boxes_per_tile) {
@@ -363,20 +365,33 @@ cov_cull_kernel(const float4* __restrict__ boxes, int boxes_per_tile, int64_t nt
             const unsigned bal = __ballot_sync(kFull, active);
             if (lane == 0) amask_g[tile * mask_stride + c] = bal;
             any |= bal;
+            npairs += __popc(bal);
         }
         if (lane == 0) flags[tile] = any != 0u;
     }
+    if (lane == 0 && npairs) atomicAdd(listed_pairs, npairs);
 }
 
 // Ascending list of flagged tiles + their count (single block: deterministic order, no atomics).
+// ints[0] = count, ints[2] = 1 when the masks list more than `dense_above` (tile, pose) pairs: the cloud has no
+// spatial coherence to exploit, the dense kernel does the call instead (it checks ints[2]) and the list is left empty.
 __global__ void __launch_bounds__(1024) cov_worklist_kernel(const unsigned char* __restrict__ flags, int64_t ntiles,
-                                                            int* __restrict__ worklist, int* __restrict__ count) {
+                                                            int* __restrict__ worklist, int* __restrict__ ints,
+                                                            unsigned long long dense_above) {
     __shared__ int warp_tot[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t chunk = (ntiles + 1023) / 1024;
-    const int64_t lo = (int64_t)tid * chunk, hi = lo + chunk < ntiles ? lo + chunk : ntiles;
+    const int64_t chunk = (((ntiles + 1023) / 1024) + 15) & ~(int64_t)15;  // flags per thread, 16 per vector load
+    const int64_t lo = (int64_t)tid * chunk < ntiles ? (int64_t)tid * chunk : ntiles;
+    const int64_t hi = lo + chunk < ntiles ? lo + chunk : ntiles;
     int c = 0;
-    for (int64_t t = lo; t < hi; ++t) c += flags[t] ? 1 : 0;
+    {
+        int64_t t = lo;
+        for (; t + 16 <= hi; t += 16) {  // flags are 0/1 bytes: popc of a word counts them
+            const uint4 v = *reinterpret_cast<const uint4*>(flags + t);
+            c += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+        }
+        for (; t < hi; ++t) c += flags[t] ? 1 : 0;
+    }
     int incl = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -393,11 +408,30 @@ __global__ void __launch_bounds__(1024) cov_worklist_kernel(const unsigned char*
             if (lane >= o) s += u;
         }
         warp_tot[lane] = s - v;  // exclusive
-        if (lane == 31) *count = s;
+        if (lane == 31) {
+            const bool dense = *reinterpret_cast<const unsigned long long*>(ints + 4) > dense_above;
+            ints[0] = dense ? 0 : s;
+            ints[2] = dense ? 1 : 0;
+        }
     }
     __syncthreads();
     int pos = warp_tot[warp] + incl - c;
-    for (int64_t t = lo; t < hi; ++t)
+    if (c == 0) return;
+    int64_t t = lo;
+    for (; t + 16 <= hi; t += 16) {
+        const uint4 v = *reinterpret_cast<const uint4*>(flags + t);
+        const unsigned words[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            unsigned wv = words[q];
+            while (wv) {
+                const int byte = (__ffs(wv) - 1) >> 3;
+                wv &= ~(0xffu << (byte * 8));
+                worklist[pos++] = (int)(t + q * 4 + byte);
+            }
+        }
+    }
+    for (; t < hi; ++t)
         if (flags[t]) worklist[pos++] = (int)t;
 }
 
@@ -526,33 +560,25 @@ cov_traj_minmax_tiles_kernel(const float* __restrict__ xyz, int64_t n, const flo
 }
 
 // =================================================== pass B ===================================================
-// Gate bit matrix addressing.  Row w holds kWarps groups of PPT ballot words (group g = the words of warp g; word k
-// of a row covers points [32k, 32k+32) of the tile, since a warp owns 32*PPT consecutive points).
-// Dense kernel: rows are padded by 4 words (conflict-free when lanes walk different rows at the same word).
-// Pruned kernel: rows are unpadded (the shared memory goes to the second tile stage) and group g sits at slot
-// g ^ (w & 7) instead, which spreads the same access pattern over 8 bank groups.
-template <int PPT, bool SWZ>
+// Gate bit matrix of the dense kernel.  Row w holds kWarps groups of PPT ballot words (group g = the words of warp g;
+// word k of a row covers points [32k, 32k+32) of the tile, since a warp owns 32*PPT consecutive points).  Rows are
+// padded by 4 words (conflict-free when lanes walk different rows at the same word).
+template <int PPT>
 __device__ __forceinline__ unsigned* bit_row_group(unsigned* bits, int w, int group) {
-    constexpr int RS = SWZ ? bit_words(PPT) : bit_stride(PPT);
-    return bits + (size_t)w * RS + (SWZ ? ((group ^ (w & 7)) * PPT) : group * PPT);
-}
-template <int PPT, bool SWZ>
-__device__ __forceinline__ unsigned bit_word(const unsigned* bits, int w, int k) {  // word k of row w (k = group*PPT + s)
-    constexpr int RS = SWZ ? bit_words(PPT) : bit_stride(PPT);
-    const int g = k / PPT, sidx = k - g * PPT;
-    return bits[(size_t)w * RS + (SWZ ? ((g ^ (w & 7)) * PPT) : g * PPT) + sidx];
+    return bits + (size_t)w * bit_stride(PPT) + group * PPT;
 }
 
-// Phase-1 body for U consecutive poses starting at w (U*PPT independent chains).  TILES = pruned kernel: the
-// conservative threshold lives in v5.w (v3.w holds qthr), bit rows are swizzled, and `gmask` collects the poses
-// that got at least one gated pair in this tile.
+// Phase-1 body for U consecutive poses starting at w (U*PPT independent chains).  Dense kernel: the ballots go to
+// the gate bit matrix.  TILES = pruned kernel: the conservative threshold lives in v5.w (v3.w holds qthr), nothing
+// is stored, and the return value says whether this warp has a gated pair for the pose (U = 1).
 template <int PPT, int U, bool AMIN, bool TILES>
-__device__ __forceinline__ void fused_pose_iter(int w, const float4* __restrict__ ptab, unsigned* __restrict__ bits,
+__device__ __forceinline__ bool fused_pose_iter(int w, const float4* __restrict__ ptab, unsigned* __restrict__ bits,
                                                 int warp, const float (&px)[PPT], const float (&py)[PPT],
                                                 const float (&pz)[PPT], float (&L)[PPT], const CovConst& C,
-                                                double* __restrict__ acc, int lane, unsigned* __restrict__ gmask) {
+                                                double* __restrict__ acc, int lane) {
     float m[U][PPT];
     float mmax[U];
+    unsigned anyb = 0u;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         const float4* row = ptab + (size_t)(w + u) * COV_ROW_F4;
@@ -587,17 +613,14 @@ __device__ __forceinline__ void fused_pose_iter(int w, const float4* __restrict_
                 }
             }
         }
-        if (lane == 0) {
-            unsigned* brow = bit_row_group<PPT, TILES>(bits, w + u, warp);
+        if (TILES) {
+#pragma unroll
+            for (int s = 0; s < PPT; ++s) anyb |= bal[s];
+        } else if (lane == 0) {
+            unsigned* brow = bit_row_group<PPT>(bits, w + u, warp);
             if (PPT == 4) *reinterpret_cast<uint4*>(brow) = make_uint4(bal[0], bal[1 % PPT], bal[2 % PPT], bal[3 % PPT]);
             else if (PPT == 2) *reinterpret_cast<uint2*>(brow) = make_uint2(bal[0], bal[1 % PPT]);
             else brow[0] = bal[0];
-            if (TILES) {
-                unsigned anyb = 0u;
-#pragma unroll
-                for (int s = 0; s < PPT; ++s) anyb |= bal[s];
-                if (anyb) atomicOr(gmask + ((w + u) >> 5), 1u << ((w + u) & 31));
-            }
         }
         if (AMIN) {  // only compact clouds whose minimum did not underflow to 0 (block-uniform choice of the loop)
             const float a = row[4].w;
@@ -608,34 +631,35 @@ __device__ __forceinline__ void fused_pose_iter(int w, const float4* __restrict_
             }
         }
     }
+    return anyb != 0u;
 }
 
-// Phase 2: the gated pairs of `nposes2` bit rows (rows alist[0..nposes2) when LIST, else rows 0..nposes2-1), each row
-// split over 2^seg_log2 lanes.  A lane pops its set bits in ascending point order, recomputes m (bit-identical) and
-// dm/dx, and accumulates in registers; segments are combined with xor-shuffles; one owner lane adds into accs.
-template <int PPT, bool TILES>
+// Phase 2 of the dense kernel: the gated pairs of all W bit rows, each row split over 2^seg_log2 lanes.  A lane pops
+// its set bits in ascending point order, recomputes m (bit-identical) and dm/dx, and accumulates in registers;
+// segments are combined with xor-shuffles; one owner lane adds into accs.
+template <int PPT>
 __device__ __forceinline__ void fused_phase2(const float4* __restrict__ ptab, const unsigned* __restrict__ bits,
                                              const float* __restrict__ pt, const float* __restrict__ Gs,
-                                             float* __restrict__ accs, const unsigned short* __restrict__ alist,
-                                             int nposes2, int seg_log2, const CovConst& C, int tid) {
+                                             float* __restrict__ accs, int W, int seg_log2, const CovConst& C, int tid) {
     constexpr int NW = bit_words(PPT);
+    constexpr int RS = bit_stride(PPT);
     const int nseg = 1 << seg_log2;       // lanes that share one pose row
     const int wps = NW >> seg_log2;       // ballot words per lane
-    const int ntask = nposes2 << seg_log2;
+    const int ntask = W << seg_log2;
     for (int base = 0; base < ntask; base += COV_THREADS) {
         const int task = base + tid;
         const bool live = task < ntask;
-        const int wi = live ? (task >> seg_log2) : 0;
-        const int w = TILES ? (int)alist[wi] : wi;
+        const int w = live ? (task >> seg_log2) : 0;
         const int seg = task & (nseg - 1);
         const float4* row = ptab + (size_t)w * COV_ROW_F4;
         const float4 v0 = row[0], v1 = row[1], v2 = row[2], v3 = row[3], v4 = row[4], v5 = row[5];
+        const unsigned* brow = bits + (size_t)w * RS;
         int k = seg * wps;
         const int kend = live ? k + wps : k;
-        unsigned word = live ? bit_word<PPT, TILES>(bits, w, k) : 0u;
+        unsigned word = live ? brow[k] : 0u;
         float f0 = 0.f, f1 = 0.f, f2 = 0.f, t0 = 0.f, t1 = 0.f, t2 = 0.f, se = 0.f, sep = 0.f;
         while (true) {
-            while (word == 0u && k + 1 < kend) word = bit_word<PPT, TILES>(bits, w, ++k);
+            while (word == 0u && k + 1 < kend) word = brow[++k];
             if (!__any_sync(kFull, word != 0u)) break;
             if (word != 0u) {
                 const int bit = __ffs(word) - 1;
@@ -698,7 +722,8 @@ cov_traj_fused_kernel(const float* __restrict__ xyz, int64_t n, const float* __r
                       const float* __restrict__ minmax, const float* __restrict__ upstream,
                       const int32_t* __restrict__ out_index, float* __restrict__ rewards,
                       float* __restrict__ partials, double* __restrict__ sumr_partials, double* __restrict__ acc,
-                      int seg_log2) {
+                      int seg_log2, const int* __restrict__ run_flag) {
+    if (run_flag && *run_flag == 0) return;  // stand-by launch behind the pruned kernel (see cov_worklist_kernel)
     constexpr int T = tile_points(PPT);
     constexpr int RS = bit_stride(PPT);
     // shared memory: pose table | the tile's points (xyz interleaved) | G_j | gate bits | block accumulators
@@ -750,10 +775,10 @@ cov_traj_fused_kernel(const float* __restrict__ xyz, int64_t n, const float* __r
         {
             int w = 0;
             if (check_amin) {  // arg-min points carry gradient: every pair must be looked at
-                for (; w < W; ++w) fused_pose_iter<PPT, 1, true, false>(w, ptab, bits, warp, px, py, pz, L, C, acc, lane, nullptr);
+                for (; w < W; ++w) fused_pose_iter<PPT, 1, true, false>(w, ptab, bits, warp, px, py, pz, L, C, acc, lane);
             } else {
-                for (; w + U <= W; w += U) fused_pose_iter<PPT, U, false, false>(w, ptab, bits, warp, px, py, pz, L, C, acc, lane, nullptr);
-                for (; w < W; ++w) fused_pose_iter<PPT, 1, false, false>(w, ptab, bits, warp, px, py, pz, L, C, acc, lane, nullptr);
+                for (; w + U <= W; w += U) fused_pose_iter<PPT, U, false, false>(w, ptab, bits, warp, px, py, pz, L, C, acc, lane);
+                for (; w < W; ++w) fused_pose_iter<PPT, 1, false, false>(w, ptab, bits, warp, px, py, pz, L, C, acc, lane);
             }
         }
 #pragma unroll
@@ -770,15 +795,26 @@ cov_traj_fused_kernel(const float* __restrict__ xyz, int64_t n, const float* __r
             Gs[lbase + s * 32] = g;
         }
         __syncthreads();
-        fused_phase2<PPT, false>(ptab, bits, pt, Gs, accs, nullptr, W, seg_log2, C, tid);
+        fused_phase2<PPT>(ptab, bits, pt, Gs, accs, W, seg_log2, C, tid);
         __syncthreads();
     }
     fused_block_epilogue(accs, W, partials, sumr_partials, sum_r, red, tid);
 }
 
 // ---- pruned: persistent blocks over the work list of tiles with a non-empty pose mask ----
+// Each warp owns 32*PPT consecutive points of the tile in registers, for both phases:
+//   phase 1  walk the tile's pose mask; a listed pose is evaluated when its qthr-ball meets the warp's own box and
+//            one of its points passes the same test; gated lanes add their log-odds; the warp notes (one bit per
+//            pose) whether it had a gated pair.  Then r_j, G_j = r_j (1 - r_j) per point, rewards stored.
+//   phase 2  (only when some warp of the block noted a gate)  the warp walks the mask again; for a noted pose it
+//            re-evaluates m for its points (bit-identical), re-derives the gate, and accumulates the 8 weighted
+//            sums of dm/dx in registers; a fixed xor-shuffle tree reduces them over the warp.  The 8 warps' partial
+//            sums meet in a slot table indexed by the pose's rank in the mask and are added to the block
+//            accumulators in warp order by one thread per (pose, component): fixed order, bitwise reproducible.
 // sumr_partials receive sum_j (r_j - 1/2) over the listed tiles (the rest is 0.5 * n, added by the reduce kernel);
 // `rewards` was pre-filled with 1/2, only other values are stored.
+constexpr int kSlotPoses = 32;  // poses per round of the slot table
+
 template <int PPT, bool HAS_UP>
 __global__ void __launch_bounds__(COV_THREADS, 2)
 cov_traj_fused_tiles_kernel(const float* __restrict__ xyz, int64_t n, const float4* __restrict__ table, int W, CovConst C,
@@ -789,21 +825,18 @@ cov_traj_fused_tiles_kernel(const float* __restrict__ xyz, int64_t n, const floa
                             const int* __restrict__ worklist, const int* __restrict__ count_ptr, int64_t ntiles,
                             unsigned long long* __restrict__ stats) {
     constexpr int T = tile_points(PPT);
-    constexpr int NW = bit_words(PPT);
     constexpr int NB = tile_boxes(PPT);
     constexpr int SF = stage_floats(PPT);
     constexpr int WB = (32 * PPT >= kBoxPts) ? (32 * PPT / kBoxPts) : 1;
-    // shared memory: pose table | 2 tile stages (points, boxes, pose mask) | G_j | gate bits | block accumulators |
-    // gated-pose list
+    // shared memory: pose table | 2 tile stages (points, boxes, pose mask) | block accumulators
     extern __shared__ float4 smem4[];
     float4* ptab = smem4;
     float* stage = reinterpret_cast<float*>(smem4) + fused_stage_offset_floats(W);
-    float* Gs = stage + 2 * SF;
-    unsigned* bits = reinterpret_cast<unsigned*>(Gs + T);
-    float* accs = reinterpret_cast<float*>(bits + (size_t)W * NW);
-    unsigned short* alist = reinterpret_cast<unsigned short*>(accs + (size_t)W * 8);
+    float* accs = stage + 2 * SF;
     __shared__ double red[kWarps];
-    __shared__ unsigned gmask[2][kMaskWords];  // poses with a gated pair in the current / next tile
+    __shared__ float slots[kSlotPoses][kWarps][8];   // per-(pose rank, warp) partial sums of one round
+    __shared__ int slot_pose[kSlotPoses];
+    __shared__ unsigned wgate[kWarps][kMaskWords];   // per warp: poses with a gated pair among its points (this tile)
     __shared__ __align__(8) unsigned long long mbar[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -814,7 +847,6 @@ cov_traj_fused_tiles_kernel(const float* __restrict__ xyz, int64_t n, const floa
     }
     for (int i = tid; i < W * COV_ROW_F4; i += COV_THREADS) ptab[i] = table[i];
     for (int i = tid; i < W * 8; i += COV_THREADS) accs[i] = 0.f;
-    if (tid < 2 * kMaskWords) (&gmask[0][0])[tid] = 0u;
     const bool check_amin = count_ptr[1] != 0;  // flags[1]: some pose has min_j m > 0
     __syncthreads();
 
@@ -823,6 +855,7 @@ cov_traj_fused_tiles_kernel(const float* __restrict__ xyz, int64_t n, const floa
     const int count = count_ptr[0];
     const int64_t nfull = n / T;
     const int nwords = (W + 31) >> 5;
+    unsigned* wg = wgate[warp];
     unsigned uses0 = 0, uses1 = 0;
     if (tid == 0 && (int)blockIdx.x < count)
         stage_issue<PPT>(stage, &mbar[0], xyz, boxes, amask_g, mask_stride, (int64_t)worklist[blockIdx.x], nfull);
@@ -834,9 +867,8 @@ cov_traj_fused_tiles_kernel(const float* __restrict__ xyz, int64_t n, const floa
                              (int64_t)worklist[i + gridDim.x], nfull);
         if (buf == 0) mbar_wait(&mbar[0], uses0++ & 1u);
         else mbar_wait(&mbar[1], uses1++ & 1u);
-        float* pt = stage + buf * SF;  // this tile's points (phase 2 reads them again)
-        unsigned* gm = gmask[buf];
-        // ------------------------------ phase 1: the (point, pose) pairs that can matter ------------------------------
+        const float* st = stage + buf * SF;
+        // ------------------------------ phase 1 ------------------------------
         float px[PPT], py[PPT], pz[PPT], L[PPT];
         bool valid[PPT];
         const int lbase = warp * (32 * PPT) + lane;
@@ -844,12 +876,12 @@ cov_traj_fused_tiles_kernel(const float* __restrict__ xyz, int64_t n, const floa
 #pragma unroll
             for (int s = 0; s < PPT; ++s) {
                 valid[s] = true;
-                px[s] = pt[(lbase + s * 32) * 3];
-                py[s] = pt[(lbase + s * 32) * 3 + 1];
-                pz[s] = pt[(lbase + s * 32) * 3 + 2];
+                px[s] = st[(lbase + s * 32) * 3];
+                py[s] = st[(lbase + s * 32) * 3 + 1];
+                pz[s] = st[(lbase + s * 32) * 3 + 2];
                 L[s] = 0.f;
             }
-        } else {  // the ragged last tile (always the last entry of the list): loaded by hand
+        } else {  // the ragged last tile: loaded by hand
 #pragma unroll
             for (int s = 0; s < PPT; ++s) {
                 const int64_t j = tile * T + lbase + s * 32;
@@ -858,50 +890,48 @@ cov_traj_fused_tiles_kernel(const float* __restrict__ xyz, int64_t n, const floa
                 px[s] = valid[s] ? __ldg(xyz + j * 3) : 3.0e18f;
                 py[s] = valid[s] ? __ldg(xyz + j * 3 + 1) : 3.0e18f;
                 pz[s] = valid[s] ? __ldg(xyz + j * 3 + 2) : 3.0e18f;
-                pt[(lbase + s * 32) * 3] = px[s];
-                pt[(lbase + s * 32) * 3 + 1] = py[s];
-                pt[(lbase + s * 32) * 3 + 2] = pz[s];
                 L[s] = 0.f;
             }
         }
-        const float4* tb = reinterpret_cast<const float4*>(pt + T * 3);
+        const float4* tb = reinterpret_cast<const float4*>(st + T * 3);
         const int b0 = (warp * 32 * PPT) / kBoxPts;
         float4 wlo = tb[2 * b0], whi = tb[2 * b0 + 1];
 #pragma unroll
         for (int k = 1; k < WB; ++k) box_union(wlo, whi, tb[2 * (b0 + k)], tb[2 * (b0 + k) + 1]);
-        const unsigned* am = reinterpret_cast<const unsigned*>(pt + T * 3 + NB * 8);
+        const unsigned* am = reinterpret_cast<const unsigned*>(st + T * 3 + NB * 8);
+        bool warp_gated = false;
         for (int c = 0; c < nwords; ++c) {
             unsigned word = am[c];
+            unsigned gbits = 0u;
             while (word) {
-                const int w = c * 32 + __ffs(word) - 1;
+                const int b = __ffs(word) - 1;
+                const int w = c * 32 + b;
                 word &= word - 1;
                 const float4 v3 = ptab[(size_t)w * COV_ROW_F4 + 3];
                 ++n_box;
-                bool run = !(box_q2lb(wlo, whi, v3) > v3.w);
-                if (run) {
-                    ++n_pre;
-                    float qmin = cov_q2(px[0], py[0], pz[0], v3);
+                if (box_q2lb(wlo, whi, v3) > v3.w) continue;
+                ++n_pre;
+                float qmin = cov_q2(px[0], py[0], pz[0], v3);
 #pragma unroll
-                    for (int s = 1; s < PPT; ++s) qmin = fminf(qmin, cov_q2(px[s], py[s], pz[s], v3));
-                    run = __any_sync(kFull, !(qmin > v3.w));
-                }
-                if (run) {  // (a row this warp skips is never read: no gated bit of it is reported in gmask)
-                    ++n_full;
-                    if (check_amin) fused_pose_iter<PPT, 1, true, true>(w, ptab, bits, warp, px, py, pz, L, C, acc, lane, gm);
-                    else fused_pose_iter<PPT, 1, false, true>(w, ptab, bits, warp, px, py, pz, L, C, acc, lane, gm);
-                } else if (lane == 0) {  // ... but another warp may report that row: this warp's words must be defined
-                    unsigned* brow = bit_row_group<PPT, true>(bits, w, warp);
-#pragma unroll
-                    for (int s = 0; s < PPT; ++s) brow[s] = 0u;
-                }
+                for (int s = 1; s < PPT; ++s) qmin = fminf(qmin, cov_q2(px[s], py[s], pz[s], v3));
+                if (!__any_sync(kFull, !(qmin > v3.w))) continue;
+                ++n_full;
+                const bool g = check_amin
+                                   ? fused_pose_iter<PPT, 1, true, true>(w, ptab, nullptr, warp, px, py, pz, L, C, acc, lane)
+                                   : fused_pose_iter<PPT, 1, false, true>(w, ptab, nullptr, warp, px, py, pz, L, C, acc, lane);
+                if (g) gbits |= 1u << b;
             }
+            if (lane == 0) wg[c] = gbits;
+            warp_gated |= gbits != 0u;
         }
+        float G[PPT];
 #pragma unroll
         for (int s = 0; s < PPT; ++s) {
-            float r = 0.5f, g = 0.25f;  // exactly what the formulas below give for L = 0
+            float r = 0.5f;
+            G[s] = 0.25f;  // exactly what the formulas below give for L = 0
             if (L[s] != 0.f) {
                 r = 1.f / (1.f + expf(-L[s]));
-                g = r * (1.f - r);
+                G[s] = r * (1.f - r);
             }
             if (valid[s]) {
                 const int64_t j = tile * T + lbase + s * 32;
@@ -910,40 +940,92 @@ cov_traj_fused_tiles_kernel(const float* __restrict__ xyz, int64_t n, const floa
                 int64_t jo = j;
                 if (out_index && (store || HAS_UP)) jo = (int64_t)out_index[j];
                 if (store) rewards[jo] = r;
-                if (HAS_UP) g *= upstream[jo];
+                if (HAS_UP) G[s] *= upstream[jo];
             }
-            Gs[lbase + s * 32] = g;
         }
-        __syncthreads();  // bits, G_j, gmask complete
-        // every warp derives the same ascending list of gated poses (identical stores to alist: no barrier needed)
-        int n2 = 0;
-        for (int c0 = 0; c0 < nwords; c0 += 32) {
-            const unsigned word = (c0 + lane < nwords) ? gm[c0 + lane] : 0u;
-            const int cnt = __popc(word);
-            int incl = cnt;
+        // one barrier per tile: protects the stage that is refilled next and tells whether anybody has a gated pair
+        if (!__syncthreads_or(warp_gated ? 1 : 0)) continue;
+        // ------------------------------ phase 2 ------------------------------
+        int listed = 0;
+        for (int c = lane; c < nwords; c += 32) listed += __popc(am[c]);
+        listed = __reduce_add_sync(kFull, listed);
+        // rounds of kSlotPoses listed poses (one round unless the cloud is unordered); slot = rank within the round
+        for (int round0 = 0; round0 < listed; round0 += kSlotPoses) {
+            int rank = 0;
+            for (int c = 0; c < nwords && rank < round0 + kSlotPoses; ++c) {
+                unsigned word = am[c];
+                const int cnt = __popc(word);
+                if (rank + cnt <= round0) {  // the whole word belongs to an earlier round
+                    rank += cnt;
+                    continue;
+                }
+                const unsigned mine = wg[c];
+                while (word) {
+                    const int b = __ffs(word) - 1;
+                    const int w = c * 32 + b;
+                    word &= word - 1;
+                    const int slot = rank - round0;
+                    ++rank;
+                    if (slot < 0) continue;
+                    if (slot >= kSlotPoses) break;
+                    float f0 = 0.f, f1 = 0.f, f2 = 0.f, t0 = 0.f, t1 = 0.f, t2 = 0.f, se = 0.f, sep = 0.f;
+                    if ((mine >> b) & 1u) {
+                        const float4* row = ptab + (size_t)w * COV_ROW_F4;
+                        const float4 v0 = row[0], v1 = row[1], v2 = row[2], v3 = row[3], v4 = row[4], v5 = row[5];
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(kFull, incl, o);
-                if (lane >= o) incl += t;
+                        for (int s = 0; s < PPT; ++s) {
+                            CovEval ev;
+                            const float m = cov_vis<true>(px[s], py[s], pz[s], v0, v1, v2, v3, C, &ev);
+                            const float d = __fsub_rn(m, v4.w);
+                            const bool act = d >= v4.x;  // exactly p >= 0.5, as in phase 1
+                            if (act) {
+                                const float p = __fdiv_rn(d, v4.y);
+                                if (p <= C.hi) {  // clamp backward gate (inclusive)
+                                    float gx, gy, gz;
+                                    cov_vis_grad(m, ev, v0, v1, v2, C, gx, gy, gz);
+                                    const float yx = px[s] - v5.x, yy = py[s] - v5.y, yz = pz[s] - v5.z;
+                                    const float e = G[s] / (p * (1.f - p));
+                                    const float om = e * v4.z;
+                                    f0 += om * gx; f1 += om * gy; f2 += om * gz;
+                                    t0 += om * (gy * yz - gz * yy);
+                                    t1 += om * (gz * yx - gx * yz);
+                                    t2 += om * (gx * yy - gy * yx);
+                                    se += e;
+                                    sep += e * p;
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            f0 += __shfl_xor_sync(kFull, f0, o); f1 += __shfl_xor_sync(kFull, f1, o);
+                            f2 += __shfl_xor_sync(kFull, f2, o); t0 += __shfl_xor_sync(kFull, t0, o);
+                            t1 += __shfl_xor_sync(kFull, t1, o); t2 += __shfl_xor_sync(kFull, t2, o);
+                            se += __shfl_xor_sync(kFull, se, o); sep += __shfl_xor_sync(kFull, sep, o);
+                        }
+                    }
+                    if (lane == 0) {
+                        float4* dst = reinterpret_cast<float4*>(&slots[slot][warp][0]);
+                        dst[0] = make_float4(f0, f1, f2, t0);
+                        dst[1] = make_float4(t1, t2, se, sep);
+                        if (warp == 0) slot_pose[slot] = w;
+                    }
+                }
             }
-            int pos = n2 + incl - cnt;
-            unsigned wv = word;
-            while (wv) {
-                alist[pos++] = (unsigned short)((c0 + lane) * 32 + __ffs(wv) - 1);
-                wv &= wv - 1;
+            __syncthreads();  // this round's partial sums are in the slot table (and nobody reads the stage any more)
+            {
+                const int nslots = (listed - round0) < kSlotPoses ? (listed - round0) : kSlotPoses;
+                const int k = tid >> 3, comp = tid & 7;
+                if (k < nslots) {
+                    float sacc = 0.f;
+#pragma unroll
+                    for (int g = 0; g < kWarps; ++g) sacc += slots[k][g][comp];
+                    accs[(size_t)slot_pose[k] * 8 + comp] += sacc;
+                }
             }
-            n2 += __shfl_sync(kFull, incl, 31);
+            if (round0 + kSlotPoses < listed) __syncthreads();  // the slot table is rewritten by the next round
         }
-        __syncwarp();
-        if (tid < kMaskWords) gmask[buf ^ 1][tid] = 0u;  // next tile's mask: its writers come after the barrier below
-        if (n2 > 0) {
-            // split each listed row over 2^seg_log2 lanes until there are >= 2 tasks per thread
-            int seg_log2 = 0;
-            while ((n2 << seg_log2) < 2 * COV_THREADS && (2 << seg_log2) <= NW && seg_log2 < 5) ++seg_log2;
-            fused_phase2<PPT, true>(ptab, bits, pt, Gs, accs, alist, n2, seg_log2, C, tid);
-        }
-        __syncthreads();  // stage, bits, G_j, alist and gmask[buf] may be reused
     }
+    __syncthreads();
     fused_block_epilogue(accs, W, partials, sumr_partials, sum_r, red, tid);
     if (lane == 0) {
         if (tid == 0 && blockIdx.x == 0) atomicAdd(stats + 0, (unsigned long long)ntiles * kWarps * W);
@@ -956,7 +1038,12 @@ cov_traj_fused_tiles_kernel(const float* __restrict__ xyz, int64_t n, const floa
 // acc[w][0..7] = sum over blocks of the fp32 slabs (fp64, fixed order); acc[W*STRIDE] = base + sum of the blocks'
 // reward sums (base = 0.5 * n for the pruned kernel, whose blocks sum r - 1/2 over the listed tiles only).
 __global__ void cov_traj_reduce_kernel(const float* __restrict__ partials, const double* __restrict__ sumr_partials,
-                                       int nblocks, int W, double base, double* __restrict__ acc) {
+                                       int nblocks, int nblocks_dense, int W, double base,
+                                       const int* __restrict__ dense_flag, double* __restrict__ acc) {
+    if (dense_flag && *dense_flag) {  // the dense kernel did the call: its blocks wrote the slabs and summed r itself
+        base = 0.0;
+        nblocks = nblocks_dense;
+    }
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < W * 8) {
         double s = 0.0;
@@ -1007,7 +1094,7 @@ __global__ void cov_traj_epilogue_kernel(const double* __restrict__ acc, const f
 }
 
 // ==================================================== host ====================================================
-constexpr size_t kSmemCap = 227 * 1024 - 1024;  // opt-in shared memory per block on sm_100, minus static use
+constexpr size_t kSmemCap = (227 - 11) * 1024;  // opt-in shared memory per block on sm_100, minus static use (slot table)
 constexpr int64_t kSeedSamples = 65536;          // pruned pass A: size of the strided sample that seeds the bounds
 constexpr int64_t kDenseBelow = 4 * kSeedSamples;  // clouds this small go straight to the dense pass A
 
@@ -1109,12 +1196,16 @@ const float4* boxes_for_call(const float* xyz, int64_t n, const float* boxes_dev
     return t.boxes;
 }
 
+// dense_frac: hand the call to the dense kernel when more than this fraction of all (tile, pose) pairs is listed
+// (2.0 = never)
 void launch_cull(const float4* boxes, int ppt, int64_t ntiles, const TrajWorkspace& t, int W, const unsigned* gmin,
-                 const unsigned* gmax, float inv_kd, cudaStream_t s) {
+                 const unsigned* gmax, float inv_kd, double dense_frac, cudaStream_t s) {
     const int grid = (int)std::min<int64_t>((ntiles + 7) / 8, (int64_t)cov_sm_count_cached() * 8);
     cov_cull_kernel<<<grid, 256, (size_t)W * sizeof(float4), s>>>(boxes, tile_boxes(ppt), ntiles, t.table, W, gmin, gmax,
-                                                                 inv_kd, t.amask, mask_stride_words(W), t.flags);
-    cov_worklist_kernel<<<1, 1024, 0, s>>>(t.flags, ntiles, t.worklist, t.ints);
+                                                                 inv_kd, t.amask, mask_stride_words(W), t.flags,
+                                                                 reinterpret_cast<unsigned long long*>(t.ints + 4));
+    cov_worklist_kernel<<<1, 1024, 0, s>>>(t.flags, ntiles, t.worklist, t.ints,
+                                           (unsigned long long)(dense_frac * (double)ntiles * (double)W));
 }
 
 }  // namespace
@@ -1200,8 +1291,9 @@ extern "C" int cov_traj_minmax(const float* xyz, int64_t n, const float* poses, 
     const int64_t nsamples = (n + stride - 1) / stride;
     LAUNCH_DENSE(1, 2, 1, nsamples, stride)
 #undef LAUNCH_DENSE
+    cudaMemsetAsync(t.ints, 0, 256, s);
     cov_pose_table_kernel<<<(W + 127) / 128, 128, 0, s>>>(poses, quats, W, K, C, nullptr, t.table, t.ints);
-    launch_cull(boxes, ppt, ntiles, t, W, gmin, gmax, 1.f / C.kd, s);
+    launch_cull(boxes, ppt, ntiles, t, W, gmin, gmax, 1.f / C.kd, 2.0, s);
     unsigned long long* stats = cov_stats_device_ptr();
 #define LAUNCH_TILES(P)                                                                                             \
     {                                                                                                               \
@@ -1232,37 +1324,51 @@ extern "C" int cov_traj_fused(const float* xyz, int64_t n, const float* poses, c
     cudaStream_t s = (cudaStream_t)stream;
     const CovConst C = cov_make_const(cam);
     const bool prune = cov_pruning_enabled() != 0;
-    const int ppt = pick_ppt(n, W, true, prune);
-    if (ppt == 0) {
+    const TrajWorkspace t = carve_workspace(ws, n, W);
+    cudaMemsetAsync(acc, 0, ((size_t)W * COV_ACC_STRIDE + 1) * sizeof(double), s);
+
+    // the dense kernel: the whole call when pruning is off, a stand-by launch behind the pruned kernel otherwise
+    // (it runs only if the cull found nothing to prune: run_flag = ints[2])
+    const int ppt_d = pick_ppt(n, W, true, false);
+    if (ppt_d == 0) {
         cov_set_error("cov_traj_fused: %d poses do not fit in shared memory", W);
         return COV_ERR_UNSUPPORTED;
     }
-    const size_t smem = fused_smem_bytes(W, ppt, prune);
-    const int64_t ntiles = (n + tile_points(ppt) - 1) / tile_points(ppt);
-    const TrajWorkspace t = carve_workspace(ws, n, W);
-    cudaMemsetAsync(acc, 0, ((size_t)W * COV_ACC_STRIDE + 1) * sizeof(double), s);
-    int grid = 1;
-    if (!prune) {
+    auto launch_dense = [&](const int* run_flag) -> int {
+        const size_t smem = fused_smem_bytes(W, ppt_d, false);
+        const int64_t ntiles = (n + tile_points(ppt_d) - 1) / tile_points(ppt_d);
         // phase-2 parallelism: split each pose row over 2^seg_log2 lanes until there are >= 2 tasks per thread
         int seg_log2 = 0;
-        while ((W << seg_log2) < 2 * COV_THREADS && (2 << seg_log2) <= bit_words(ppt) && seg_log2 < 5) ++seg_log2;
+        while ((W << seg_log2) < 2 * COV_THREADS && (2 << seg_log2) <= bit_words(ppt_d) && seg_log2 < 5) ++seg_log2;
+        int grid = 1;
 #define LAUNCH_F(P, UP)                                                                                           \
     {                                                                                                             \
         grid = grid_for(cov_traj_fused_kernel<P, UP, 1>, smem, ntiles);                                           \
         cov_traj_fused_kernel<P, UP, 1><<<grid, COV_THREADS, smem, s>>>(xyz, n, poses, quats, W, K, C, minmax,    \
                                                                         upstream, reward_index, rewards, t.partials, \
-                                                                        t.sumr, acc, seg_log2);                   \
+                                                                        t.sumr, acc, seg_log2, run_flag);         \
     }
         if (upstream) {
-            if (ppt == 4) LAUNCH_F(4, true) else if (ppt == 2) LAUNCH_F(2, true) else LAUNCH_F(1, true)
+            if (ppt_d == 4) LAUNCH_F(4, true) else if (ppt_d == 2) LAUNCH_F(2, true) else LAUNCH_F(1, true)
         } else {
-            if (ppt == 4) LAUNCH_F(4, false) else if (ppt == 2) LAUNCH_F(2, false) else LAUNCH_F(1, false)
+            if (ppt_d == 4) LAUNCH_F(4, false) else if (ppt_d == 2) LAUNCH_F(2, false) else LAUNCH_F(1, false)
         }
 #undef LAUNCH_F
-        cov_traj_reduce_kernel<<<(W * 8 + 255) / 256, 256, 0, s>>>(t.partials, t.sumr, grid, W, 0.0, acc);
+        return grid;
+    };
+    if (!prune) {
+        const int grid = launch_dense(nullptr);
+        cov_traj_reduce_kernel<<<(W * 8 + 255) / 256, 256, 0, s>>>(t.partials, t.sumr, grid, grid, W, 0.0, nullptr, acc);
         return cov_check_launch("cov_traj_fused");
     }
     // pruned: rewards start at 1/2; cull tiles against the gate thresholds; evaluate the listed tiles
+    const int ppt = pick_ppt(n, W, true, true);
+    if (ppt == 0) {
+        cov_set_error("cov_traj_fused: %d poses do not fit in shared memory", W);
+        return COV_ERR_UNSUPPORTED;
+    }
+    const size_t smem = fused_smem_bytes(W, ppt, true);
+    const int64_t ntiles = (n + tile_points(ppt) - 1) / tile_points(ppt);
     const float4* boxes = boxes_for_call(xyz, n, boxes_dev, t, s);
     cudaMemsetAsync(t.ints, 0, 256, s);
     cov_pose_table_kernel<<<(W + 127) / 128, 128, 0, s>>>(poses, quats, W, K, C, minmax, t.table, t.ints);
@@ -1270,8 +1376,9 @@ extern "C" int cov_traj_fused(const float* xyz, int64_t n, const float* poses, c
         const int fgrid = (int)std::min<int64_t>((n + 1023) / 1024, (int64_t)cov_sm_count_cached() * 16);
         cov_fill_kernel<<<fgrid, 256, 0, s>>>(rewards, n, 0.5f);
     }
-    launch_cull(boxes, ppt, ntiles, t, W, nullptr, nullptr, 0.f, s);
+    launch_cull(boxes, ppt, ntiles, t, W, nullptr, nullptr, 0.f, 0.25, s);
     unsigned long long* stats = cov_stats_device_ptr();
+    int grid = 1;
 #define LAUNCH_FT(P, UP)                                                                                          \
     {                                                                                                             \
         grid = grid_for(cov_traj_fused_tiles_kernel<P, UP>, smem, ntiles);                                        \
@@ -1285,7 +1392,9 @@ extern "C" int cov_traj_fused(const float* xyz, int64_t n, const float* poses, c
         if (ppt == 4) LAUNCH_FT(4, false) else if (ppt == 2) LAUNCH_FT(2, false) else LAUNCH_FT(1, false)
     }
 #undef LAUNCH_FT
-    cov_traj_reduce_kernel<<<(W * 8 + 255) / 256, 256, 0, s>>>(t.partials, t.sumr, grid, W, 0.5 * (double)n, acc);
+    const int grid_dense = launch_dense(t.ints + 2);
+    cov_traj_reduce_kernel<<<(W * 8 + 255) / 256, 256, 0, s>>>(t.partials, t.sumr, grid, grid_dense, W, 0.5 * (double)n,
+                                                               t.ints + 2, acc);
     return cov_check_launch("cov_traj_fused");
 }
 
