@@ -321,9 +321,10 @@ __global__ void __launch_bounds__(256) cov_tile_boxes_kernel(const float* __rest
     }
 }
 
-// Cull: one warp per tile.  mask[tile][c] bit i <=> pose 32c+i can matter for some point of the tile; flags[tile] =
-// the mask is not empty.  Pass A passes gmin/gmax (after the seed launch) and the cap is derived here; pass B
-// reads qthr from the table.
+// Cull: mask[tile][c] bit i <=> pose 32c+i can matter for some point of the tile; flags[tile] = the mask is not
+// empty.  One warp per GROUP of 8 consecutive tiles: every pose is tested against the group's box first (one lane
+// per pose), and only the few that pass are tested against the 8 tile boxes (one lane per tile).  Pass A passes
+// gmin/gmax (after the seed launch) and the cap is derived here; pass B reads qthr from the table.
 __global__ void __launch_bounds__(256)
 cov_cull_kernel(const float4* __restrict__ boxes, int boxes_per_tile, int64_t ntiles, const float4* __restrict__ table,
                 int W, const unsigned* __restrict__ gmin, const unsigned* __restrict__ gmax, float inv_kd,
@@ -339,36 +340,59 @@ cov_cull_kernel(const float4* __restrict__ boxes, int boxes_per_tile, int64_t nt
     __syncthreads();
     const float inf = __uint_as_float(0x7f800000u);
     const int nwords = (W + 31) >> 5;
+    const int64_t ngroups = (ntiles + 7) / 8;
+    const int sub = lane >> 3, tl = lane & 7;  // box loads: lane = (pass-local box slot, tile of the group)
     unsigned long long npairs = 0;
-    for (int64_t tile = (int64_t)blockIdx.x * 8 + (tid >> 5); tile < ntiles; tile += (int64_t)gridDim.x * 8) {
+    for (int64_t grp = (int64_t)blockIdx.x * 8 + (tid >> 5); grp < ngroups; grp += (int64_t)gridDim.x * 8) {
+        // lane -> tile tl; the 4 lanes with the same tl share the tile's boxes_per_tile boxes (<= 16)
+        const int64_t tile_l = grp * 8 + tl;
         float4 lo = make_float4(inf, inf, inf, 0.f), hi = make_float4(-inf, -inf, -inf, 0.f);
-        if (lane < boxes_per_tile) {
-            lo = boxes[(tile * boxes_per_tile + lane) * 2];
-            hi = boxes[(tile * boxes_per_tile + lane) * 2 + 1];
+        if (tile_l < ntiles) {
+            for (int b = sub; b < boxes_per_tile; b += 4) {
+                const float4 l2 = boxes[(tile_l * boxes_per_tile + b) * 2], h2 = boxes[(tile_l * boxes_per_tile + b) * 2 + 1];
+                box_union(lo, hi, l2, h2);
+            }
         }
 #pragma unroll
-        for (int o = 1; o < 16; o <<= 1) {  // boxes_per_tile <= 16
+        for (int o = 8; o < 32; o <<= 1) {  // join the 4 lanes of a tile: afterwards every lane holds ITS tile's box
             lo.x = fminf(lo.x, __shfl_xor_sync(kFull, lo.x, o)); lo.y = fminf(lo.y, __shfl_xor_sync(kFull, lo.y, o));
             lo.z = fminf(lo.z, __shfl_xor_sync(kFull, lo.z, o)); hi.x = fmaxf(hi.x, __shfl_xor_sync(kFull, hi.x, o));
             hi.y = fmaxf(hi.y, __shfl_xor_sync(kFull, hi.y, o)); hi.z = fmaxf(hi.z, __shfl_xor_sync(kFull, hi.z, o));
         }
-        lo.x = __shfl_sync(kFull, lo.x, 0); lo.y = __shfl_sync(kFull, lo.y, 0); lo.z = __shfl_sync(kFull, lo.z, 0);
-        hi.x = __shfl_sync(kFull, hi.x, 0); hi.y = __shfl_sync(kFull, hi.y, 0); hi.z = __shfl_sync(kFull, hi.z, 0);
-        unsigned any = 0u;
+        float4 glo = lo, ghi = hi;  // the group's box: join the 8 tiles
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            glo.x = fminf(glo.x, __shfl_xor_sync(kFull, glo.x, o)); glo.y = fminf(glo.y, __shfl_xor_sync(kFull, glo.y, o));
+            glo.z = fminf(glo.z, __shfl_xor_sync(kFull, glo.z, o)); ghi.x = fmaxf(ghi.x, __shfl_xor_sync(kFull, ghi.x, o));
+            ghi.y = fmaxf(ghi.y, __shfl_xor_sync(kFull, ghi.y, o)); ghi.z = fmaxf(ghi.z, __shfl_xor_sync(kFull, ghi.z, o));
+        }
+        unsigned any = 0u;  // lanes 0..7: tile tl has a non-empty mask
         for (int c = 0; c < mask_stride; ++c) {
             const int w = c * 32 + lane;
-            bool active = false;
+            bool cand = false;
             if (c < nwords && w < W) {
                 const float4 v3 = v3s[w];
-                active = !(box_q2lb(lo, hi, v3) > v3.w);  // NaN cap: evaluate
+                cand = !(box_q2lb(glo, ghi, v3) > v3.w);  // NaN cap: evaluate
             }
-            const unsigned bal = __ballot_sync(kFull, active);
-            if (lane == 0) amask_g[tile * mask_stride + c] = bal;
-            any |= bal;
-            npairs += __popc(bal);
+            unsigned gword = __ballot_sync(kFull, cand);
+            unsigned mine = 0u;  // lanes 0..7: word c of tile tl's mask
+            while (gword) {
+                const int b = __ffs(gword) - 1;
+                gword &= gword - 1;
+                const float4 v3 = v3s[c * 32 + b];
+                const bool hit = !(box_q2lb(lo, hi, v3) > v3.w);  // an empty box (+inf, -inf) gives +inf: never hit
+                const unsigned tb = __ballot_sync(kFull, hit) & 0xffu;  // lanes 0..7 speak for the 8 tiles
+                if ((tb >> tl) & 1u) mine |= 1u << b;
+            }
+            if (lane < 8 && tile_l < ntiles) {
+                amask_g[tile_l * mask_stride + c] = mine;
+                any |= mine;
+                npairs += __popc(mine);
+            }
         }
-        if (lane == 0) flags[tile] = any != 0u;
+        if (lane < 8 && tile_l < ntiles) flags[tile_l] = any != 0u;
     }
+    npairs = __reduce_add_sync(kFull, (unsigned)npairs);
     if (lane == 0 && npairs) atomicAdd(listed_pairs, npairs);
 }
 
@@ -1044,16 +1068,20 @@ __global__ void cov_traj_reduce_kernel(const float* __restrict__ partials, const
         base = 0.0;
         nblocks = nblocks_dense;
     }
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < W * 8) {
-        double s = 0.0;
-        for (int b = 0; b < nblocks; ++b) s += (double)partials[(size_t)b * W * 8 + i];
-        acc[(size_t)(i >> 3) * COV_ACC_STRIDE + (i & 7)] = s;
-    }
-    if (i == 0) {
-        double s = 0.0;
-        for (int b = 0; b < nblocks; ++b) s += sumr_partials[b];
-        acc[(size_t)W * COV_ACC_STRIDE] = base + s;
+    // 8 lanes per output: lane q adds blocks q, q+8, ... in order, then a fixed xor tree joins the 8 partial sums
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = gid >> 3, q = gid & 7;
+    double s = 0.0;
+    if (i < W * 8)
+        for (int b = q; b < nblocks; b += 8) s += (double)partials[(size_t)b * W * 8 + i];
+    else if (i == W * 8)
+        for (int b = q; b < nblocks; b += 8) s += sumr_partials[b];
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (q == 0) {
+        if (i < W * 8) acc[(size_t)(i >> 3) * COV_ACC_STRIDE + (i & 7)] = s;
+        else if (i == W * 8) acc[(size_t)W * COV_ACC_STRIDE] = base + s;
     }
 }
 
@@ -1200,7 +1228,7 @@ const float4* boxes_for_call(const float* xyz, int64_t n, const float* boxes_dev
 // (2.0 = never)
 void launch_cull(const float4* boxes, int ppt, int64_t ntiles, const TrajWorkspace& t, int W, const unsigned* gmin,
                  const unsigned* gmax, float inv_kd, double dense_frac, cudaStream_t s) {
-    const int grid = (int)std::min<int64_t>((ntiles + 7) / 8, (int64_t)cov_sm_count_cached() * 8);
+    const int grid = (int)std::min<int64_t>((ntiles + 63) / 64, (int64_t)cov_sm_count_cached() * 8);
     cov_cull_kernel<<<grid, 256, (size_t)W * sizeof(float4), s>>>(boxes, tile_boxes(ppt), ntiles, t.table, W, gmin, gmax,
                                                                  inv_kd, t.amask, mask_stride_words(W), t.flags,
                                                                  reinterpret_cast<unsigned long long*>(t.ints + 4));
@@ -1358,7 +1386,7 @@ extern "C" int cov_traj_fused(const float* xyz, int64_t n, const float* poses, c
     };
     if (!prune) {
         const int grid = launch_dense(nullptr);
-        cov_traj_reduce_kernel<<<(W * 8 + 255) / 256, 256, 0, s>>>(t.partials, t.sumr, grid, grid, W, 0.0, nullptr, acc);
+        cov_traj_reduce_kernel<<<((W * 8 + 1) * 8 + 255) / 256, 256, 0, s>>>(t.partials, t.sumr, grid, grid, W, 0.0, nullptr, acc);
         return cov_check_launch("cov_traj_fused");
     }
     // pruned: rewards start at 1/2; cull tiles against the gate thresholds; evaluate the listed tiles
@@ -1393,7 +1421,7 @@ extern "C" int cov_traj_fused(const float* xyz, int64_t n, const float* poses, c
     }
 #undef LAUNCH_FT
     const int grid_dense = launch_dense(t.ints + 2);
-    cov_traj_reduce_kernel<<<(W * 8 + 255) / 256, 256, 0, s>>>(t.partials, t.sumr, grid, grid_dense, W, 0.5 * (double)n,
+    cov_traj_reduce_kernel<<<((W * 8 + 1) * 8 + 255) / 256, 256, 0, s>>>(t.partials, t.sumr, grid, grid_dense, W, 0.5 * (double)n,
                                                                t.ints + 2, acc);
     return cov_check_launch("cov_traj_fused");
 }
