@@ -106,10 +106,13 @@ int cov_traj_epilogue(const double* acc_dev, const float* minmax_dev, const floa
 /* Forward-only candidate sweep: n_traj trajectories x poses_per_traj poses each, sharing one cloud.
  * ref: no reference implementation (BASELINE config 5); semantics = ModelTraj.forward per trajectory
  * with every pose evaluated.  sum_rewards_dev[t] += sum_j rewards_j(t) over this shard (doubles,
- * zero it first); minmax_dev is (2, n_traj*poses_per_traj) produced by cov_traj_minmax. */
+ * zero it first); minmax_dev is (2, n_traj*poses_per_traj) produced by cov_traj_minmax.
+ * boxes_dev as for cov_traj_fused; workspace_dev: cov_traj_workspace_bytes(n, min(n_traj*poses_per_traj, 2048))
+ * bytes, 256-byte aligned (the pruned pipeline runs the trajectories in chunks of pose-table size). */
 int cov_sweep_rewards(const float* xyz_dev, int64_t n, const float* poses_dev, const float* quats_dev, int n_traj,
-                      int poses_per_traj, const float* K_dev, const cov_camera* cam, const float* minmax_dev,
-                      double* sum_rewards_dev, void* stream);
+                      int poses_per_traj, const float* K_dev, const cov_camera* cam, const float* boxes_dev,
+                      const float* minmax_dev, double* sum_rewards_dev, void* workspace_dev, size_t workspace_bytes,
+                      void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Multi-camera front end: n_body waypoints (x, y, z, yaw) x n_cams fixed extrinsics -> camera poses in the layout

@@ -236,7 +236,17 @@ def test_sweep_matches_per_trajectory_forward(dev, mod):
     ang = yaw[None, :] + gen.normal(0, 0.3, (T, Pn))
     quats = np.stack([np.cos(ang / 2), 0 * ang, 0 * ang, np.sin(ang / 2)], -1).astype(np.float32)
     K, Wd, Hd = tools.load_intrinsics(dev)
+    from trajectory_optimization_b200 import _lib
     means = ops.sweep_rewards(pts, torch.from_numpy(poses.astype(np.float32)), torch.from_numpy(quats), K, Wd, Hd)
+    try:  # the dense sweep (pruning off) and the pruned pipeline agree; so does the pruned one on the cloud as given
+        _lib.lib().cov_set_pruning(0)
+        means_dense = ops.sweep_rewards(pts, torch.from_numpy(poses.astype(np.float32)), torch.from_numpy(quats), K, Wd, Hd)
+    finally:
+        _lib.lib().cov_set_pruning(1)
+    means_unsorted = ops.sweep_rewards(pts, torch.from_numpy(poses.astype(np.float32)), torch.from_numpy(quats), K, Wd, Hd,
+                                       presorted=True)
+    assert rel_err(means.cpu().numpy(), means_dense.cpu().numpy()) < 1e-9
+    assert rel_err(means_unsorted.cpu().numpy(), means_dense.cpu().numpy()) < 1e-9
     for t in range(0, T, 6):
         _, mean = ops.coverage_traj(pts, torch.from_numpy(poses[t].astype(np.float32)).to(dev),
                                     torch.from_numpy(quats[t]).to(dev), K, Wd, Hd)

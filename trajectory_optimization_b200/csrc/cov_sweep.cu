@@ -102,9 +102,10 @@ cov_sweep_kernel(const float* __restrict__ xyz, int64_t n, const float* __restri
 
 }  // namespace
 
-extern "C" int cov_sweep_rewards(const float* xyz, int64_t n, const float* poses, const float* quats, int n_traj,
-                                 int per_traj, const float* K, const cov_camera* cam, const float* minmax,
-                                 double* sum_rewards, void* stream) {
+// Dense sweep (cov_set_pruning(0)); the pruned pipeline and the C entry point are in cov_traj.cu.
+int cov_sweep_rewards_dense(const float* xyz, int64_t n, const float* poses, const float* quats, int n_traj,
+                            int per_traj, const float* K, const cov_camera* cam, const float* minmax,
+                            double* sum_rewards, void* stream) {
     if (!xyz || n <= 0 || !poses || !quats || n_traj <= 0 || per_traj <= 0 || !K || !cam || !minmax || !sum_rewards) {
         cov_set_error("cov_sweep_rewards: bad argument");
         return COV_ERR_ARG;

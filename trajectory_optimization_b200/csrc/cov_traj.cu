@@ -633,7 +633,7 @@ __device__ __forceinline__ bool fused_pose_iter(int w, const float4* __restrict_
                     const float p = __fmul_rn(d, v4.z);
                     const float qc = fminf(p, C.hi);
                     L[s] += COV_LN2_F * cov_lg2(qc * cov_rcp(1.f - qc));
-                    if (d == v4.y) tie_accumulate(px[s], py[s], pz[s], row, C, acc, (w + u) * COV_ACC_STRIDE + 8);
+                    if (acc && d == v4.y) tie_accumulate(px[s], py[s], pz[s], row, C, acc, (w + u) * COV_ACC_STRIDE + 8);
                 }
             }
         }
@@ -1059,6 +1059,122 @@ cov_traj_fused_tiles_kernel(const float* __restrict__ xyz, int64_t n, const floa
     }
 }
 
+// ---- candidate sweep, pruned (BASELINE config 5): forward only, per-trajectory sum_j r_j ----
+// Poses are trajectory-major (pose = traj * per_traj + i), so walking a tile's pose mask in ascending order visits the
+// trajectories one after the other: a warp keeps the log-odds sums of its points for the current trajectory, and when
+// the trajectory changes it adds sum_j (sigmoid(L_j) - 1/2) to that trajectory's total (fp64 shared atomic).
+// Trajectories no pose of which is listed for a tile contribute exactly 1/2 per point: 0.5 * n is added once.
+template <int PPT>
+__global__ void __launch_bounds__(COV_THREADS, 2)
+cov_sweep_tiles_kernel(const float* __restrict__ xyz, int64_t n, const float4* __restrict__ table, int W, int per_traj,
+                       int n_traj, CovConst C, const float4* __restrict__ boxes, const unsigned* __restrict__ amask_g,
+                       int mask_stride, const int* __restrict__ worklist, const int* __restrict__ count_ptr,
+                       double* __restrict__ sum_out) {
+    constexpr int T = tile_points(PPT);
+    constexpr int NB = tile_boxes(PPT);
+    constexpr int SF = stage_floats(PPT);
+    constexpr int WB = (32 * PPT >= kBoxPts) ? (32 * PPT / kBoxPts) : 1;
+    extern __shared__ float4 smem4[];
+    float4* ptab = smem4;
+    float* stage = reinterpret_cast<float*>(smem4) + fused_stage_offset_floats(W);
+    double* ssum = reinterpret_cast<double*>(stage + 2 * SF);
+    __shared__ __align__(8) unsigned long long mbar[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        mbar_fence_init();
+    }
+    for (int i = tid; i < W * COV_ROW_F4; i += COV_THREADS) ptab[i] = table[i];
+    for (int t = tid; t < n_traj; t += COV_THREADS) ssum[t] = 0.0;
+    __syncthreads();
+    const int count = count_ptr[0];
+    const int64_t nfull = n / T;
+    const int nwords = (W + 31) >> 5;
+    unsigned uses0 = 0, uses1 = 0;
+    if (tid == 0 && (int)blockIdx.x < count)
+        stage_issue<PPT>(stage, &mbar[0], xyz, boxes, amask_g, mask_stride, (int64_t)worklist[blockIdx.x], nfull);
+    int buf = 0;
+    for (int i = blockIdx.x; i < count; i += gridDim.x, buf ^= 1) {
+        const int64_t tile = worklist[i];
+        if (tid == 0 && i + (int)gridDim.x < count)
+            stage_issue<PPT>(stage + (buf ^ 1) * SF, &mbar[buf ^ 1], xyz, boxes, amask_g, mask_stride,
+                             (int64_t)worklist[i + gridDim.x], nfull);
+        if (buf == 0) mbar_wait(&mbar[0], uses0++ & 1u);
+        else mbar_wait(&mbar[1], uses1++ & 1u);
+        const float* st = stage + buf * SF;
+        float px[PPT], py[PPT], pz[PPT], L[PPT];
+        bool valid[PPT];
+        const int lbase = warp * (32 * PPT) + lane;
+        if (tile < nfull) {
+#pragma unroll
+            for (int s = 0; s < PPT; ++s) {
+                valid[s] = true;
+                px[s] = st[(lbase + s * 32) * 3];
+                py[s] = st[(lbase + s * 32) * 3 + 1];
+                pz[s] = st[(lbase + s * 32) * 3 + 2];
+            }
+        } else {
+#pragma unroll
+            for (int s = 0; s < PPT; ++s) {
+                const int64_t j = tile * T + lbase + s * 32;
+                valid[s] = j < n;
+                px[s] = valid[s] ? __ldg(xyz + j * 3) : 3.0e18f;  // past the end: m = 0 exactly, never gated
+                py[s] = valid[s] ? __ldg(xyz + j * 3 + 1) : 3.0e18f;
+                pz[s] = valid[s] ? __ldg(xyz + j * 3 + 2) : 3.0e18f;
+            }
+        }
+        const float4* tb = reinterpret_cast<const float4*>(st + T * 3);
+        const int b0 = (warp * 32 * PPT) / kBoxPts;
+        float4 wlo = tb[2 * b0], whi = tb[2 * b0 + 1];
+#pragma unroll
+        for (int k = 1; k < WB; ++k) box_union(wlo, whi, tb[2 * (b0 + k)], tb[2 * (b0 + k) + 1]);
+        const unsigned* am = reinterpret_cast<const unsigned*>(st + T * 3 + NB * 8);
+        int cur = -1;      // trajectory whose log-odds sums are in L
+        bool touched = false;
+        auto flush = [&]() {
+            if (cur >= 0 && touched) {
+                float a = 0.f;
+#pragma unroll
+                for (int s = 0; s < PPT; ++s)
+                    if (valid[s] && L[s] != 0.f) a += 1.f / (1.f + expf(-L[s])) - 0.5f;
+                a = cov_warp_sum(a);
+                if (lane == 0 && a != 0.f) atomicAdd(ssum + cur, (double)a);
+            }
+        };
+        for (int c = 0; c < nwords; ++c) {
+            unsigned word = am[c];
+            while (word) {
+                const int w = c * 32 + __ffs(word) - 1;
+                word &= word - 1;
+                const float4 v3 = ptab[(size_t)w * COV_ROW_F4 + 3];
+                if (box_q2lb(wlo, whi, v3) > v3.w) continue;
+                float qmin = cov_q2(px[0], py[0], pz[0], v3);
+#pragma unroll
+                for (int s = 1; s < PPT; ++s) qmin = fminf(qmin, cov_q2(px[s], py[s], pz[s], v3));
+                if (!__any_sync(kFull, !(qmin > v3.w))) continue;
+                const int t = w / per_traj;
+                if (t != cur) {
+                    flush();
+                    cur = t;
+                    touched = false;
+#pragma unroll
+                    for (int s = 0; s < PPT; ++s) L[s] = 0.f;
+                }
+                touched |= fused_pose_iter<PPT, 1, false, true>(w, ptab, nullptr, warp, px, py, pz, L, C, nullptr, lane);
+            }
+        }
+        flush();
+        __syncthreads();  // every warp is done with this stage before it is refilled
+    }
+    __syncthreads();
+    for (int t = tid; t < n_traj; t += COV_THREADS) {
+        double v = ssum[t];
+        if (blockIdx.x == 0) v += 0.5 * (double)n;
+        if (v != 0.0) atomicAdd(sum_out + t, v);
+    }
+}
+
 // acc[w][0..7] = sum over blocks of the fp32 slabs (fp64, fixed order); acc[W*STRIDE] = base + sum of the blocks'
 // reward sums (base = 0.5 * n for the pruned kernel, whose blocks sum r - 1/2 over the listed tiles only).
 __global__ void cov_traj_reduce_kernel(const float* __restrict__ partials, const double* __restrict__ sumr_partials,
@@ -1424,6 +1540,57 @@ extern "C" int cov_traj_fused(const float* xyz, int64_t n, const float* poses, c
     cov_traj_reduce_kernel<<<((W * 8 + 1) * 8 + 255) / 256, 256, 0, s>>>(t.partials, t.sumr, grid, grid_dense, W, 0.5 * (double)n,
                                                                t.ints + 2, acc);
     return cov_check_launch("cov_traj_fused");
+}
+
+extern "C" int cov_sweep_rewards(const float* xyz, int64_t n, const float* poses, const float* quats, int n_traj,
+                                 int per_traj, const float* K, const cov_camera* cam, const float* boxes_dev,
+                                 const float* minmax, double* sum_rewards, void* ws, size_t ws_bytes, void* stream) {
+    if (!xyz || n <= 0 || !poses || !quats || n_traj <= 0 || per_traj <= 0 || !K || !cam || !minmax || !sum_rewards) {
+        cov_set_error("cov_sweep_rewards: bad argument");
+        return COV_ERR_ARG;
+    }
+    if (!cov_pruning_enabled())
+        return cov_sweep_rewards_dense(xyz, n, poses, quats, n_traj, per_traj, K, cam, minmax, sum_rewards, stream);
+    // trajectories per launch: pose table + two stages + per-trajectory sums within ~100 KB (two blocks per SM)
+    constexpr int PPT = 4;
+    auto smem_for = [&](int nt) {
+        return (size_t)fused_stage_offset_floats(nt * per_traj) * 4 + 2 * (size_t)stage_floats(PPT) * 4 + (size_t)nt * sizeof(double);
+    };
+    if (smem_for(1) > kSmemCap || per_traj > 32 * kMaskWords) {
+        cov_set_error("cov_sweep_rewards: %d poses per trajectory do not fit in shared memory", per_traj);
+        return COV_ERR_UNSUPPORTED;
+    }
+    int chunk = 1;
+    while (chunk < n_traj && smem_for(chunk + 1) <= 100 * 1024 && (chunk + 1) * per_traj <= 32 * kMaskWords) ++chunk;
+    const int Wc = chunk * per_traj;
+    if (!ws || ws_bytes < cov_traj_workspace_bytes(n, Wc) || (((uintptr_t)ws) & 255) || (((uintptr_t)xyz) & 15)) {
+        cov_set_error("cov_sweep_rewards: workspace missing, misaligned or smaller than cov_traj_workspace_bytes(n, %d) = %zu",
+                      Wc, cov_traj_workspace_bytes(n, Wc));
+        return COV_ERR_WORKSPACE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const CovConst C = cov_make_const(cam);
+    const TrajWorkspace t = carve_workspace(ws, n, Wc);
+    const float4* boxes = boxes_for_call(xyz, n, boxes_dev, t, s);
+    const int W = n_traj * per_traj;
+    const int64_t ntiles = (n + tile_points(PPT) - 1) / tile_points(PPT);
+    float* mm = reinterpret_cast<float*>(t.partials);  // the chunk's minima and maxima, contiguous (2 * Wc floats)
+    for (int t0 = 0; t0 < n_traj; t0 += chunk) {
+        const int nt = (n_traj - t0 < chunk) ? n_traj - t0 : chunk;
+        const int w0 = t0 * per_traj, Wn = nt * per_traj;
+        cudaMemcpyAsync(mm, minmax + w0, (size_t)Wn * sizeof(float), cudaMemcpyDeviceToDevice, s);
+        cudaMemcpyAsync(mm + Wn, minmax + W + w0, (size_t)Wn * sizeof(float), cudaMemcpyDeviceToDevice, s);
+        cudaMemsetAsync(t.ints, 0, 256, s);
+        cov_pose_table_kernel<<<(Wn + 127) / 128, 128, 0, s>>>(poses + 3 * (size_t)w0, quats + 4 * (size_t)w0, Wn, K, C, mm,
+                                                              t.table, t.ints);
+        launch_cull(boxes, PPT, ntiles, t, Wn, nullptr, nullptr, 0.f, 2.0, s);
+        const size_t smem = smem_for(nt);
+        const int grid = grid_for(cov_sweep_tiles_kernel<PPT>, smem, ntiles);
+        cov_sweep_tiles_kernel<PPT><<<grid, COV_THREADS, smem, s>>>(xyz, n, t.table, Wn, per_traj, nt, C, boxes, t.amask,
+                                                                   mask_stride_words(Wn), t.worklist, t.ints,
+                                                                   sum_rewards + t0);
+    }
+    return cov_check_launch("cov_sweep_rewards");
 }
 
 extern "C" int cov_traj_epilogue(const double* acc, const float* minmax, const float* quats, int W, int64_t n_total,

@@ -268,10 +268,14 @@ def spatial_sort(points):
 
 @torch.no_grad()
 def sweep_rewards(points, poses, quats, intrins, img_width, img_height, min_dist=1.0, max_dist=5.0, eps=1e-6,
-                  n_total=None, group=None, boxes=None):
-    """Forward-only mean reward of many candidate trajectories: poses (T, P, 3), quats (T, P, 4) -> (T,) fp64."""
+                  n_total=None, group=None, boxes=None, presorted=False):
+    """Forward-only mean reward of many candidate trajectories: poses (T, P, 3), quats (T, P, 4) -> (T,) fp64.
+    The cloud is Morton-ordered first (no per-point output exists, so the order is free) unless `presorted`;
+    callers that sweep the same cloud repeatedly order it once (`spatial_sort`, `tile_boxes`) and pass both."""
     L = _lib.lib()
     pts = _dev_f32(points, what="points")
+    if not presorted and boxes is None and pts.shape[0] > 0:
+        pts, _ = spatial_sort(pts)
     dev = pts.device
     T, Pn = poses.shape[0], poses.shape[1]
     P = _dev_f32(poses, dev, "poses").reshape(-1, 3)
@@ -282,7 +286,7 @@ def sweep_rewards(points, poses, quats, intrins, img_width, img_height, min_dist
     minmax = torch.empty(2 * W, dtype=torch.float32, device=dev)
     chunk = L.cov_traj_max_poses()
     boxes = tile_boxes(pts) if boxes is None else boxes
-    ws_bytes = L.cov_traj_workspace_bytes(n, min(W, chunk))
+    ws_bytes = L.cov_traj_workspace_bytes(n, min(W, 2048))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     for w0 in range(0, W, chunk):  # pass A reuses the trajectory kernel, one pose-table-full at a time
         w1 = min(W, w0 + chunk)
@@ -297,8 +301,8 @@ def sweep_rewards(points, poses, quats, intrins, img_width, img_height, min_dist
         _all_reduce(minmax[:W], mn, group)
         _all_reduce(minmax[W:], mx, group)
     sums = torch.zeros(T, dtype=torch.float64, device=dev)
-    _lib.check(L.cov_sweep_rewards(_ptr(pts), n, _ptr(P), _ptr(Q), T, Pn, _ptr(Kd), ctypes.byref(cam), _ptr(minmax),
-                                   _ptr(sums), _stream()), "cov_sweep_rewards")
+    _lib.check(L.cov_sweep_rewards(_ptr(pts), n, _ptr(P), _ptr(Q), T, Pn, _ptr(Kd), ctypes.byref(cam), _ptr(boxes),
+                                   _ptr(minmax), _ptr(sums), _ptr(ws), ws_bytes, _stream()), "cov_sweep_rewards")
     if group is not None:
         _all_reduce(sums, _reduce_ops()[2], group)
     return sums / float(n if n_total is None else n_total)
