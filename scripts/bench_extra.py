@@ -64,6 +64,18 @@ torch.cuda.synchronize()
 wall = (time.perf_counter() - t0) / 200 * 1e3
 print(json.dumps({"config": "c1: ModelPose opt step (zero_grad+fwd+bwd+Adam), 100k points", "gpu_ms_per_step": ms,
                   "wall_ms_per_step": wall, "evals_per_s": 1e5 / (wall * 1e-3)}), flush=True)
+from trajectory_optimization_b200.graphs import GraphedStep  # noqa: E402
+mg = model.ModelPose(pts, torch.tensor([[6.0, 2.0, 0.0]]), torch.tensor([[0.92, 0.0, 0.0, 0.39]]), K, iw, ih, device=dev)
+optg = torch.optim.Adam([{"params": [mg.trans], "lr": 0.02}, {"params": [mg.quat], "lr": 0.02}], capturable=True)
+gstep = GraphedStep(mg, optg)
+ms = events(gstep.step, 500)
+t0 = time.perf_counter()
+for _ in range(500):
+    gstep.step()
+torch.cuda.synchronize()
+wall = (time.perf_counter() - t0) / 500 * 1e3
+print(json.dumps({"config": "c1: ModelPose opt step as one CUDA graph (graphs.GraphedStep), 100k points", "gpu_ms_per_step": ms,
+                  "wall_ms_per_step": wall}), flush=True)
 # ModelPose kernel alone at 1e8 points vs HBM
 big = box(100_000_000, 1)
 T = torch.tensor([[6.0, 2.0, 0.0]], device=dev, requires_grad=True)
