@@ -294,6 +294,48 @@ __global__ void cov_pose_table_kernel(const float* __restrict__ poses, const flo
     for (int i = 0; i < COV_ROW_F4; ++i) table[(size_t)w * COV_ROW_F4 + i] = row[i];
 }
 
+// Seed of the pruned pass A: every `stride`-th point against all poses (dense), so that the cull starts from a good
+// lower bound of each maximum and knows which minima are exactly 0.  Grid = (sample blocks) x (chunks of 32 poses):
+// a thread owns one sample point, a block 32 pose rows of the table; per pose one REDUX pair per warp, the 8 warps
+// meet in shared memory, 32 global atomics per block.
+__global__ void __launch_bounds__(COV_THREADS)
+cov_traj_seed_kernel(const float* __restrict__ xyz, int64_t nsamples, int64_t stride, const float4* __restrict__ table,
+                     int W, CovConst C, unsigned* __restrict__ gmin, unsigned* __restrict__ gmax) {
+    __shared__ float4 rows[32 * 4];
+    __shared__ unsigned smn[32], smx[32];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int w0 = blockIdx.y * 32;
+    const int wn = (W - w0 < 32) ? (W - w0) : 32;
+    if (tid < wn * 4) rows[tid] = table[(size_t)(w0 + (tid >> 2)) * COV_ROW_F4 + (tid & 3)];
+    if (tid < 32) {
+        smn[tid] = 0x7f800000u;
+        smx[tid] = 0u;
+    }
+    __syncthreads();
+    int64_t j = (int64_t)blockIdx.x * COV_THREADS + tid;
+    j = (j < nsamples ? j : nsamples - 1) * stride;  // a duplicate cannot change a min or a max
+    const float x = __ldg(xyz + j * 3), y = __ldg(xyz + j * 3 + 1), z = __ldg(xyz + j * 3 + 2);
+    unsigned keep_mn = 0x7f800000u, keep_mx = 0u;
+    for (int i = 0; i < wn; ++i) {
+        const float m = cov_vis<false>(x, y, z, rows[4 * i], rows[4 * i + 1], rows[4 * i + 2], rows[4 * i + 3], C, nullptr);
+        const unsigned umn = __reduce_min_sync(kFull, __float_as_uint(m));
+        const unsigned umx = __reduce_max_sync(kFull, __float_as_uint(m));
+        if (lane == i) {
+            keep_mn = umn;
+            keep_mx = umx;
+        }
+    }
+    if (lane < wn) {
+        atomicMin(smn + lane, keep_mn);
+        atomicMax(smx + lane, keep_mx);
+    }
+    __syncthreads();
+    if (tid < wn) {
+        atomicMin(gmin + w0 + tid, smn[tid]);
+        atomicMax(gmax + w0 + tid, smx[tid]);
+    }
+}
+
 // Bounding boxes of runs of kBoxPts consecutive points: boxes[2b] = (lo, 0), boxes[2b+1] = (hi, 0); boxes past the
 // end of the cloud are empty (+inf, -inf).  One warp per box.
 __global__ void __launch_bounds__(256) cov_tile_boxes_kernel(const float* __restrict__ xyz, int64_t n, int64_t nboxes,
@@ -1019,19 +1061,39 @@ cov_traj_fused_tiles_kernel(const float* __restrict__ xyz, int64_t n, const floa
                                 }
                             }
                         }
+                        // 8 sums over 32 lanes in 9 shuffles: halve the number of values a lane carries at offsets 16,
+                        // 8, 4 (a lane keeps the half its lane bit selects and hands the other half over), then two
+                        // plain steps; lane l ends with component (l>>2)&7 ... in bit order (16,8,4) -> (4,2,1)
+                        float v[8] = {f0, f1, f2, t0, t1, t2, se, sep};
+                        {
+                            const bool up = (lane & 16) != 0;
 #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) {
-                            f0 += __shfl_xor_sync(kFull, f0, o); f1 += __shfl_xor_sync(kFull, f1, o);
-                            f2 += __shfl_xor_sync(kFull, f2, o); t0 += __shfl_xor_sync(kFull, t0, o);
-                            t1 += __shfl_xor_sync(kFull, t1, o); t2 += __shfl_xor_sync(kFull, t2, o);
-                            se += __shfl_xor_sync(kFull, se, o); sep += __shfl_xor_sync(kFull, sep, o);
+                            for (int q = 0; q < 4; ++q) {
+                                const float keep = up ? v[q + 4] : v[q], send = up ? v[q] : v[q + 4];
+                                v[q] = keep + __shfl_xor_sync(kFull, send, 16);
+                            }
                         }
+                        {
+                            const bool up = (lane & 8) != 0;
+#pragma unroll
+                            for (int q = 0; q < 2; ++q) {
+                                const float keep = up ? v[q + 2] : v[q], send = up ? v[q] : v[q + 2];
+                                v[q] = keep + __shfl_xor_sync(kFull, send, 8);
+                            }
+                        }
+                        {
+                            const bool up = (lane & 4) != 0;
+                            const float keep = up ? v[1] : v[0], send = up ? v[0] : v[1];
+                            v[0] = keep + __shfl_xor_sync(kFull, send, 4);
+                        }
+                        v[0] += __shfl_xor_sync(kFull, v[0], 2);
+                        v[0] += __shfl_xor_sync(kFull, v[0], 1);
+                        f0 = v[0];
                     }
-                    if (lane == 0) {
-                        float4* dst = reinterpret_cast<float4*>(&slots[slot][warp][0]);
-                        dst[0] = make_float4(f0, f1, f2, t0);
-                        dst[1] = make_float4(t1, t2, se, sep);
-                        if (warp == 0) slot_pose[slot] = w;
+                    if ((lane & 3) == 0) {
+                        const int comp = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                        slots[slot][warp][comp] = f0;  // 0 when this warp has no gated pair for the pose
+                        if (tid == 0) slot_pose[slot] = w;
                     }
                 }
             }
@@ -1239,7 +1301,7 @@ __global__ void cov_traj_epilogue_kernel(const double* __restrict__ acc, const f
 
 // ==================================================== host ====================================================
 constexpr size_t kSmemCap = (227 - 11) * 1024;  // opt-in shared memory per block on sm_100, minus static use (slot table)
-constexpr int64_t kSeedSamples = 65536;          // pruned pass A: size of the strided sample that seeds the bounds
+constexpr int64_t kSeedSamples = 16384;          // pruned pass A: size of the strided sample that seeds the bounds
 constexpr int64_t kDenseBelow = 4 * kSeedSamples;  // clouds this small go straight to the dense pass A
 
 int pick_ppt(int64_t n, int W, bool fused, bool prune) {
@@ -1428,15 +1490,18 @@ extern "C" int cov_traj_minmax(const float* xyz, int64_t n, const float* poses, 
         else LAUNCH_DENSE(1, 2, 1, n, 1)
         return cov_check_launch("cov_traj_minmax");
     }
+#undef LAUNCH_DENSE
     // pruned: seed the bounds on a strided sample, cull tiles against them, evaluate the listed tiles
     const TrajWorkspace t = carve_workspace(ws, n, W);
     const float4* boxes = boxes_for_call(xyz, n, boxes_dev, t, s);
-    const int64_t stride = (n + kSeedSamples - 1) / kSeedSamples;
-    const int64_t nsamples = (n + stride - 1) / stride;
-    LAUNCH_DENSE(1, 2, 1, nsamples, stride)
-#undef LAUNCH_DENSE
     cudaMemsetAsync(t.ints, 0, 256, s);
     cov_pose_table_kernel<<<(W + 127) / 128, 128, 0, s>>>(poses, quats, W, K, C, nullptr, t.table, t.ints);
+    {
+        const int64_t stride = (n + kSeedSamples - 1) / kSeedSamples;
+        const int64_t nsamples = (n + stride - 1) / stride;
+        const dim3 sgrid((unsigned)((nsamples + COV_THREADS - 1) / COV_THREADS), (unsigned)((W + 31) / 32));
+        cov_traj_seed_kernel<<<sgrid, COV_THREADS, 0, s>>>(xyz, nsamples, stride, t.table, W, C, gmin, gmax);
+    }
     launch_cull(boxes, ppt, ntiles, t, W, gmin, gmax, 1.f / C.kd, 2.0, s);
     unsigned long long* stats = cov_stats_device_ptr();
 #define LAUNCH_TILES(P)                                                                                             \
