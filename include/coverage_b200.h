@@ -157,6 +157,25 @@ size_t cov_hpr_hull_workspace_bytes(int64_t n);
 int cov_hpr_hull(const float* flipped_dev, int64_t n, uint8_t* vertex_mask_dev, int32_t* info_dev,
                  void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * PointCloud2 payload <-> xyz on the device (keeps the host out of the per-message path).
+ * ref: src/pointcloud_utils.py:58-80 (pointcloud2_to_array), :180-198 (get_xyz_points, pointcloud2_to_xyz_array),
+ *      :290-338 (xyz_array_to_pointcloud2, xyzi_array_to_pointcloud2).
+ *   data_dev: the message's `data` bytes on the device, n = width*height records of point_step bytes (little
+ *   endian, as the reference assumes); off_x/y/z: byte offsets of the x, y, z fields; datatype: their PointField
+ *   datatype, 7 = FLOAT32 or 8 = FLOAT64 (converted to fp32); fields need not be aligned.
+ *   remove_nans != 0: keep only points whose x, y, z are all finite, order preserved (np.isfinite mask).
+ *   xyz_dev (n,3) fp32 out, first *count_dev rows valid; count_dev int64 out.
+ *   cov_xyz_to_pc2: (n,3) fp32 [+ (n) fp32 fourth field, or NULL] -> n records of 12 [16] bytes;
+ *   is_dense_dev (int) != 0 iff every value written is finite (the message's is_dense).
+ * ------------------------------------------------------------------------------------------ */
+size_t cov_pc2_workspace_bytes(int64_t n);
+int cov_pc2_to_xyz(const uint8_t* data_dev, int64_t n, int point_step, int off_x, int off_y, int off_z, int datatype,
+                   int remove_nans, float* xyz_dev, int64_t* count_dev, void* workspace_dev, size_t workspace_bytes,
+                   void* stream);
+int cov_xyz_to_pc2(const float* xyz_dev, const float* extra_dev, int64_t n, uint8_t* data_dev, int* is_dense_dev,
+                   void* stream);
+
 /* Exact pruning of (point, pose) pairs in cov_traj_minmax / cov_traj_fused (default on): a pair whose distance
  * Gaussian alone bounds m below what could matter (a sampled lower bound of the maximum in pass A once a zero
  * minimum is known; the gate threshold in pass B) is never evaluated.  Pipeline per call: cull (one warp per tile of

@@ -410,3 +410,38 @@ def hidden_pts_removal(points, R_param=2):
     mask = np.zeros(len(f), dtype=np.float32)
     mask[vis] = 1
     return vis, mask
+
+
+# ------------------------------------------------------------------------------------------
+# PointCloud2 codec (src/pointcloud_utils.py:22-80, :180-198, :290-338)
+# ------------------------------------------------------------------------------------------
+PF_SIZES = {1: 1, 2: 1, 3: 2, 4: 2, 5: 4, 6: 4, 7: 4, 8: 8}           # sensor_msgs/PointField datatype -> bytes
+PF_NUMPY = {1: np.int8, 2: np.uint8, 3: np.int16, 4: np.uint16, 5: np.int32, 6: np.uint32, 7: np.float32, 8: np.float64}
+
+
+def pc2_to_xyz(data, n_points, point_step, fields, remove_nans=True):
+    """`fields` = [(name, offset, datatype)] in message order.  Follows the reference: a structured dtype with one
+    uint8 dummy per padding byte (pointcloud2_to_dtype :22-40), parse (:71), NaN/inf filter on x, y, z and copy into an
+    (M,3) float64 array (get_xyz_points :180-195)."""
+    dtype_list, offset = [], 0
+    for name, off, dt in fields:
+        while offset < off:
+            dtype_list.append(("__%d" % offset, np.uint8))
+            offset += 1
+        dtype_list.append((name, PF_NUMPY[dt]))
+        offset += PF_SIZES[dt]
+    while offset < point_step:
+        dtype_list.append(("__%d" % offset, np.uint8))
+        offset += 1
+    arr = np.frombuffer(bytes(data), dtype=np.dtype(dtype_list), count=n_points)
+    if remove_nans:
+        arr = arr[np.isfinite(arr["x"]) & np.isfinite(arr["y"]) & np.isfinite(arr["z"])]
+    out = np.zeros((arr.shape[0], 3), dtype=np.float64)
+    out[:, 0], out[:, 1], out[:, 2] = arr["x"], arr["y"], arr["z"]
+    return out
+
+
+def xyz_to_pc2(points):
+    """xyz(i)_array_to_pointcloud2 (:290-338): payload bytes, point_step, is_dense."""
+    pts = np.asarray(points, np.float32)
+    return pts.tobytes(), 4 * pts.shape[1], int(np.isfinite(pts).all())

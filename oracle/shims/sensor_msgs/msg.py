@@ -1,5 +1,17 @@
+class _Header:
+    stamp = None
+    frame_id = ""
+
+
 class PointCloud2:
-    pass
+    def __init__(self):
+        self.header = _Header()
+        self.height = self.width = 0
+        self.fields = []
+        self.is_bigendian = False
+        self.point_step = self.row_step = 0
+        self.data = b""
+        self.is_dense = False
 
 
 class CameraInfo:
@@ -16,3 +28,6 @@ class CompressedImage:
 
 class PointField:
     INT8, UINT8, INT16, UINT16, INT32, UINT32, FLOAT32, FLOAT64 = range(1, 9)
+
+    def __init__(self, name="", offset=0, datatype=0, count=1):
+        self.name, self.offset, self.datatype, self.count = name, offset, datatype, count

@@ -23,6 +23,9 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 REF = os.environ.get("REFERENCE_ROOT", "/root/reference")
 sys.path[:0] = [os.path.join(ROOT, "oracle", "shims"), os.path.join(REF, "src")]
 np.float = float  # src/pointcloud_utils.py:180
+if not hasattr(np, "_fromstring_text"):  # src/pointcloud_utils.py:71 uses the binary mode of np.fromstring, which
+    np._fromstring_text = np.fromstring  # numpy >= 2.3 removed; it was frombuffer + copy
+    np.fromstring = lambda data, dtype=float, **kw: np.frombuffer(data, dtype=dtype).copy()
 
 import torch  # noqa: E402
 import model as ref_model  # noqa: E402  (the reference)
@@ -113,7 +116,51 @@ def box_cloud(gen, n, lo=(-10, -10, -1), hi=(30, 30, 4)):
     return (torch.rand(n, 3, generator=gen) * (hi - lo) + lo).float()
 
 
+def codec_fixtures():
+    """PointCloud2 decode (src/pointcloud_utils.py:58-80,180-198) on synthetic messages of three layouts."""
+    import pointcloud_utils as ref_pc  # the reference
+    from sensor_msgs.msg import PointCloud2, PointField
+    gnp = np.random.default_rng(7)
+
+    def message(n, step, fields, nan_frac):
+        # random payload bytes, then the x/y/z fields overwritten with values (some NaN / inf)
+        raw = gnp.integers(0, 256, size=(n, step), dtype=np.uint8)
+        vals = gnp.normal(0, 10, (n, 3))
+        bad = gnp.random((n, 3)) < nan_frac
+        vals[bad] = gnp.choice([np.nan, np.inf, -np.inf], size=int(bad.sum()))
+        for k, (name, off, dt) in enumerate(f for f in fields if f[0] in "xyz"):
+            b = vals[:, k].astype(np.float32 if dt == 7 else np.float64).view(np.uint8).reshape(n, 4 if dt == 7 else 8)
+            raw[:, off:off + b.shape[1]] = b
+        for name, off, dt in fields:   # other float fields must hold valid floats for np.isfinite on the record
+            if name not in "xyz" and dt in (7, 8):
+                b = gnp.normal(0, 1, n).astype(np.float32 if dt == 7 else np.float64).view(np.uint8).reshape(n, 4 if dt == 7 else 8)
+                raw[:, off:off + b.shape[1]] = b
+        msg = PointCloud2()
+        msg.height, msg.width, msg.point_step, msg.row_step = 1, n, step, n * step
+        msg.fields = [PointField(nm, off, dt, 1) for nm, off, dt in fields]
+        msg.data = raw.tobytes()
+        return msg, raw
+
+    cases = {
+        "pc2_xyz12": (3000, 12, [("x", 0, 7), ("y", 4, 7), ("z", 8, 7)], 0.02),
+        "pc2_xyzi_padded32": (2049, 32, [("x", 0, 7), ("y", 4, 7), ("z", 8, 7), ("intensity", 16, 7), ("ring", 20, 4)], 0.05),
+        "pc2_unaligned_f64": (1000, 29, [("tag", 0, 2), ("x", 1, 8), ("y", 9, 8), ("z", 17, 8), ("i", 25, 7)], 0.1),
+        "pc2_dense": (300, 16, [("x", 0, 7), ("y", 4, 7), ("z", 8, 7), ("i", 12, 7)], 0.0),
+        "pc2_empty": (0, 16, [("x", 0, 7), ("y", 4, 7), ("z", 8, 7), ("i", 12, 7)], 0.0),
+    }
+    for name, (n, step, fields, frac) in cases.items():
+        msg, raw = message(n, step, fields, frac)
+        out = ref_pc.pointcloud2_to_xyz_array(msg) if n else np.zeros((0, 3))
+        out_all = ref_pc.pointcloud2_to_xyz_array(msg, remove_nans=False) if n else np.zeros((0, 3))
+        save(name, dict(data=raw.reshape(-1), n=n, point_step=step,
+                        field_names=np.array([f[0] for f in fields]), field_offsets=np.array([f[1] for f in fields]),
+                        field_types=np.array([f[2] for f in fields])),
+             dict(xyz=np.asarray(out, np.float64).reshape(-1, 3), xyz_all=np.asarray(out_all, np.float64).reshape(-1, 3)))
+
+
 def main():
+    if "--only-codec" in sys.argv:
+        return codec_fixtures()
     sample = np.load(os.path.join(REF, "data/points/point_cloud_10.npz"))["pts"].astype(np.float32)
     path = np.load(os.path.join(REF, "data/paths/path_poses_10.npz"))["poses"].astype(np.float32)
     np.savez_compressed(os.path.join(HERE, "sample_inputs.npz"), pts=sample, poses=path)
@@ -205,6 +252,7 @@ def main():
     cam = ref_model.to_camera_frame(pts, q0, t0)
     vis, mask = ref_tools.hidden_pts_removal(cam, CPU)
     save("hpr_sample", dict(points=cam, R_param=2), dict(idx=np.flatnonzero(mask.numpy())))
+    codec_fixtures()
 
 
 if __name__ == "__main__":

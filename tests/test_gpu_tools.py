@@ -120,3 +120,71 @@ def test_model_pose_hpr_branch(dev, tools):
     ref = orc.pose_objective(g["in_points"], [0.1, 0.2, 0.0], [1.0, 0, 0, 0], K_np, IMG_W, IMG_H, weight=mask.cpu().numpy())
     assert abs(loss_hpr.item() - float(ref["loss"])) / float(ref["loss"]) < 1e-4
     assert np.abs(m.trans.grad.cpu().numpy().ravel() - ref["g_trans"]).max() / np.abs(ref["g_trans"]).max() < 1e-4
+
+
+# ---------------- PointCloud2 codec (reference src/pointcloud_utils.py) ----------------
+PC2_CASES = ["pc2_xyz12", "pc2_xyzi_padded32", "pc2_unaligned_f64", "pc2_dense", "pc2_empty"]
+
+
+class _Field:
+    def __init__(self, name, offset, datatype):
+        self.name, self.offset, self.datatype, self.count = name, offset, datatype, 1
+
+
+class _Msg:
+    is_bigendian = False
+    height = 1
+
+
+@pytest.mark.parametrize("name", PC2_CASES)
+def test_pointcloud2_decode_matches_reference(name, dev):
+    """cov_pc2_to_xyz against the reference's pointcloud2_to_xyz_array output (fixture), bit for bit in fp32."""
+    from trajectory_optimization_b200 import pointcloud_utils as pcu
+    g = load_golden(name)
+    msg = _Msg()
+    msg.width, msg.point_step = int(g["in_n"]), int(g["in_point_step"])
+    msg.fields = [_Field(str(nm), int(o), int(t)) for nm, o, t in zip(g["in_field_names"], g["in_field_offsets"], g["in_field_types"])]
+    msg.data = g["in_data"].tobytes()
+    out = pcu.pointcloud2_to_xyz_tensor(msg, device=dev)
+    ref = g["out_xyz"].reshape(-1, 3)
+    assert out.dtype == torch.float32 and out.shape == ref.shape
+    assert np.array_equal(out.cpu().numpy(), ref.astype(np.float32))
+    out_all = pcu.pointcloud2_to_xyz_tensor(msg, remove_nans=False, device=dev)
+    assert np.array_equal(out_all.cpu().numpy(), g["out_xyz_all"].reshape(-1, 3).astype(np.float32), equal_nan=True)
+    arr = pcu.pointcloud2_to_xyz_array(msg, device=dev)     # the reference's return type
+    assert arr.dtype == np.float64 and arr.shape == ref.shape
+
+
+@pytest.mark.parametrize("n", [1, 255, 257, 1_000_003])
+def test_pointcloud2_codec_round_trip_and_oracle(n, dev):
+    from trajectory_optimization_b200 import pointcloud_utils as pcu
+    gen = np.random.default_rng(n)
+    pts = gen.normal(0, 20, (n, 3)).astype(np.float32)
+    inten = gen.random(n).astype(np.float32)
+    bad = gen.random(n) < 0.03
+    pts[bad, gen.integers(0, 3, int(bad.sum()))] = np.nan
+    pts[gen.random(n) < 0.01, 1] = np.inf
+    for extra in (None, inten):
+        payload, dense = pcu.xyz_to_payload(torch.from_numpy(pts).to(dev), None if extra is None else torch.from_numpy(extra).to(dev))
+        ref_bytes, step, ref_dense = orc.xyz_to_pc2(pts if extra is None else np.concatenate([pts, extra[:, None]], 1))
+        assert payload.cpu().numpy().tobytes() == ref_bytes and dense == bool(ref_dense)
+        back = pcu.payload_to_xyz(payload, n, step, 0, 4, 8)
+        fields = [("x", 0, 7), ("y", 4, 7), ("z", 8, 7)] + ([] if extra is None else [("i", 12, 7)])
+        ref = orc.pc2_to_xyz(ref_bytes, n, step, fields)
+        assert np.array_equal(back.cpu().numpy(), ref.astype(np.float32))
+        assert back.shape[0] == int(np.isfinite(pts).all(1).sum())
+    clean = torch.from_numpy(np.nan_to_num(pts, nan=0.0, posinf=1.0)).to(dev)
+    assert pcu.xyz_to_payload(clean)[1] is True
+
+
+def test_pointcloud2_errors_are_loud(dev):
+    from trajectory_optimization_b200 import pointcloud_utils as pcu
+    with pytest.raises(RuntimeError):
+        pcu.payload_to_xyz(torch.zeros(48, dtype=torch.uint8), 4, 12, 0, 4, 8)          # CPU tensor
+    with pytest.raises(RuntimeError, match="bad argument"):
+        pcu.payload_to_xyz(torch.zeros(48, dtype=torch.uint8, device=dev), 4, 12, 0, 4, 10)   # z field runs past the record
+    msg = _Msg()
+    msg.width, msg.point_step, msg.data = 1, 12, bytes(12)
+    msg.fields = [_Field("x", 0, 7), _Field("y", 4, 7)]
+    with pytest.raises(ValueError):
+        pcu.pointcloud2_to_xyz_tensor(msg, device=dev)

@@ -154,3 +154,23 @@ def test_torch_port_pose_matches_reference(sample_inputs):
     loss.backward()
     assert rel_err(loss.item(), g["out_loss"]) < 1e-6 and rel_err(obs.detach().numpy(), g["out_obs"]) < 1e-6
     assert rel_err(t.grad.numpy(), g["out_g_trans"]) < 1e-5 and rel_err(q.grad.numpy(), g["out_g_quat"]) < 1e-5
+
+
+PC2_CASES = ["pc2_xyz12", "pc2_xyzi_padded32", "pc2_unaligned_f64", "pc2_dense", "pc2_empty"]
+
+
+@pytest.mark.parametrize("name", PC2_CASES)
+def test_pointcloud2_decode_restatement_matches_reference(name):
+    """oracle.pc2_to_xyz against the reference's pointcloud2_to_xyz_array (fixtures made by running it)."""
+    g = load_golden(name)
+    fields = list(zip([str(s) for s in g["in_field_names"]], [int(v) for v in g["in_field_offsets"]],
+                      [int(v) for v in g["in_field_types"]]))
+    n, step = int(g["in_n"]), int(g["in_point_step"])
+    out = orc.pc2_to_xyz(g["in_data"].tobytes(), n, step, fields, remove_nans=True)
+    out_all = orc.pc2_to_xyz(g["in_data"].tobytes(), n, step, fields, remove_nans=False)
+    assert out.dtype == np.float64 and np.array_equal(out, g["out_xyz"].reshape(-1, 3))
+    assert np.array_equal(out_all, g["out_xyz_all"].reshape(-1, 3), equal_nan=True)
+    assert out.shape[0] <= n and (name != "pc2_dense" or out.shape[0] == n)
+    payload, step_out, dense = orc.xyz_to_pc2(out.astype(np.float32))
+    back = orc.pc2_to_xyz(payload, out.shape[0], step_out, [("x", 0, 7), ("y", 4, 7), ("z", 8, 7)], remove_nans=False)
+    assert step_out == 12 and dense == 1 and np.array_equal(back.astype(np.float32), out.astype(np.float32))

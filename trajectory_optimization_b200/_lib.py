@@ -47,6 +47,9 @@ PROTOTYPES = {
     "cov_hpr_flip": (_int, [_vp, _i64, _f, _vp, _vp, _vp]),
     "cov_hpr_hull_workspace_bytes": (_sz, [_i64]),
     "cov_hpr_hull": (_int, [_vp, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "cov_pc2_workspace_bytes": (_sz, [_i64]),
+    "cov_pc2_to_xyz": (_int, [_vp, _i64, _int, _int, _int, _int, _int, _int, _vp, _vp, _vp, _sz, _vp]),
+    "cov_xyz_to_pc2": (_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "cov_set_pruning": (None, [_int]),
     "cov_get_pruning": (_int, []),
     "cov_stats": (_int, [_int, _vp]),

@@ -118,6 +118,113 @@ __global__ void __launch_bounds__(256) flip_apply_kernel(const float* __restrict
     if (blockIdx.x == 0 && threadIdx.x == 0) radius_io[0] = radius;
 }
 
+// ---- PointCloud2 payload <-> xyz (reference src/pointcloud_utils.py:58-80,180-198,290-338) ----
+// One record of `point_step` bytes per point; x, y, z are FLOAT32 (PointField datatype 7) or FLOAT64 (8) fields at
+// byte offsets that need not be aligned.  Points whose x, y, z are all finite are kept (np.isfinite), in order.
+__device__ __forceinline__ float pc2_field(const uint8_t* __restrict__ rec, int off, int datatype, bool& finite) {
+    if (datatype == 8) {
+        unsigned long long b = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) b |= (unsigned long long)rec[off + i] << (8 * i);
+        finite = finite && ((b >> 52) & 0x7ffull) != 0x7ffull;  // judged on the double, before the conversion to fp32
+        return (float)__longlong_as_double((long long)b);
+    }
+    unsigned b = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) b |= (unsigned)rec[off + i] << (8 * i);
+    finite = finite && ((b >> 23) & 0xffu) != 0xffu;
+    return __uint_as_float(b);
+}
+// x, y, z of record j; returns whether all three are finite (np.isfinite: neither NaN nor +-inf)
+__device__ __forceinline__ bool pc2_load(const uint8_t* __restrict__ data, int64_t j, int step, int ox, int oy, int oz,
+                                         int datatype, bool aligned4, float& x, float& y, float& z) {
+    const uint8_t* rec = data + j * step;
+    bool finite = true;
+    if (aligned4 && datatype == 7) {  // the common layout: 4-byte aligned float fields
+        x = *reinterpret_cast<const float*>(rec + ox);
+        y = *reinterpret_cast<const float*>(rec + oy);
+        z = *reinterpret_cast<const float*>(rec + oz);
+        const float inf = __uint_as_float(0x7f800000u);
+        finite = fabsf(x) < inf && fabsf(y) < inf && fabsf(z) < inf;
+    } else {
+        x = pc2_field(rec, ox, datatype, finite);
+        y = pc2_field(rec, oy, datatype, finite);
+        z = pc2_field(rec, oz, datatype, finite);
+    }
+    return finite;
+}
+__device__ __forceinline__ bool pc2_finite(float x, float y, float z) {
+    const float inf = __uint_as_float(0x7f800000u);
+    return fabsf(x) < inf && fabsf(y) < inf && fabsf(z) < inf;  // false for NaN and +-inf
+}
+
+__global__ void __launch_bounds__(kCullBlock)
+pc2_flags_kernel(const uint8_t* __restrict__ data, int64_t n, int step, int ox, int oy, int oz, int datatype,
+                 bool aligned4, int remove_nans, int* __restrict__ block_counts) {
+    const int64_t j = (int64_t)blockIdx.x * kCullBlock + threadIdx.x;
+    bool keep = false;
+    if (j < n) {
+        float x, y, z;
+        const bool fin = pc2_load(data, j, step, ox, oy, oz, datatype, aligned4, x, y, z);
+        keep = !remove_nans || fin;
+    }
+    const int c = __syncthreads_count(keep);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = c;
+}
+
+__global__ void __launch_bounds__(kCullBlock)
+pc2_scatter_kernel(const uint8_t* __restrict__ data, int64_t n, int step, int ox, int oy, int oz, int datatype,
+                   bool aligned4, int remove_nans, const int* __restrict__ block_offsets, float* __restrict__ xyz) {
+    __shared__ int warp_off[kCullBlock / 32];
+    const int64_t j = (int64_t)blockIdx.x * kCullBlock + threadIdx.x;
+    float x = 0.f, y = 0.f, z = 0.f;
+    bool keep = false;
+    if (j < n) {
+        const bool fin = pc2_load(data, j, step, ox, oy, oz, datatype, aligned4, x, y, z);
+        keep = !remove_nans || fin;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) warp_off[warp] = __popc(bal);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int i = 0; i < kCullBlock / 32; ++i) {
+            const int c = warp_off[i];
+            warp_off[i] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    if (keep) {
+        const int64_t o = (int64_t)block_offsets[blockIdx.x] + warp_off[warp] + __popc(bal & ((1u << lane) - 1u));
+        xyz[o * 3] = x;
+        xyz[o * 3 + 1] = y;
+        xyz[o * 3 + 2] = z;
+    }
+}
+
+// xyz (+ optional 4th float per point) -> little-endian FLOAT32 records of 12 or 16 bytes; dense[0] &= all finite
+__global__ void __launch_bounds__(256)
+pc2_pack_kernel(const float* __restrict__ xyz, const float* __restrict__ extra, int64_t n, float* __restrict__ out,
+                int* __restrict__ dense) {
+    bool ok = true;
+    const int per = extra ? 4 : 3;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+        const float x = xyz[j * 3], y = xyz[j * 3 + 1], z = xyz[j * 3 + 2];
+        out[j * per] = x;
+        out[j * per + 1] = y;
+        out[j * per + 2] = z;
+        ok = ok && pc2_finite(x, y, z);
+        if (extra) {
+            const float e = extra[j];
+            out[j * per + 3] = e;
+            ok = ok && pc2_finite(e, 0.f, 0.f);
+        }
+    }
+    if (!__all_sync(0xffffffffu, ok) && (threadIdx.x & 31) == 0) atomicAnd(dense, 0);
+}
+
 }  // namespace
 
 extern "C" size_t cov_cull_workspace_bytes(int64_t n) {
@@ -170,4 +277,57 @@ extern "C" int cov_hpr_flip(const float* xyz, int64_t n, float scale, float* fli
     flip_maxnorm_kernel<<<(unsigned)nb, 256, 0, s>>>(xyz, n, reinterpret_cast<unsigned*>(radius + 1));
     flip_apply_kernel<<<(unsigned)nb, 256, 0, s>>>(xyz, n, scale, radius, flipped);
     return cov_check_launch("cov_hpr_flip");
+}
+
+extern "C" size_t cov_pc2_workspace_bytes(int64_t n) { return cov_cull_workspace_bytes(n); }
+
+extern "C" int cov_pc2_to_xyz(const uint8_t* data, int64_t n, int point_step, int off_x, int off_y, int off_z,
+                              int datatype, int remove_nans, float* xyz, int64_t* count, void* ws, size_t ws_bytes,
+                              void* stream) {
+    const int fsz = datatype == 8 ? 8 : 4;
+    if (n < 0 || !count || (datatype != 7 && datatype != 8) || point_step <= 0 || off_x < 0 || off_y < 0 || off_z < 0 ||
+        off_x + fsz > point_step || off_y + fsz > point_step || off_z + fsz > point_step ||
+        (n > 0 && (!data || !xyz || !ws))) {
+        cov_set_error("cov_pc2_to_xyz: bad argument (n=%lld, point_step=%d, offsets %d/%d/%d, datatype %d: only "
+                      "FLOAT32=7 and FLOAT64=8 fields are supported)", (long long)n, point_step, off_x, off_y, off_z, datatype);
+        return COV_ERR_ARG;
+    }
+    if (n >= (int64_t)1 << 31) {
+        cov_set_error("cov_pc2_to_xyz: n >= 2^31 not supported");
+        return COV_ERR_UNSUPPORTED;
+    }
+    if (ws_bytes < cov_pc2_workspace_bytes(n)) {
+        cov_set_error("cov_pc2_to_xyz: workspace too small");
+        return COV_ERR_WORKSPACE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0) {
+        cudaMemsetAsync(count, 0, sizeof(int64_t), s);
+        return cov_check_launch("cov_pc2_to_xyz");
+    }
+    const bool aligned4 = ((((uintptr_t)data) | (unsigned)point_step | (unsigned)off_x | (unsigned)off_y | (unsigned)off_z) & 3) == 0;
+    const int64_t nb = (n + kCullBlock - 1) / kCullBlock;
+    int* counts = (int*)ws;
+    pc2_flags_kernel<<<(unsigned)nb, kCullBlock, 0, s>>>(data, n, point_step, off_x, off_y, off_z, datatype, aligned4,
+                                                        remove_nans, counts);
+    cull_scan_kernel<<<1, 1024, 0, s>>>(counts, nb, count);
+    pc2_scatter_kernel<<<(unsigned)nb, kCullBlock, 0, s>>>(data, n, point_step, off_x, off_y, off_z, datatype, aligned4,
+                                                          remove_nans, counts, xyz);
+    return cov_check_launch("cov_pc2_to_xyz");
+}
+
+extern "C" int cov_xyz_to_pc2(const float* xyz, const float* extra, int64_t n, uint8_t* data, int* is_dense, void* stream) {
+    if (n < 0 || !is_dense || (n > 0 && (!xyz || !data)) || (((uintptr_t)data) & 3)) {
+        cov_set_error("cov_xyz_to_pc2: bad argument (null pointer, negative n or payload not 4-byte aligned)");
+        return COV_ERR_ARG;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaMemsetAsync(is_dense, 1, sizeof(int), s);  // nonzero = dense; the kernel clears it on the first non-finite value
+    if (n > 0) {
+        int64_t nb = (n + 255) / 256;
+        const int64_t cap = (int64_t)cov_sm_count_cached() * 16;
+        if (nb > cap) nb = cap;
+        pc2_pack_kernel<<<(unsigned)nb, 256, 0, s>>>(xyz, extra, n, reinterpret_cast<float*>(data), is_dense);
+    }
+    return cov_check_launch("cov_xyz_to_pc2");
 }
