@@ -26,7 +26,7 @@
 //     pass B: bound = the conservative gate threshold (a + b/2)(1 - 2^-20): a pair below it is neither gated nor
 //             the arg-max, adds logit(1/2) = 0 to the log-odds sum and nothing to the gradient.
 //   cov_cull_kernel      one warp per tile: union of the tile's boxes against every pose -> per-tile pose bit mask
-//   cov_worklist_kernel  ascending list of the tiles with a non-empty mask (single block scan: deterministic)
+//   cov_worklist_kernel  list of the tiles with a non-empty mask, heaviest first (single block scan: deterministic)
 //   *_tiles_kernel       persistent blocks walk the work list; tile points, boxes and mask arrive together through a
 //                        double-buffered TMA bulk copy (one mbarrier per buffer); a warp evaluates a listed pose only
 //                        if its own 128-point box and then one of its points pass the same test.
@@ -408,7 +408,7 @@ cov_cull_kernel(const float4* __restrict__ boxes, int boxes_per_tile, int64_t nt
             glo.z = fminf(glo.z, __shfl_xor_sync(kFull, glo.z, o)); ghi.x = fmaxf(ghi.x, __shfl_xor_sync(kFull, ghi.x, o));
             ghi.y = fmaxf(ghi.y, __shfl_xor_sync(kFull, ghi.y, o)); ghi.z = fmaxf(ghi.z, __shfl_xor_sync(kFull, ghi.z, o));
         }
-        unsigned any = 0u;  // lanes 0..7: tile tl has a non-empty mask
+        unsigned any = 0u;  // lanes 0..7: number of poses listed for tile tl
         for (int c = 0; c < mask_stride; ++c) {
             const int w = c * 32 + lane;
             bool cand = false;
@@ -428,77 +428,102 @@ cov_cull_kernel(const float4* __restrict__ boxes, int boxes_per_tile, int64_t nt
             }
             if (lane < 8 && tile_l < ntiles) {
                 amask_g[tile_l * mask_stride + c] = mine;
-                any |= mine;
-                npairs += __popc(mine);
+                any += __popc(mine);
             }
         }
-        if (lane < 8 && tile_l < ntiles) flags[tile_l] = any != 0u;
+        if (lane < 8 && tile_l < ntiles) {
+            npairs += any;
+            // cost class of the tile for the work list: 0 = nothing listed, 1..4 = 1-2, 3-6, 7-14, >= 15 poses
+            flags[tile_l] = (unsigned char)(any == 0u ? 0 : any <= 2u ? 1 : any <= 6u ? 2 : any <= 14u ? 3 : 4);
+        }
     }
     npairs = __reduce_add_sync(kFull, (unsigned)npairs);
     if (lane == 0 && npairs) atomicAdd(listed_pairs, npairs);
 }
 
-// Ascending list of flagged tiles + their count (single block: deterministic order, no atomics).
+// Work list of the tiles with a non-empty mask: heaviest cost class first, ascending tile index within a class, so
+// that blocks taking entries i, i + grid, i + 2 grid, ... all get the same mix of heavy and light tiles (the order is
+// a pure function of the masks: deterministic, no atomics; single block).
 // ints[0] = count, ints[2] = 1 when the masks list more than `dense_above` (tile, pose) pairs: the cloud has no
 // spatial coherence to exploit, the dense kernel does the call instead (it checks ints[2]) and the list is left empty.
 __global__ void __launch_bounds__(1024) cov_worklist_kernel(const unsigned char* __restrict__ flags, int64_t ntiles,
                                                             int* __restrict__ worklist, int* __restrict__ ints,
                                                             unsigned long long dense_above) {
-    __shared__ int warp_tot[32];
+    __shared__ int warp_tot[32][4];
+    __shared__ int class_start[4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t chunk = (((ntiles + 1023) / 1024) + 15) & ~(int64_t)15;  // flags per thread, 16 per vector load
     const int64_t lo = (int64_t)tid * chunk < ntiles ? (int64_t)tid * chunk : ntiles;
     const int64_t hi = lo + chunk < ntiles ? lo + chunk : ntiles;
-    int c = 0;
+    int c[4] = {0, 0, 0, 0};  // tiles of class 4, 3, 2, 1 in this thread's chunk
     {
         int64_t t = lo;
-        for (; t + 16 <= hi; t += 16) {  // flags are 0/1 bytes: popc of a word counts them
+        for (; t + 16 <= hi; t += 16) {
             const uint4 v = *reinterpret_cast<const uint4*>(flags + t);
-            c += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
-        }
-        for (; t < hi; ++t) c += flags[t] ? 1 : 0;
-    }
-    int incl = c;
+            const unsigned words[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(kFull, incl, o);
-        if (lane >= o) incl += v;
+            for (int q = 0; q < 4; ++q) {
+                if (words[q] == 0u) continue;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const unsigned f = (words[q] >> (8 * k)) & 0xffu;
+                    if (f) ++c[4 - f];
+                }
+            }
+        }
+        for (; t < hi; ++t) {
+            const unsigned f = flags[t];
+            if (f) ++c[4 - f];
+        }
     }
-    if (lane == 31) warp_tot[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        int v = warp_tot[lane], s = v;
+    int incl[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        incl[k] = c[k];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const int u = __shfl_up_sync(kFull, s, o);
-            if (lane >= o) s += u;
+            const int v = __shfl_up_sync(kFull, incl[k], o);
+            if (lane >= o) incl[k] += v;
         }
-        warp_tot[lane] = s - v;  // exclusive
-        if (lane == 31) {
+        if (lane == 31) warp_tot[warp][k] = incl[k];
+    }
+    __syncthreads();
+    if (warp == 0) {
+        int tot[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int v = warp_tot[lane][k];
+            int sc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(kFull, sc, o);
+                if (lane >= o) sc += u;
+            }
+            warp_tot[lane][k] = sc - v;  // exclusive over warps
+            tot[k] = __shfl_sync(kFull, sc, 31);
+        }
+        if (lane == 0) {
             const bool dense = *reinterpret_cast<const unsigned long long*>(ints + 4) > dense_above;
-            ints[0] = dense ? 0 : s;
+            class_start[0] = 0;
+            class_start[1] = tot[0];
+            class_start[2] = tot[0] + tot[1];
+            class_start[3] = tot[0] + tot[1] + tot[2];
+            ints[0] = dense ? 0 : tot[0] + tot[1] + tot[2] + tot[3];
             ints[2] = dense ? 1 : 0;
         }
     }
     __syncthreads();
-    int pos = warp_tot[warp] + incl - c;
-    if (c == 0) return;
-    int64_t t = lo;
-    for (; t + 16 <= hi; t += 16) {
-        const uint4 v = *reinterpret_cast<const uint4*>(flags + t);
-        const unsigned words[4] = {v.x, v.y, v.z, v.w};
+    int pos[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            unsigned wv = words[q];
-            while (wv) {
-                const int byte = (__ffs(wv) - 1) >> 3;
-                wv &= ~(0xffu << (byte * 8));
-                worklist[pos++] = (int)(t + q * 4 + byte);
-            }
-        }
+    for (int k = 0; k < 4; ++k) pos[k] = class_start[k] + warp_tot[warp][k] + incl[k] - c[k];
+    if (c[0] + c[1] + c[2] + c[3] == 0) return;
+    for (int64_t t = lo; t < hi; ++t) {
+        const unsigned f = flags[t];
+        if (f == 4u) worklist[pos[0]++] = (int)t;
+        else if (f == 3u) worklist[pos[1]++] = (int)t;
+        else if (f == 2u) worklist[pos[2]++] = (int)t;
+        else if (f == 1u) worklist[pos[3]++] = (int)t;
     }
-    for (; t < hi; ++t)
-        if (flags[t]) worklist[pos++] = (int)t;
 }
 
 // =============================================== pass A, pruned ===============================================
