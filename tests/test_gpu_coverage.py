@@ -475,3 +475,75 @@ def test_graphed_optimisation_step_matches_eager(dev, mod):
     for _ in range(20):
         l1 = gp.step().item()
     assert l1 < l0   # the optimiser is making progress on 1/(sum of observations)
+
+
+@pytest.mark.parametrize("n,W,mode", [(1, 1, "box"), (31, 7, "box"), (129, 33, "box"), (4097, 100, "box"), (70_001, 500, "box"),
+                                      (300_000, 64, "far"), (200_003, 40, "mixed"), (1_000_001, 1100, "box")])
+def test_pruned_pipeline_equals_dense_on_edge_shapes(n, W, mode, dev, mod):
+    """Cull -> work list -> tiles kernels against the dense kernels on ragged sizes, one pose, more poses than one
+    mask word / one slot round, clouds that are almost entirely out of reach and clouds with a far-away half."""
+    from trajectory_optimization_b200 import _lib
+    model, tools, ops = mod
+    L = _lib.lib()
+    gen = np.random.default_rng(n + W)
+    pts_np = _box(gen, n)
+    if mode == "far":
+        pts_np[100:] += np.float32(500.0)           # all but 100 points are out of reach of every pose
+    elif mode == "mixed":
+        pts_np[: n // 2] += np.float32(300.0)
+    poses = (gen.random((W, 3), dtype=np.float32) * np.array([30, 30, 2], np.float32) + np.array([-5, -5, -0.5], np.float32))
+    quats = gen.normal(0, 1, (W, 4)).astype(np.float32)
+    K, Wd, Hd = tools.load_intrinsics(dev)
+    outs = []
+    try:
+        for prune in (1, 0):
+            L.cov_set_pruning(prune)
+            for ordered in ((True, False) if prune else (False,)):
+                pts = torch.from_numpy(pts_np).to(dev)
+                perm = boxes = None
+                if ordered:
+                    pts, perm = ops.spatial_sort(pts)
+                    boxes = ops.tile_boxes(pts)
+                P = torch.from_numpy(poses).to(dev).requires_grad_(True)
+                Q = torch.from_numpy(quats).to(dev).requires_grad_(True)
+                rewards, mean = ops.coverage_traj(pts, P, Q, K, Wd, Hd, reward_index=perm, boxes=boxes)
+                gp, gq = torch.autograd.grad(mean, [P, Q])
+                outs.append((rewards, mean, gp, gq))
+    finally:
+        L.cov_set_pruning(1)
+    dense = outs[-1]
+    if bool(torch.isnan(dense[1])):   # one point: min == max, the reference's normalisation is 0/0 there too
+        assert n == 1 and all(bool(torch.isnan(got[0]).all()) and bool(torch.isnan(got[1])) for got in outs)
+        return
+    for got in outs[:-1]:
+        assert torch.equal(got[0], dense[0])
+        assert rel_err(got[1].item(), dense[1].item()) < 1e-12
+        scale_p, scale_q = float(dense[2].abs().max()), float(dense[3].abs().max())
+        if scale_p > 0:
+            assert rel_err(got[2].cpu().numpy(), dense[2].cpu().numpy()) < 5e-6
+        if scale_q > 0:
+            assert rel_err(got[3].cpu().numpy(), dense[3].cpu().numpy()) < 5e-6
+    if mode == "far":
+        assert float(dense[0][100:].min()) == 0.5 and float(dense[0][100:].max()) == 0.5
+
+
+def test_pose_that_sees_nothing_gives_nan_like_the_reference(dev, mod):
+    """max_j m = 0 for a pose makes the reference's normalisation 0/0: rewards, mean and loss are NaN (src/model.py:226-231).
+    The kernels reproduce that instead of inventing a value; dense and pruned paths agree."""
+    from trajectory_optimization_b200 import _lib
+    model, tools, ops = mod
+    gen = np.random.default_rng(2)
+    pts_np = _box(gen, 5000) + np.float32(500.0)
+    poses, yaw = _s_curve(3, 2.0)
+    quats = np.stack([np.cos(yaw / 2), 0 * yaw, 0 * yaw, np.sin(yaw / 2)], 1).astype(np.float32)
+    K, Wd, Hd = tools.load_intrinsics(dev)
+    ref = orc.traj_objective(pts_np, poses, quats, K_np, IMG_W, IMG_H, dtype=np.float32)
+    assert np.isnan(ref["vis"]) and np.isnan(ref["rewards"]).all()
+    try:
+        for prune in (1, 0):
+            _lib.lib().cov_set_pruning(prune)
+            rewards, mean = ops.coverage_traj(torch.from_numpy(pts_np).to(dev), torch.from_numpy(poses).to(dev),
+                                              torch.from_numpy(quats).to(dev), K, Wd, Hd)
+            assert bool(torch.isnan(mean)) and bool(torch.isnan(rewards).all())
+    finally:
+        _lib.lib().cov_set_pruning(1)

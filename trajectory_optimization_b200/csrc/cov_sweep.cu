@@ -73,7 +73,8 @@ cov_sweep_kernel(const float* __restrict__ xyz, int64_t n, const float* __restri
                     for (int s = 0; s < PPT; ++s) {
                         const float d = __fsub_rn(m[s], v4.w);
                         if (d >= v4.x) {
-                            const float qc = fminf(__fmul_rn(d, v4.z), C.hi);
+                            const float pn = __fmul_rn(d, v4.z);
+                            const float qc = (pn > C.hi) ? C.hi : pn;  // NaN (pose that sees nothing) stays NaN, as torch.clip
                             L[s] += COV_LN2_F * cov_lg2(qc * cov_rcp(1.f - qc));
                         }
                     }

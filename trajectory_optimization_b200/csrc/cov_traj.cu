@@ -698,7 +698,7 @@ __device__ __forceinline__ bool fused_pose_iter(int w, const float4* __restrict_
                 bal[s] = __ballot_sync(kFull, act);
                 if (act) {
                     const float p = __fmul_rn(d, v4.z);
-                    const float qc = fminf(p, C.hi);
+                    const float qc = (p > C.hi) ? C.hi : p;  // upper clip; a NaN p (pose that sees nothing: 0/0) stays NaN, as torch.clip
                     L[s] += COV_LN2_F * cov_lg2(qc * cov_rcp(1.f - qc));
                     if (acc && d == v4.y) tie_accumulate(px[s], py[s], pz[s], row, C, acc, (w + u) * COV_ACC_STRIDE + 8);
                 }
