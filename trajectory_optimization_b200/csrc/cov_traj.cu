@@ -70,7 +70,8 @@ __host__ __device__ inline int fused_stage_offset_floats(int W) {
 }
 size_t fused_smem_bytes(int W, int ppt, bool prune) {
     if (prune)  // pose table | 2 tile stages | block accumulators
-        return (size_t)fused_stage_offset_floats(W) * 4 + 2 * (size_t)stage_floats(ppt) * 4 + (size_t)W * 8 * sizeof(float);
+        return (size_t)fused_stage_offset_floats(W) * 4 + 2 * (size_t)(stage_floats(ppt) + tile_points(ppt)) * 4 +
+               (size_t)W * 8 * sizeof(float);
     // pose table | tile points | G_j | gate bits | block accumulators
     return (size_t)fused_stage_offset_floats(W) * 4 + (size_t)tile_points(ppt) * 12 + (size_t)tile_points(ppt) * 4 +
            (size_t)W * bit_stride(ppt) * sizeof(unsigned) + (size_t)W * 8 * sizeof(float);
@@ -154,18 +155,21 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         : "memory");
 }
 
-// One staged tile: points (unless the tile is the ragged last one), its boxes and its pose mask, on one mbarrier.
+// One staged tile: points (unless the tile is the ragged last one), its boxes and its pose mask — and, for pass B on an
+// ordered cloud, the tile's slice of the permutation — on one mbarrier.
 template <int PPT>
 __device__ __forceinline__ void stage_issue(float* stage, unsigned long long* bar, const float* __restrict__ xyz,
                                             const float4* __restrict__ boxes, const unsigned* __restrict__ amask_g,
-                                            int mask_stride, int64_t tile, int64_t nfull) {
+                                            int mask_stride, int64_t tile, int64_t nfull,
+                                            const int32_t* __restrict__ perm = nullptr) {
     constexpr int T = tile_points(PPT);
     constexpr int NB = tile_boxes(PPT);
     const bool whole = tile < nfull;
-    mbar_expect_tx(bar, (whole ? T * 12u : 0u) + NB * 32u + (unsigned)mask_stride * 4u);
+    mbar_expect_tx(bar, (whole ? T * 12u : 0u) + NB * 32u + (unsigned)mask_stride * 4u + ((whole && perm) ? T * 4u : 0u));
     if (whole) tma_copy(stage, xyz + tile * (T * 3), T * 12u, bar);
     tma_copy(stage + T * 3, boxes + tile * (NB * 2), NB * 32u, bar);
     tma_copy(stage + T * 3 + NB * 8, amask_g + tile * mask_stride, (unsigned)mask_stride * 4u, bar);
+    if (whole && perm) tma_copy(stage + stage_floats(PPT), perm + tile * T, T * 4u, bar);
 }
 
 // =============================================== pass A, dense ===============================================
@@ -467,13 +471,13 @@ __global__ void __launch_bounds__(1024) cov_worklist_kernel(const unsigned char*
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const unsigned f = (words[q] >> (8 * k)) & 0xffu;
-                    if (f) ++c[4 - f];
+                    c[0] += f == 4u; c[1] += f == 3u; c[2] += f == 2u; c[3] += f == 1u;
                 }
             }
         }
         for (; t < hi; ++t) {
             const unsigned f = flags[t];
-            if (f) ++c[4 - f];
+            c[0] += f == 4u; c[1] += f == 3u; c[2] += f == 2u; c[3] += f == 1u;
         }
     }
     int incl[4];
@@ -517,7 +521,25 @@ __global__ void __launch_bounds__(1024) cov_worklist_kernel(const unsigned char*
 #pragma unroll
     for (int k = 0; k < 4; ++k) pos[k] = class_start[k] + warp_tot[warp][k] + incl[k] - c[k];
     if (c[0] + c[1] + c[2] + c[3] == 0) return;
-    for (int64_t t = lo; t < hi; ++t) {
+    int64_t t = lo;
+    for (; t + 16 <= hi; t += 16) {
+        const uint4 v = *reinterpret_cast<const uint4*>(flags + t);
+        const unsigned words[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (words[q] == 0u) continue;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const unsigned f = (words[q] >> (8 * k)) & 0xffu;
+                const int tile = (int)(t + q * 4 + k);
+                if (f == 4u) worklist[pos[0]++] = tile;
+                else if (f == 3u) worklist[pos[1]++] = tile;
+                else if (f == 2u) worklist[pos[2]++] = tile;
+                else if (f == 1u) worklist[pos[3]++] = tile;
+            }
+        }
+    }
+    for (; t < hi; ++t) {
         const unsigned f = flags[t];
         if (f == 4u) worklist[pos[0]++] = (int)t;
         else if (f == 3u) worklist[pos[1]++] = (int)t;
@@ -917,7 +939,7 @@ cov_traj_fused_tiles_kernel(const float* __restrict__ xyz, int64_t n, const floa
                             unsigned long long* __restrict__ stats) {
     constexpr int T = tile_points(PPT);
     constexpr int NB = tile_boxes(PPT);
-    constexpr int SF = stage_floats(PPT);
+    constexpr int SF = stage_floats(PPT) + T;  // + the tile's slice of the permutation
     constexpr int WB = (32 * PPT >= kBoxPts) ? (32 * PPT / kBoxPts) : 1;
     // shared memory: pose table | 2 tile stages (points, boxes, pose mask) | block accumulators
     extern __shared__ float4 smem4[];
@@ -949,13 +971,13 @@ cov_traj_fused_tiles_kernel(const float* __restrict__ xyz, int64_t n, const floa
     unsigned* wg = wgate[warp];
     unsigned uses0 = 0, uses1 = 0;
     if (tid == 0 && (int)blockIdx.x < count)
-        stage_issue<PPT>(stage, &mbar[0], xyz, boxes, amask_g, mask_stride, (int64_t)worklist[blockIdx.x], nfull);
+        stage_issue<PPT>(stage, &mbar[0], xyz, boxes, amask_g, mask_stride, (int64_t)worklist[blockIdx.x], nfull, out_index);
     int buf = 0;
     for (int i = blockIdx.x; i < count; i += gridDim.x, buf ^= 1) {
         const int64_t tile = worklist[i];
         if (tid == 0 && i + (int)gridDim.x < count)  // the other stage was last read before the previous barrier
             stage_issue<PPT>(stage + (buf ^ 1) * SF, &mbar[buf ^ 1], xyz, boxes, amask_g, mask_stride,
-                             (int64_t)worklist[i + gridDim.x], nfull);
+                             (int64_t)worklist[i + gridDim.x], nfull, out_index);
         if (buf == 0) mbar_wait(&mbar[0], uses0++ & 1u);
         else mbar_wait(&mbar[1], uses1++ & 1u);
         const float* st = stage + buf * SF;
@@ -990,6 +1012,7 @@ cov_traj_fused_tiles_kernel(const float* __restrict__ xyz, int64_t n, const floa
 #pragma unroll
         for (int k = 1; k < WB; ++k) box_union(wlo, whi, tb[2 * (b0 + k)], tb[2 * (b0 + k) + 1]);
         const unsigned* am = reinterpret_cast<const unsigned*>(st + T * 3 + NB * 8);
+        const int32_t* sperm = reinterpret_cast<const int32_t*>(st + stage_floats(PPT));
         bool warp_gated = false;
         for (int c = 0; c < nwords; ++c) {
             unsigned word = am[c];
@@ -1029,7 +1052,8 @@ cov_traj_fused_tiles_kernel(const float* __restrict__ xyz, int64_t n, const floa
                 sum_r += (double)(r - 0.5f);
                 const bool store = r != 0.5f;
                 int64_t jo = j;
-                if (out_index && (store || HAS_UP)) jo = (int64_t)out_index[j];
+                if (out_index && (store || HAS_UP))
+                    jo = tile < nfull ? (int64_t)sperm[lbase + s * 32] : (int64_t)out_index[j];  // staged with the tile
                 if (store) rewards[jo] = r;
                 if (HAS_UP) G[s] *= upstream[jo];
             }
@@ -1075,7 +1099,7 @@ cov_traj_fused_tiles_kernel(const float* __restrict__ xyz, int64_t n, const floa
                                     float gx, gy, gz;
                                     cov_vis_grad(m, ev, v0, v1, v2, C, gx, gy, gz);
                                     const float yx = px[s] - v5.x, yy = py[s] - v5.y, yz = pz[s] - v5.z;
-                                    const float e = G[s] / (p * (1.f - p));
+                                    const float e = G[s] * cov_rcp(p * (1.f - p));
                                     const float om = e * v4.z;
                                     f0 += om * gx; f1 += om * gy; f2 += om * gz;
                                     t0 += om * (gy * yz - gz * yy);
@@ -1551,8 +1575,8 @@ extern "C" int cov_traj_fused(const float* xyz, int64_t n, const float* poses, c
         cov_set_error("cov_traj_fused: null minmax/rewards/acc");
         return COV_ERR_ARG;
     }
-    if (boxes_dev && (((uintptr_t)boxes_dev) & 15)) {
-        cov_set_error("cov_traj_fused: boxes must be 16-byte aligned");
+    if ((boxes_dev && (((uintptr_t)boxes_dev) & 15)) || (reward_index && (((uintptr_t)reward_index) & 15))) {
+        cov_set_error("cov_traj_fused: boxes and reward_index must be 16-byte aligned");
         return COV_ERR_ALIGN;
     }
     cudaStream_t s = (cudaStream_t)stream;
