@@ -380,9 +380,7 @@ def main():
 
     def global_minmax():
         pass_a()
-        if group is not None:
-            dist.all_reduce(minmax[:W], op=dist.ReduceOp.MIN)
-            dist.all_reduce(minmax[W:], op=dist.ReduceOp.MAX)
+        ops._all_reduce_minmax(minmax, W, group)
 
     global_minmax()
     pass_b()
