@@ -77,9 +77,13 @@ size_t fused_smem_bytes(int W, int ppt, bool prune) {
            (size_t)W * bit_stride(ppt) * sizeof(unsigned) + (size_t)W * 8 * sizeof(float);
 }
 
-// Unweighted dm/dy and dm/dy x y of one (point, pose) into a tie-set accumulator (7 doubles).
-__device__ __noinline__ void tie_accumulate(float x, float y, float z, const float4* row, CovConst C, double* acc,
-                                            int slot) {
+// Unweighted dm/dy and dm/dy x y of one (point, pose) into a tie-set accumulator (7 doubles).  Rare (one point per
+// pose and step), so it is a real call; it takes the pose INDEX and finds the row in the pose table at the start of
+// dynamic shared memory (where every kernel of this file keeps it) — passing a row pointer would make the callers
+// compute a generic shared-memory address on every iteration of their hot loops.
+__device__ __noinline__ void tie_accumulate(float x, float y, float z, int w, CovConst C, double* acc, int slot) {
+    extern __shared__ float4 smem4[];
+    const float4* row = smem4 + (size_t)w * COV_ROW_F4;
     double* dst = acc + slot;
     CovEval ev;
     const float m = cov_vis<true>(x, y, z, row[0], row[1], row[2], row[3], C, &ev);
@@ -124,6 +128,16 @@ __device__ __forceinline__ float minmax_qcap(unsigned mn, unsigned mx, float inv
     float cap = __uint_as_float(0x7f800000u);
     if (mn == 0u && mx != 0u) cap = (1e-4f - __log2f(__uint_as_float(mx))) * inv_kd * 1.000001f;
     return cap;
+}
+
+// Pose-table row loads by 32-bit shared address (the address is formed once per kernel; with generic pointers the
+// compiler re-derives the shared window base inside the hot loops).  The table is constant after the prologue barrier.
+__device__ __forceinline__ float4 lds_row(unsigned table_saddr, int w, int i) {
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+        : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+        : "r"(table_saddr + (unsigned)(w * COV_ROW_F4 + i) * 16u));
+    return v;
 }
 
 // ---- TMA bulk copies (global -> shared) completing on an mbarrier ------------------------------------------------
@@ -685,7 +699,7 @@ __device__ __forceinline__ unsigned* bit_row_group(unsigned* bits, int w, int gr
 // the gate bit matrix.  TILES = pruned kernel: the conservative threshold lives in v5.w (v3.w holds qthr), nothing
 // is stored, and the return value says whether this warp has a gated pair for the pose (U = 1).
 template <int PPT, int U, bool AMIN, bool TILES>
-__device__ __forceinline__ bool fused_pose_iter(int w, const float4* __restrict__ ptab, unsigned* __restrict__ bits,
+__device__ __forceinline__ bool fused_pose_iter(int w, unsigned ptab, unsigned* __restrict__ bits,
                                                 int warp, const float (&px)[PPT], const float (&py)[PPT],
                                                 const float (&pz)[PPT], float (&L)[PPT], const CovConst& C,
                                                 double* __restrict__ acc, int lane) {
@@ -694,8 +708,8 @@ __device__ __forceinline__ bool fused_pose_iter(int w, const float4* __restrict_
     unsigned anyb = 0u;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-        const float4* row = ptab + (size_t)(w + u) * COV_ROW_F4;
-        const float4 v0 = row[0], v1 = row[1], v2 = row[2], v3 = row[3];
+        const float4 v0 = lds_row(ptab, w + u, 0), v1 = lds_row(ptab, w + u, 1), v2 = lds_row(ptab, w + u, 2),
+                     v3 = lds_row(ptab, w + u, 3);
 #pragma unroll
         for (int s = 0; s < PPT; ++s) m[u][s] = cov_vis<false>(px[s], py[s], pz[s], v0, v1, v2, v3, C, nullptr);
         mmax[u] = m[u][0];
@@ -703,16 +717,15 @@ __device__ __forceinline__ bool fused_pose_iter(int w, const float4* __restrict_
         for (int s = 1; s + 1 < PPT; s += 2) mmax[u] = fmaxf(mmax[u], fmaxf(m[u][s], m[u][s + 1]));
         if ((PPT & 1) == 0) mmax[u] = fmaxf(mmax[u], m[u][PPT - 1]);
         // >= 0  <=>  some point of this lane may pass the gate (conservative threshold)
-        mmax[u] -= TILES ? row[5].w : v3.w;
+        mmax[u] -= TILES ? lds_row(ptab, w + u, 5).w : v3.w;
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-        const float4* row = ptab + (size_t)(w + u) * COV_ROW_F4;
         unsigned bal[PPT];
 #pragma unroll
         for (int s = 0; s < PPT; ++s) bal[s] = 0u;
         if (__any_sync(kFull, mmax[u] >= 0.f)) {  // warp-uniform; a few % of (warp, pose) iterations
-            const float4 v4 = row[4];
+            const float4 v4 = lds_row(ptab, w + u, 4);
 #pragma unroll
             for (int s = 0; s < PPT; ++s) {
                 const float d = __fsub_rn(m[u][s], v4.w);
@@ -722,7 +735,7 @@ __device__ __forceinline__ bool fused_pose_iter(int w, const float4* __restrict_
                     const float p = __fmul_rn(d, v4.z);
                     const float qc = (p > C.hi) ? C.hi : p;  // upper clip; a NaN p (pose that sees nothing: 0/0) stays NaN, as torch.clip
                     L[s] += COV_LN2_F * cov_lg2(qc * cov_rcp(1.f - qc));
-                    if (acc && d == v4.y) tie_accumulate(px[s], py[s], pz[s], row, C, acc, (w + u) * COV_ACC_STRIDE + 8);
+                    if (acc && d == v4.y) tie_accumulate(px[s], py[s], pz[s], w + u, C, acc, (w + u) * COV_ACC_STRIDE + 8);
                 }
             }
         }
@@ -736,11 +749,11 @@ __device__ __forceinline__ bool fused_pose_iter(int w, const float4* __restrict_
             else brow[0] = bal[0];
         }
         if (AMIN) {  // only compact clouds whose minimum did not underflow to 0 (block-uniform choice of the loop)
-            const float a = row[4].w;
+            const float a = lds_row(ptab, w + u, 4).w;
             if (a > 0.f) {
 #pragma unroll
                 for (int s = 0; s < PPT; ++s)
-                    if (m[u][s] == a) tie_accumulate(px[s], py[s], pz[s], row, C, acc, (w + u) * COV_ACC_STRIDE + 15);
+                    if (m[u][s] == a) tie_accumulate(px[s], py[s], pz[s], w + u, C, acc, (w + u) * COV_ACC_STRIDE + 15);
             }
         }
     }
@@ -868,6 +881,7 @@ cov_traj_fused_kernel(const float* __restrict__ xyz, int64_t n, const float* __r
     double sum_r = 0.0;
     const int64_t ntiles = (n + T - 1) / T;
     const bool check_amin = amin_pos != 0;
+    const unsigned ptab_s = smem_u32(ptab);
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         float px[PPT], py[PPT], pz[PPT], L[PPT];
         bool valid[PPT];
@@ -888,10 +902,10 @@ cov_traj_fused_kernel(const float* __restrict__ xyz, int64_t n, const float* __r
         {
             int w = 0;
             if (check_amin) {  // arg-min points carry gradient: every pair must be looked at
-                for (; w < W; ++w) fused_pose_iter<PPT, 1, true, false>(w, ptab, bits, warp, px, py, pz, L, C, acc, lane);
+                for (; w < W; ++w) fused_pose_iter<PPT, 1, true, false>(w, ptab_s, bits, warp, px, py, pz, L, C, acc, lane);
             } else {
-                for (; w + U <= W; w += U) fused_pose_iter<PPT, U, false, false>(w, ptab, bits, warp, px, py, pz, L, C, acc, lane);
-                for (; w < W; ++w) fused_pose_iter<PPT, 1, false, false>(w, ptab, bits, warp, px, py, pz, L, C, acc, lane);
+                for (; w + U <= W; w += U) fused_pose_iter<PPT, U, false, false>(w, ptab_s, bits, warp, px, py, pz, L, C, acc, lane);
+                for (; w < W; ++w) fused_pose_iter<PPT, 1, false, false>(w, ptab_s, bits, warp, px, py, pz, L, C, acc, lane);
             }
         }
 #pragma unroll
@@ -969,6 +983,7 @@ cov_traj_fused_tiles_kernel(const float* __restrict__ xyz, int64_t n, const floa
     const int64_t nfull = n / T;
     const int nwords = (W + 31) >> 5;
     unsigned* wg = wgate[warp];
+    const unsigned ptab_s = smem_u32(ptab);
     unsigned uses0 = 0, uses1 = 0;
     if (tid == 0 && (int)blockIdx.x < count)
         stage_issue<PPT>(stage, &mbar[0], xyz, boxes, amask_g, mask_stride, (int64_t)worklist[blockIdx.x], nfull, out_index);
@@ -1031,8 +1046,8 @@ cov_traj_fused_tiles_kernel(const float* __restrict__ xyz, int64_t n, const floa
                 if (!__any_sync(kFull, !(qmin > v3.w))) continue;
                 ++n_full;
                 const bool g = check_amin
-                                   ? fused_pose_iter<PPT, 1, true, true>(w, ptab, nullptr, warp, px, py, pz, L, C, acc, lane)
-                                   : fused_pose_iter<PPT, 1, false, true>(w, ptab, nullptr, warp, px, py, pz, L, C, acc, lane);
+                                   ? fused_pose_iter<PPT, 1, true, true>(w, ptab_s, nullptr, warp, px, py, pz, L, C, acc, lane)
+                                   : fused_pose_iter<PPT, 1, false, true>(w, ptab_s, nullptr, warp, px, py, pz, L, C, acc, lane);
                 if (g) gbits |= 1u << b;
             }
             if (lane == 0) wg[c] = gbits;
@@ -1202,6 +1217,7 @@ cov_sweep_tiles_kernel(const float* __restrict__ xyz, int64_t n, const float4* _
     const int count = count_ptr[0];
     const int64_t nfull = n / T;
     const int nwords = (W + 31) >> 5;
+    const unsigned ptab_s = smem_u32(ptab);
     unsigned uses0 = 0, uses1 = 0;
     if (tid == 0 && (int)blockIdx.x < count)
         stage_issue<PPT>(stage, &mbar[0], xyz, boxes, amask_g, mask_stride, (int64_t)worklist[blockIdx.x], nfull);
@@ -1272,7 +1288,7 @@ cov_sweep_tiles_kernel(const float* __restrict__ xyz, int64_t n, const float4* _
 #pragma unroll
                     for (int s = 0; s < PPT; ++s) L[s] = 0.f;
                 }
-                touched |= fused_pose_iter<PPT, 1, false, true>(w, ptab, nullptr, warp, px, py, pz, L, C, nullptr, lane);
+                touched |= fused_pose_iter<PPT, 1, false, true>(w, ptab_s, nullptr, warp, px, py, pz, L, C, nullptr, lane);
             }
         }
         flush();
