@@ -467,7 +467,7 @@ def main():
             "pass_a": {"tile_listed": frac(st[7], st[2]), "prefiltered": frac(st[5], st[2]), "full": frac(st[3], st[2])}},
         "dense": {
             "note": "pruning off: every (point, pose) pair fully evaluated; FP32-issue bound; 64 flop per forward evaluation",
-            "pass_b": {"kernel": "cov_traj_fused_kernel<4,0,1>", "bound": "fp32", "ms_per_launch": ms_b_dense,
+            "pass_b": {"kernel": "cov_traj_fused_kernel<4,0,2>", "bound": "fp32", "ms_per_launch": ms_b_dense,
                        "achieved": dense_tf_b, "peak": fp32_meas, "unit": "TFLOP/s", "frac": dense_tf_b / fp32_meas,
                        "frac_of_nominal": dense_tf_b / FP32_NOMINAL_TFLOPS},
             "pass_a": {"kernel": "cov_traj_minmax_kernel<8,2,2>", "bound": "fp32", "ms_per_launch": ms_a_dense,

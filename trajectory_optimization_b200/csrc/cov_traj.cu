@@ -1617,8 +1617,8 @@ extern "C" int cov_traj_fused(const float* xyz, int64_t n, const float* poses, c
         int grid = 1;
 #define LAUNCH_F(P, UP)                                                                                           \
     {                                                                                                             \
-        grid = grid_for(cov_traj_fused_kernel<P, UP, 1>, smem, ntiles);                                           \
-        cov_traj_fused_kernel<P, UP, 1><<<grid, COV_THREADS, smem, s>>>(xyz, n, poses, quats, W, K, C, minmax,    \
+        grid = grid_for(cov_traj_fused_kernel<P, UP, 2>, smem, ntiles);                                           \
+        cov_traj_fused_kernel<P, UP, 2><<<grid, COV_THREADS, smem, s>>>(xyz, n, poses, quats, W, K, C, minmax,    \
                                                                         upstream, reward_index, rewards, t.partials, \
                                                                         t.sumr, acc, seg_log2, run_flag);         \
     }
