@@ -16,6 +16,8 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000_000
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 dev = torch.device("cuda:0")
 L = _lib.lib()
+if os.environ.get("COV_PRUNING", "1") == "0":  # profile the dense kernels instead
+    L.cov_set_pruning(0)
 pts, perm = ops.spatial_sort(bench.make_cloud_shard(n, 0, 1, dev))
 boxes = ops.tile_boxes(pts)
 K, iw, ih = tools.load_intrinsics(dev)
