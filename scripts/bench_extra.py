@@ -76,6 +76,32 @@ torch.cuda.synchronize()
 wall = (time.perf_counter() - t0) / 500 * 1e3
 print(json.dumps({"config": "c1: ModelPose opt step as one CUDA graph (graphs.GraphedStep), 100k points", "gpu_ms_per_step": ms,
                   "wall_ms_per_step": wall}), flush=True)
+# the reference's trajectory optimisation step (src/trajectory_optimization.py:106-116; its comment: "~125 msec") on the
+# sample inputs the reference ships (40 k points, 27 waypoints), eager and as one CUDA graph
+sample = np.load(os.path.join(ROOT, "tests", "golden", "sample_inputs.npz"))
+spts, sposes = torch.from_numpy(sample["pts"]).float(), torch.from_numpy(sample["poses"]).float()
+squats = torch.tensor([[1.0, 0.0, 0.0, 0.0]]).repeat(sposes.shape[0], 1)
+for graphed in (False, True):
+    mt = model.ModelTraj(spts, sposes, squats, K, iw, ih, device=dev)
+    optt = torch.optim.Adam([{"params": [mt.poses], "lr": 0.1}, {"params": [mt.quats], "lr": 0.02}], capturable=graphed)
+    if graphed:
+        gs = GraphedStep(mt, optt)
+        fn = gs.step
+    else:
+        def fn():
+            optt.zero_grad()
+            loss = mt()
+            loss.backward()
+            optt.step()
+    ms = events(fn, 200)
+    t0 = time.perf_counter()
+    for _ in range(200):
+        fn()
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / 200 * 1e3
+    print(json.dumps({"config": "ModelTraj opt step (zero_grad+fwd+bwd+Adam) on the reference's sample cloud and path, "
+                                + ("one CUDA graph" if graphed else "eager"),
+                      "gpu_ms_per_step": ms, "wall_ms_per_step": wall}), flush=True)
 # ModelPose kernel alone at 1e8 points vs HBM
 big = box(100_000_000, 1)
 T = torch.tensor([[6.0, 2.0, 0.0]], device=dev, requires_grad=True)

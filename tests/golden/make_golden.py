@@ -158,9 +158,47 @@ def codec_fixtures():
              dict(xyz=np.asarray(out, np.float64).reshape(-1, 3), xyz_all=np.asarray(out_all, np.float64).reshape(-1, 3)))
 
 
+def opt_loop_fixtures():
+    """The optimisation loops of src/pose_optimization.py:82-137 and src/trajectory_optimization.py:83-116 (model +
+    Adam with per-parameter learning rates, zero_grad / forward / backward / step), 10 steps on the sample inputs."""
+    sample = np.load(os.path.join(HERE, "sample_inputs.npz"))
+    pts = torch.from_numpy(sample["pts"]).float()
+    steps, lr_pose, lr_quat = 10, 0.1, 0.02
+    m = ref_model.ModelPose(pts, torch.tensor([[6.0, 2.0, 0.0]]), torch.tensor([[1.0, 0.0, 0.0, 0.0]]), K, IMG_W, IMG_H,
+                            1.0, 5.0, CPU)
+    opt = torch.optim.Adam([{"params": [m.trans], "lr": lr_pose}, {"params": [m.quat], "lr": lr_quat}])
+    hist = []
+    for _ in range(steps):
+        opt.zero_grad()
+        loss = m()
+        loss.backward()
+        opt.step()
+        hist.append(loss.item())
+    save("opt_pose_sample", dict(trans0=np.array([[6.0, 2.0, 0.0]], np.float32), quat0=np.array([[1.0, 0, 0, 0]], np.float32),
+                                 steps=steps, lr_pose=lr_pose, lr_quat=lr_quat),
+         dict(loss_history=np.array(hist), trans=m.trans.detach().numpy().copy(), quat=m.quat.detach().numpy().copy()))
+    poses = torch.from_numpy(sample["poses"]).float()
+    quats = torch.tensor([[1.0, 0.0, 0.0, 0.0]]).repeat(poses.shape[0], 1)
+    mt = ref_model.ModelTraj(pts, poses, quats, K, IMG_W, IMG_H, device=CPU)
+    opt = torch.optim.Adam([{"params": [mt.poses], "lr": lr_pose}, {"params": [mt.quats], "lr": lr_quat}])
+    hist, vis = [], []
+    for _ in range(steps):
+        opt.zero_grad()
+        loss = mt()
+        loss.backward()
+        opt.step()
+        hist.append(loss.item())
+        vis.append(float(mt.loss["vis"]))
+    save("opt_traj_sample", dict(steps=steps, lr_pose=lr_pose, lr_quat=lr_quat),
+         dict(loss_history=np.array(hist), vis_history=np.array(vis), poses=mt.poses.detach().numpy().copy(),
+              quats=mt.quats.detach().numpy().copy(), mean_reward=float(mt.rewards.mean())))
+
+
 def main():
     if "--only-codec" in sys.argv:
         return codec_fixtures()
+    if "--only-opt" in sys.argv:
+        return opt_loop_fixtures()
     sample = np.load(os.path.join(REF, "data/points/point_cloud_10.npz"))["pts"].astype(np.float32)
     path = np.load(os.path.join(REF, "data/paths/path_poses_10.npz"))["poses"].astype(np.float32)
     np.savez_compressed(os.path.join(HERE, "sample_inputs.npz"), pts=sample, poses=path)
@@ -253,6 +291,7 @@ def main():
     vis, mask = ref_tools.hidden_pts_removal(cam, CPU)
     save("hpr_sample", dict(points=cam, R_param=2), dict(idx=np.flatnonzero(mask.numpy())))
     codec_fixtures()
+    opt_loop_fixtures()
 
 
 if __name__ == "__main__":

@@ -547,3 +547,65 @@ def test_pose_that_sees_nothing_gives_nan_like_the_reference(dev, mod):
             assert bool(torch.isnan(mean)) and bool(torch.isnan(rewards).all())
     finally:
         _lib.lib().cov_set_pruning(1)
+
+
+def _import_dropin(name):
+    """Import `model` / `tools` by MODULE NAME from the drop-in directory, the way the reference's nodes do
+    (sys.path.append(<pkg>/src); from model import ModelTraj — src/trajectory_optimization.py:6-9)."""
+    import importlib
+    import os
+    import sys
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "trajectory_optimization_b200", "dropin")
+    sys.path.insert(0, d)
+    try:
+        sys.modules.pop(name, None)
+        return importlib.import_module(name)
+    finally:
+        sys.path.remove(d)
+        sys.modules.pop(name, None)
+
+
+def test_reference_optimisation_loops_run_unchanged_on_the_dropin(dev, sample_inputs):
+    """The loops of src/pose_optimization.py:129-137 and src/trajectory_optimization.py:106-116, verbatim, on the drop-in
+    `model`/`tools` modules: 10 Adam steps follow the loss history and reach the parameters of the reference run on CPU
+    (fixtures opt_pose_sample / opt_traj_sample, made by running the reference)."""
+    model = _import_dropin("model")
+    tools = _import_dropin("tools")
+    K, Wd, Hd = tools.load_intrinsics(device=dev)
+    pts = torch.from_numpy(sample_inputs["pts"]).float().to(dev)
+    g = load_golden("opt_pose_sample")
+    m = model.ModelPose(points=pts, trans0=torch.from_numpy(g["in_trans0"]).to(dev), q0=torch.from_numpy(g["in_quat0"]).to(dev),
+                        intrins=K, img_width=Wd, img_height=Hd, device=dev).to(dev)
+    optimizer = torch.optim.Adam([{"params": list([m.trans]), "lr": float(g["in_lr_pose"])},
+                                  {"params": list([m.quat]), "lr": float(g["in_lr_quat"])}])
+    hist = []
+    for _ in range(int(g["in_steps"])):
+        optimizer.zero_grad()
+        loss = m(debug=False)
+        loss.backward()
+        optimizer.step()
+        hist.append(loss.item())
+    assert rel_err(np.array(hist), g["out_loss_history"]) < 1e-4
+    assert rel_err(m.trans.detach().cpu().numpy(), g["out_trans"]) < 1e-3
+    assert rel_err(m.quat.detach().cpu().numpy(), g["out_quat"]) < 1e-3
+
+    g = load_golden("opt_traj_sample")
+    poses = torch.from_numpy(sample_inputs["poses"]).float()
+    quats = torch.tensor([[1.0, 0.0, 0.0, 0.0]]).repeat(poses.shape[0], 1)
+    mt = model.ModelTraj(points=pts, wps_poses=poses, wps_quats=quats, intrins=K, img_width=Wd, img_height=Hd,
+                         device=dev).to(dev)
+    optimizer = torch.optim.Adam([{"params": list([mt.poses]), "lr": float(g["in_lr_pose"])},
+                                  {"params": list([mt.quats]), "lr": float(g["in_lr_quat"])}])
+    hist, vis = [], []
+    for _ in range(int(g["in_steps"])):
+        optimizer.zero_grad()
+        loss = mt()
+        loss.backward()
+        optimizer.step()
+        hist.append(loss.item())
+        vis.append(float(mt.loss["vis"]))
+    assert rel_err(np.array(hist), g["out_loss_history"]) < 2e-4
+    assert rel_err(np.array(vis), g["out_vis_history"]) < 2e-4
+    assert rel_err(mt.poses.detach().cpu().numpy(), g["out_poses"]) < 1e-3
+    assert rel_err(mt.quats.detach().cpu().numpy(), g["out_quats"]) < 1e-3
+    assert rel_err(float(torch.mean(mt.rewards)), float(g["out_mean_reward"])) < 1e-4
