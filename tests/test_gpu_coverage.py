@@ -478,13 +478,16 @@ def test_graphed_optimisation_step_matches_eager(dev, mod):
 
 
 @pytest.mark.parametrize("n,W,mode", [(1, 1, "box"), (31, 7, "box"), (129, 33, "box"), (4097, 100, "box"), (70_001, 500, "box"),
-                                      (300_000, 64, "far"), (200_003, 40, "mixed"), (1_000_001, 1100, "box")])
+                                      (300_000, 64, "far"), (200_003, 40, "mixed"), (1_000_001, 1100, "box"),
+                                      (70_003, -1, "box"), (66_000, -2, "box")])
 def test_pruned_pipeline_equals_dense_on_edge_shapes(n, W, mode, dev, mod):
     """Cull -> work list -> tiles kernels against the dense kernels on ragged sizes, one pose, more poses than one
     mask word / one slot round, clouds that are almost entirely out of reach and clouds with a far-away half."""
     from trajectory_optimization_b200 import _lib
     model, tools, ops = mod
     L = _lib.lib()
+    if W < 0:   # the largest pose tables: 1 and 2 points per thread, one block per SM, several mask words and slot rounds
+        W = L.cov_traj_max_poses() if W == -1 else (L.cov_traj_max_poses() * 3) // 4
     gen = np.random.default_rng(n + W)
     pts_np = _box(gen, n)
     if mode == "far":
