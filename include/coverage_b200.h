@@ -176,6 +176,22 @@ int cov_pc2_to_xyz(const uint8_t* data_dev, int64_t n, int point_step, int off_x
 int cov_xyz_to_pc2(const float* xyz_dev, const float* extra_dev, int64_t n, uint8_t* data_dev, int* is_dense_dev,
                    void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Voxel-grid downsample with an optional pass-through on one axis.
+ * ref: launch/voxels_filtering.launch:8-21 (pcl/VoxelGrid nodelet in front of the optimiser: leaf_size 0.1,
+ * filter_field_name z, filter_limit_min/max, filter_limit_negative False).  Algorithm restated from
+ * pcl::VoxelGrid<PointXYZ>::applyFilter (PCL 1.8-1.10, third party, not in the reference tree): finite points with
+ * limit_min <= p[filter_axis] <= limit_max (filter_axis -1: no pass-through) are binned into voxels of edge `leaf`
+ * anchored at floor(min/leaf); output = one fp32 centroid per occupied voxel, ascending voxel index (x fastest).
+ *   xyz_out_dev (n,3) fp32, first *count_dev rows valid;  info_dev 8 int32: [0..2] min_b, [3..5] div_b,
+ *   [6] != 0: the grid would have more than 2^31-1 cells (PCL: "Leaf size is too small"), nothing is written,
+ *   [7] number of voxels.
+ * ------------------------------------------------------------------------------------------ */
+size_t cov_voxel_grid_workspace_bytes(int64_t n);
+int cov_voxel_grid(const float* xyz_dev, int64_t n, float leaf, int filter_axis, float limit_min, float limit_max,
+                   float* xyz_out_dev, int64_t* count_dev, int32_t* info_dev, void* workspace_dev,
+                   size_t workspace_bytes, void* stream);
+
 /* Exact pruning of (point, pose) pairs in cov_traj_minmax / cov_traj_fused (default on): a pair whose distance
  * Gaussian alone bounds m below what could matter (a sampled lower bound of the maximum in pass A once a zero
  * minimum is known; the gate threshold in pass B) is never evaluated.  Pipeline per call: cull (one warp per tile of

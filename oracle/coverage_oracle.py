@@ -445,3 +445,36 @@ def xyz_to_pc2(points):
     """xyz(i)_array_to_pointcloud2 (:290-338): payload bytes, point_step, is_dense."""
     pts = np.asarray(points, np.float32)
     return pts.tobytes(), 4 * pts.shape[1], int(np.isfinite(pts).all())
+
+
+# ------------------------------------------------------------------------------------------
+# voxel-grid filter: restatement of pcl::VoxelGrid<PointXYZ>::applyFilter (PCL 1.8-1.10; third party, not in the
+# reference tree, configured by launch/voxels_filtering.launch:8-21).  PARITY UNPINNED: no PCL in this image and the
+# reference holds no golden output; PCL's own output is defined only up to the fp32 summation order inside a voxel
+# (std::sort is unstable).  This restatement fixes that order to the original point order.
+# ------------------------------------------------------------------------------------------
+def voxel_grid(points, leaf=0.1, axis=2, limit_min=-2.5, limit_max=2.5):
+    p = np.asarray(points, np.float32)
+    keep = np.isfinite(p).all(1)
+    if axis is not None and axis >= 0:
+        keep &= ~((p[:, axis] > np.float32(limit_max)) | (p[:, axis] < np.float32(limit_min)))
+    q = p[keep]
+    if q.shape[0] == 0:
+        return np.zeros((0, 3), np.float32)
+    inv = np.float32(1.0) / np.float32(leaf)
+    min_b = np.floor(q.min(0) * inv).astype(np.int64)
+    max_b = np.floor(q.max(0) * inv).astype(np.int64)
+    div_b = max_b - min_b + 1
+    if int(div_b[0]) * int(div_b[1]) * int(div_b[2]) > 2 ** 31 - 1:
+        raise OverflowError("Leaf size is too small for the input dataset. Integer indices would overflow.")
+    ijk = (np.floor(q * inv) - min_b.astype(np.float32)).astype(np.int64)
+    idx = ijk[:, 0] + ijk[:, 1] * div_b[0] + ijk[:, 2] * div_b[0] * div_b[1]
+    order = np.argsort(idx, kind="stable")
+    sidx, sq = idx[order], q[order]
+    starts = np.flatnonzero(np.r_[True, sidx[1:] != sidx[:-1]])
+    counts = np.diff(np.r_[starts, len(sidx)])
+    acc = np.zeros((len(starts), 3), np.float32)
+    for r in range(int(counts.max())):          # r-th member of every voxel: sequential fp32 sums, in point order
+        sel = counts > r
+        acc[sel] = acc[sel] + sq[starts[sel] + r]
+    return acc / counts.astype(np.float32)[:, None]

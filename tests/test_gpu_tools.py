@@ -188,3 +188,28 @@ def test_pointcloud2_errors_are_loud(dev):
     msg.fields = [_Field("x", 0, 7), _Field("y", 4, 7)]
     with pytest.raises(ValueError):
         pcu.pointcloud2_to_xyz_tensor(msg, device=dev)
+
+
+# ---------------- voxel-grid filter (launch/voxels_filtering.launch, pcl::VoxelGrid restated) ----------------
+@pytest.mark.parametrize("n,leaf,axis", [(1, 0.1, 2), (1000, 0.1, 2), (20_000, 0.25, 2), (300_007, 0.1, None), (50_000, 50.0, 0)])
+def test_voxel_grid_matches_oracle(n, leaf, axis, dev, tools):
+    gen = np.random.default_rng(n)
+    pts = (gen.random((n, 3)) * np.array([12, 9, 8]) + np.array([-6, -4, -4])).astype(np.float32)
+    if n > 100:
+        pts[::53, 0] = np.nan
+        pts[7] = [np.inf, 0, 0]
+        pts[11:13] = pts[10]                       # duplicates share a voxel
+    name = None if axis is None else "xyz"[axis]
+    out = tools.voxel_grid_filter(torch.from_numpy(pts).to(dev), leaf, name, -2.5, 2.5)
+    ref = orc.voxel_grid(pts, leaf, axis, -2.5, 2.5)
+    assert out.dtype == torch.float32 and tuple(out.shape) == ref.shape
+    assert np.array_equal(out.cpu().numpy(), ref)           # same voxels, same order, same fp32 centroids
+    out2 = tools.voxel_grid_filter(torch.from_numpy(pts).to(dev), leaf, name, -2.5, 2.5)
+    assert torch.equal(out, out2)                            # deterministic
+
+
+def test_voxel_grid_rejects_too_fine_a_grid(dev, tools):
+    pts = torch.tensor([[0.0, 0.0, 0.0], [100.0, 100.0, 1.0]], device=dev)
+    with pytest.raises(RuntimeError, match="too small"):
+        tools.voxel_grid_filter(pts, 1e-3, None)
+    assert tools.voxel_grid_filter(torch.zeros(0, 3, device=dev)).shape == (0, 3)

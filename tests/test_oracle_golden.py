@@ -174,3 +174,33 @@ def test_pointcloud2_decode_restatement_matches_reference(name):
     payload, step_out, dense = orc.xyz_to_pc2(out.astype(np.float32))
     back = orc.pc2_to_xyz(payload, out.shape[0], step_out, [("x", 0, 7), ("y", 4, 7), ("z", 8, 7)], remove_nans=False)
     assert step_out == 12 and dense == 1 and np.array_equal(back.astype(np.float32), out.astype(np.float32))
+
+
+def test_voxel_grid_restatement_properties():
+    """pcl::VoxelGrid restatement (parity unpinned: no PCL here): one point per occupied voxel, every centroid inside its
+    voxel, voxels in ascending index, pass-through limits inclusive, non-finite points dropped."""
+    gen = np.random.default_rng(0)
+    pts = (gen.random((20000, 3)) * np.array([6, 5, 8]) + np.array([-3, -2, -4])).astype(np.float32)
+    pts[::97, 1] = np.nan
+    pts[5] = [0.0, 0.0, 2.5]      # on the upper limit: kept
+    pts[6] = [0.0, 0.0, 2.5001]   # just outside: dropped
+    leaf = 0.25
+    out = orc.voxel_grid(pts, leaf, 2, -2.5, 2.5)
+    keep = np.isfinite(pts).all(1) & (pts[:, 2] >= -2.5) & (pts[:, 2] <= 2.5)
+    q = pts[keep]
+    inv = np.float32(1) / np.float32(leaf)
+    cell = np.floor(q * inv).astype(np.int64)
+    assert out.shape[0] == len(np.unique(cell, axis=0)) and out.dtype == np.float32
+    ocell = np.floor(out * inv + 0.0).astype(np.int64)
+    lo = ocell.astype(np.float32) * np.float32(leaf)
+    assert (out >= lo - 1e-5).all() and (out <= lo + np.float32(leaf) + 1e-5).all()
+    mn = cell.min(0)
+    d = cell.max(0) - mn + 1
+    lin = (ocell[:, 0] - mn[0]) + (ocell[:, 1] - mn[1]) * d[0] + (ocell[:, 2] - mn[2]) * d[0] * d[1]
+    assert (np.diff(lin) > 0).all()
+    assert out[:, 2].max() <= 2.5 and np.isfinite(out).all()
+    assert orc.voxel_grid(pts, 100.0, None).shape == (8, 3)          # the cloud straddles the origin: 2 x 2 x 2 voxels
+    one = orc.voxel_grid(np.nan_to_num(pts) + np.float32(10.0), 100.0, None)
+    assert one.shape == (1, 3) and np.allclose(one[0], (np.nan_to_num(pts) + np.float32(10.0)).mean(0), rtol=1e-4)
+    with pytest.raises(OverflowError):
+        orc.voxel_grid(pts, 1e-4, None)

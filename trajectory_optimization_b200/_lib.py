@@ -50,6 +50,8 @@ PROTOTYPES = {
     "cov_pc2_workspace_bytes": (_sz, [_i64]),
     "cov_pc2_to_xyz": (_int, [_vp, _i64, _int, _int, _int, _int, _int, _int, _vp, _vp, _vp, _sz, _vp]),
     "cov_xyz_to_pc2": (_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
+    "cov_voxel_grid_workspace_bytes": (_sz, [_i64]),
+    "cov_voxel_grid": (_int, [_vp, _i64, _f, _int, _f, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
     "cov_set_pruning": (None, [_int]),
     "cov_get_pruning": (_int, []),
     "cov_stats": (_int, [_int, _vp]),

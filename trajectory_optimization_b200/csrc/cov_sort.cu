@@ -10,6 +10,7 @@
 //      set-up work outside the per-step hot path)
 //   4. gather xyz_sorted[j] = xyz[perm[j]]
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "cov_common.cuh"
 #include "../../include/coverage_b200.h"
@@ -148,4 +149,209 @@ extern "C" int cov_spatial_sort(const float* xyz, int64_t n, float* xyz_sorted, 
     const int ggrid = (int)std::min<int64_t>((3 * n + 255) / 256, (int64_t)cov_sm_count_cached() * 32);
     sort_gather_kernel<<<ggrid, 256, 0, s>>>(xyz, n, perm, xyz_sorted);
     return cov_check_launch("cov_spatial_sort");
+}
+
+// ================================= voxel-grid downsample =================================
+// The reference runs a pcl/VoxelGrid nodelet in front of the optimiser (launch/voxels_filtering.launch:8-21: leaf_size,
+// pass-through on z, filter_limit_negative False).  PCL is a third-party dependency that is not in the tree; this is a
+// restatement of pcl::VoxelGrid<PointXYZ>::applyFilter (PCL 1.8-1.10): finite points inside the pass-through limits
+// (inclusive) are binned into leaf-sized voxels, index = (floor(x/leaf) - floor(min/leaf)) + ... x fastest; one output
+// point per occupied voxel = the fp32 centroid of its points, in ascending voxel index.  PCL sorts the point indices
+// with std::sort (unstable), so its own centroids are only reproducible up to fp32 summation order; here the sort is
+// stable (original order within a voxel) and the sum sequential: bitwise deterministic.
+namespace {
+
+struct VoxHeader {          // first 256 bytes of the workspace
+    unsigned box[6];        // ord-mapped min xyz, max xyz of the kept points
+    int min_b[3], div_b[3];
+    int overflow;           // the grid has more than 2^31-1 cells (PCL: "Leaf size is too small")
+    int n_voxels;
+};
+
+__device__ __forceinline__ bool vox_keep(float x, float y, float z, int axis, float lo, float hi) {
+    const float inf = __uint_as_float(0x7f800000u);
+    if (!(fabsf(x) < inf && fabsf(y) < inf && fabsf(z) < inf)) return false;
+    if (axis < 0) return true;
+    const float v = axis == 0 ? x : (axis == 1 ? y : z);
+    return !(v > hi || v < lo);
+}
+
+__global__ void vox_init_kernel(VoxHeader* h) {
+    if (threadIdx.x < 3) h->box[threadIdx.x] = 0xffffffffu;
+    else if (threadIdx.x < 6) h->box[threadIdx.x] = 0u;
+    if (threadIdx.x == 0) {
+        h->overflow = 0;
+        h->n_voxels = 0;
+    }
+}
+
+__global__ void __launch_bounds__(256) vox_box_kernel(const float* __restrict__ xyz, int64_t n, int axis, float lo, float hi,
+                                                      VoxHeader* __restrict__ h) {
+    const float inf = __uint_as_float(0x7f800000u);
+    float mn[3] = {inf, inf, inf}, mx[3] = {-inf, -inf, -inf};
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+        const float p[3] = {__ldg(xyz + j * 3), __ldg(xyz + j * 3 + 1), __ldg(xyz + j * 3 + 2)};
+        if (vox_keep(p[0], p[1], p[2], axis, lo, hi)) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                mn[k] = fminf(mn[k], p[k]);
+                mx[k] = fmaxf(mx[k], p[k]);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const unsigned l = __reduce_min_sync(0xffffffffu, sort_f2ord(mn[k]));
+        const unsigned u = __reduce_max_sync(0xffffffffu, sort_f2ord(mx[k]));
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(&h->box[k], l);
+            atomicMax(&h->box[3 + k], u);
+        }
+    }
+}
+
+__global__ void vox_dims_kernel(VoxHeader* h, float leaf) {
+    if (threadIdx.x != 0) return;
+    const float inv = __fdiv_rn(1.f, leaf);
+    long long cells = 1;
+    for (int k = 0; k < 3; ++k) {
+        const float mn = sort_ord2f(h->box[k]), mx = sort_ord2f(h->box[3 + k]);
+        if (!(mn <= mx)) {  // no point kept
+            h->min_b[k] = 0;
+            h->div_b[k] = 1;
+            continue;
+        }
+        const float fmn = floorf(__fmul_rn(mn, inv)), fmx = floorf(__fmul_rn(mx, inv));
+        if (!(fabsf(fmn) < 2.0e9f && fabsf(fmx) < 2.0e9f)) {
+            h->overflow = 1;
+            h->min_b[k] = 0;
+            h->div_b[k] = 1;
+            continue;
+        }
+        h->min_b[k] = (int)fmn;
+        h->div_b[k] = (int)fmx - (int)fmn + 1;
+        cells *= (long long)h->div_b[k];
+        if (cells > 2147483647LL) h->overflow = 1;
+    }
+}
+
+__global__ void __launch_bounds__(256) vox_key_kernel(const float* __restrict__ xyz, int64_t n, float leaf, int axis, float lo,
+                                                      float hi, const VoxHeader* __restrict__ h, unsigned* __restrict__ keys,
+                                                      int32_t* __restrict__ idx) {
+    const float inv = __fdiv_rn(1.f, leaf);
+    const float b0 = (float)h->min_b[0], b1 = (float)h->min_b[1], b2 = (float)h->min_b[2];
+    const int d0 = h->div_b[0], d01 = h->div_b[0] * h->div_b[1];
+    const bool bad = h->overflow != 0;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+        const float x = __ldg(xyz + j * 3), y = __ldg(xyz + j * 3 + 1), z = __ldg(xyz + j * 3 + 2);
+        unsigned key = 0xffffffffu;  // dropped points sort to the end
+        if (!bad && vox_keep(x, y, z, axis, lo, hi)) {
+            const int i0 = (int)__fsub_rn(floorf(__fmul_rn(x, inv)), b0);
+            const int i1 = (int)__fsub_rn(floorf(__fmul_rn(y, inv)), b1);
+            const int i2 = (int)__fsub_rn(floorf(__fmul_rn(z, inv)), b2);
+            key = (unsigned)(i0 + i1 * d0 + i2 * d01);
+        }
+        keys[j] = key;
+        idx[j] = (int32_t)j;
+    }
+}
+
+__global__ void __launch_bounds__(256) vox_head_kernel(const unsigned* __restrict__ keys, int64_t n, int* __restrict__ head) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned k = keys[i];
+        head[i] = (k != 0xffffffffu && (i == 0 || keys[i - 1] != k)) ? 1 : 0;
+    }
+}
+
+__global__ void __launch_bounds__(256) vox_centroid_kernel(const float* __restrict__ xyz, const unsigned* __restrict__ keys,
+                                                           const int32_t* __restrict__ idx, const int* __restrict__ head,
+                                                           const int* __restrict__ pos, int64_t n, float* __restrict__ out,
+                                                           int64_t* __restrict__ count, VoxHeader* __restrict__ h) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (i == n - 1) {
+            const int total = pos[i] + head[i];
+            *count = total;
+            h->n_voxels = total;
+        }
+        if (!head[i]) continue;
+        const unsigned k = keys[i];
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+        int cnt = 0;
+        for (int64_t j = i; j < n && keys[j] == k; ++j) {  // ascending original index: the sort is stable
+            const int64_t p = idx[j];
+            sx = __fadd_rn(sx, xyz[p * 3]);
+            sy = __fadd_rn(sy, xyz[p * 3 + 1]);
+            sz = __fadd_rn(sz, xyz[p * 3 + 2]);
+            ++cnt;
+        }
+        const float c = (float)cnt;
+        const int64_t o = pos[i];
+        out[o * 3] = __fdiv_rn(sx, c);
+        out[o * 3 + 1] = __fdiv_rn(sy, c);
+        out[o * 3 + 2] = __fdiv_rn(sz, c);
+    }
+}
+
+size_t vox_sort_temp_bytes(int64_t n) {
+    size_t a = 0, b = 0;
+    cub::DoubleBuffer<unsigned> k(nullptr, nullptr);
+    cub::DoubleBuffer<int32_t> v(nullptr, nullptr);
+    cub::DeviceRadixSort::SortPairs(nullptr, a, k, v, (int)n, 0, 32, (cudaStream_t)0);
+    cub::DeviceScan::ExclusiveSum(nullptr, b, (const int*)nullptr, (int*)nullptr, (int)n, (cudaStream_t)0);
+    return a > b ? a : b;
+}
+
+}  // namespace
+
+// workspace: [header 256 B][keys A][keys B][idx A][idx B][head][pos][cub temp]
+extern "C" size_t cov_voxel_grid_workspace_bytes(int64_t n) {
+    if (n < 1) n = 1;
+    return 256 + 6 * align256((size_t)n * 4) + align256(vox_sort_temp_bytes(n)) + 256;
+}
+
+extern "C" int cov_voxel_grid(const float* xyz, int64_t n, float leaf, int filter_axis, float limit_min, float limit_max,
+                              float* xyz_out, int64_t* count, int32_t* info, void* ws, size_t ws_bytes, void* stream) {
+    if (!xyz || !xyz_out || !count || !info || !ws || n <= 0 || !(leaf > 0.f) || filter_axis < -1 || filter_axis > 2) {
+        cov_set_error("cov_voxel_grid: bad argument (n=%lld, leaf=%g, filter_axis=%d)", (long long)n, (double)leaf, filter_axis);
+        return COV_ERR_ARG;
+    }
+    if (n >= ((int64_t)1 << 31)) {
+        cov_set_error("cov_voxel_grid: %lld points exceed the int32 index range", (long long)n);
+        return COV_ERR_UNSUPPORTED;
+    }
+    if (ws_bytes < cov_voxel_grid_workspace_bytes(n) || (((uintptr_t)ws) & 255)) {
+        cov_set_error("cov_voxel_grid: workspace too small or not 256-byte aligned");
+        return COV_ERR_WORKSPACE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    char* base = reinterpret_cast<char*>(ws);
+    VoxHeader* h = reinterpret_cast<VoxHeader*>(base);
+    const size_t col = align256((size_t)n * 4);
+    unsigned* keys_a = reinterpret_cast<unsigned*>(base + 256);
+    unsigned* keys_b = reinterpret_cast<unsigned*>(base + 256 + col);
+    int32_t* idx_a = reinterpret_cast<int32_t*>(base + 256 + 2 * col);
+    int32_t* idx_b = reinterpret_cast<int32_t*>(base + 256 + 3 * col);
+    int* head = reinterpret_cast<int*>(base + 256 + 4 * col);
+    int* pos = reinterpret_cast<int*>(base + 256 + 5 * col);
+    void* temp = base + 256 + 6 * col;
+    size_t temp_bytes = vox_sort_temp_bytes(n);
+    const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)cov_sm_count_cached() * 16);
+    vox_init_kernel<<<1, 32, 0, s>>>(h);
+    vox_box_kernel<<<grid, 256, 0, s>>>(xyz, n, filter_axis, limit_min, limit_max, h);
+    vox_dims_kernel<<<1, 32, 0, s>>>(h, leaf);
+    vox_key_kernel<<<grid, 256, 0, s>>>(xyz, n, leaf, filter_axis, limit_min, limit_max, h, keys_a, idx_a);
+    cub::DoubleBuffer<unsigned> k(keys_a, keys_b);
+    cub::DoubleBuffer<int32_t> v(idx_a, idx_b);
+    if (cub::DeviceRadixSort::SortPairs(temp, temp_bytes, k, v, (int)n, 0, 32, s) != cudaSuccess) {
+        cov_check_launch("cov_voxel_grid (radix sort)");
+        return COV_ERR_CUDA;
+    }
+    vox_head_kernel<<<grid, 256, 0, s>>>(k.Current(), n, head);
+    if (cub::DeviceScan::ExclusiveSum(temp, temp_bytes, head, pos, (int)n, s) != cudaSuccess) {
+        cov_check_launch("cov_voxel_grid (scan)");
+        return COV_ERR_CUDA;
+    }
+    vox_centroid_kernel<<<grid, 256, 0, s>>>(xyz, k.Current(), v.Current(), head, pos, n, xyz_out, count, h);
+    cudaMemcpyAsync(info, &h->min_b[0], 8 * sizeof(int), cudaMemcpyDeviceToDevice, s);  // min_b, div_b, overflow, n_voxels
+    return cov_check_launch("cov_voxel_grid");
 }

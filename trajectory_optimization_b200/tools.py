@@ -214,3 +214,34 @@ def publish_path(path_list, orient_list=None, topic_name="/path", frame_id="worl
         path.header = msg.header
         path.poses.append(msg)
     rospy.Publisher(topic_name, Path, queue_size=1).publish(path)
+
+
+# ------------------------------------------------------------------------------------------
+# voxel-grid filter (launch/voxels_filtering.launch:8-21: the pcl/VoxelGrid nodelet in front of the optimiser)
+# ------------------------------------------------------------------------------------------
+@torch.no_grad()
+def voxel_grid_filter(points, leaf_size=0.1, filter_field_name="z", filter_limit_min=-2.5, filter_limit_max=2.5):
+    """Downsample a cloud to one centroid per occupied voxel, after dropping non-finite points and those outside
+    [filter_limit_min, filter_limit_max] along `filter_field_name` (None: no pass-through).  Defaults are the launch
+    file's.  Returns an (M,3) fp32 CUDA tensor, voxels in ascending index order (x fastest), as pcl::VoxelGrid emits them."""
+    import ctypes
+    from . import _lib
+    L = _lib.lib()
+    pts = ops._dev_f32(points, what="points")
+    n = pts.shape[0]
+    if n == 0:
+        return pts.new_zeros((0, 3))
+    axis = -1 if filter_field_name is None else {"x": 0, "y": 1, "z": 2}[filter_field_name]
+    out = torch.empty_like(pts)
+    cnt = torch.zeros(1, dtype=torch.int64, device=pts.device)
+    info = torch.zeros(8, dtype=torch.int32, device=pts.device)
+    ws_bytes = L.cov_voxel_grid_workspace_bytes(n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=pts.device)
+    _lib.check(L.cov_voxel_grid(pts.data_ptr(), n, float(leaf_size), axis, float(filter_limit_min), float(filter_limit_max),
+                                out.data_ptr(), cnt.data_ptr(), info.data_ptr(), ws.data_ptr(), ws_bytes,
+                                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "cov_voxel_grid")
+    info_h = info.tolist()
+    if info_h[6]:
+        raise RuntimeError("voxel_grid_filter: leaf size is too small for the input dataset (integer voxel indices would "
+                           "overflow) — pcl::VoxelGrid refuses the same input")
+    return out[:int(cnt.item())]
