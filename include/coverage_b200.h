@@ -103,6 +103,14 @@ int cov_traj_fused(const float* xyz_dev, int64_t n, const float* poses_dev, cons
 int cov_traj_epilogue(const double* acc_dev, const float* minmax_dev, const float* quats_dev, int n_poses,
                       int64_t n_total, int upstream_mode, float* out_dev, void* stream);
 
+/* The O(W) regularisers of ModelTraj.criterion and their gradients in one launch.
+ * ref: src/model.py:244-260 (criterion: l2, smooth, length), :135-139 (length_calc), :142-155 (mean_angle_calc).
+ *   poses_dev, poses0_dev (W,3) fp32, W >= 3.  out_dev: 3 + 9*W floats: [0] l2 = |poses[0]-poses0[0]|,
+ *   [1] smooth = w_s/(mean interior angle + eps), [2] length = w_l*|len(poses) - len(poses0)|, then d l2/d poses,
+ *   d smooth/d poses, d length/d poses, (W,3) each.  fp64 inside; torch's conventions at the kinks (gradient 0). */
+int cov_traj_regularizers(const float* poses_dev, const float* poses0_dev, int n_poses, float smoothness_weight,
+                          float traj_length_weight, float eps, float* out_dev, void* stream);
+
 /* Forward-only candidate sweep: n_traj trajectories x poses_per_traj poses each, sharing one cloud.
  * ref: no reference implementation (BASELINE config 5); semantics = ModelTraj.forward per trajectory
  * with every pose evaluated.  sum_rewards_dev[t] += sum_j rewards_j(t) over this shard (doubles,

@@ -81,8 +81,8 @@ print(json.dumps({"config": "c1: ModelPose opt step as one CUDA graph (graphs.Gr
 sample = np.load(os.path.join(ROOT, "tests", "golden", "sample_inputs.npz"))
 spts, sposes = torch.from_numpy(sample["pts"]).float(), torch.from_numpy(sample["poses"]).float()
 squats = torch.tensor([[1.0, 0.0, 0.0, 0.0]]).repeat(sposes.shape[0], 1)
-for graphed in (False, True):
-    mt = model.ModelTraj(spts, sposes, squats, K, iw, ih, device=dev)
+for graphed, fused in ((False, False), (True, False), (False, True), (True, True)):
+    mt = model.ModelTraj(spts, sposes, squats, K, iw, ih, device=dev, fused_regularizers=fused)
     optt = torch.optim.Adam([{"params": [mt.poses], "lr": 0.1}, {"params": [mt.quats], "lr": 0.02}], capturable=graphed)
     if graphed:
         gs = GraphedStep(mt, optt)
@@ -100,7 +100,7 @@ for graphed in (False, True):
     torch.cuda.synchronize()
     wall = (time.perf_counter() - t0) / 200 * 1e3
     print(json.dumps({"config": "ModelTraj opt step (zero_grad+fwd+bwd+Adam) on the reference's sample cloud and path, "
-                                + ("one CUDA graph" if graphed else "eager"),
+                                + ("one CUDA graph" if graphed else "eager") + (", fused regularisers" if fused else ""),
                       "gpu_ms_per_step": ms, "wall_ms_per_step": wall}), flush=True)
 # ModelPose kernel alone at 1e8 points vs HBM
 big = box(100_000_000, 1)

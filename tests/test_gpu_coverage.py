@@ -612,3 +612,44 @@ def test_reference_optimisation_loops_run_unchanged_on_the_dropin(dev, sample_in
     assert rel_err(mt.poses.detach().cpu().numpy(), g["out_poses"]) < 1e-3
     assert rel_err(mt.quats.detach().cpu().numpy(), g["out_quats"]) < 1e-3
     assert rel_err(float(torch.mean(mt.rewards)), float(g["out_mean_reward"])) < 1e-4
+
+
+def test_fused_regularisers_match_the_torch_terms(dev, mod):
+    """cov_traj_regularizers against the same three terms written with torch ops (the reference's formulas, vectorised)
+    and their autograd gradients, on a wiggly path, a path with a repeated waypoint, and the unmoved path (l2 = 0)."""
+    model, tools, ops = mod
+    gen = np.random.default_rng(12)
+    K, Wd, Hd = tools.load_intrinsics(dev)
+    pts = torch.from_numpy(_box(gen, 2000))
+    for case in ("wiggly", "repeated", "unmoved", "long"):
+        W = 300 if case == "long" else 17
+        poses0, _ = _s_curve(W, 14.0)
+        poses = poses0 + (0 if case == "unmoved" else gen.normal(0, 0.15, poses0.shape).astype(np.float32))
+        if case == "repeated":
+            poses[5] = poses[4]
+        quats = np.tile(np.array([1.0, 0, 0, 0], np.float32), (W, 1))
+        m = model.ModelTraj(pts, torch.from_numpy(poses0), torch.from_numpy(quats), K, Wd, Hd, device=dev)
+        with torch.no_grad():
+            m.poses.copy_(torch.from_numpy(poses))
+        m.loss["vis"] = torch.zeros((), device=dev)
+        reg = ops.traj_regularizers(m.poses, m.poses0, m.smoothness_weight, m.traj_length_weight, m.eps)
+        wts = torch.tensor([0.7, 1.3, 2.1], device=dev)
+        (g_fused,) = torch.autograd.grad((reg * wts).sum(), [m.poses])
+        m._criterion_terms_torch()
+        ref = torch.stack([m.loss["l2"], m.loss["smooth"], m.loss["length"]])
+        (g_ref,) = torch.autograd.grad((ref * wts).sum(), [m.poses])
+        assert rel_err(reg.detach().cpu().numpy(), ref.detach().cpu().numpy()) < 2e-5, case
+        if case == "repeated":   # |ab| = 0 at the repeated waypoint: both follow d|v|/dv = 0 there
+            assert torch.isfinite(g_fused).all() and torch.isfinite(g_ref).all()
+        assert rel_err(g_fused.cpu().numpy(), g_ref.cpu().numpy()) < (2e-3 if case == "unmoved" else 2e-4), case
+    # through the model: the opt-in flag changes the loss and its gradient only at the fp32-vs-fp64 level
+    outs = []
+    for flag in (False, True):
+        m = model.ModelTraj(pts, torch.from_numpy(poses0), torch.from_numpy(quats), K, Wd, Hd, device=dev, fused_regularizers=flag)
+        with torch.no_grad():
+            m.poses.add_(0.1 * torch.sin(torch.arange(m.poses.numel(), device=dev).reshape(m.poses.shape).float()))
+        loss = m(vis_wps_dist=0.0)
+        loss.backward()
+        outs.append((loss.item(), m.poses.grad.clone()))
+    assert rel_err(outs[1][0], outs[0][0]) < 1e-5
+    assert rel_err(outs[1][1].cpu().numpy(), outs[0][1].cpu().numpy()) < 2e-4

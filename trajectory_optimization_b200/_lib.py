@@ -39,6 +39,7 @@ PROTOTYPES = {
     "cov_traj_minmax": (_int, [_vp, _i64, _vp, _vp, _int, _vp, _cam, _vp, _vp, _vp, _sz, _vp]),
     "cov_traj_fused": (_int, [_vp, _i64, _vp, _vp, _int, _vp, _cam, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "cov_traj_epilogue": (_int, [_vp, _vp, _vp, _int, _i64, _int, _vp, _vp]),
+    "cov_traj_regularizers": (_int, [_vp, _vp, _int, _f, _f, _f, _vp, _vp]),
     "cov_sweep_rewards": (_int, [_vp, _i64, _vp, _vp, _int, _int, _vp, _cam, _vp, _vp, _vp, _vp, _sz, _vp]),
     "cov_rig_poses": (_int, [_vp, _int, _vp, _int, _vp, _vp, _vp]),
     "cov_rig_poses_backward": (_int, [_vp, _int, _vp, _int, _vp, _vp, _f, _vp, _vp]),

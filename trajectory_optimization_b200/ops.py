@@ -225,6 +225,35 @@ class CoverageTrajFn(torch.autograd.Function):
                 None, None, None, None, None, None)
 
 
+class TrajRegularizersFn(torch.autograd.Function):
+    """(l2, smooth, length) of ModelTraj.criterion (reference src/model.py:248-259) and their gradients w.r.t. the
+    waypoints in one launch (cov_traj_regularizers)."""
+
+    @staticmethod
+    def forward(ctx, poses, poses0, smoothness_weight, traj_length_weight, eps):
+        P = _dev_f32(poses, what="poses").reshape(-1, 3)
+        P0 = _dev_f32(poses0, P.device, "poses0").reshape(-1, 3)
+        W = P.shape[0]
+        out = torch.empty(3 + 9 * W, dtype=torch.float32, device=P.device)
+        _lib.check(_lib.lib().cov_traj_regularizers(_ptr(P), _ptr(P0), W, float(smoothness_weight), float(traj_length_weight),
+                                                    float(eps), _ptr(out), _stream()), "cov_traj_regularizers")
+        ctx.save_for_backward(out)
+        ctx.shape = poses.shape
+        return out[:3].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        (out,) = ctx.saved_tensors
+        W = (out.numel() - 3) // 9
+        grads = out[3:].reshape(3, W * 3)
+        return (g.reshape(1, 3) @ grads).reshape(ctx.shape), None, None, None, None
+
+
+def traj_regularizers(poses, poses0, smoothness_weight, traj_length_weight, eps=1e-6):
+    """Returns a (3,) tensor (l2, smooth, length), differentiable w.r.t. `poses` ((W,3), W >= 3, CUDA)."""
+    return TrajRegularizersFn.apply(poses, poses0, smoothness_weight, traj_length_weight, eps)
+
+
 def coverage_pose(points, trans, quat, intrins, img_width, img_height, min_dist=1.0, max_dist=5.0, eps=1e-6,
                   weight=None, group=None):
     """Fused ModelPose objective.  Returns (observations (N,), total = sum(observations));
