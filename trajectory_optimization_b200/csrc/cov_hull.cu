@@ -8,7 +8,7 @@
 // few dozen..thousand points within a small cap around its direction; a counting sort by direction voxel
 // makes those contiguous.  Kernels:
 //   hull_prep      voxel key + histogram + max |f|                       (12 B/point read)
-//   hull_scan      exclusive scan of the G^3 histogram (one block)
+//   hull_scan      exclusive scan of the G^3 histogram (one block, coalesced chunks with a running carry)
 //   hull_occupied  compact list of non-empty voxels (for the far phase)
 //   hull_scatter   counting-sort scatter into (x, y, z, original index) records
 //   hull_classify  one thread per point: hull_classify_point -> vertex mask, counters
@@ -76,31 +76,51 @@ hull_prep_kernel(const float* __restrict__ f, int64_t n, int G, int* __restrict_
     if ((threadIdx.x & 31) == 0) atomicMax(rho_max_bits, (unsigned long long)__double_as_longlong(mx));
 }
 
-// exclusive scan in place over ncell+1 entries (entry ncell receives the total)
+// exclusive scan in place over ncell+1 entries (entry ncell receives the total).  One block walks the histogram in
+// chunks of 4096 consecutive cells (4 per thread, so a warp touches 512 contiguous bytes) and carries the running total.
 __global__ void __launch_bounds__(1024) hull_scan_kernel(int* __restrict__ cnt, int64_t ncell, int* __restrict__ n_valid) {
-    __shared__ long long sh[1024];
-    const int t = threadIdx.x;
-    const int64_t per = (ncell + 1023) / 1024;
-    const int64_t lo = (int64_t)t * per, hi = (lo + per < ncell) ? lo + per : ncell;
-    long long s = 0;
-    for (int64_t i = lo; i < hi; ++i) s += cnt[i];
-    sh[t] = s;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-        const long long v = (t >= o) ? sh[t - o] : 0;
+    __shared__ int wtot[32];
+    __shared__ int chunk_total;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    int carry = 0;
+    for (int64_t base = 0; base < ncell; base += 4096) {
+        const int64_t i = base + (int64_t)t * 4;
+        int v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = (i + k < ncell) ? cnt[i + k] : 0;
+        const int s = v[0] + v[1] + v[2] + v[3];
+        int incl = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) wtot[warp] = incl;
         __syncthreads();
-        sh[t] += v;
+        if (warp == 0) {
+            const int w = wtot[lane];
+            int sc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, sc, o);
+                if (lane >= o) sc += u;
+            }
+            wtot[lane] = sc - w;  // exclusive over warps
+            if (lane == 31) chunk_total = sc;
+        }
         __syncthreads();
+        int run = carry + wtot[warp] + incl - s;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (i + k < ncell) cnt[i + k] = run;
+            run += v[k];
+        }
+        carry += chunk_total;
+        __syncthreads();  // wtot / chunk_total are rewritten by the next chunk
     }
-    long long run = sh[t] - s;
-    for (int64_t i = lo; i < hi; ++i) {
-        const int c = cnt[i];
-        cnt[i] = (int)run;
-        run += c;
-    }
-    if (t == 1023) {
-        cnt[ncell] = (int)sh[1023];
-        *n_valid = (int)sh[1023];
+    if (t == 0) {
+        cnt[ncell] = carry;
+        *n_valid = carry;
     }
 }
 
