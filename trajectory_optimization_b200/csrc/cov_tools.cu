@@ -43,30 +43,50 @@ cull_flags_kernel(const float* __restrict__ xyz, int64_t n, const float* __restr
     if (threadIdx.x == 0) block_counts[blockIdx.x] = c;
 }
 
-// exclusive scan of block_counts in place (one block); total -> count_out
+// exclusive scan of block_counts in place (one block); total -> count_out.  The array is walked in chunks of 4096
+// consecutive entries (4 per thread: coalesced) with a running carry.
 __global__ void __launch_bounds__(1024) cull_scan_kernel(int* __restrict__ block_counts, int64_t nblocks,
                                                           int64_t* __restrict__ count_out) {
-    __shared__ long long sh[1024];
-    const int t = threadIdx.x;
-    const int64_t per = (nblocks + 1023) / 1024;
-    const int64_t lo = (int64_t)t * per, hi = (lo + per < nblocks) ? lo + per : nblocks;
-    long long s = 0;
-    for (int64_t i = lo; i < hi; ++i) s += block_counts[i];
-    sh[t] = s;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan
-        long long v = (t >= o) ? sh[t - o] : 0;
+    __shared__ int wtot[32];
+    __shared__ int chunk_total;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    long long carry = 0;
+    for (int64_t base = 0; base < nblocks; base += 4096) {
+        const int64_t i = base + (int64_t)t * 4;
+        int v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = (i + k < nblocks) ? block_counts[i + k] : 0;
+        const int s = v[0] + v[1] + v[2] + v[3];
+        int incl = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) wtot[warp] = incl;
         __syncthreads();
-        sh[t] += v;
+        if (warp == 0) {
+            const int w = wtot[lane];
+            int sc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, sc, o);
+                if (lane >= o) sc += u;
+            }
+            wtot[lane] = sc - w;  // exclusive over warps
+            if (lane == 31) chunk_total = sc;
+        }
         __syncthreads();
+        long long run = carry + wtot[warp] + incl - s;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (i + k < nblocks) block_counts[i + k] = (int)run;  // < 2^31 points kept per call (idx is int32)
+            run += v[k];
+        }
+        carry += chunk_total;
+        __syncthreads();  // wtot / chunk_total are rewritten by the next chunk
     }
-    long long run = sh[t] - s;
-    for (int64_t i = lo; i < hi; ++i) {
-        const int c = block_counts[i];
-        block_counts[i] = (int)run;  // < 2^31 points kept per call (idx is int32)
-        run += c;
-    }
-    if (t == 1023) *count_out = sh[1023];
+    if (t == 0) *count_out = carry;
 }
 
 __global__ void __launch_bounds__(kCullBlock)
