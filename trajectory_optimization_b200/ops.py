@@ -360,7 +360,7 @@ def frustum_cull(points_nx3, intrins, img_width, img_height, min_dist=1.0, max_d
                                   float(max_dist), _ptr(dm), _ptr(fm), _ptr(idx), _ptr(cnt), _ptr(ws), ws_bytes,
                                   _stream()), "cov_frustum_cull")
     m = int(cnt.item())
-    return idx[:m].long(), dm.bool(), fm.bool()
+    return idx[:m].long(), dm.view(torch.bool), fm.view(torch.bool)   # the masks hold 0/1 bytes: zero-copy views
 
 
 @torch.no_grad()
