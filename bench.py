@@ -166,7 +166,8 @@ def run_reference(args):
         return
     from trajectory_optimization_b200 import multicam
     body, rig = body_waypoints(), multicam.ring_rig(N_CAMS)
-    base, ms = cpu_reference_rate(body, rig, args.steps, args.warmup, budget_s=90.0)
+    base, ms = cpu_reference_rate(body, rig, args.steps, args.warmup,
+                                  budget_s=float(os.environ.get("COV_BENCH_REF_BUDGET_S", "90")))
     line = {"impl": "reference", "metric": "coverage fwd+bwd point*pose evals/s", "value": base["value"],
             "unit": "point*pose evals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
