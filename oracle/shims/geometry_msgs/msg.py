@@ -1,6 +1,12 @@
-class TransformStamped:
-    pass
+from _msgbag import Bag, Header
 
 
-class PoseStamped:
-    pass
+class TransformStamped(Bag):
+    def __init__(self):
+        self.header = Header()
+        self.child_frame_id = ""
+
+
+class PoseStamped(Bag):
+    def __init__(self):
+        self.header = Header()

@@ -1,6 +1,12 @@
-class Odometry:
-    pass
+from _msgbag import Bag, Header
 
 
-class Path:
-    pass
+class Odometry(Bag):
+    def __init__(self):
+        self.header = Header()
+
+
+class Path(Bag):
+    def __init__(self):
+        self.header = Header()
+        self.poses = []

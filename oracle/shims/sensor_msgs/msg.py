@@ -1,6 +1,6 @@
 class _Header:
-    stamp = None
-    frame_id = ""
+    def __init__(self):
+        self.stamp, self.frame_id, self.seq = None, "", 0
 
 
 class PointCloud2:
@@ -15,7 +15,8 @@ class PointCloud2:
 
 
 class CameraInfo:
-    pass
+    def __init__(self):
+        self.header = _Header()
 
 
 class Image:

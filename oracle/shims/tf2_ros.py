@@ -1,1 +1,16 @@
-"""Empty stand-in (oracle/shims/README.md)."""
+"""Stand-in for tf2_ros (oracle/shims/README.md): broadcast transforms are recorded next to published messages."""
+import rospy
+
+
+class TransformBroadcaster:
+    def sendTransform(self, t):
+        rospy.PUBLISHED.append(("/tf", t))
+
+
+class Buffer:
+    pass
+
+
+class TransformListener:
+    def __init__(self, *a, **k):
+        pass

@@ -10,10 +10,11 @@ import pytest
 import torch
 
 from oracle import coverage_oracle as orc
-from tests.conftest import load_golden, rel_err
+from tests.conftest import load_golden, rel_err, row_rel_err
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
+TOL_ROW = 2e-4   # per-pose gradient rows, each against its own magnitude (conftest.row_rel_err)
 K_np, IMG_W, IMG_H = orc.load_intrinsics()
 
 
@@ -82,6 +83,8 @@ def test_model_traj_matches_reference(name, dev, mod, sample_inputs):
         assert rel_err(m.rewards.detach().cpu().numpy(), g["out_rewards" + sfx]) < TOL
         assert rel_err(gv[0].detach().cpu().numpy(), g["out_gv_poses" + sfx]) < TOL
         assert rel_err(gv[1].detach().cpu().numpy(), g["out_gv_quats" + sfx]) < TOL
+        assert row_rel_err(gv[0].detach().cpu().numpy(), g["out_gv_poses" + sfx]) < TOL_ROW
+        assert row_rel_err(gv[1].detach().cpu().numpy(), g["out_gv_quats" + sfx]) < TOL_ROW
     assert rel_err(m.poses.grad.detach().cpu().numpy(), g["out_g_poses"]) < TOL
     assert rel_err(m.quats.grad.detach().cpu().numpy(), g["out_g_quats"]) < TOL
     step = int(g["out_wps_step"])
@@ -120,6 +123,56 @@ def test_traj_matches_oracle_on_seeded_clouds(n, W, ragged, dev, mod):
     assert rel_err(rewards.detach().cpu().numpy(), ref["rewards"]) < TOL
     assert rel_err(P.grad.detach().cpu().numpy(), ref["g_poses"]) < TOL
     assert rel_err(Q.grad.detach().cpu().numpy(), ref["g_quats"]) < TOL
+    assert row_rel_err(P.grad.detach().cpu().numpy(), ref["g_poses"]) < TOL_ROW
+    assert row_rel_err(Q.grad.detach().cpu().numpy(), ref["g_quats"]) < TOL_ROW
+
+
+def test_config3_size_against_the_oracle_on_a_point_subsample(dev, mod):
+    """BASELINE config 3 (1e7 points x 100 poses) against the oracle: the oracle cannot hold 1e9 pairs, but with the
+    GLOBAL normalisers passed in (`minmax=`) its per-point rewards and its gradient accumulators are sums over points,
+    so a random subsample of 50 000 points is checked exactly: rewards on the subsample, and the subsample's share of the
+    accumulators against a CUDA evaluation of the same subsample with the same normalisers."""
+    model, tools, ops = mod
+    from trajectory_optimization_b200 import _lib
+    n, W = 10_000_000, 100
+    g = torch.Generator(device=dev).manual_seed(11)
+    lo = torch.tensor([-10.0, -10.0, -1.0], device=dev)
+    hi = torch.tensor([30.0, 30.0, 4.0], device=dev)
+    pts = torch.rand(n, 3, generator=g, device=dev) * (hi - lo) + lo
+    poses_np, _ = _s_curve(W, L=30.0)
+    gen = np.random.default_rng(5)
+    quats_np = (gen.standard_normal((W, 4)) * 0.3 + np.array([1.0, 0, 0, 0])).astype(np.float32)
+    P = torch.from_numpy(poses_np).to(dev).requires_grad_(True)
+    Q = torch.from_numpy(quats_np).to(dev).requires_grad_(True)
+    K, Wd, Hd = tools.load_intrinsics(dev)
+    m = model.ModelTraj(pts, P.detach(), Q.detach(), K, Wd, Hd, device=dev)   # Morton-ordered, pruned: the product path
+    m(vis_wps_dist=0.0)
+    m.loss["vis"].backward()
+    rewards = m.rewards.detach()
+    # global normalisers from the raw C ABI (pass A on the whole cloud)
+    cam = _lib.camera(Wd, Hd, 1.0, 5.0, 1e-6)
+    minmax = ops._BACKEND.traj_minmax(ops._dev_f32(pts), P.detach(), Q.detach(), K.reshape(9), cam)
+    mm = minmax.cpu().numpy().astype(np.float64)
+    idx = torch.randperm(n, generator=torch.Generator().manual_seed(3))[:50_000].sort().values
+    sub = pts[idx.to(dev)].cpu().numpy()
+    ref = orc.traj_partials(sub, poses_np, quats_np, K_np, IMG_W, IMG_H, minmax=(mm[:W], mm[W:]), dtype=np.float64)
+    assert rel_err(rewards[idx.to(dev)].cpu().numpy(), ref["rewards"]) < TOL
+    assert float(rewards.min()) >= 0.5 and float(rewards.max()) <= 1.0
+    # mean reward of the whole cloud vs the subsample's (statistical, 5e4 samples): sanity only
+    assert abs(float(rewards.mean()) - float(ref["rewards"].mean())) < 5e-3
+    # the subsample's share of the gradient: CUDA pass B + epilogue on the subsample with the GLOBAL normalisers vs the
+    # oracle's accumulators for the same points (the global arg-max points are not in the subsample: no tie terms)
+    sub_dev = torch.from_numpy(sub).to(dev)
+    n_sub = len(sub)
+    acc = ops._BACKEND.traj_fused(sub_dev, P.detach(), Q.detach(), K.reshape(9), cam, minmax, None,
+                                  torch.empty(n_sub, device=dev))
+    out = ops._BACKEND.traj_epilogue(acc, minmax, Q.detach(), n_sub, 0).cpu().numpy().astype(np.float64)
+    refg = orc.traj_grads_from_partials(ref, poses_np, quats_np, n_sub)
+    assert rel_err(out[0], refg["mean"]) < 1e-6
+    gp = -refg["vis"] ** 2 * out[1:1 + 3 * W].reshape(W, 3)
+    gq = -refg["vis"] ** 2 * out[1 + 3 * W:].reshape(W, 4)
+    assert rel_err(gp, refg["g_poses"]) < TOL and rel_err(gq, refg["g_quats"]) < TOL
+    assert row_rel_err(gp, refg["g_poses"]) < TOL_ROW and row_rel_err(gq, refg["g_quats"]) < TOL_ROW
 
 
 def test_pose_matches_oracle_large_and_ragged(dev, mod):
@@ -653,3 +706,67 @@ def test_fused_regularisers_match_the_torch_terms(dev, mod):
         outs.append((loss.item(), m.poses.grad.clone()))
     assert rel_err(outs[1][0], outs[0][0]) < 1e-5
     assert rel_err(outs[1][1].cpu().numpy(), outs[0][1].cpu().numpy()) < 2e-4
+
+
+def test_model_cloud_cache_follows_in_place_edits_and_set_points(dev, mod):
+    """The Morton-ordered copy / permutation / boxes are keyed on identity AND version of `model.points`: an in-place
+    edit, an assignment and `set_points` all re-order; `refresh_points_` rewrites the cached buffers in place."""
+    model, tools, ops = mod
+    gen = np.random.default_rng(21)
+    a, b = _box(gen, 150_000), _box(gen, 150_000, (-5, -8, -1), (20, 25, 3))
+    poses, _ = _s_curve(9)
+    quats = (gen.standard_normal((9, 4)) * 0.3 + np.array([1.0, 0, 0, 0])).astype(np.float32)
+    K, Wd, Hd = tools.load_intrinsics(dev)
+
+    def fresh(pts):
+        m = model.ModelTraj(torch.from_numpy(pts), torch.from_numpy(poses), torch.from_numpy(quats), K, Wd, Hd, device=dev)
+        m(vis_wps_dist=0.0)
+        return m.rewards.clone(), float(m.loss["vis"])
+
+    ra, va = fresh(a)
+    rb, vb = fresh(b)
+    assert not torch.equal(ra, rb)
+    m = model.ModelTraj(torch.from_numpy(a), torch.from_numpy(poses), torch.from_numpy(quats), K, Wd, Hd, device=dev)
+    m(vis_wps_dist=0.0)
+    assert torch.equal(m.rewards, ra)
+    ptr = m._pts32.data_ptr()
+    m.points.copy_(torch.from_numpy(b))              # in-place edit: same object, new version
+    m(vis_wps_dist=0.0)
+    assert torch.equal(m.rewards, rb) and float(m.loss["vis"]) == vb
+    m.set_points(torch.from_numpy(a))
+    m(vis_wps_dist=0.0)
+    assert torch.equal(m.rewards, ra)
+    m.points = torch.from_numpy(b).to(dev)           # plain assignment, as a caller of the reference would do
+    m(vis_wps_dist=0.0)
+    assert torch.equal(m.rewards, rb)
+    ptr = m._pts32.data_ptr()
+    m.refresh_points_(torch.from_numpy(a).to(dev))   # graph-safe refresh: buffers keep their addresses
+    assert m._pts32.data_ptr() == ptr
+    m(vis_wps_dist=0.0)
+    assert torch.equal(m.rewards, ra) and float(m.loss["vis"]) == va
+    mp = model.ModelPose(torch.from_numpy(a).double(), torch.zeros(1, 3), torch.tensor([[1.0, 0, 0, 0]]), K, Wd, Hd, device=dev)
+    l0 = float(mp())
+    mp.points.copy_(torch.from_numpy(b).double())    # ModelPose keeps an fp32 working copy of an fp64 cloud
+    assert float(mp()) != l0
+
+
+def test_ops_follow_the_tensors_device_not_the_current_device(mod):
+    """`ModelPose(..., device='cuda:1')` while cuda:0 is current: kernels, streams and workspaces must be on
+    the tensors' device."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    model, tools, ops = mod
+    g = load_golden("traj_box")
+    d0, d1 = torch.device("cuda:0"), torch.device("cuda:1")
+    torch.cuda.set_device(d0)
+    out = []
+    for d in (d0, d1):
+        K, Wd, Hd = tools.load_intrinsics(d)
+        m = model.ModelTraj(torch.from_numpy(g["in_points"]), torch.from_numpy(g["in_poses"]), torch.from_numpy(g["in_quats"]),
+                            K, Wd, Hd, device=d)
+        loss = m(vis_wps_dist=0.0)
+        loss.backward()
+        assert m.rewards.device == d and m.poses.grad.device == d
+        out.append((float(loss), m.rewards.cpu(), m.poses.grad.cpu()))
+    assert torch.cuda.current_device() == 0
+    assert out[0][0] == out[1][0] and torch.equal(out[0][1], out[1][1]) and torch.equal(out[0][2], out[1][2])

@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from oracle import coverage_oracle as orc
-from tests.conftest import load_golden
+from tests.conftest import load_golden, rel_err
 
 pytestmark = pytest.mark.gpu
 K_np, IMG_W, IMG_H = orc.load_intrinsics()
@@ -213,3 +213,59 @@ def test_voxel_grid_rejects_too_fine_a_grid(dev, tools):
     with pytest.raises(RuntimeError, match="too small"):
         tools.voxel_grid_filter(pts, 1e-3, None)
     assert tools.voxel_grid_filter(torch.zeros(0, 3, device=dev)).shape == (0, 3)
+
+
+def test_standalone_helpers_match_reference_fixture(dev):
+    """to_camera_frame / get_dist_mask / get_fov_mask (src/model.py:13-57) on CUDA tensors vs values recorded by running
+    the reference (tests/golden/helpers.npz); fp32 tolerance 1e-5 relative."""
+    from trajectory_optimization_b200 import model, tools as T
+    g = load_golden("helpers")
+    K, W, H = T.load_intrinsics(dev)
+    pts = torch.from_numpy(g["in_points"]).to(dev)
+    cam = model.to_camera_frame(pts, torch.from_numpy(g["in_quat"]).to(dev), torch.from_numpy(g["in_trans"]).to(dev))
+    assert rel_err(cam.cpu().numpy(), g["out_cam"]) < 1e-5
+    cam_ref = torch.from_numpy(g["out_cam"]).to(dev)
+    assert rel_err(model.get_dist_mask(cam_ref, 1.0, 5.0).cpu().numpy(), g["out_dist"]) < 1e-5
+    assert rel_err(model.get_fov_mask(cam_ref, H, W, K).cpu().numpy(), g["out_fov"]) < 1e-5
+    # and they stay differentiable like the reference's
+    q = torch.from_numpy(g["in_quat"]).to(dev).requires_grad_(True)
+    t = torch.from_numpy(g["in_trans"]).to(dev).requires_grad_(True)
+    c = model.to_camera_frame(pts, q, t)
+    (model.get_dist_mask(c) * model.get_fov_mask(c, H, W, K)).sum().backward()
+    assert torch.isfinite(q.grad).all() and torch.isfinite(t.grad).all() and float(t.grad.abs().max()) > 0
+
+
+def test_pointcloud2_builders_take_numpy_like_the_reference(dev):
+    """xyz/xyzi_array_to_pointcloud2 with the NUMPY arrays the unmodified nodes pass (src/pose_optimization.py:108-112,
+    src/trajectory_optimization.py:147-157 -> src/tools.py:224-231): payload bytes and flags equal the reference's
+    host encoder (np.asarray(points, np.float32).tobytes(), np.isfinite(points).all())."""
+    import os
+    import sys
+    shims = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "shims")
+    sys.path.insert(0, shims)
+    try:
+        from trajectory_optimization_b200 import pointcloud_utils as pcu
+        from trajectory_optimization_b200 import tools as T
+        import rospy
+        gen = np.random.default_rng(2)
+        xyz64 = gen.normal(size=(1001, 3)) * 7
+        xyzi = np.concatenate([xyz64.astype(np.float32), gen.random((1001, 1))], axis=1)   # float64, as np.concatenate gives
+        for arr in (xyz64, xyz64.astype(np.float32), torch.from_numpy(xyz64), torch.from_numpy(xyz64).to(dev)):
+            m = pcu.xyz_array_to_pointcloud2(arr, stamp=1.0, frame_id="map")
+            assert m.data == np.asarray(xyz64, np.float32).tobytes() and m.is_dense == 1
+            assert (m.width, m.height, m.point_step, m.row_step) == (1001, 1, 12, 1001)
+        m = pcu.xyzi_array_to_pointcloud2(xyzi, frame_id="map")
+        assert m.data == np.asarray(xyzi, np.float32).tobytes() and m.is_dense == 1 and m.point_step == 16
+        xyzi[5, 3] = np.nan
+        assert pcu.xyzi_array_to_pointcloud2(xyzi).is_dense == 0
+        big = xyz64.copy()
+        big[0, 0] = 1e300   # finite in fp64: the reference's flag looks at the input, the payload holds inf
+        assert pcu.xyz_array_to_pointcloud2(big).is_dense == 1
+        del rospy.PUBLISHED[:]
+        T.publish_pointcloud(xyzi, "/pts/rewards", rospy.Time.now(), "map")   # the call the nodes make
+        assert rospy.PUBLISHED[0][0] == "/pts/rewards" and len(rospy.PUBLISHED[0][1].data) == 16 * 1001
+        # decode of what we encode, through the pinned staging path
+        back = pcu.pointcloud2_to_xyz_array(pcu.xyz_array_to_pointcloud2(xyz64))
+        assert back.dtype == np.float64 and np.array_equal(back, xyz64.astype(np.float32).astype(np.float64))
+    finally:
+        sys.path.remove(shims)

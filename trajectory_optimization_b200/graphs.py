@@ -6,8 +6,11 @@ src/trajectory_optimization.py:106-116) — into one `torch.cuda.CUDAGraph` and 
 instead of ~60 (ModelPose) to ~150 (ModelTraj with its regularisers).  Every kernel of libcovb200.so is
 capturable: the library launches only on the stream it is given, never allocates and never synchronises.
 
-The optimiser must keep its step counter on the device (`torch.optim.Adam(..., capturable=True)`); tensors the
-model reads (`model.points`, parameters) must stay the same objects between replays (update them in place).
+The optimiser must keep its step counter on the device (`torch.optim.Adam(..., capturable=True)`); parameters must
+stay the same objects between replays (update them in place).  A captured graph holds the ADDRESSES of the buffers the
+kernels read — for `ModelTraj` that is the Morton-ordered copy of the cloud, its permutation and its tile boxes, not
+`model.points` itself — so a new cloud of the same size goes in through `model.refresh_points_(new_points)`, which
+re-orders into those same buffers; a cloud of another size needs `model.set_points()` and a new capture.
 """
 import torch
 

@@ -98,11 +98,18 @@ class ModelPose(nn.Module):
         self.to(self.device)
 
     def _cloud(self):
-        # fp32, contiguous, aligned copy made once (the reference keeps whatever dtype it was given)
-        if self._pts32 is None or self._pts32_src is not self.points:
-            self._pts32 = ops._dev_f32(self.points, what="points")
-            self._pts32_src = self.points
+        # fp32, contiguous, aligned copy made once per cloud (the reference keeps whatever dtype it was given); the
+        # cache follows `self.points` by identity AND by torch's version counter, so an in-place edit is seen too
+        key = (id(self.points), self.points._version)
+        if self._pts32 is None or self._pts32_key != key:
+            self._pts32 = ops._BACKEND.prepare(self.points, what="points")
+            self._pts32_key = key
         return self._pts32
+
+    def set_points(self, points):
+        """Replace the cloud (same as assigning `model.points`; the fp32 working copy is rebuilt on the next forward)."""
+        self.points = points.to(self.device)
+        self._pts32 = None
 
     def forward(self, debug=False, hpr=False):
         t0 = time()
@@ -115,7 +122,8 @@ class ModelPose(nn.Module):
         self.observations = obs
         self._total = total
         if debug:
-            torch.cuda.synchronize()
+            if obs.is_cuda:
+                torch.cuda.synchronize(obs.device)
             print(f"\nFused transformation + visibility estimation took: {1000 * (time() - t0)} msec")
             print(f"Point cloud size {self.points.size()}")
         return self.criterion(self.observations)
@@ -196,15 +204,41 @@ class ModelTraj(nn.Module):
         self.to(self.device)
 
     def _cloud(self):
-        if self._pts32 is None or self._pts32_src is not self.points:
-            pts = ops._dev_f32(self.points, what="points")
-            self._perm = None
-            if self.spatial_sort and pts.shape[0] > 0:
-                pts, self._perm = ops.spatial_sort(pts)
-            self._boxes = ops.tile_boxes(pts)
-            self._pts32 = pts
-            self._pts32_src = self.points
+        # The ordered copy, its permutation and the tile boxes belong to ONE state of `self.points`: the cache is keyed
+        # on identity and on torch's version counter, so both `model.points = new` and an in-place `model.points.copy_()`
+        # trigger a re-sort (the exact pruning relies on the boxes bounding the points the kernels read).
+        key = (id(self.points), self.points._version)
+        if self._pts32 is None or self._pts32_key != key:
+            pts = ops._BACKEND.prepare(self.points, what="points")
+            self._pts32, self._perm, self._boxes = ops._BACKEND.order_cloud(pts, self.spatial_sort)
+            self._pts32_key = key
         return self._pts32
+
+    def set_points(self, points):
+        """Replace the cloud; the Morton-ordered copy, permutation and boxes are rebuilt on the next forward.  Inside a
+        captured CUDA graph use `refresh_points_()` instead (same shapes, buffers rewritten in place)."""
+        self.points = torch.as_tensor(points, dtype=torch.float32).to(self.device)
+        self._pts32 = None
+
+    @torch.no_grad()
+    def refresh_points_(self, points):
+        """In-place cloud update for CUDA-graph replays (graphs.GraphedStep): `points` must have the shape of the
+        current cloud; `self.points`, the ordered copy, the permutation and the boxes keep their addresses and are
+        rewritten, so a graph captured earlier evaluates the NEW cloud on its next replay."""
+        if self._pts32 is None:
+            self._cloud()
+        if tuple(points.shape) != tuple(self.points.shape):
+            raise ValueError("refresh_points_ needs a cloud of the same shape; use set_points() and re-capture")
+        self.points.copy_(points)
+        pts = ops._BACKEND.prepare(self.points, what="points")
+        new_pts, new_perm, new_boxes = ops._BACKEND.order_cloud(pts, self.spatial_sort)
+        if self._pts32.data_ptr() != self.points.data_ptr():
+            self._pts32.copy_(new_pts)
+        if self._perm is not None:
+            self._perm.copy_(new_perm)
+        if self._boxes is not None and new_boxes is not None:
+            self._boxes.copy_(new_boxes)
+        self._pts32_key = (id(self.points), self.points._version)
 
     def _wps_step(self, vis_wps_dist):
         # src/model.py:214-215.  poses0 never changes, so the host sync happens once per distance
@@ -226,7 +260,8 @@ class ModelTraj(nn.Module):
         self.rewards = rewards
         self._mean = mean
         if debug:
-            torch.cuda.synchronize()
+            if rewards.is_cuda:
+                torch.cuda.synchronize(rewards.device)
             print(f"Trajectory evaluation took {1000 * (time() - t0)} msec")
         t1 = time()
         loss = self.criterion(self.rewards)

@@ -6,12 +6,11 @@ multi-camera setting comes from tf extrinsics of a 5-6 camera rig (src/pc_proces
 Here a rig is a list of (R_body_cam, t_body_cam); the autograd chain from the per-camera gradients
 the kernels return back to the 4 body parameters is handled by torch on (W, 4)-sized tensors.
 """
-import ctypes
 import math
 
 import torch
 
-from . import _lib
+from . import ops
 
 # body (x fwd, y left, z up) <- optical (x right, y down, z fwd)
 R_BODY_OPTICAL = torch.tensor([[0.0, 0.0, 1.0], [-1.0, 0.0, 0.0], [0.0, -1.0, 0.0]])
@@ -76,9 +75,9 @@ class RigPosesFn(torch.autograd.Function):
         B, C = b.shape[0], rig7.shape[0]
         poses = torch.empty(B * C, 3, dtype=torch.float32, device=b.device)
         quats = torch.empty(B * C, 4, dtype=torch.float32, device=b.device)
-        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        _lib.check(_lib.lib().cov_rig_poses(b.data_ptr(), B, rig7.data_ptr(), C, poses.data_ptr(), quats.data_ptr(), stream),
-                   "cov_rig_poses")
+        if rig7.device != b.device:
+            raise RuntimeError(f"rig tensor is on {rig7.device}, body parameters on {b.device}")
+        ops._call("cov_rig_poses", b, b.data_ptr(), B, rig7.data_ptr(), C, poses.data_ptr(), quats.data_ptr())
         ctx.save_for_backward(b, rig7)
         ctx.set_materialize_grads(False)
         return poses, quats
@@ -91,10 +90,8 @@ class RigPosesFn(torch.autograd.Function):
         gp = None if g_poses is None else g_poses.contiguous().float()
         gq = None if g_quats is None else g_quats.contiguous().float()
         out = torch.empty_like(b)
-        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        _lib.check(_lib.lib().cov_rig_poses_backward(b.data_ptr(), b.shape[0], rig7.data_ptr(), rig7.shape[0],
-                                                     0 if gp is None else gp.data_ptr(), 0 if gq is None else gq.data_ptr(),
-                                                     1.0, out.data_ptr(), stream), "cov_rig_poses_backward")
+        ops._call("cov_rig_poses_backward", b, b.data_ptr(), b.shape[0], rig7.data_ptr(), rig7.shape[0],
+                  0 if gp is None else gp.data_ptr(), 0 if gq is None else gq.data_ptr(), 1.0, out.data_ptr())
         return out, None
 
 

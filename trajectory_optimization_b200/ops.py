@@ -14,8 +14,24 @@ import torch
 from . import _lib
 
 
-def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None):
+    """The caller's current stream ON THE TENSORS' DEVICE (not on whatever device happens to be current)."""
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _guard(t):
+    """Device guard for a C-ABI call: the library launches on the CUDA device that is current, so the tensors'
+    device is made current for the duration of the call (`ModelPose(..., device='cuda:1')` while cuda:0 is current)."""
+    return torch.cuda.device(t.device)
+
+
+def _call(name, on, *args):
+    """One C-ABI call on the device of tensor `on` and on that device's current stream (every entry point takes the
+    stream last); raises RuntimeError with the library's message on a non-zero return code."""
+    L = _lib.lib()
+    with _guard(on):
+        rc = getattr(L, name)(*args, _stream(on.device))
+    _lib.check(rc, name)
 
 
 def _dev_f32(t, device=None, what="tensor"):
@@ -69,19 +85,26 @@ class CudaBackend:
     def prepare(self, t, device=None, what="tensor"):
         return _dev_f32(t, device, what)
 
+    def order_cloud(self, pts, spatial_sort_cloud=True):
+        """Once per cloud (ModelTraj): Morton-ordered copy, its permutation and the 128-point boxes."""
+        perm = None
+        if spatial_sort_cloud and pts.shape[0] > 0:
+            pts, perm = spatial_sort(pts)
+        return pts, perm, tile_boxes(pts)
+
     def pose_fused(self, pts, t, q, Kd, cam, w, obs):
         L = _lib.lib()
         n = pts.shape[0]
         acc = torch.empty(_lib.POSE_ACC, dtype=torch.float64, device=pts.device)
         ws_bytes = L.cov_pose_workspace_bytes(n)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=pts.device)
-        _lib.check(L.cov_pose_fused(_ptr(pts), n, _ptr(w), _ptr(t), _ptr(q), _ptr(Kd), ctypes.byref(cam), _ptr(obs),
-                                    _ptr(acc), _ptr(ws), ws_bytes, _stream()), "cov_pose_fused")
+        _call("cov_pose_fused", pts, _ptr(pts), n, _ptr(w), _ptr(t), _ptr(q), _ptr(Kd), ctypes.byref(cam), _ptr(obs),
+                                    _ptr(acc), _ptr(ws), ws_bytes)
         return acc
 
     def pose_epilogue(self, acc, t, q):
         out = torch.empty(8, dtype=torch.float32, device=acc.device)
-        _lib.check(_lib.lib().cov_pose_epilogue(_ptr(acc), _ptr(t), _ptr(q), _ptr(out), _stream()), "cov_pose_epilogue")
+        _call("cov_pose_epilogue", acc, _ptr(acc), _ptr(t), _ptr(q), _ptr(out))
         return out
 
     def traj_workspace(self, pts, W):
@@ -92,9 +115,8 @@ class CudaBackend:
         W = P.shape[0]
         minmax = torch.empty(2 * W, dtype=torch.float32, device=pts.device)
         ws = self.traj_workspace(pts, W) if ws is None else ws
-        _lib.check(_lib.lib().cov_traj_minmax(_ptr(pts), pts.shape[0], _ptr(P), _ptr(Q), W, _ptr(Kd), ctypes.byref(cam),
-                                              _ptr(boxes), _ptr(minmax), _ptr(ws), ws.numel(), _stream()),
-                   "cov_traj_minmax")
+        _call("cov_traj_minmax", pts, _ptr(pts), pts.shape[0], _ptr(P), _ptr(Q), W, _ptr(Kd), ctypes.byref(cam),
+                                              _ptr(boxes), _ptr(minmax), _ptr(ws), ws.numel())
         return minmax
 
     def traj_fused(self, pts, P, Q, Kd, cam, minmax, upstream, rewards, reward_index=None, boxes=None, ws=None):
@@ -102,17 +124,15 @@ class CudaBackend:
         W, n = P.shape[0], pts.shape[0]
         acc = torch.empty(W * _lib.ACC_STRIDE + 1, dtype=torch.float64, device=pts.device)
         ws = self.traj_workspace(pts, W) if ws is None else ws
-        _lib.check(L.cov_traj_fused(_ptr(pts), n, _ptr(P), _ptr(Q), W, _ptr(Kd), ctypes.byref(cam), _ptr(boxes),
+        _call("cov_traj_fused", pts, _ptr(pts), n, _ptr(P), _ptr(Q), W, _ptr(Kd), ctypes.byref(cam), _ptr(boxes),
                                     _ptr(minmax), _ptr(upstream), _ptr(reward_index), _ptr(rewards), _ptr(acc), _ptr(ws),
-                                    ws.numel(), _stream()),
-                   "cov_traj_fused")
+                                    ws.numel())
         return acc
 
     def traj_epilogue(self, acc, minmax, Q, n_total, upstream_mode):
         W = Q.shape[0]
         out = torch.empty(1 + 7 * W, dtype=torch.float32, device=acc.device)
-        _lib.check(_lib.lib().cov_traj_epilogue(_ptr(acc), _ptr(minmax), _ptr(Q), W, n_total, upstream_mode, _ptr(out),
-                                                _stream()), "cov_traj_epilogue")
+        _call("cov_traj_epilogue", acc, _ptr(acc), _ptr(minmax), _ptr(Q), W, n_total, upstream_mode, _ptr(out))
         return out
 
 
@@ -235,8 +255,8 @@ class TrajRegularizersFn(torch.autograd.Function):
         P0 = _dev_f32(poses0, P.device, "poses0").reshape(-1, 3)
         W = P.shape[0]
         out = torch.empty(3 + 9 * W, dtype=torch.float32, device=P.device)
-        _lib.check(_lib.lib().cov_traj_regularizers(_ptr(P), _ptr(P0), W, float(smoothness_weight), float(traj_length_weight),
-                                                    float(eps), _ptr(out), _stream()), "cov_traj_regularizers")
+        _call("cov_traj_regularizers", P, _ptr(P), _ptr(P0), W, float(smoothness_weight), float(traj_length_weight),
+                                                    float(eps), _ptr(out))
         ctx.save_for_backward(out)
         ctx.shape = poses.shape
         return out[:3].clone()
@@ -280,7 +300,7 @@ def tile_boxes(points):
     n = pts.shape[0]
     boxes = torch.empty(max(int(L.cov_tile_boxes_count(n)), 1), 8, dtype=torch.float32, device=pts.device)
     if n > 0:
-        _lib.check(L.cov_tile_boxes(_ptr(pts), n, _ptr(boxes), _stream()), "cov_tile_boxes")
+        _call("cov_tile_boxes", pts, _ptr(pts), n, _ptr(boxes))
     return boxes
 
 
@@ -297,8 +317,7 @@ def spatial_sort(points):
         return out, perm
     ws_bytes = L.cov_spatial_sort_workspace_bytes(n)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=pts.device)
-    _lib.check(L.cov_spatial_sort(_ptr(pts), n, _ptr(out), _ptr(perm), _ptr(ws), ws_bytes, _stream()),
-               "cov_spatial_sort")
+    _call("cov_spatial_sort", pts, _ptr(pts), n, _ptr(out), _ptr(perm), _ptr(ws), ws_bytes)
     return out, perm
 
 
@@ -327,15 +346,14 @@ def sweep_rewards(points, poses, quats, intrins, img_width, img_height, min_dist
     for w0 in range(0, W, chunk):  # pass A reuses the trajectory kernel, one pose-table-full at a time
         w1 = min(W, w0 + chunk)
         mm = torch.empty(2 * (w1 - w0), dtype=torch.float32, device=dev)
-        _lib.check(L.cov_traj_minmax(_ptr(pts), n, _ptr(P[w0:w1]), _ptr(Q[w0:w1]), w1 - w0, _ptr(Kd),
-                                     ctypes.byref(cam), _ptr(boxes), _ptr(mm), _ptr(ws), ws_bytes, _stream()),
-                   "cov_traj_minmax")
+        _call("cov_traj_minmax", pts, _ptr(pts), n, _ptr(P[w0:w1]), _ptr(Q[w0:w1]), w1 - w0, _ptr(Kd),
+                                     ctypes.byref(cam), _ptr(boxes), _ptr(mm), _ptr(ws), ws_bytes)
         minmax[w0:w1] = mm[:w1 - w0]
         minmax[W + w0:W + w1] = mm[w1 - w0:]
     _all_reduce_minmax(minmax, W, group)
     sums = torch.zeros(T, dtype=torch.float64, device=dev)
-    _lib.check(L.cov_sweep_rewards(_ptr(pts), n, _ptr(P), _ptr(Q), T, Pn, _ptr(Kd), ctypes.byref(cam), _ptr(boxes),
-                                   _ptr(minmax), _ptr(sums), _ptr(ws), ws_bytes, _stream()), "cov_sweep_rewards")
+    _call("cov_sweep_rewards", pts, _ptr(pts), n, _ptr(P), _ptr(Q), T, Pn, _ptr(Kd), ctypes.byref(cam), _ptr(boxes),
+                                   _ptr(minmax), _ptr(sums), _ptr(ws), ws_bytes)
     if group is not None:
         _all_reduce(sums, _reduce_ops()[2], group)
     return sums / float(n if n_total is None else n_total)
@@ -356,9 +374,8 @@ def frustum_cull(points_nx3, intrins, img_width, img_height, min_dist=1.0, max_d
     cnt = torch.zeros(1, dtype=torch.int64, device=dev)
     ws_bytes = L.cov_cull_workspace_bytes(n)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    _lib.check(L.cov_frustum_cull(_ptr(pts), n, _ptr(Kd), float(img_width), float(img_height), float(min_dist),
-                                  float(max_dist), _ptr(dm), _ptr(fm), _ptr(idx), _ptr(cnt), _ptr(ws), ws_bytes,
-                                  _stream()), "cov_frustum_cull")
+    _call("cov_frustum_cull", pts, _ptr(pts), n, _ptr(Kd), float(img_width), float(img_height), float(min_dist),
+                                  float(max_dist), _ptr(dm), _ptr(fm), _ptr(idx), _ptr(cnt), _ptr(ws), ws_bytes)
     m = int(cnt.item())
     return idx[:m].long(), dm.view(torch.bool), fm.view(torch.bool)   # the masks hold 0/1 bytes: zero-copy views
 
@@ -371,7 +388,7 @@ def spherical_flip(points, param):
     n = pts.shape[0]
     out = torch.empty_like(pts)
     rad = torch.empty(2, dtype=torch.float32, device=pts.device)
-    _lib.check(L.cov_hpr_flip(_ptr(pts), n, float(10.0 ** param), _ptr(out), _ptr(rad), _stream()), "cov_hpr_flip")
+    _call("cov_hpr_flip", pts, _ptr(pts), n, float(10.0 ** param), _ptr(out), _ptr(rad))
     return out, rad[0]
 
 
@@ -386,6 +403,6 @@ def hpr_hull_mask(flipped):
     info = torch.zeros(4, dtype=torch.int32, device=f.device)
     ws_bytes = L.cov_hpr_hull_workspace_bytes(n)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=f.device)
-    _lib.check(L.cov_hpr_hull(_ptr(f), n, _ptr(mask), _ptr(info), _ptr(ws), ws_bytes, _stream()), "cov_hpr_hull")
+    _call("cov_hpr_hull", f, _ptr(f), n, _ptr(mask), _ptr(info), _ptr(ws), ws_bytes)
     info_h = info.tolist()
     return mask, bool(info_h[0]), int(info_h[1])

@@ -148,7 +148,7 @@ def publish_odom(pose, quat, frame="/odom", topic="/odom_0"):
 def publish_pointcloud(points, topic_name, stamp, frame_id):
     import rospy
     from sensor_msgs.msg import PointCloud2
-    from pointcloud_utils import xyz_array_to_pointcloud2, xyzi_array_to_pointcloud2
+    from .pointcloud_utils import xyz_array_to_pointcloud2, xyzi_array_to_pointcloud2
     build = {3: xyz_array_to_pointcloud2, 4: xyzi_array_to_pointcloud2}[points.shape[1]]
     rospy.Publisher(topic_name, PointCloud2, queue_size=1).publish(build(points, stamp=stamp, frame_id=frame_id))
 
@@ -224,7 +224,6 @@ def voxel_grid_filter(points, leaf_size=0.1, filter_field_name="z", filter_limit
     """Downsample a cloud to one centroid per occupied voxel, after dropping non-finite points and those outside
     [filter_limit_min, filter_limit_max] along `filter_field_name` (None: no pass-through).  Defaults are the launch
     file's.  Returns an (M,3) fp32 CUDA tensor, voxels in ascending index order (x fastest), as pcl::VoxelGrid emits them."""
-    import ctypes
     from . import _lib
     L = _lib.lib()
     pts = ops._dev_f32(points, what="points")
@@ -237,9 +236,8 @@ def voxel_grid_filter(points, leaf_size=0.1, filter_field_name="z", filter_limit
     info = torch.zeros(8, dtype=torch.int32, device=pts.device)
     ws_bytes = L.cov_voxel_grid_workspace_bytes(n)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=pts.device)
-    _lib.check(L.cov_voxel_grid(pts.data_ptr(), n, float(leaf_size), axis, float(filter_limit_min), float(filter_limit_max),
-                                out.data_ptr(), cnt.data_ptr(), info.data_ptr(), ws.data_ptr(), ws_bytes,
-                                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "cov_voxel_grid")
+    ops._call("cov_voxel_grid", pts, pts.data_ptr(), n, float(leaf_size), axis, float(filter_limit_min),
+              float(filter_limit_max), out.data_ptr(), cnt.data_ptr(), info.data_ptr(), ws.data_ptr(), ws_bytes)
     info_h = info.tolist()
     if info_h[6]:
         raise RuntimeError("voxel_grid_filter: leaf size is too small for the input dataset (integer voxel indices would "
