@@ -10,7 +10,8 @@
  *     the stream passed as `stream` (a cudaStream_t cast to void*; NULL = legacy default);
  *   - return value 0 = success, negative = COV_ERR_*; cov_last_error() returns a
  *     thread-local message for the most recent failure on the calling thread;
- *   - re-entrant: no global mutable state besides that thread-local string.
+ *   - re-entrant: no process-wide switches or counters; the only mutable state in the library is the thread-local
+ *     error string and a mutex-protected cache of per-kernel occupancy figures (pure function of kernel, device, size);
  *   - quaternions are (w, x, y, z), unnormalised (the kernels apply F.normalize, eps 1e-12);
  *     point clouds are row-major (N,3) fp32, 16-byte aligned (COV_ERR_ALIGN otherwise).
  *
@@ -88,16 +89,34 @@ int cov_pose_epilogue(const double* acc_dev, const float* trans_dev, const float
  * ------------------------------------------------------------------------------------------ */
 int cov_traj_max_poses(void);
 size_t cov_traj_workspace_bytes(int64_t n, int n_poses);
+
+/* Per-call options of cov_traj_minmax / cov_traj_fused / cov_sweep_rewards; NULL = all zero = the defaults.
+ * Exact pruning (default): a (point, pose) pair whose distance Gaussian alone bounds m below what could matter (a
+ * sampled lower bound of the maximum in pass A once a zero minimum is known; the gate threshold in pass B) is never
+ * evaluated.  Per call: pose table -> cull (boxes of 128 consecutive points against every pose) + ascending work list of
+ * the tiles with a non-empty pose mask -> persistent evaluation kernel over the list (tile, boxes and mask arrive by
+ * TMA; each warp re-tests against the box of its own points, then per point).  Normalisers and rewards are
+ * bit-identical to the dense evaluation on ANY point order; the saving grows with the spatial coherence of
+ * consecutive points (cov_spatial_sort).  Clouds below 65536 points always take the dense kernels. */
+typedef struct cov_traj_opts {
+    int dense;                     /* != 0: evaluate every (point, pose) pair (what an unordered cloud should ask for) */
+    int rewards_prefilled;         /* cov_traj_fused: != 0: rewards_dev already holds 1/2 everywhere (skip the pre-fill) */
+    unsigned long long* stats_dev; /* NULL, or 8 device counters the evaluation kernels ADD to, in (warp, pose) pairs:
+                                      [0] pass B all pairs, [1] fully evaluated, [2],[3] same for pass A, [4]/[5] pass
+                                      B/A pairs that ran the per-point pre-filter, [6]/[7] pass B/A pairs the cull listed
+                                      (benchmark reporting; NULL in production) */
+} cov_traj_opts;
+
 /* boxes_dev: NULL, or the bounding boxes cov_tile_boxes made for this cloud (built once per cloud; with NULL the
  * pruned kernels rebuild them into the workspace on every call).  workspace_dev: cov_traj_workspace_bytes(n, n_poses)
- * bytes, 256-byte aligned, shared by both calls. */
+ * bytes, 256-byte aligned, shared by both calls (callers keep one per cloud: nothing in it outlives a call). */
 int cov_traj_minmax(const float* xyz_dev, int64_t n, const float* poses_dev, const float* quats_dev, int n_poses,
                     const float* K_dev, const cov_camera* cam, const float* boxes_dev, float* minmax_dev,
-                    void* workspace_dev, size_t workspace_bytes, void* stream);
+                    const cov_traj_opts* opts, void* workspace_dev, size_t workspace_bytes, void* stream);
 int cov_traj_fused(const float* xyz_dev, int64_t n, const float* poses_dev, const float* quats_dev, int n_poses,
                    const float* K_dev, const cov_camera* cam, const float* boxes_dev, const float* minmax_dev,
                    const float* upstream_dev, const int32_t* reward_index_dev, float* rewards_dev, double* acc_dev,
-                   void* workspace_dev, size_t workspace_bytes, void* stream);
+                   const cov_traj_opts* opts, void* workspace_dev, size_t workspace_bytes, void* stream);
 /* out_dev: [0] mean reward, then (W,3) d/d poses, then (W,4) d/d quats  (1 + 7*W floats).
  * With upstream_mode != 0 the gradients are those of sum_j upstream_j * rewards_j (no 1/N). */
 int cov_traj_epilogue(const double* acc_dev, const float* minmax_dev, const float* quats_dev, int n_poses,
@@ -115,12 +134,13 @@ int cov_traj_regularizers(const float* poses_dev, const float* poses0_dev, int n
  * ref: no reference implementation (BASELINE config 5); semantics = ModelTraj.forward per trajectory
  * with every pose evaluated.  sum_rewards_dev[t] += sum_j rewards_j(t) over this shard (doubles,
  * zero it first); minmax_dev is (2, n_traj*poses_per_traj) produced by cov_traj_minmax.
- * boxes_dev as for cov_traj_fused; workspace_dev: cov_traj_workspace_bytes(n, min(n_traj*poses_per_traj, 2048))
- * bytes, 256-byte aligned (the pruned pipeline runs the trajectories in chunks of pose-table size). */
+ * boxes_dev as for cov_traj_fused; workspace_dev: cov_sweep_workspace_bytes(n, n_traj, poses_per_traj) bytes,
+ * 256-byte aligned (the pruned pipeline runs the trajectories in chunks of pose-table size). */
+size_t cov_sweep_workspace_bytes(int64_t n, int n_traj, int poses_per_traj);
 int cov_sweep_rewards(const float* xyz_dev, int64_t n, const float* poses_dev, const float* quats_dev, int n_traj,
                       int poses_per_traj, const float* K_dev, const cov_camera* cam, const float* boxes_dev,
-                      const float* minmax_dev, double* sum_rewards_dev, void* workspace_dev, size_t workspace_bytes,
-                      void* stream);
+                      const float* minmax_dev, double* sum_rewards_dev, const cov_traj_opts* opts, void* workspace_dev,
+                      size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Multi-camera front end: n_body waypoints (x, y, z, yaw) x n_cams fixed extrinsics -> camera poses in the layout
@@ -200,21 +220,6 @@ int cov_voxel_grid(const float* xyz_dev, int64_t n, float leaf, int filter_axis,
                    float* xyz_out_dev, int64_t* count_dev, int32_t* info_dev, void* workspace_dev,
                    size_t workspace_bytes, void* stream);
 
-/* Exact pruning of (point, pose) pairs in cov_traj_minmax / cov_traj_fused (default on): a pair whose distance
- * Gaussian alone bounds m below what could matter (a sampled lower bound of the maximum in pass A once a zero
- * minimum is known; the gate threshold in pass B) is never evaluated.  Pipeline per call: cull (one warp per tile of
- * 256-2048 consecutive points: union of the tile's boxes against every pose) -> ascending work list of the tiles
- * with a non-empty pose mask -> persistent evaluation kernel over the work list (tile, boxes and mask arrive by TMA;
- * each warp re-tests against the box of its own points, then per point).  Normalisers and rewards are bit-identical
- * to the dense evaluation on ANY point order; the saving grows with the spatial coherence of consecutive points
- * (cov_spatial_sort below).  Process-wide switch, meant for A/B measurements.  cov_stats copies eight counters of
- * (warp, pose) pairs to the host (this call synchronises): [0] pass B all pairs, [1] fully evaluated, [2],[3] same
- * for pass A, [4]/[5] pass B/A pairs that ran the per-point pre-filter, [6]/[7] pass B/A pairs listed by the cull;
- * reset != 0 clears them. */
-void cov_set_pruning(int enabled);
-int cov_get_pruning(void);
-int cov_stats(int reset, unsigned long long* out8_host);
-
 /* Spatial (Morton) ordering of a cloud, done once per cloud (the reference hands the optimiser one fixed cloud:
  * src/trajectory_optimization.py:83-96, src/model.py:164), so that consecutive points are close in space and the
  * tile-level pruning above applies.  Keys are 30-bit Morton codes of the points quantised to a cubic grid of
@@ -234,6 +239,7 @@ int cov_spatial_sort(const float* xyz_dev, int64_t n, float* xyz_sorted_dev, int
  * Each runs `iters` dependent-chain iterations on a full grid and writes a checksum; the caller
  * times them with CUDA events.  Returns the number of FMA (or ex2) operations issued. */
 int64_t cov_probe_fma(int iters, float* sink_dev, void* stream);
+int64_t cov_probe_fma2(int iters, float* sink_dev, void* stream); /* packed pairs: fma.rn.f32x2 (FFMA2) */
 int64_t cov_probe_ex2(int iters, float* sink_dev, void* stream);
 
 #ifdef __cplusplus

@@ -33,14 +33,19 @@ ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
 stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 REPS = int(os.environ.get("KBENCH_REPS", "5"))
 
-state = {"pts": pts_raw, "perm": None, "boxes": None}
+state = {"pts": pts_raw, "perm": None, "boxes": None, "dense": False}
+stats_dev = torch.zeros(8, dtype=torch.int64, device=dev)
+
+
+def opts():
+    return ctypes.byref(_lib.traj_opts(dense=state["dense"], stats=stats_dev))
 
 
 def pass_a():
     p = state["pts"]
     _lib.check(L.cov_traj_minmax(p.data_ptr(), n, P.data_ptr(), Q.data_ptr(), W, K.data_ptr(), ctypes.byref(cam),
                                  state["boxes"].data_ptr() if state["boxes"] is not None else None, minmax.data_ptr(),
-                                 ws.data_ptr(), wsb, stream), "minmax")
+                                 opts(), ws.data_ptr(), wsb, stream), "minmax")
 
 
 def pass_b():
@@ -48,7 +53,7 @@ def pass_b():
     _lib.check(L.cov_traj_fused(p.data_ptr(), n, P.data_ptr(), Q.data_ptr(), W, K.data_ptr(), ctypes.byref(cam),
                                 state["boxes"].data_ptr() if state["boxes"] is not None else None,
                                 minmax.data_ptr(), None, None if perm is None else perm.data_ptr(), rewards.data_ptr(),
-                                acc.data_ptr(), ws.data_ptr(), wsb, stream), "fused")
+                                acc.data_ptr(), opts(), ws.data_ptr(), wsb, stream), "fused")
 
 
 def timeit(fn, reps=None):
@@ -65,13 +70,11 @@ def timeit(fn, reps=None):
 
 
 def run(label):
-    stats = (ctypes.c_ulonglong * 8)()
-    L.cov_stats(1, None)
+    stats_dev.zero_()
     ms_a = timeit(pass_a)
     mm = minmax.clone()
     ms_b = timeit(pass_b)
-    L.cov_stats(1, stats)
-    s = list(stats)
+    s = stats_dev.tolist()
     fr = lambda a, b: a / max(b, 1)  # noqa: E731
     print(f"{label:14s}: pass A {ms_a:8.3f} ms, pass B {ms_b:8.3f} ms -> {n * W / (ms_a + ms_b) / 1e6:9.1f} G evals/s "
           f"(dense-equivalent) | B: tile-listed {fr(s[6], s[0]):.4f} prefiltered {fr(s[4], s[0]):.4f} full {fr(s[1], s[0]):.4f}"
@@ -79,9 +82,9 @@ def run(label):
     return mm, rewards.clone(), acc.clone()
 
 
-L.cov_set_pruning(0)
+state["dense"] = True
 mm_d, rew_d, acc_d = run("dense")
-L.cov_set_pruning(1)
+state["dense"] = False
 mm_u, rew_u, acc_u = run("pruned/unsorted")
 print(f"   == dense: minmax {torch.equal(mm_u, mm_d)} rewards {torch.equal(rew_u, rew_d)} acc {torch.equal(acc_u, acc_d)} "
       f"acc_rel {float(((acc_u - acc_d).abs().max() / acc_d.abs().max()).item()):.2e}", flush=True)
@@ -102,8 +105,8 @@ print(f"   == dense: minmax {torch.equal(mm_s, mm_d)} rewards {torch.equal(rew_s
       f"sum_r_rel {abs(float(acc_s[-1] - acc_d[-1])) / float(acc_d[-1]):.2e}", flush=True)
 mm_s2, rew_s2, acc_s2 = run("pruned/sorted")
 print(f"   run-to-run: minmax {torch.equal(mm_s2, mm_s)} rewards {torch.equal(rew_s2, rew_s)} acc {torch.equal(acc_s2, acc_s)}", flush=True)
-L.cov_set_pruning(0)
+state["dense"] = True
 mm_ds, rew_ds, acc_ds = run("dense/sorted")
 print(f"   sorted pruned == sorted dense: minmax {torch.equal(mm_s, mm_ds)} rewards {torch.equal(rew_s, rew_ds)} "
-      f"acc {torch.equal(acc_s, acc_ds)}", flush=True)
-L.cov_set_pruning(1)
+      f"acc_rel {float(((acc_s - acc_ds).abs().max() / acc_ds.abs().max()).item()):.2e}", flush=True)
+state["dense"] = False

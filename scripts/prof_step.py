@@ -16,8 +16,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000_000
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 dev = torch.device("cuda:0")
 L = _lib.lib()
-if os.environ.get("COV_PRUNING", "1") == "0":  # profile the dense kernels instead
-    L.cov_set_pruning(0)
+opts = _lib.traj_opts(dense=os.environ.get("COV_PRUNING", "1") == "0")  # COV_PRUNING=0: profile the dense kernels
 pts, perm = ops.spatial_sort(bench.make_cloud_shard(n, 0, 1, dev))
 boxes = ops.tile_boxes(pts)
 K, iw, ih = tools.load_intrinsics(dev)
@@ -33,9 +32,9 @@ ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
 stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 for _ in range(reps):
     _lib.check(L.cov_traj_minmax(pts.data_ptr(), n, P.data_ptr(), Q.data_ptr(), W, K.data_ptr(), ctypes.byref(cam),
-                                 boxes.data_ptr(), minmax.data_ptr(), ws.data_ptr(), wsb, stream), "minmax")
+                                 boxes.data_ptr(), minmax.data_ptr(), ctypes.byref(opts), ws.data_ptr(), wsb, stream), "minmax")
     _lib.check(L.cov_traj_fused(pts.data_ptr(), n, P.data_ptr(), Q.data_ptr(), W, K.data_ptr(), ctypes.byref(cam),
                                 boxes.data_ptr(), minmax.data_ptr(), None, perm.data_ptr(), rewards.data_ptr(), acc.data_ptr(),
-                                ws.data_ptr(), wsb, stream), "fused")
+                                ctypes.byref(opts), ws.data_ptr(), wsb, stream), "fused")
 torch.cuda.synchronize()
 print("mean reward", float(acc[-1]) / n)

@@ -251,7 +251,7 @@ def test_sharded_accumulators_equal_whole_cloud(dev, mod):
         wsb = L.cov_traj_workspace_bytes(s.shape[0], W)
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
         _lib.check(L.cov_traj_minmax(s.data_ptr(), s.shape[0], P.data_ptr(), Q.data_ptr(), W, K.data_ptr(),
-                                     ctypes.byref(cam), None, t.data_ptr(), ws.data_ptr(), wsb, stream), "minmax")
+                                     ctypes.byref(cam), None, t.data_ptr(), None, ws.data_ptr(), wsb, stream), "minmax")
         mm.append(t)
     minmax = torch.cat([torch.minimum(mm[0][:W], mm[1][:W]), torch.maximum(mm[0][W:], mm[1][W:])])
     acc = torch.zeros(W * _lib.ACC_STRIDE + 1, dtype=torch.float64, device=dev)
@@ -263,7 +263,7 @@ def test_sharded_accumulators_equal_whole_cloud(dev, mod):
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
         _lib.check(L.cov_traj_fused(s.data_ptr(), s.shape[0], P.data_ptr(), Q.data_ptr(), W, K.data_ptr(),
                                     ctypes.byref(cam), None, minmax.data_ptr(), None, None, r.data_ptr(), a.data_ptr(),
-                                    ws.data_ptr(), wsb, stream), "fused")
+                                    None, ws.data_ptr(), wsb, stream), "fused")
         acc += a
         rew.append(r)
     out = torch.empty(1 + 7 * W, device=dev)
@@ -273,10 +273,12 @@ def test_sharded_accumulators_equal_whole_cloud(dev, mod):
     assert rel_err(out[0].item(), mean.item()) < 1e-6
     assert rel_err(out[1:1 + 3 * W].detach().cpu().numpy(), gp.reshape(-1).detach().cpu().numpy()) < 1e-5
     assert rel_err(out[1 + 3 * W:].detach().cpu().numpy(), gq.reshape(-1).detach().cpu().numpy()) < 1e-5
-    # run-to-run determinism of the whole pipeline (fixed-order reductions)
+    # run to run: per-point outputs are bitwise reproducible; the accumulators are sums of the same fp32 block partials
+    # added with fp64 atomics, so only the order of ~1e-16-relative roundings can differ
     rewards2, mean2 = ops.coverage_traj(pts, Pg, Qg, K, Wd, Hd)
     gp2, gq2 = torch.autograd.grad(mean2, [Pg, Qg])
-    assert torch.equal(rewards2, rewards) and torch.equal(mean2, mean) and torch.equal(gp2, gp) and torch.equal(gq2, gq)
+    assert torch.equal(rewards2, rewards) and rel_err(mean2.item(), mean.item()) < 1e-7
+    assert rel_err(gp2.cpu().numpy(), gp.cpu().numpy()) < 1e-6 and rel_err(gq2.cpu().numpy(), gq.cpu().numpy()) < 1e-6
 
 
 def test_sweep_matches_per_trajectory_forward(dev, mod):
@@ -292,10 +294,10 @@ def test_sweep_matches_per_trajectory_forward(dev, mod):
     from trajectory_optimization_b200 import _lib
     means = ops.sweep_rewards(pts, torch.from_numpy(poses.astype(np.float32)), torch.from_numpy(quats), K, Wd, Hd)
     try:  # the dense sweep (pruning off) and the pruned pipeline agree; so does the pruned one on the cloud as given
-        _lib.lib().cov_set_pruning(0)
+        ops._MODE.dense = not 0
         means_dense = ops.sweep_rewards(pts, torch.from_numpy(poses.astype(np.float32)), torch.from_numpy(quats), K, Wd, Hd)
     finally:
-        _lib.lib().cov_set_pruning(1)
+        ops._MODE.dense = not 1
     means_unsorted = ops.sweep_rewards(pts, torch.from_numpy(poses.astype(np.float32)), torch.from_numpy(quats), K, Wd, Hd,
                                        presorted=True)
     assert rel_err(means.cpu().numpy(), means_dense.cpu().numpy()) < 1e-9
@@ -340,14 +342,14 @@ def test_pruned_evaluation_is_bit_identical_to_dense(dev, mod):
     outs = []
     try:
         for mode in (1, 0):
-            L.cov_set_pruning(mode)
+            ops._MODE.dense = not mode
             P = torch.from_numpy(poses).to(dev).requires_grad_(True)
             Q = torch.from_numpy(quats).to(dev).requires_grad_(True)
             rewards, mean = ops.coverage_traj(pts, P, Q, K, Wd, Hd)
             gp, gq = torch.autograd.grad(mean, [P, Q])
             outs.append((rewards, mean, gp, gq))
     finally:
-        L.cov_set_pruning(1)
+        ops._MODE.dense = not 1
     (r1, m1, gp1, gq1), (r0, m0, gp0, gq0) = outs
     assert torch.equal(r1, r0) and torch.equal(m1, m0)           # per-point outputs and their mean: every bit
     # the gradient accumulators see the same addends in a different fp32 summation order
@@ -438,19 +440,19 @@ def test_tile_pruning_on_sorted_cloud_is_bit_identical_to_dense(dev, mod):
         outs = []
         try:
             for mode in (1, 0):
-                L.cov_set_pruning(mode)
+                ops._MODE.dense = not mode
                 mm = torch.empty(2 * W, device=dev)
                 wsb = L.cov_traj_workspace_bytes(n, W)
                 ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
                 _lib.check(L.cov_traj_minmax(pts.data_ptr(), n, P.data_ptr(), Q.data_ptr(), W, K.data_ptr(),
-                                             ctypes.byref(cam), boxes.data_ptr(), mm.data_ptr(), ws.data_ptr(), wsb,
-                                             stream), "minmax")
+                                             ctypes.byref(cam), boxes.data_ptr(), mm.data_ptr(),
+                                             ctypes.byref(_lib.traj_opts(dense=not mode)), ws.data_ptr(), wsb, stream), "minmax")
                 Pg, Qg = P.clone().requires_grad_(True), Q.clone().requires_grad_(True)
                 rewards, mean = ops.coverage_traj(pts, Pg, Qg, K, Wd, Hd, reward_index=perm, boxes=boxes)
                 gp, gq = torch.autograd.grad(mean, [Pg, Qg])
                 outs.append((mm, rewards, mean, gp, gq))
         finally:
-            L.cov_set_pruning(1)
+            ops._MODE.dense = not 1
         (mm1, r1, m1, gp1, gq1), (mm0, r0, m0, gp0, gq0) = outs
         assert torch.equal(mm1, mm0) and torch.equal(r1, r0) and torch.equal(m1, m0)
         assert rel_err(gp1.cpu().numpy(), gp0.cpu().numpy()) < 2e-6 and rel_err(gq1.cpu().numpy(), gq0.cpu().numpy()) < 2e-6
@@ -553,7 +555,7 @@ def test_pruned_pipeline_equals_dense_on_edge_shapes(n, W, mode, dev, mod):
     outs = []
     try:
         for prune in (1, 0):
-            L.cov_set_pruning(prune)
+            ops._MODE.dense = not prune
             for ordered in ((True, False) if prune else (False,)):
                 pts = torch.from_numpy(pts_np).to(dev)
                 perm = boxes = None
@@ -566,7 +568,7 @@ def test_pruned_pipeline_equals_dense_on_edge_shapes(n, W, mode, dev, mod):
                 gp, gq = torch.autograd.grad(mean, [P, Q])
                 outs.append((rewards, mean, gp, gq))
     finally:
-        L.cov_set_pruning(1)
+        ops._MODE.dense = not 1
     dense = outs[-1]
     if bool(torch.isnan(dense[1])):   # one point: min == max, the reference's normalisation is 0/0 there too
         assert n == 1 and all(bool(torch.isnan(got[0]).all()) and bool(torch.isnan(got[1])) for got in outs)
@@ -597,12 +599,12 @@ def test_pose_that_sees_nothing_gives_nan_like_the_reference(dev, mod):
     assert np.isnan(ref["vis"]) and np.isnan(ref["rewards"]).all()
     try:
         for prune in (1, 0):
-            _lib.lib().cov_set_pruning(prune)
+            ops._MODE.dense = not prune
             rewards, mean = ops.coverage_traj(torch.from_numpy(pts_np).to(dev), torch.from_numpy(poses).to(dev),
                                               torch.from_numpy(quats).to(dev), K, Wd, Hd)
             assert bool(torch.isnan(mean)) and bool(torch.isnan(rewards).all())
     finally:
-        _lib.lib().cov_set_pruning(1)
+        ops._MODE.dense = not 1
 
 
 def _import_dropin(name):

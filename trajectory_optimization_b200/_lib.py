@@ -23,8 +23,14 @@ class Camera(C.Structure):
                 ("max_dist", C.c_float), ("eps", C.c_float)]
 
 
+class TrajOpts(C.Structure):
+    """struct cov_traj_opts (per-call options; all zero = defaults)."""
+    _fields_ = [("dense", C.c_int), ("rewards_prefilled", C.c_int), ("stats_dev", C.c_void_p)]
+
+
 _vp, _i64, _int, _f, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_size_t
 _cam = C.POINTER(Camera)
+_opts = C.POINTER(TrajOpts)
 
 # name -> (restype, argtypes); must list every symbol include/coverage_b200.h declares
 PROTOTYPES = {
@@ -36,11 +42,12 @@ PROTOTYPES = {
     "cov_pose_epilogue": (_int, [_vp, _vp, _vp, _vp, _vp]),
     "cov_traj_max_poses": (_int, []),
     "cov_traj_workspace_bytes": (_sz, [_i64, _int]),
-    "cov_traj_minmax": (_int, [_vp, _i64, _vp, _vp, _int, _vp, _cam, _vp, _vp, _vp, _sz, _vp]),
-    "cov_traj_fused": (_int, [_vp, _i64, _vp, _vp, _int, _vp, _cam, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "cov_traj_minmax": (_int, [_vp, _i64, _vp, _vp, _int, _vp, _cam, _vp, _vp, _opts, _vp, _sz, _vp]),
+    "cov_traj_fused": (_int, [_vp, _i64, _vp, _vp, _int, _vp, _cam, _vp, _vp, _vp, _vp, _vp, _vp, _opts, _vp, _sz, _vp]),
     "cov_traj_epilogue": (_int, [_vp, _vp, _vp, _int, _i64, _int, _vp, _vp]),
     "cov_traj_regularizers": (_int, [_vp, _vp, _int, _f, _f, _f, _vp, _vp]),
-    "cov_sweep_rewards": (_int, [_vp, _i64, _vp, _vp, _int, _int, _vp, _cam, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "cov_sweep_workspace_bytes": (_sz, [_i64, _int, _int]),
+    "cov_sweep_rewards": (_int, [_vp, _i64, _vp, _vp, _int, _int, _vp, _cam, _vp, _vp, _vp, _opts, _vp, _sz, _vp]),
     "cov_rig_poses": (_int, [_vp, _int, _vp, _int, _vp, _vp, _vp]),
     "cov_rig_poses_backward": (_int, [_vp, _int, _vp, _int, _vp, _vp, _f, _vp, _vp]),
     "cov_cull_workspace_bytes": (_sz, [_i64]),
@@ -53,14 +60,12 @@ PROTOTYPES = {
     "cov_xyz_to_pc2": (_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "cov_voxel_grid_workspace_bytes": (_sz, [_i64]),
     "cov_voxel_grid": (_int, [_vp, _i64, _f, _int, _f, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "cov_set_pruning": (None, [_int]),
-    "cov_get_pruning": (_int, []),
-    "cov_stats": (_int, [_int, _vp]),
     "cov_spatial_sort_workspace_bytes": (_sz, [_i64]),
     "cov_spatial_sort": (_int, [_vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "cov_tile_boxes_count": (_i64, [_i64]),
     "cov_tile_boxes": (_int, [_vp, _i64, _vp, _vp]),
     "cov_probe_fma": (_i64, [_int, _vp, _vp]),
+    "cov_probe_fma2": (_i64, [_int, _vp, _vp]),
     "cov_probe_ex2": (_i64, [_int, _vp, _vp]),
 }
 
@@ -91,3 +96,8 @@ def check(rc, what):
 
 def camera(img_width, img_height, min_dist, max_dist, eps):
     return Camera(float(img_width), float(img_height), float(min_dist), float(max_dist), float(eps))
+
+
+def traj_opts(dense=False, rewards_prefilled=False, stats=None):
+    """cov_traj_opts; `stats`: None or a CUDA int64/uint64 tensor of 8 counters the evaluation kernels add to."""
+    return TrajOpts(1 if dense else 0, 1 if rewards_prefilled else 0, None if stats is None else stats.data_ptr())

@@ -56,31 +56,7 @@ int cov_sm_count_cached() {
     return sms;
 }
 
-// Exact bound-based pruning of (point, pose) pairs (cov_traj.cu); process-wide switch for A/B measurements.
-static int g_pruning = 1;
-int cov_pruning_enabled() { return g_pruning; }
-extern "C" void cov_set_pruning(int enabled) { g_pruning = enabled ? 1 : 0; }
-extern "C" int cov_get_pruning(void) { return g_pruning; }
-
-// Work counters (development / benchmark reporting only), in (warp, pose) pairs: [0] pass B all pairs, [1] fully
-// evaluated, [2] pass A all pairs, [3] fully evaluated, [4]/[5] pass B/A pairs that ran the per-point distance
-// pre-filter, [6]/[7] pass B/A pairs that survived the tile-level box test.
-__device__ unsigned long long g_cov_stats[8];
-unsigned long long* cov_stats_device_ptr() {
-    unsigned long long* p = nullptr;
-    cudaGetSymbolAddress((void**)&p, g_cov_stats);
-    return p;
-}
-extern "C" int cov_stats(int reset, unsigned long long* out8_host) {
-    unsigned long long* p = cov_stats_device_ptr();
-    if (!p) return COV_ERR_CUDA;
-    if (out8_host && cudaMemcpy(out8_host, p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess)
-        return COV_ERR_CUDA;
-    if (reset && cudaMemset(p, 0, 8 * sizeof(unsigned long long)) != cudaSuccess) return COV_ERR_CUDA;
-    return COV_OK;
-}
-
-extern "C" int cov_version(void) { return 100; }
+extern "C" int cov_version(void) { return 200; }
 extern "C" const char* cov_last_error(void) { return g_err; }
 extern "C" int cov_device_sm_count(void) {
     int n = 0;
@@ -108,6 +84,33 @@ __global__ void __launch_bounds__(256) probe_fma_kernel(int iters, float* sink) 
     for (int i = 0; i < kProbeIlp; ++i) s += a[i];
     if (s == 123.456f) sink[0] = s;
 }
+// packed fp32 pairs: one FFMA2 per instruction = two FMAs per lane (sm_100 fma.rn.f32x2)
+__global__ void __launch_bounds__(256) probe_fma2_kernel(int iters, float* sink) {
+    unsigned long long a[kProbeIlp];
+#pragma unroll
+    for (int i = 0; i < kProbeIlp; ++i) {
+        const float lo = 1.0f + 1e-3f * (threadIdx.x + i), hi = 1.0f + 2e-3f * (threadIdx.x + i);
+        asm("mov.b64 %0, {%1, %2};" : "=l"(a[i]) : "f"(lo), "f"(hi));
+    }
+    unsigned long long b, c;
+    {
+        const float bf = 0.999f, cf = 1e-4f;
+        asm("mov.b64 %0, {%1, %1};" : "=l"(b) : "f"(bf));
+        asm("mov.b64 %0, {%1, %1};" : "=l"(c) : "f"(cf));
+    }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < kProbeIlp; ++i) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a[i]) : "l"(b), "l"(c));
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kProbeIlp; ++i) {
+        float lo, hi;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a[i]));
+        s += lo + hi;
+    }
+    if (s == 123.456f) sink[0] = s;
+}
 __global__ void __launch_bounds__(256) probe_ex2_kernel(int iters, float* sink) {
     float a[kProbeIlp];
 #pragma unroll
@@ -128,6 +131,12 @@ extern "C" int64_t cov_probe_fma(int iters, float* sink, void* stream) {
     probe_fma_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(iters, sink);
     if (cov_check_launch("cov_probe_fma")) return -1;
     return (int64_t)grid * 256 * kProbeIlp * iters;
+}
+extern "C" int64_t cov_probe_fma2(int iters, float* sink, void* stream) {
+    const int grid = cov_sm_count_cached() * 8;
+    probe_fma2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(iters, sink);
+    if (cov_check_launch("cov_probe_fma2")) return -1;
+    return (int64_t)grid * 256 * kProbeIlp * iters * 2;
 }
 extern "C" int64_t cov_probe_ex2(int iters, float* sink, void* stream) {
     const int grid = cov_sm_count_cached() * 8;

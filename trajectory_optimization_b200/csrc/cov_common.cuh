@@ -160,8 +160,6 @@ void cov_set_error(const char* fmt, ...);
 int cov_check_launch(const char* what);
 CovConst cov_make_const(const struct cov_camera* cam);
 int cov_sm_count_cached();
-int cov_pruning_enabled();
-unsigned long long* cov_stats_device_ptr();
 int cov_sweep_rewards_dense(const float* xyz, int64_t n, const float* poses, const float* quats, int n_traj, int per_traj,
                             const float* K, const struct cov_camera* cam, const float* minmax, double* sum_rewards,
                             void* stream);

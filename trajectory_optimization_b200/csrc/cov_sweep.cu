@@ -103,7 +103,7 @@ cov_sweep_kernel(const float* __restrict__ xyz, int64_t n, const float* __restri
 
 }  // namespace
 
-// Dense sweep (cov_set_pruning(0)); the pruned pipeline and the C entry point are in cov_traj.cu.
+// Dense sweep (cov_traj_opts.dense); the pruned pipeline and the C entry point are in cov_traj.cu.
 int cov_sweep_rewards_dense(const float* xyz, int64_t n, const float* poses, const float* quats, int n_traj,
                             int per_traj, const float* K, const cov_camera* cam, const float* minmax,
                             double* sum_rewards, void* stream) {
@@ -123,7 +123,8 @@ int cov_sweep_rewards_dense(const float* xyz, int64_t n, const float* poses, con
     constexpr int T = COV_THREADS * kSweepPpt;
     const int64_t ntiles = (n + T - 1) / T;
     const size_t smem_max = sweep_smem_bytes(chunk, per_traj);
-    cudaFuncSetAttribute(cov_sweep_kernel<kSweepPpt>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+    // always the same value: two host threads with different trajectory counts cannot race between set and launch
+    cudaFuncSetAttribute(cov_sweep_kernel<kSweepPpt>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256);
     int per_sm = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cov_sweep_kernel<kSweepPpt>, COV_THREADS, smem_max) !=
             cudaSuccess || per_sm < 1)

@@ -25,19 +25,26 @@
 //             minimum is known to be exactly 0 (skipped points have m >= 0);
 //     pass B: bound = the conservative gate threshold (a + b/2)(1 - 2^-20): a pair below it is neither gated nor
 //             the arg-max, adds logit(1/2) = 0 to the log-odds sum and nothing to the gradient.
-//   cov_cull_kernel      one warp per tile: union of the tile's boxes against every pose -> per-tile pose bit mask
-//   cov_worklist_kernel  list of the tiles with a non-empty mask, heaviest first (single block scan: deterministic)
+//   cov_traj_prepare_kernel (A) / cov_traj_table_kernel (B)   pose table; A also evaluates a strided sample of the
+//                        cloud (lower bounds of the maxima, which minima are exactly 0); B zeroes the accumulators
+//   cov_cull_kernel      one warp per group of 8 tiles: boxes against every pose -> per-tile pose bit mask, and the
+//                        ascending work list of the tiles with a non-empty mask, positions from a decoupled
+//                        look-back scan over the blocks' counts (deterministic; no second kernel); in pass B the
+//                        same blocks pre-fill the rewards with 1/2 (what every unlisted point gets, exactly)
 //   *_tiles_kernel       persistent blocks walk the work list; tile points, boxes and mask arrive together through a
 //                        double-buffered TMA bulk copy (one mbarrier per buffer); a warp evaluates a listed pose only
-//                        if its own 128-point box and then one of its points pass the same test.
+//                        if its own 128-point box and then one of its points pass the same test.  Pass B queues its
+//                        gated (point, pose) pairs per warp and differentiates them 32 at a time with every lane busy.
 //   Tiles that are not listed are never read: their rewards are the pre-filled 1/2 (exact), their sum is 0.5 * count.
 //
-// Block accumulators go to a [block][W][8] fp32 slab; a small kernel adds the slabs in fp64 in a fixed order.
-// The arg-max / arg-min tie sets of the normalisation backward are rare (one point per pose unless the minimum
-// underflowed to 0, in which case their gradient is exactly negligible and skipped) and go straight to the fp64
-// accumulator with atomics.
+// Block accumulators are added to the caller's fp64 accumulator rows with fp64 atomics (the order of those additions is
+// the only thing that differs between runs: ~1e-16 relative).  The arg-max / arg-min tie sets of the normalisation
+// backward are rare (one point per pose unless the minimum underflowed to 0, in which case their gradient is exactly
+// negligible and skipped) and go straight to the fp64 accumulator as well.
 #include <algorithm>
 #include <cstdlib>
+#include <map>
+#include <mutex>
 
 #include "cov_common.cuh"
 #include "../../include/coverage_b200.h"
@@ -69,9 +76,8 @@ __host__ __device__ inline int fused_stage_offset_floats(int W) {
     return (int)((((size_t)W * COV_ROW_F4 * 16 + 127) & ~(size_t)127) / 4);
 }
 size_t fused_smem_bytes(int W, int ppt, bool prune) {
-    if (prune)  // pose table | 2 tile stages | block accumulators
-        return (size_t)fused_stage_offset_floats(W) * 4 + 2 * (size_t)(stage_floats(ppt) + tile_points(ppt)) * 4 +
-               (size_t)W * 8 * sizeof(float);
+    if (prune)  // 2 tile stages (the pose table stays in global memory, the accumulators are the caller's)
+        return 2 * (size_t)(stage_floats(ppt) + tile_points(ppt)) * 4;
     // pose table | tile points | G_j | gate bits | block accumulators
     return (size_t)fused_stage_offset_floats(W) * 4 + (size_t)tile_points(ppt) * 12 + (size_t)tile_points(ppt) * 4 +
            (size_t)W * bit_stride(ppt) * sizeof(unsigned) + (size_t)W * 8 * sizeof(float);
@@ -90,6 +96,24 @@ __device__ __noinline__ void tie_accumulate(float x, float y, float z, int w, Co
     float gx, gy, gz;
     cov_vis_grad(m, ev, row[0], row[1], row[2], C, gx, gy, gz);
     const float yx = x - row[5].x, yy = y - row[5].y, yz = z - row[5].z;
+    atomicAdd(dst + 0, (double)gx);
+    atomicAdd(dst + 1, (double)gy);
+    atomicAdd(dst + 2, (double)gz);
+    atomicAdd(dst + 3, (double)(gy * yz - gz * yy));
+    atomicAdd(dst + 4, (double)(gz * yx - gx * yz));
+    atomicAdd(dst + 5, (double)(gx * yy - gy * yx));
+    atomicAdd(dst + 6, 1.0);
+}
+
+// Same for the pruned pass B, whose pose table stays in global memory (read through L1, a handful of rows per tile).
+__device__ __noinline__ void tie_accumulate_g(float x, float y, float z, const float4* __restrict__ row, CovConst C,
+                                              double* dst) {
+    const float4 v0 = __ldg(row), v1 = __ldg(row + 1), v2 = __ldg(row + 2), v3 = __ldg(row + 3), v5 = __ldg(row + 5);
+    CovEval ev;
+    const float m = cov_vis<true>(x, y, z, v0, v1, v2, v3, C, &ev);
+    float gx, gy, gz;
+    cov_vis_grad(m, ev, v0, v1, v2, C, gx, gy, gz);
+    const float yx = x - v5.x, yy = y - v5.y, yz = z - v5.z;
     atomicAdd(dst + 0, (double)gx);
     atomicAdd(dst + 1, (double)gy);
     atomicAdd(dst + 2, (double)gz);
@@ -266,17 +290,6 @@ cov_traj_minmax_kernel(const float* __restrict__ xyz, int64_t n, int64_t point_s
     }
 }
 
-__global__ void __launch_bounds__(256) cov_fill_kernel(float* __restrict__ dst, int64_t n, float v) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
-    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
-        if (i + 4 <= n && ((reinterpret_cast<uintptr_t>(dst + i) & 15) == 0)) {
-            *reinterpret_cast<float4*>(dst + i) = make_float4(v, v, v, v);
-        } else {
-            for (int64_t k = i; k < n && k < i + 4; ++k) dst[k] = v;
-        }
-    }
-}
-
 __global__ void cov_minmax_init_kernel(unsigned* gmin, unsigned* gmax, int W) {
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w < W) {
@@ -286,46 +299,47 @@ __global__ void cov_minmax_init_kernel(unsigned* gmin, unsigned* gmax, int W) {
 }
 
 // ============================================ pruned passes: set-up ============================================
-// Pose table in global memory, built once per call (the pruned kernels copy it to shared memory).  With `minmax`
-// (pass B) the rows carry the normalisation constants: v3.w = qthr, v4 = (b/2, b, 1/b, a), v5.w = thr.
-// flags[1] is set when some pose has min_j m > 0.
-__global__ void cov_pose_table_kernel(const float* __restrict__ poses, const float* __restrict__ quats, int W,
-                                      const float* __restrict__ K9, CovConst C, const float* __restrict__ minmax,
-                                      float4* __restrict__ table, int* __restrict__ flags) {
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= W) return;
-    float4 row[COV_ROW_F4];
-    cov_pose_row(poses + 3 * w, quats + 4 * w, K9, C, row);
-    if (minmax) {
-        const float a = minmax[w];
-        const float b = __fsub_rn(minmax[W + w], a);
-        const float hb = 0.5f * b;
-        const float thr = (a + hb) * (1.f - 9.5367431640625e-07f);  // conservative gate threshold
-        row[5].w = thr;
-        // q2 above qthr cannot reach thr (thr <= 0 or NaN, or a > 0 — arg-min points carry gradient: never prune)
-        row[3].w = (thr > 0.f && !(a > 0.f)) ? (float)((1e-4 - log2((double)thr)) / (double)C.kd * 1.000001)
-                                             : __uint_as_float(0x7f800000u);
-        row[4] = make_float4(hb, b, __frcp_rn(b), a);
-        if (a > 0.f) atomicOr(flags + 1, 1);
-    }
-#pragma unroll
-    for (int i = 0; i < COV_ROW_F4; ++i) table[(size_t)w * COV_ROW_F4 + i] = row[i];
+// Control words of one pruned call, at the head of the workspace (zeroed once per call: by a memset node in pass A,
+// by cov_traj_table_kernel in pass B):
+//   ctrl[0] work-list length   ctrl[1] some pose has min_j m > 0   ctrl[2] block ticket of the evaluation kernel
+//   ctrl[4..5] (tile, pose) pairs the cull listed (u64)
+//   enc[0..W)  ~bits(min_j m)   enc[W..2W) bits(max_j m)   pass A's extrema in an encoding whose neutral element is 0:
+//              m >= +0, so the unsigned order of the bits is the float order; both are kept with atomicMax
+//   desc[c]    look-back descriptor of cull chunk c (status in the top two bits)
+constexpr int kCtrlInts = 16;
+constexpr unsigned long long kDescAgg = 1ull << 62, kDescPrefix = 2ull << 62, kDescValue = (1ull << 62) - 1;
+constexpr int kChunkTiles = 64;  // tiles per cull block iteration (8 warps x 8 tiles) = one look-back descriptor
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// Seed of the pruned pass A: every `stride`-th point against all poses (dense), so that the cull starts from a good
-// lower bound of each maximum and knows which minima are exactly 0.  Grid = (sample blocks) x (chunks of 32 poses):
-// a thread owns one sample point, a block 32 pose rows of the table; per pose one REDUX pair per warp, the 8 warps
-// meet in shared memory, 32 global atomics per block.
+// Pass A, first launch: pose table + seed.  Grid = (sample blocks) x (chunks of 32 poses).  The first 32 threads of a
+// block build the chunk's pose rows in shared memory (fp64 inside; blocks of the first grid column also store them to
+// the global table the later kernels copy), then every thread evaluates ONE point of a strided sample of the cloud
+// against the 32 poses (dense), so that the cull starts from a good lower bound of each maximum and knows which
+// minima are exactly 0.  Per pose one REDUX pair per warp, the 8 warps meet in shared memory, 64 global atomics per
+// block into the zero-initialised encoded extrema.
 __global__ void __launch_bounds__(COV_THREADS)
-cov_traj_seed_kernel(const float* __restrict__ xyz, int64_t nsamples, int64_t stride, const float4* __restrict__ table,
-                     int W, CovConst C, unsigned* __restrict__ gmin, unsigned* __restrict__ gmax) {
-    __shared__ float4 rows[32 * 4];
+cov_traj_prepare_kernel(const float* __restrict__ xyz, int64_t nsamples, int64_t stride, const float* __restrict__ poses,
+                        const float* __restrict__ quats, int W, const float* __restrict__ K9, CovConst C,
+                        float4* __restrict__ table, unsigned* __restrict__ enc) {
+    __shared__ float4 rows[32 * COV_ROW_F4];
     __shared__ unsigned smn[32], smx[32];
     const int tid = threadIdx.x, lane = tid & 31;
     const int w0 = blockIdx.y * 32;
     const int wn = (W - w0 < 32) ? (W - w0) : 32;
-    if (tid < wn * 4) rows[tid] = table[(size_t)(w0 + (tid >> 2)) * COV_ROW_F4 + (tid & 3)];
-    if (tid < 32) {
+    if (tid < wn) {
+        cov_pose_row(poses + 3 * (w0 + tid), quats + 4 * (w0 + tid), K9, C, rows + tid * COV_ROW_F4);
+        if (blockIdx.x == 0) {
+#pragma unroll
+            for (int i = 0; i < COV_ROW_F4; ++i) table[(size_t)(w0 + tid) * COV_ROW_F4 + i] = rows[tid * COV_ROW_F4 + i];
+        }
         smn[tid] = 0x7f800000u;
         smx[tid] = 0u;
     }
@@ -335,7 +349,8 @@ cov_traj_seed_kernel(const float* __restrict__ xyz, int64_t nsamples, int64_t st
     const float x = __ldg(xyz + j * 3), y = __ldg(xyz + j * 3 + 1), z = __ldg(xyz + j * 3 + 2);
     unsigned keep_mn = 0x7f800000u, keep_mx = 0u;
     for (int i = 0; i < wn; ++i) {
-        const float m = cov_vis<false>(x, y, z, rows[4 * i], rows[4 * i + 1], rows[4 * i + 2], rows[4 * i + 3], C, nullptr);
+        const float4* r = rows + i * COV_ROW_F4;
+        const float m = cov_vis<false>(x, y, z, r[0], r[1], r[2], r[3], C, nullptr);
         const unsigned umn = __reduce_min_sync(kFull, __float_as_uint(m));
         const unsigned umx = __reduce_max_sync(kFull, __float_as_uint(m));
         if (lane == i) {
@@ -349,8 +364,41 @@ cov_traj_seed_kernel(const float* __restrict__ xyz, int64_t nsamples, int64_t st
     }
     __syncthreads();
     if (tid < wn) {
-        atomicMin(gmin + w0 + tid, smn[tid]);
-        atomicMax(gmax + w0 + tid, smx[tid]);
+        atomicMax(enc + w0 + tid, ~smn[tid]);
+        atomicMax(enc + W + w0 + tid, smx[tid]);
+    }
+}
+
+// Pass B, first launch (one block): zero the control words, the look-back descriptors and the caller's accumulator
+// rows (acc[W * STRIDE] starts at `sum_base` = 0.5 * n: what the unlisted points add to the reward sum), then build
+// the pose table with the normalisation constants: v3.w = qthr, v4 = (b/2, b, 1/b, a), v5.w = thr.
+__global__ void __launch_bounds__(256)
+cov_traj_table_kernel(const float* __restrict__ poses, const float* __restrict__ quats, int W,
+                      const float* __restrict__ K9, CovConst C, const float* __restrict__ minmax,
+                      float4* __restrict__ table, int* __restrict__ ctrl, int ctrl_words, double* __restrict__ acc,
+                      double sum_base) {
+    const int tid = threadIdx.x;
+    for (int i = tid; i < ctrl_words; i += blockDim.x) ctrl[i] = 0;
+    if (acc) {
+        for (int i = tid; i < W * COV_ACC_STRIDE; i += blockDim.x) acc[i] = 0.0;
+        if (tid == 0) acc[(size_t)W * COV_ACC_STRIDE] = sum_base;
+    }
+    __syncthreads();
+    for (int w = tid; w < W; w += blockDim.x) {
+        float4 row[COV_ROW_F4];
+        cov_pose_row(poses + 3 * w, quats + 4 * w, K9, C, row);
+        const float a = minmax[w];
+        const float b = __fsub_rn(minmax[W + w], a);
+        const float hb = 0.5f * b;
+        const float thr = (a + hb) * (1.f - 9.5367431640625e-07f);  // conservative gate threshold
+        row[5].w = thr;
+        // q2 above qthr cannot reach thr (thr <= 0 or NaN, or a > 0 — arg-min points carry gradient: never prune)
+        row[3].w = (thr > 0.f && !(a > 0.f)) ? (float)((1e-4 - log2((double)thr)) / (double)C.kd * 1.000001)
+                                             : __uint_as_float(0x7f800000u);
+        row[4] = make_float4(hb, b, __frcp_rn(b), a);
+        if (a > 0.f) atomicOr(ctrl + 1, 1);
+#pragma unroll
+        for (int i = 0; i < COV_ROW_F4; ++i) table[(size_t)w * COV_ROW_F4 + i] = row[i];
     }
 }
 
@@ -381,31 +429,48 @@ __global__ void __launch_bounds__(256) cov_tile_boxes_kernel(const float* __rest
     }
 }
 
-// Cull: mask[tile][c] bit i <=> pose 32c+i can matter for some point of the tile; flags[tile] = the mask is not
-// empty.  One warp per GROUP of 8 consecutive tiles: every pose is tested against the group's box first (one lane
-// per pose), and only the few that pass are tested against the 8 tile boxes (one lane per tile).  Pass A passes
-// gmin/gmax (after the seed launch) and the cap is derived here; pass B reads qthr from the table.
+// Cull + work list.  mask[tile][c] bit i <=> pose 32c+i can matter for some point of the tile.  One warp per GROUP of 8
+// consecutive tiles: every pose is tested against the group's box first (one lane per pose), and only the few that
+// pass are tested against the 8 tile boxes (one lane per tile).  Pass A passes `enc` (after the prepare launch) and the
+// cap is derived here; pass B reads qthr from the table.
+// A block iteration covers a CHUNK of 64 consecutive tiles and appends the chunk's listed tiles to the work list in
+// ascending order: the chunk's offset is the exclusive prefix sum of the chunks' counts, obtained with a decoupled
+// look-back over per-chunk descriptors (publish the own aggregate, then sum predecessors until one carries an
+// inclusive prefix).  The list is a pure function of the masks (deterministic).  Grid <= resident capacity, so every
+// predecessor a block waits for is running.  `fill_dst` (pass B): the same blocks write 1/2 to every reward.
 __global__ void __launch_bounds__(256)
 cov_cull_kernel(const float4* __restrict__ boxes, int boxes_per_tile, int64_t ntiles, const float4* __restrict__ table,
-                int W, const unsigned* __restrict__ gmin, const unsigned* __restrict__ gmax, float inv_kd,
-                unsigned* __restrict__ amask_g, int mask_stride, unsigned char* __restrict__ flags,
-                unsigned long long* __restrict__ listed_pairs) {
+                int W, const unsigned* __restrict__ enc, float inv_kd, unsigned* __restrict__ amask_g, int mask_stride,
+                int* __restrict__ worklist, int* __restrict__ ctrl, unsigned long long* __restrict__ desc,
+                float* __restrict__ fill_dst, int64_t fill_n) {
     extern __shared__ float4 v3s[];
-    const int tid = threadIdx.x, lane = tid & 31;
+    __shared__ unsigned warp_listed[8];
+    __shared__ int warp_base[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int w = tid; w < W; w += blockDim.x) {
         float4 v3 = table[(size_t)w * COV_ROW_F4 + 3];
-        if (gmin) v3.w = minmax_qcap(gmin[w], gmax[w], inv_kd);
+        if (enc) v3.w = minmax_qcap(~enc[w], enc[W + w], inv_kd);
         v3s[w] = v3;
+    }
+    if (fill_dst) {  // fire-and-forget stores: they drain while the blocks cull
+        const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+        for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + tid) * 4; i < fill_n; i += stride) {
+            if (i + 4 <= fill_n && ((reinterpret_cast<uintptr_t>(fill_dst + i) & 15) == 0)) {
+                __stcs(reinterpret_cast<float4*>(fill_dst + i), make_float4(0.5f, 0.5f, 0.5f, 0.5f));
+            } else {
+                for (int64_t k = i; k < fill_n && k < i + 4; ++k) fill_dst[k] = 0.5f;
+            }
+        }
     }
     __syncthreads();
     const float inf = __uint_as_float(0x7f800000u);
     const int nwords = (W + 31) >> 5;
-    const int64_t ngroups = (ntiles + 7) / 8;
+    const int64_t nchunks = (ntiles + kChunkTiles - 1) / kChunkTiles;
     const int sub = lane >> 3, tl = lane & 7;  // box loads: lane = (pass-local box slot, tile of the group)
     unsigned long long npairs = 0;
-    for (int64_t grp = (int64_t)blockIdx.x * 8 + (tid >> 5); grp < ngroups; grp += (int64_t)gridDim.x * 8) {
-        // lane -> tile tl; the 4 lanes with the same tl share the tile's boxes_per_tile boxes (<= 16)
-        const int64_t tile_l = grp * 8 + tl;
+    for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        // lane -> tile tl of this warp's group; the 4 lanes with the same tl share the tile's boxes_per_tile boxes (<= 16)
+        const int64_t tile_l = (chunk * 8 + warp) * 8 + tl;
         float4 lo = make_float4(inf, inf, inf, 0.f), hi = make_float4(-inf, -inf, -inf, 0.f);
         if (tile_l < ntiles) {
             for (int b = sub; b < boxes_per_tile; b += 4) {
@@ -449,126 +514,62 @@ cov_cull_kernel(const float4* __restrict__ boxes, int boxes_per_tile, int64_t nt
                 any += __popc(mine);
             }
         }
-        if (lane < 8 && tile_l < ntiles) {
-            npairs += any;
-            // cost class of the tile for the work list: 0 = nothing listed, 1..4 = 1-2, 3-6, 7-14, >= 15 poses
-            flags[tile_l] = (unsigned char)(any == 0u ? 0 : any <= 2u ? 1 : any <= 6u ? 2 : any <= 14u ? 3 : 4);
-        }
-    }
-    npairs = __reduce_add_sync(kFull, (unsigned)npairs);
-    if (lane == 0 && npairs) atomicAdd(listed_pairs, npairs);
-}
-
-// Work list of the tiles with a non-empty mask: heaviest cost class first, ascending tile index within a class, so
-// that blocks taking entries i, i + grid, i + 2 grid, ... all get the same mix of heavy and light tiles (the order is
-// a pure function of the masks: deterministic, no atomics; single block).
-// ints[0] = count, ints[2] = 1 when the masks list more than `dense_above` (tile, pose) pairs: the cloud has no
-// spatial coherence to exploit, the dense kernel does the call instead (it checks ints[2]) and the list is left empty.
-__global__ void __launch_bounds__(1024) cov_worklist_kernel(const unsigned char* __restrict__ flags, int64_t ntiles,
-                                                            int* __restrict__ worklist, int* __restrict__ ints,
-                                                            unsigned long long dense_above) {
-    __shared__ int warp_tot[32][4];
-    __shared__ int class_start[4];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t chunk = (((ntiles + 1023) / 1024) + 15) & ~(int64_t)15;  // flags per thread, 16 per vector load
-    const int64_t lo = (int64_t)tid * chunk < ntiles ? (int64_t)tid * chunk : ntiles;
-    const int64_t hi = lo + chunk < ntiles ? lo + chunk : ntiles;
-    int c[4] = {0, 0, 0, 0};  // tiles of class 4, 3, 2, 1 in this thread's chunk
-    {
-        int64_t t = lo;
-        for (; t + 16 <= hi; t += 16) {
-            const uint4 v = *reinterpret_cast<const uint4*>(flags + t);
-            const unsigned words[4] = {v.x, v.y, v.z, v.w};
+        const bool listed = lane < 8 && tile_l < ntiles && any != 0u;
+        if (listed) npairs += any;
+        const unsigned listed8 = __ballot_sync(kFull, listed);
+        if (lane == 0) warp_listed[warp] = listed8;
+        __syncthreads();
+        if (warp == 0) {
+            const unsigned mine = lane < 8 ? warp_listed[lane] : 0u;
+            const int cnt = __popc(mine);
+            int incl = cnt;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                if (words[q] == 0u) continue;
+            for (int o = 1; o < 8; o <<= 1) {
+                const int v = __shfl_up_sync(kFull, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const unsigned long long total = (unsigned long long)__shfl_sync(kFull, incl, 7);
+            unsigned long long excl = 0ull;
+            if (chunk > 0) {
+                if (lane == 0) st_release_u64(desc + chunk, kDescAgg | total);
+                int64_t look = chunk - 1;
+                while (true) {  // windows of 32 predecessors, nearest first
+                    const int64_t idx = look - lane;
+                    unsigned long long d = kDescPrefix;  // before chunk 0: an inclusive prefix of 0
+                    if (idx >= 0) d = ld_acquire_u64(desc + idx);
+                    const unsigned empty = __ballot_sync(kFull, (d >> 62) == 0ull);
+                    const unsigned pref = __ballot_sync(kFull, (d >> 62) == 2ull);
+                    const int first_pref = pref ? (__ffs(pref) - 1) : 32;
+                    const unsigned need = first_pref >= 31 ? kFull : ((2u << first_pref) - 1u);
+                    if (empty & need) continue;  // a predecessor in the window has not published yet: look again
+                    unsigned long long v = (lane <= first_pref) ? (d & kDescValue) : 0ull;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const unsigned f = (words[q] >> (8 * k)) & 0xffu;
-                    c[0] += f == 4u; c[1] += f == 3u; c[2] += f == 2u; c[3] += f == 1u;
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+                    excl += v;
+                    if (first_pref < 32) break;
+                    look -= 32;
                 }
             }
-        }
-        for (; t < hi; ++t) {
-            const unsigned f = flags[t];
-            c[0] += f == 4u; c[1] += f == 3u; c[2] += f == 2u; c[3] += f == 1u;
-        }
-    }
-    int incl[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        incl[k] = c[k];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(kFull, incl[k], o);
-            if (lane >= o) incl[k] += v;
-        }
-        if (lane == 31) warp_tot[warp][k] = incl[k];
-    }
-    __syncthreads();
-    if (warp == 0) {
-        int tot[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int v = warp_tot[lane][k];
-            int sc = v;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int u = __shfl_up_sync(kFull, sc, o);
-                if (lane >= o) sc += u;
+            if (lane == 0) {
+                st_release_u64(desc + chunk, kDescPrefix | (excl + total));
+                if (chunk == nchunks - 1) ctrl[0] = (int)(excl + total);
             }
-            warp_tot[lane][k] = sc - v;  // exclusive over warps
-            tot[k] = __shfl_sync(kFull, sc, 31);
+            if (lane < 8) warp_base[lane] = (int)excl + incl - cnt;
         }
-        if (lane == 0) {
-            const bool dense = *reinterpret_cast<const unsigned long long*>(ints + 4) > dense_above;
-            class_start[0] = 0;
-            class_start[1] = tot[0];
-            class_start[2] = tot[0] + tot[1];
-            class_start[3] = tot[0] + tot[1] + tot[2];
-            ints[0] = dense ? 0 : tot[0] + tot[1] + tot[2] + tot[3];
-            ints[2] = dense ? 1 : 0;
-        }
+        __syncthreads();
+        if (listed) worklist[warp_base[warp] + __popc(listed8 & ((1u << lane) - 1u))] = (int)tile_l;
     }
-    __syncthreads();
-    int pos[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) pos[k] = class_start[k] + warp_tot[warp][k] + incl[k] - c[k];
-    if (c[0] + c[1] + c[2] + c[3] == 0) return;
-    int64_t t = lo;
-    for (; t + 16 <= hi; t += 16) {
-        const uint4 v = *reinterpret_cast<const uint4*>(flags + t);
-        const unsigned words[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            if (words[q] == 0u) continue;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const unsigned f = (words[q] >> (8 * k)) & 0xffu;
-                const int tile = (int)(t + q * 4 + k);
-                if (f == 4u) worklist[pos[0]++] = tile;
-                else if (f == 3u) worklist[pos[1]++] = tile;
-                else if (f == 2u) worklist[pos[2]++] = tile;
-                else if (f == 1u) worklist[pos[3]++] = tile;
-            }
-        }
-    }
-    for (; t < hi; ++t) {
-        const unsigned f = flags[t];
-        if (f == 4u) worklist[pos[0]++] = (int)t;
-        else if (f == 3u) worklist[pos[1]++] = (int)t;
-        else if (f == 2u) worklist[pos[2]++] = (int)t;
-        else if (f == 1u) worklist[pos[3]++] = (int)t;
-    }
+    npairs = __reduce_add_sync(kFull, (unsigned)npairs);
+    if (lane == 0 && npairs) atomicAdd(reinterpret_cast<unsigned long long*>(ctrl + 4), npairs);
 }
 
 // =============================================== pass A, pruned ===============================================
 template <int PPT, int MINB>
 __global__ void __launch_bounds__(COV_THREADS, MINB)
 cov_traj_minmax_tiles_kernel(const float* __restrict__ xyz, int64_t n, const float4* __restrict__ table, int W, CovConst C,
-                             unsigned* __restrict__ gmin, unsigned* __restrict__ gmax, const float4* __restrict__ boxes,
+                             unsigned* __restrict__ enc, float* __restrict__ minmax_out, const float4* __restrict__ boxes,
                              const unsigned* __restrict__ amask_g, int mask_stride, const int* __restrict__ worklist,
-                             const int* __restrict__ count_ptr, int64_t ntiles, unsigned long long* __restrict__ stats) {
+                             int* __restrict__ ctrl, int64_t ntiles, unsigned long long* __restrict__ stats) {
     constexpr int T = tile_points(PPT);
     constexpr int NB = tile_boxes(PPT);
     constexpr int SF = stage_floats(PPT);
@@ -592,10 +593,10 @@ cov_traj_minmax_tiles_kernel(const float* __restrict__ xyz, int64_t n, const flo
     for (int w = tid; w < W; w += COV_THREADS) {
         smin[w] = 0x7f800000u;
         smax[w] = 0u;
-        sqcap[w] = minmax_qcap(gmin[w], gmax[w], inv_kd);  // from the seed launch (any later value is tighter and valid)
+        sqcap[w] = minmax_qcap(~enc[w], enc[W + w], inv_kd);  // from the seed (any later value is tighter and valid)
     }
     __syncthreads();
-    const int count = *count_ptr;
+    const int count = ctrl[0];
     const int64_t nfull = n / T;
     const int nwords = (W + 31) >> 5;
     unsigned uses0 = 0, uses1 = 0;
@@ -674,15 +675,29 @@ cov_traj_minmax_tiles_kernel(const float* __restrict__ xyz, int64_t n, const flo
     }
     for (int w = tid; w < W; w += COV_THREADS) {
         if (smax[w] != 0u || smin[w] != 0x7f800000u) {
-            atomicMin(gmin + w, smin[w]);
-            atomicMax(gmax + w, smax[w]);
+            atomicMax(enc + w, ~smin[w]);
+            atomicMax(enc + W + w, smax[w]);
         }
     }
-    if (lane == 0) {
+    if (stats && lane == 0) {
         if (tid == 0 && blockIdx.x == 0) atomicAdd(stats + 2, (unsigned long long)ntiles * kWarps * W);
         atomicAdd(stats + 3, (unsigned long long)n_full);
         atomicAdd(stats + 5, (unsigned long long)n_pre);
         atomicAdd(stats + 7, (unsigned long long)n_box);
+    }
+    // the last block to arrive decodes the extrema into the caller's floats (minima, then maxima)
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(ctrl + 2, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        unsigned* out = reinterpret_cast<unsigned*>(minmax_out);
+        for (int w = tid; w < W; w += COV_THREADS) {
+            out[w] = ~__ldcg(enc + w);
+            out[W + w] = __ldcg(enc + W + w);
+        }
     }
 }
 
@@ -760,6 +775,50 @@ __device__ __forceinline__ bool fused_pose_iter(int w, unsigned ptab, unsigned* 
     return anyb != 0u;
 }
 
+// Forward of one listed pose for a warp of the pruned kernel: m for the warp's points, log-odds of the gated ones added to
+// L; returns whether the warp has a gated pair for the pose.  `row` = the pose's 6 float4 in the global table (L1 hits:
+// a tile touches a handful of rows).  The conservative threshold lives in v5.w (v3.w holds qthr); the exact gate test
+// runs only when some lane may pass.
+template <int PPT, bool AMIN>
+__device__ __forceinline__ bool tiles_pose_iter(const float4* __restrict__ row, const float4& v3, const float (&px)[PPT],
+                                                const float (&py)[PPT], const float (&pz)[PPT], float (&L)[PPT],
+                                                const CovConst& C, double* __restrict__ acc_row) {
+    float m[PPT];
+    const float4 v0 = __ldg(row), v1 = __ldg(row + 1), v2 = __ldg(row + 2);
+    const float thr = __ldg(&row[5].w);
+#pragma unroll
+    for (int s = 0; s < PPT; ++s) m[s] = cov_vis<false>(px[s], py[s], pz[s], v0, v1, v2, v3, C, nullptr);
+    float mmax = m[0];
+#pragma unroll
+    for (int s = 1; s < PPT; ++s) mmax = fmaxf(mmax, m[s]);
+    bool any = false;
+    if (__any_sync(kFull, mmax >= thr)) {  // warp-uniform: some point may pass the gate (conservative threshold)
+        const float4 v4 = __ldg(row + 4);
+#pragma unroll
+        for (int s = 0; s < PPT; ++s) {
+            const float d = __fsub_rn(m[s], v4.w);
+            const bool act = d >= v4.x;  // exactly p >= 0.5
+            any |= act;
+            if (act) {
+                const float p = __fmul_rn(d, v4.z);
+                const float qc = (p > C.hi) ? C.hi : p;  // upper clip; a NaN p (pose that sees nothing: 0/0) stays NaN, as torch.clip
+                L[s] += COV_LN2_F * cov_lg2(qc * cov_rcp(1.f - qc));
+                if (d == v4.y) tie_accumulate_g(px[s], py[s], pz[s], row, C, acc_row + 8);
+            }
+        }
+        any = __any_sync(kFull, any);
+    }
+    if (AMIN) {  // only compact clouds whose minimum did not underflow to 0 (block-uniform choice of the caller)
+        const float a = __ldg(&row[4].w);
+        if (a > 0.f) {
+#pragma unroll
+            for (int s = 0; s < PPT; ++s)
+                if (m[s] == a) tie_accumulate_g(px[s], py[s], pz[s], row, C, acc_row + 15);
+        }
+    }
+    return any;
+}
+
 // Phase 2 of the dense kernel: the gated pairs of all W bit rows, each row split over 2^seg_log2 lanes.  A lane pops
 // its set bits in ascending point order, recomputes m (bit-identical) and dm/dx, and accumulates in registers;
 // segments are combined with xor-shuffles; one owner lane adds into accs.
@@ -825,18 +884,21 @@ __device__ __forceinline__ void fused_phase2(const float4* __restrict__ ptab, co
     }
 }
 
-__device__ __forceinline__ void fused_block_epilogue(const float* accs, int W, float* __restrict__ partials,
-                                                     double* __restrict__ sumr_partials, double sum_r, double* red,
-                                                     int tid) {
-    float* slab = partials + (size_t)blockIdx.x * W * 8;
-    for (int i = tid; i < W * 8; i += COV_THREADS) slab[i] = accs[i];
+// A block's accumulators -> the caller's fp64 rows (fp64 atomics; the reward sum likewise).
+template <typename T>
+__device__ __forceinline__ void fused_block_flush(const T* accs, int W, double* __restrict__ acc, double sum_r,
+                                                  double* red, int tid) {
+    for (int i = tid; i < W * 8; i += COV_THREADS) {
+        const T v = accs[i];
+        if (v != (T)0) atomicAdd(acc + (size_t)(i >> 3) * COV_ACC_STRIDE + (i & 7), (double)v);
+    }
     const double ws = cov_warp_sum(sum_r);
     if ((tid & 31) == 0) red[tid >> 5] = ws;
     __syncthreads();
     if (tid == 0) {
         double t = 0.0;
         for (int i = 0; i < kWarps; ++i) t += red[i];
-        sumr_partials[blockIdx.x] = t;
+        if (t != 0.0) atomicAdd(acc + (size_t)W * COV_ACC_STRIDE, t);
     }
 }
 
@@ -846,10 +908,8 @@ __global__ void __launch_bounds__(COV_THREADS, 2)
 cov_traj_fused_kernel(const float* __restrict__ xyz, int64_t n, const float* __restrict__ poses,
                       const float* __restrict__ quats, int W, const float* __restrict__ K9, CovConst C,
                       const float* __restrict__ minmax, const float* __restrict__ upstream,
-                      const int32_t* __restrict__ out_index, float* __restrict__ rewards,
-                      float* __restrict__ partials, double* __restrict__ sumr_partials, double* __restrict__ acc,
-                      int seg_log2, const int* __restrict__ run_flag) {
-    if (run_flag && *run_flag == 0) return;  // stand-by launch behind the pruned kernel (see cov_worklist_kernel)
+                      const int32_t* __restrict__ out_index, float* __restrict__ rewards, double* __restrict__ acc,
+                      int seg_log2) {
     constexpr int T = tile_points(PPT);
     constexpr int RS = bit_stride(PPT);
     // shared memory: pose table | the tile's points (xyz interleaved) | G_j | gate bits | block accumulators
@@ -925,94 +985,112 @@ cov_traj_fused_kernel(const float* __restrict__ xyz, int64_t n, const float* __r
         fused_phase2<PPT>(ptab, bits, pt, Gs, accs, W, seg_log2, C, tid);
         __syncthreads();
     }
-    fused_block_epilogue(accs, W, partials, sumr_partials, sum_r, red, tid);
+    fused_block_flush(accs, W, acc, sum_r, red, tid);
 }
 
-// ---- pruned: persistent blocks over the work list of tiles with a non-empty pose mask ----
-// Each warp owns 32*PPT consecutive points of the tile in registers, for both phases:
-//   phase 1  walk the tile's pose mask; a listed pose is evaluated when its qthr-ball meets the warp's own box and
-//            one of its points passes the same test; gated lanes add their log-odds; the warp notes (one bit per
-//            pose) whether it had a gated pair.  Then r_j, G_j = r_j (1 - r_j) per point, rewards stored.
-//   phase 2  (only when some warp of the block noted a gate)  the warp walks the mask again; for a noted pose it
-//            re-evaluates m for its points (bit-identical), re-derives the gate, and accumulates the 8 weighted
-//            sums of dm/dx in registers; a fixed xor-shuffle tree reduces them over the warp.  The 8 warps' partial
-//            sums meet in a slot table indexed by the pose's rank in the mask and are added to the block
-//            accumulators in warp order by one thread per (pose, component): fixed order, bitwise reproducible.
-// sumr_partials receive sum_j (r_j - 1/2) over the listed tiles (the rest is 0.5 * n, added by the reduce kernel);
-// `rewards` was pre-filled with 1/2, only other values are stored.
-constexpr int kSlotPoses = 32;  // poses per round of the slot table
+// ---- pruned: persistent WARPS over the work list of tiles with a non-empty pose mask ----
+// The unit of work is one box of 128 consecutive points (one eighth of a listed tile), taken by ONE WARP from a global
+// ticket counter: warps never wait for each other (no block barrier, no static assignment), so neither the uneven cost
+// of neighbouring boxes nor a heavy tile at the end of the list leaves lanes idle.  A warp keeps two private stages in
+// shared memory; its lane 0 draws the next ticket and issues the TMA bulk copies for it (points, the box, the tile's pose
+// mask, the slice of the permutation — one mbarrier per stage) before the warp starts on the current item.
+//   forward   walk the tile's pose mask; a listed pose is evaluated when its qthr-ball meets the warp's box; gated lanes
+//             add their log-odds; the warp notes (one bit per pose) whether it had a gated pair.  Then r_j,
+//             G_j = r_j (1 - r_j) per point; rewards stored.
+//   backward  the warp walks its noted poses: m again for its points (bit-identical), the gate, dm/dx, the 8 weighted
+//             sums in registers; a fixed 9-shuffle tree reduces them over the warp and one lane per component adds the
+//             result to the caller's fp64 accumulator row (fire-and-forget RED.F64).
+// On the bench cloud ~58 % of the point slots of an evaluated (warp, pose) are gated (profiles/r02_*), so the
+// re-evaluation keeps most lanes busy.  The pose table stays in global memory (a box touches ~5 rows: L1 hits).
+// `rewards` was pre-filled with 1/2, only other values are stored; the warps add sum_j (r_j - 1/2) of the listed
+// tiles to acc[W * STRIDE], which starts at 0.5 * n.
+constexpr int kItemPts = 128;                 // points per work item = one warp's registers = one precomputed box
+constexpr int kItemsPerTile = 8;              // a listed tile (1024 points) is eight items
+constexpr int kItemPpt = kItemPts / 32;
+constexpr int kItemStageWords = kItemPts * 3 + 8 + kMaskWords + kItemPts;  // points | box | pose mask | permutation
+constexpr int kTilesMinBlocks = 3;            // resident blocks per SM the register allocation aims at
 
-template <int PPT, bool HAS_UP>
-__global__ void __launch_bounds__(COV_THREADS, 2)
+template <bool HAS_UP>
+__global__ void __launch_bounds__(COV_THREADS, kTilesMinBlocks)
 cov_traj_fused_tiles_kernel(const float* __restrict__ xyz, int64_t n, const float4* __restrict__ table, int W, CovConst C,
                             const float* __restrict__ upstream, const int32_t* __restrict__ out_index,
-                            float* __restrict__ rewards, float* __restrict__ partials,
-                            double* __restrict__ sumr_partials, double* __restrict__ acc,
+                            float* __restrict__ rewards, double* __restrict__ acc,
                             const float4* __restrict__ boxes, const unsigned* __restrict__ amask_g, int mask_stride,
-                            const int* __restrict__ worklist, const int* __restrict__ count_ptr, int64_t ntiles,
+                            const int* __restrict__ worklist, int* __restrict__ ctrl, int64_t ntiles,
                             unsigned long long* __restrict__ stats) {
-    constexpr int T = tile_points(PPT);
-    constexpr int NB = tile_boxes(PPT);
-    constexpr int SF = stage_floats(PPT) + T;  // + the tile's slice of the permutation
-    constexpr int WB = (32 * PPT >= kBoxPts) ? (32 * PPT / kBoxPts) : 1;
-    // shared memory: pose table | 2 tile stages (points, boxes, pose mask) | block accumulators
-    extern __shared__ float4 smem4[];
-    float4* ptab = smem4;
-    float* stage = reinterpret_cast<float*>(smem4) + fused_stage_offset_floats(W);
-    float* accs = stage + 2 * SF;
-    __shared__ double red[kWarps];
-    __shared__ float slots[kSlotPoses][kWarps][8];   // per-(pose rank, warp) partial sums of one round
-    __shared__ int slot_pose[kSlotPoses];
-    __shared__ unsigned wgate[kWarps][kMaskWords];   // per warp: poses with a gated pair among its points (this tile)
-    __shared__ __align__(8) unsigned long long mbar[2];
+    constexpr int PPT = kItemPpt;
+    __shared__ __align__(128) float stages[kWarps][2][kItemStageWords];
+    __shared__ unsigned wgate[kWarps][kMaskWords];   // per warp: poses with a gated pair among its points (this item)
+    __shared__ __align__(8) unsigned long long mbar[kWarps][2];
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) {
-        mbar_init(&mbar[0], 1);
-        mbar_init(&mbar[1], 1);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long* bar = mbar[warp];
+    if (lane == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
         mbar_fence_init();
     }
-    for (int i = tid; i < W * COV_ROW_F4; i += COV_THREADS) ptab[i] = table[i];
-    for (int i = tid; i < W * 8; i += COV_THREADS) accs[i] = 0.f;
-    const bool check_amin = count_ptr[1] != 0;  // flags[1]: some pose has min_j m > 0
-    __syncthreads();
-
-    double sum_r = 0.0;
-    unsigned n_box = 0, n_pre = 0, n_full = 0;
-    const int count = count_ptr[0];
-    const int64_t nfull = n / T;
+    __syncwarp();
+    const bool check_amin = ctrl[1] != 0;  // some pose has min_j m > 0
+    const int n_items = ctrl[0] * kItemsPerTile;
     const int nwords = (W + 31) >> 5;
     unsigned* wg = wgate[warp];
-    const unsigned ptab_s = smem_u32(ptab);
+    int* ticket = ctrl + 3;
+
+    // lane 0: stage item `it` (tile = worklist[it / 8], box k = it % 8) unless it is past the end or ragged
+    auto issue = [&](int it, int b) {
+        if (it >= n_items) return;
+        const int64_t tile = worklist[it >> 3];
+        const int64_t j0 = tile * (kItemsPerTile * kItemPts) + (int64_t)(it & 7) * kItemPts;
+        float* st = stages[warp][b];
+        const bool whole = j0 + kItemPts <= n;
+        const bool with_perm = whole && out_index != nullptr;
+        mbar_expect_tx(&bar[b], (whole ? kItemPts * 12u : 0u) + 32u + (unsigned)mask_stride * 4u + (with_perm ? kItemPts * 4u : 0u));
+        if (whole) tma_copy(st, xyz + j0 * 3, kItemPts * 12u, &bar[b]);
+        tma_copy(st + kItemPts * 3, boxes + (j0 / kBoxPts) * 2, 32u, &bar[b]);
+        tma_copy(st + kItemPts * 3 + 8, amask_g + tile * mask_stride, (unsigned)mask_stride * 4u, &bar[b]);
+        if (with_perm) tma_copy(st + kItemPts * 3 + 8 + kMaskWords, out_index + j0, kItemPts * 4u, &bar[b]);
+    };
+
+    double sum_r = 0.0;
+    unsigned n_box = 0, n_full = 0;
     unsigned uses0 = 0, uses1 = 0;
-    if (tid == 0 && (int)blockIdx.x < count)
-        stage_issue<PPT>(stage, &mbar[0], xyz, boxes, amask_g, mask_stride, (int64_t)worklist[blockIdx.x], nfull, out_index);
+    int cur = 0;
+    if (lane == 0) {
+        cur = atomicAdd(ticket, 1);
+        issue(cur, 0);
+    }
+    cur = __shfl_sync(kFull, cur, 0);
     int buf = 0;
-    for (int i = blockIdx.x; i < count; i += gridDim.x, buf ^= 1) {
-        const int64_t tile = worklist[i];
-        if (tid == 0 && i + (int)gridDim.x < count)  // the other stage was last read before the previous barrier
-            stage_issue<PPT>(stage + (buf ^ 1) * SF, &mbar[buf ^ 1], xyz, boxes, amask_g, mask_stride,
-                             (int64_t)worklist[i + gridDim.x], nfull, out_index);
-        if (buf == 0) mbar_wait(&mbar[0], uses0++ & 1u);
-        else mbar_wait(&mbar[1], uses1++ & 1u);
-        const float* st = stage + buf * SF;
-        // ------------------------------ phase 1 ------------------------------
+    while (cur < n_items) {
+        int nxt = 0;
+        if (lane == 0) {  // the other stage was last read before the __syncwarp that ended the previous item
+            nxt = atomicAdd(ticket, 1);
+            issue(nxt, buf ^ 1);
+        }
+        nxt = __shfl_sync(kFull, nxt, 0);
+        if (buf == 0) mbar_wait(&bar[0], uses0++ & 1u);
+        else mbar_wait(&bar[1], uses1++ & 1u);
+        const float* st = stages[warp][buf];
+        const int64_t tile = worklist[cur >> 3];
+        const int64_t j0 = tile * (kItemsPerTile * kItemPts) + (int64_t)(cur & 7) * kItemPts;
+        const bool whole = j0 + kItemPts <= n;
+        // ------------------------------ forward ------------------------------
         float px[PPT], py[PPT], pz[PPT], L[PPT];
         bool valid[PPT];
-        const int lbase = warp * (32 * PPT) + lane;
-        if (tile < nfull) {
+        if (whole) {
 #pragma unroll
             for (int s = 0; s < PPT; ++s) {
                 valid[s] = true;
-                px[s] = st[(lbase + s * 32) * 3];
-                py[s] = st[(lbase + s * 32) * 3 + 1];
-                pz[s] = st[(lbase + s * 32) * 3 + 2];
+                px[s] = st[(s * 32 + lane) * 3];
+                py[s] = st[(s * 32 + lane) * 3 + 1];
+                pz[s] = st[(s * 32 + lane) * 3 + 2];
                 L[s] = 0.f;
             }
-        } else {  // the ragged last tile: loaded by hand
+        } else {  // the ragged end of the cloud: loaded by hand
 #pragma unroll
             for (int s = 0; s < PPT; ++s) {
-                const int64_t j = tile * T + lbase + s * 32;
+                const int64_t j = j0 + s * 32 + lane;
                 valid[s] = j < n;
                 // a point past the end sits 3e18 m away: m = 0 exactly, never gated, never a tie
                 px[s] = valid[s] ? __ldg(xyz + j * 3) : 3.0e18f;
@@ -1021,13 +1099,10 @@ cov_traj_fused_tiles_kernel(const float* __restrict__ xyz, int64_t n, const floa
                 L[s] = 0.f;
             }
         }
-        const float4* tb = reinterpret_cast<const float4*>(st + T * 3);
-        const int b0 = (warp * 32 * PPT) / kBoxPts;
-        float4 wlo = tb[2 * b0], whi = tb[2 * b0 + 1];
-#pragma unroll
-        for (int k = 1; k < WB; ++k) box_union(wlo, whi, tb[2 * (b0 + k)], tb[2 * (b0 + k) + 1]);
-        const unsigned* am = reinterpret_cast<const unsigned*>(st + T * 3 + NB * 8);
-        const int32_t* sperm = reinterpret_cast<const int32_t*>(st + stage_floats(PPT));
+        const float4* tb = reinterpret_cast<const float4*>(st + kItemPts * 3);
+        const float4 wlo = tb[0], whi = tb[1];
+        const unsigned* am = reinterpret_cast<const unsigned*>(st + kItemPts * 3 + 8);
+        const int32_t* sperm = reinterpret_cast<const int32_t*>(st + kItemPts * 3 + 8 + kMaskWords);
         bool warp_gated = false;
         for (int c = 0; c < nwords; ++c) {
             unsigned word = am[c];
@@ -1036,18 +1111,16 @@ cov_traj_fused_tiles_kernel(const float* __restrict__ xyz, int64_t n, const floa
                 const int b = __ffs(word) - 1;
                 const int w = c * 32 + b;
                 word &= word - 1;
-                const float4 v3 = ptab[(size_t)w * COV_ROW_F4 + 3];
+                const float4* row = table + (size_t)w * COV_ROW_F4;
+                const float4 v3 = __ldg(row + 3);
                 ++n_box;
+                // the warp's own box against the pose's qthr-ball; no per-point pre-filter here: it rejected only 11 % of
+                // what the box test let through and cost a fifth of the evaluation it saved
                 if (box_q2lb(wlo, whi, v3) > v3.w) continue;
-                ++n_pre;
-                float qmin = cov_q2(px[0], py[0], pz[0], v3);
-#pragma unroll
-                for (int s = 1; s < PPT; ++s) qmin = fminf(qmin, cov_q2(px[s], py[s], pz[s], v3));
-                if (!__any_sync(kFull, !(qmin > v3.w))) continue;
                 ++n_full;
-                const bool g = check_amin
-                                   ? fused_pose_iter<PPT, 1, true, true>(w, ptab_s, nullptr, warp, px, py, pz, L, C, acc, lane)
-                                   : fused_pose_iter<PPT, 1, false, true>(w, ptab_s, nullptr, warp, px, py, pz, L, C, acc, lane);
+                double* acc_row = acc + (size_t)w * COV_ACC_STRIDE;
+                const bool g = check_amin ? tiles_pose_iter<PPT, true>(row, v3, px, py, pz, L, C, acc_row)
+                                          : tiles_pose_iter<PPT, false>(row, v3, px, py, pz, L, C, acc_row);
                 if (g) gbits |= 1u << b;
             }
             if (lane == 0) wg[c] = gbits;
@@ -1063,124 +1136,95 @@ cov_traj_fused_tiles_kernel(const float* __restrict__ xyz, int64_t n, const floa
                 G[s] = r * (1.f - r);
             }
             if (valid[s]) {
-                const int64_t j = tile * T + lbase + s * 32;
+                const int64_t j = j0 + s * 32 + lane;
                 sum_r += (double)(r - 0.5f);
                 const bool store = r != 0.5f;
                 int64_t jo = j;
                 if (out_index && (store || HAS_UP))
-                    jo = tile < nfull ? (int64_t)sperm[lbase + s * 32] : (int64_t)out_index[j];  // staged with the tile
+                    jo = whole ? (int64_t)sperm[s * 32 + lane] : (int64_t)out_index[j];  // staged with the item
                 if (store) rewards[jo] = r;
                 if (HAS_UP) G[s] *= upstream[jo];
             }
         }
-        // one barrier per tile: protects the stage that is refilled next and tells whether anybody has a gated pair
-        if (!__syncthreads_or(warp_gated ? 1 : 0)) continue;
-        // ------------------------------ phase 2 ------------------------------
-        int listed = 0;
-        for (int c = lane; c < nwords; c += 32) listed += __popc(am[c]);
-        listed = __reduce_add_sync(kFull, listed);
-        // rounds of kSlotPoses listed poses (one round unless the cloud is unordered); slot = rank within the round
-        for (int round0 = 0; round0 < listed; round0 += kSlotPoses) {
-            int rank = 0;
-            for (int c = 0; c < nwords && rank < round0 + kSlotPoses; ++c) {
-                unsigned word = am[c];
-                const int cnt = __popc(word);
-                if (rank + cnt <= round0) {  // the whole word belongs to an earlier round
-                    rank += cnt;
-                    continue;
-                }
-                const unsigned mine = wg[c];
+        // ------------------------------ backward ------------------------------
+        if (warp_gated) {
+            __syncwarp();  // lane 0's notes are visible to the warp
+            for (int c = 0; c < nwords; ++c) {
+                unsigned word = wg[c];
                 while (word) {
-                    const int b = __ffs(word) - 1;
-                    const int w = c * 32 + b;
+                    const int w = c * 32 + __ffs(word) - 1;
                     word &= word - 1;
-                    const int slot = rank - round0;
-                    ++rank;
-                    if (slot < 0) continue;
-                    if (slot >= kSlotPoses) break;
-                    float f0 = 0.f, f1 = 0.f, f2 = 0.f, t0 = 0.f, t1 = 0.f, t2 = 0.f, se = 0.f, sep = 0.f;
-                    if ((mine >> b) & 1u) {
-                        const float4* row = ptab + (size_t)w * COV_ROW_F4;
-                        const float4 v0 = row[0], v1 = row[1], v2 = row[2], v3 = row[3], v4 = row[4], v5 = row[5];
+                    const float4* row = table + (size_t)w * COV_ROW_F4;
+                    const float4 v0 = __ldg(row), v1 = __ldg(row + 1), v2 = __ldg(row + 2), v3 = __ldg(row + 3),
+                                 v4 = __ldg(row + 4), v5 = __ldg(row + 5);
+                    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                        for (int s = 0; s < PPT; ++s) {
-                            CovEval ev;
-                            const float m = cov_vis<true>(px[s], py[s], pz[s], v0, v1, v2, v3, C, &ev);
-                            const float d = __fsub_rn(m, v4.w);
-                            const bool act = d >= v4.x;  // exactly p >= 0.5, as in phase 1
-                            if (act) {
-                                const float p = __fdiv_rn(d, v4.y);
-                                if (p <= C.hi) {  // clamp backward gate (inclusive)
-                                    float gx, gy, gz;
-                                    cov_vis_grad(m, ev, v0, v1, v2, C, gx, gy, gz);
-                                    const float yx = px[s] - v5.x, yy = py[s] - v5.y, yz = pz[s] - v5.z;
-                                    const float e = G[s] * cov_rcp(p * (1.f - p));
-                                    const float om = e * v4.z;
-                                    f0 += om * gx; f1 += om * gy; f2 += om * gz;
-                                    t0 += om * (gy * yz - gz * yy);
-                                    t1 += om * (gz * yx - gx * yz);
-                                    t2 += om * (gx * yy - gy * yx);
-                                    se += e;
-                                    sep += e * p;
-                                }
+                    for (int s = 0; s < PPT; ++s) {
+                        CovEval ev;
+                        const float m = cov_vis<true>(px[s], py[s], pz[s], v0, v1, v2, v3, C, &ev);
+                        const float d = __fsub_rn(m, v4.w);
+                        if (d >= v4.x) {  // exactly p >= 0.5, as in the forward
+                            const float p = __fdiv_rn(d, v4.y);
+                            if (p <= C.hi) {  // clamp backward gate (inclusive)
+                                float gx, gy, gz;
+                                cov_vis_grad(m, ev, v0, v1, v2, C, gx, gy, gz);
+                                const float yx = px[s] - v5.x, yy = py[s] - v5.y, yz = pz[s] - v5.z;
+                                const float e = G[s] * cov_rcp(p * (1.f - p));
+                                const float om = e * v4.z;
+                                v[0] += om * gx; v[1] += om * gy; v[2] += om * gz;
+                                v[3] += om * (gy * yz - gz * yy);
+                                v[4] += om * (gz * yx - gx * yz);
+                                v[5] += om * (gx * yy - gy * yx);
+                                v[6] += e;
+                                v[7] += e * p;
                             }
                         }
-                        // 8 sums over 32 lanes in 9 shuffles: halve the number of values a lane carries at offsets 16,
-                        // 8, 4 (a lane keeps the half its lane bit selects and hands the other half over), then two
-                        // plain steps; lane l ends with component (l>>2)&7 ... in bit order (16,8,4) -> (4,2,1)
-                        float v[8] = {f0, f1, f2, t0, t1, t2, se, sep};
-                        {
-                            const bool up = (lane & 16) != 0;
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const float keep = up ? v[q + 4] : v[q], send = up ? v[q] : v[q + 4];
-                                v[q] = keep + __shfl_xor_sync(kFull, send, 16);
-                            }
-                        }
-                        {
-                            const bool up = (lane & 8) != 0;
-#pragma unroll
-                            for (int q = 0; q < 2; ++q) {
-                                const float keep = up ? v[q + 2] : v[q], send = up ? v[q] : v[q + 2];
-                                v[q] = keep + __shfl_xor_sync(kFull, send, 8);
-                            }
-                        }
-                        {
-                            const bool up = (lane & 4) != 0;
-                            const float keep = up ? v[1] : v[0], send = up ? v[0] : v[1];
-                            v[0] = keep + __shfl_xor_sync(kFull, send, 4);
-                        }
-                        v[0] += __shfl_xor_sync(kFull, v[0], 2);
-                        v[0] += __shfl_xor_sync(kFull, v[0], 1);
-                        f0 = v[0];
                     }
-                    if ((lane & 3) == 0) {
+                    // 8 sums over 32 lanes in 9 shuffles: halve the number of values a lane carries at offsets 16, 8, 4
+                    // (a lane keeps the half its lane bit selects and hands the other half over), then two plain steps;
+                    // lanes with (lane & 3) == 0 end with component (lane bits 4,3,2)
+                    {
+                        const bool up = (lane & 16) != 0;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float keep = up ? v[q + 4] : v[q], send = up ? v[q] : v[q + 4];
+                            v[q] = keep + __shfl_xor_sync(kFull, send, 16);
+                        }
+                    }
+                    {
+                        const bool up = (lane & 8) != 0;
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const float keep = up ? v[q + 2] : v[q], send = up ? v[q] : v[q + 2];
+                            v[q] = keep + __shfl_xor_sync(kFull, send, 8);
+                        }
+                    }
+                    {
+                        const bool up = (lane & 4) != 0;
+                        const float keep = up ? v[1] : v[0], send = up ? v[0] : v[1];
+                        v[0] = keep + __shfl_xor_sync(kFull, send, 4);
+                    }
+                    v[0] += __shfl_xor_sync(kFull, v[0], 2);
+                    v[0] += __shfl_xor_sync(kFull, v[0], 1);
+                    if ((lane & 3) == 0 && v[0] != 0.f) {  // one fire-and-forget fp64 RED per component
                         const int comp = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-                        slots[slot][warp][comp] = f0;  // 0 when this warp has no gated pair for the pose
-                        if (tid == 0) slot_pose[slot] = w;
+                        atomicAdd(acc + (size_t)w * COV_ACC_STRIDE + comp, (double)v[0]);
                     }
                 }
             }
-            __syncthreads();  // this round's partial sums are in the slot table (and nobody reads the stage any more)
-            {
-                const int nslots = (listed - round0) < kSlotPoses ? (listed - round0) : kSlotPoses;
-                const int k = tid >> 3, comp = tid & 7;
-                if (k < nslots) {
-                    float sacc = 0.f;
-#pragma unroll
-                    for (int g = 0; g < kWarps; ++g) sacc += slots[k][g][comp];
-                    accs[(size_t)slot_pose[k] * 8 + comp] += sacc;
-                }
-            }
-            if (round0 + kSlotPoses < listed) __syncthreads();  // the slot table is rewritten by the next round
         }
+        __syncwarp();  // every lane is done with this stage (and with wg) before lane 0 refills it
+        cur = nxt;
+        buf ^= 1;
     }
-    __syncthreads();
-    fused_block_epilogue(accs, W, partials, sumr_partials, sum_r, red, tid);
-    if (lane == 0) {
-        if (tid == 0 && blockIdx.x == 0) atomicAdd(stats + 0, (unsigned long long)ntiles * kWarps * W);
+    {
+        const double ws = cov_warp_sum(sum_r);
+        if (lane == 0 && ws != 0.0) atomicAdd(acc + (size_t)W * COV_ACC_STRIDE, ws);
+    }
+    if (stats && lane == 0) {
+        if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(stats + 0, (unsigned long long)ntiles * kWarps * W);
         atomicAdd(stats + 1, (unsigned long long)n_full);
-        atomicAdd(stats + 4, (unsigned long long)n_pre);
+        atomicAdd(stats + 4, (unsigned long long)n_full);
         atomicAdd(stats + 6, (unsigned long long)n_box);
     }
 }
@@ -1302,32 +1346,6 @@ cov_sweep_tiles_kernel(const float* __restrict__ xyz, int64_t n, const float4* _
     }
 }
 
-// acc[w][0..7] = sum over blocks of the fp32 slabs (fp64, fixed order); acc[W*STRIDE] = base + sum of the blocks'
-// reward sums (base = 0.5 * n for the pruned kernel, whose blocks sum r - 1/2 over the listed tiles only).
-__global__ void cov_traj_reduce_kernel(const float* __restrict__ partials, const double* __restrict__ sumr_partials,
-                                       int nblocks, int nblocks_dense, int W, double base,
-                                       const int* __restrict__ dense_flag, double* __restrict__ acc) {
-    if (dense_flag && *dense_flag) {  // the dense kernel did the call: its blocks wrote the slabs and summed r itself
-        base = 0.0;
-        nblocks = nblocks_dense;
-    }
-    // 8 lanes per output: lane q adds blocks q, q+8, ... in order, then a fixed xor tree joins the 8 partial sums
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = gid >> 3, q = gid & 7;
-    double s = 0.0;
-    if (i < W * 8)
-        for (int b = q; b < nblocks; b += 8) s += (double)partials[(size_t)b * W * 8 + i];
-    else if (i == W * 8)
-        for (int b = q; b < nblocks; b += 8) s += sumr_partials[b];
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 4);
-    if (q == 0) {
-        if (i < W * 8) acc[(size_t)(i >> 3) * COV_ACC_STRIDE + (i & 7)] = s;
-        else if (i == W * 8) acc[(size_t)W * COV_ACC_STRIDE] = base + s;
-    }
-}
-
 // fold the min/max-path terms in and map (F, T) to (d/dt, d/dq~).
 __global__ void cov_traj_epilogue_kernel(const double* __restrict__ acc, const float* __restrict__ minmax,
                                          const float* __restrict__ quats, int W, double n_total, int upstream_mode,
@@ -1365,9 +1383,58 @@ __global__ void cov_traj_epilogue_kernel(const double* __restrict__ acc, const f
 }
 
 // ==================================================== host ====================================================
-constexpr size_t kSmemCap = (227 - 11) * 1024;  // opt-in shared memory per block on sm_100, minus static use (slot table)
+constexpr size_t kSmemCap = (227 - 4) * 1024;  // opt-in shared memory per block on sm_100, minus static use
 constexpr int64_t kSeedSamples = 16384;          // pruned pass A: size of the strided sample that seeds the bounds
-constexpr int64_t kDenseBelow = 4 * kSeedSamples;  // clouds this small go straight to the dense pass A
+constexpr int64_t kDenseBelow = 4 * kSeedSamples;  // clouds this small go straight to the dense kernels
+
+// Resident blocks per SM of a kernel at a given dynamic shared-memory size, cached per (kernel, device, size): the
+// opt-in shared-memory attribute is raised once per kernel and device to the cap (not per call: two host threads with
+// different pose counts must not race between "set" and "launch"), the occupancy query runs once per size.
+struct OccKey {
+    const void* fn;
+    int dev;
+    size_t smem;
+    bool operator<(const OccKey& o) const {
+        return fn != o.fn ? fn < o.fn : dev != o.dev ? dev < o.dev : smem < o.smem;
+    }
+};
+std::mutex g_occ_mutex;
+std::map<OccKey, int> g_occ;
+
+template <typename Kern>
+int blocks_per_sm(Kern kern, int threads, size_t smem) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const OccKey key{reinterpret_cast<const void*>(kern), dev, smem};
+    std::lock_guard<std::mutex> lock(g_occ_mutex);
+    auto it = g_occ.find(key);
+    if (it != g_occ.end()) return it->second;
+    const OccKey attr_key{reinterpret_cast<const void*>(kern), dev, (size_t)-1};
+    if (g_occ.find(attr_key) == g_occ.end()) {
+        cudaFuncAttributes fa;
+        size_t cap = kSmemCap;
+        if (cudaFuncGetAttributes(&fa, kern) == cudaSuccess && fa.sharedSizeBytes + cap > 227 * 1024)
+            cap = 227 * 1024 - fa.sharedSizeBytes;  // opt-in limit covers static + dynamic
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap) != cudaSuccess)
+            cudaGetLastError();
+        g_occ[attr_key] = 1;
+    }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 1;
+    }
+    g_occ[key] = per_sm;
+    return per_sm;
+}
+
+template <typename Kern>
+int grid_for(Kern kern, size_t smem, int64_t ntiles) {
+    int64_t g = (int64_t)blocks_per_sm(kern, COV_THREADS, smem) * cov_sm_count_cached();
+    if (g > ntiles) g = ntiles;
+    if (g > COV_MAX_GRID) g = COV_MAX_GRID;
+    return g < 1 ? 1 : (int)g;
+}
 
 int pick_ppt(int64_t n, int W, bool fused, bool prune) {
     const int sms = cov_sm_count_cached();
@@ -1383,46 +1450,38 @@ int pick_ppt(int64_t n, int W, bool fused, bool prune) {
     return 0;
 }
 
-template <typename Kern>
-int grid_for(Kern kern, size_t smem, int64_t ntiles) {
-    int per_sm = 0;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, COV_THREADS, smem) != cudaSuccess || per_sm < 1)
-        per_sm = 1;
-    int64_t g = (int64_t)per_sm * cov_sm_count_cached();
-    if (g > ntiles) g = ntiles;
-    if (g > COV_MAX_GRID) g = COV_MAX_GRID;
-    return g < 1 ? 1 : (int)g;
-}
-
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 int64_t boxes_padded(int64_t n) { return ((n + 2047) / 2048) * (2048 / kBoxPts); }
 
 // Workspace of both passes (every region 256-byte aligned):
-//   [reward-sum partials][accumulator slabs][pose table][ints: count, amin flag][work list][tile flags][tile masks][boxes]
+//   [control: ctrl ints | encoded extrema 2W | look-back descriptors][pose table][work list][tile masks][boxes]
 struct TrajWorkspace {
-    double* sumr;
-    float* partials;
+    int* ctrl;
+    unsigned* enc;
+    unsigned long long* desc;
+    size_t ctrl_bytes;  // the span a pruned call zeroes first
     float4* table;
-    int* ints;
     int* worklist;
-    unsigned char* flags;
     unsigned* amask;
     float4* boxes;
     size_t bytes;
 };
 TrajWorkspace carve_workspace(void* ws, int64_t n, int W) {
     const int64_t nt = (n + 255) / 256;  // tiles at the smallest tile size
+    const int64_t nchunks = (nt + kChunkTiles - 1) / kChunkTiles;
     char* p = reinterpret_cast<char*>(ws);
     size_t off = 0;
     TrajWorkspace t;
     auto take = [&](size_t bytes) { char* q = p + off; off += align256(bytes); return q; };
-    t.sumr = reinterpret_cast<double*>(take(COV_MAX_GRID * sizeof(double)));
-    t.partials = reinterpret_cast<float*>(take((size_t)COV_MAX_GRID * W * 8 * sizeof(float)));
+    const size_t enc_off = kCtrlInts * sizeof(int);
+    const size_t desc_off = (enc_off + 2 * (size_t)W * sizeof(unsigned) + 7) & ~(size_t)7;
+    t.ctrl_bytes = desc_off + (size_t)nchunks * sizeof(unsigned long long);
+    char* c = take(t.ctrl_bytes);
+    t.ctrl = reinterpret_cast<int*>(c);
+    t.enc = reinterpret_cast<unsigned*>(c + enc_off);
+    t.desc = reinterpret_cast<unsigned long long*>(c + desc_off);
     t.table = reinterpret_cast<float4*>(take((size_t)W * COV_ROW_F4 * sizeof(float4)));
-    t.ints = reinterpret_cast<int*>(take(256));
     t.worklist = reinterpret_cast<int*>(take((size_t)nt * sizeof(int)));
-    t.flags = reinterpret_cast<unsigned char*>(take((size_t)nt));
     t.amask = reinterpret_cast<unsigned*>(take((size_t)nt * mask_stride_words(W) * sizeof(unsigned)));
     t.boxes = reinterpret_cast<float4*>(take((size_t)boxes_padded(n) * 2 * sizeof(float4)));
     t.bytes = off;
@@ -1467,25 +1526,29 @@ const float4* boxes_for_call(const float* xyz, int64_t n, const float* boxes_dev
     return t.boxes;
 }
 
-// dense_frac: hand the call to the dense kernel when more than this fraction of all (tile, pose) pairs is listed
-// (2.0 = never)
-void launch_cull(const float4* boxes, int ppt, int64_t ntiles, const TrajWorkspace& t, int W, const unsigned* gmin,
-                 const unsigned* gmax, float inv_kd, double dense_frac, cudaStream_t s) {
-    const int grid = (int)std::min<int64_t>((ntiles + 63) / 64, (int64_t)cov_sm_count_cached() * 8);
-    cov_cull_kernel<<<grid, 256, (size_t)W * sizeof(float4), s>>>(boxes, tile_boxes(ppt), ntiles, t.table, W, gmin, gmax,
-                                                                 inv_kd, t.amask, mask_stride_words(W), t.flags,
-                                                                 reinterpret_cast<unsigned long long*>(t.ints + 4));
-    cov_worklist_kernel<<<1, 1024, 0, s>>>(t.flags, ntiles, t.worklist, t.ints,
-                                           (unsigned long long)(dense_frac * (double)ntiles * (double)W));
+// cull + work list in one launch; every block must be resident (the blocks wait on one another's descriptors)
+void launch_cull(const float4* boxes, int ppt, int64_t ntiles, const TrajWorkspace& t, int W, const unsigned* enc,
+                 float inv_kd, float* fill_dst, int64_t fill_n, cudaStream_t s) {
+    const size_t smem = (size_t)W * sizeof(float4);
+    const int64_t nchunks = (ntiles + kChunkTiles - 1) / kChunkTiles;
+    const int64_t resident = (int64_t)blocks_per_sm(cov_cull_kernel, 256, smem) * cov_sm_count_cached();
+    int64_t want = nchunks;
+    if (fill_dst) want = std::max<int64_t>(want, (int64_t)cov_sm_count_cached() * 4);  // enough stores in flight for the fill
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, resident));
+    cov_cull_kernel<<<grid, 256, smem, s>>>(boxes, tile_boxes(ppt), ntiles, t.table, W, enc, inv_kd, t.amask,
+                                            mask_stride_words(W), t.worklist, t.ctrl, t.desc, fill_dst, fill_n);
 }
 
 }  // namespace
 
 extern "C" int cov_traj_max_poses(void) {
+    static int cached = 0;
+    if (cached) return cached;
     int w = 1;
     while (w < 32 * kMaskWords && fused_smem_bytes(w + 1, 1, false) <= kSmemCap && fused_smem_bytes(w + 1, 1, true) <= kSmemCap &&
            minmax_tiles_smem_bytes(w + 1, 1) <= kSmemCap && (size_t)(w + 1) * sizeof(float4) <= 48 * 1024)
         ++w;
+    cached = w;
     return w;
 }
 
@@ -1513,8 +1576,8 @@ extern "C" int cov_tile_boxes(const float* xyz, int64_t n, float* boxes, void* s
 }
 
 extern "C" int cov_traj_minmax(const float* xyz, int64_t n, const float* poses, const float* quats, int W,
-                               const float* K, const cov_camera* cam, const float* boxes_dev, float* minmax, void* ws,
-                               size_t ws_bytes, void* stream) {
+                               const float* K, const cov_camera* cam, const float* boxes_dev, float* minmax,
+                               const cov_traj_opts* opts, void* ws, size_t ws_bytes, void* stream) {
     int rc = check_traj_args("cov_traj_minmax", xyz, n, poses, quats, W, K, cam, ws, ws_bytes);
     if (rc) return rc;
     if (!minmax) {
@@ -1527,10 +1590,7 @@ extern "C" int cov_traj_minmax(const float* xyz, int64_t n, const float* poses, 
     }
     cudaStream_t s = (cudaStream_t)stream;
     const CovConst C = cov_make_const(cam);
-    unsigned* gmin = reinterpret_cast<unsigned*>(minmax);
-    unsigned* gmax = gmin + W;
-    cov_minmax_init_kernel<<<(W + 255) / 256, 256, 0, s>>>(gmin, gmax, W);
-    const bool prune = cov_pruning_enabled() != 0 && n >= kDenseBelow;
+    const bool prune = !(opts && opts->dense) && n >= kDenseBelow;
     int ppt = pick_ppt(n, W, false, prune);
     if (ppt == 4 && (n + tile_points(8) - 1) / tile_points(8) >= 4 * (int64_t)cov_sm_count_cached() &&
         (!prune || minmax_tiles_smem_bytes(W, 8) <= kSmemCap))
@@ -1539,42 +1599,42 @@ extern "C" int cov_traj_minmax(const float* xyz, int64_t n, const float* poses, 
         cov_set_error("cov_traj_minmax: %d poses do not fit in shared memory", W);
         return COV_ERR_UNSUPPORTED;
     }
-    const size_t smem = minmax_smem_bytes(W);
     const int64_t ntiles = (n + tile_points(ppt) - 1) / tile_points(ppt);
-#define LAUNCH_DENSE(P, B, U, NPTS, STRIDE)                                                                           \
-    {                                                                                                                 \
-        const int64_t nt_ = ((NPTS) + tile_points(P) - 1) / tile_points(P);                                           \
-        const int grid = grid_for(cov_traj_minmax_kernel<P, B, U>, smem, nt_);                                        \
-        cov_traj_minmax_kernel<P, B, U><<<grid, COV_THREADS, smem, s>>>(xyz, NPTS, STRIDE, poses, quats, W, K, C, gmin, \
-                                                                        gmax);                                        \
-    }
     if (!prune) {
-        if (ppt == 8) LAUNCH_DENSE(8, 2, 2, n, 1)
-        else if (ppt == 4) LAUNCH_DENSE(4, 2, 1, n, 1)
-        else if (ppt == 2) LAUNCH_DENSE(2, 2, 1, n, 1)
-        else LAUNCH_DENSE(1, 2, 1, n, 1)
+        unsigned* gmin = reinterpret_cast<unsigned*>(minmax);
+        unsigned* gmax = gmin + W;
+        const size_t smem = minmax_smem_bytes(W);
+        cov_minmax_init_kernel<<<(W + 255) / 256, 256, 0, s>>>(gmin, gmax, W);
+#define LAUNCH_DENSE(P, B, U)                                                                                        \
+    {                                                                                                                \
+        const int grid = grid_for(cov_traj_minmax_kernel<P, B, U>, smem, ntiles);                                    \
+        cov_traj_minmax_kernel<P, B, U><<<grid, COV_THREADS, smem, s>>>(xyz, n, 1, poses, quats, W, K, C, gmin, gmax); \
+    }
+        if (ppt == 8) LAUNCH_DENSE(8, 2, 2)
+        else if (ppt == 4) LAUNCH_DENSE(4, 2, 1)
+        else if (ppt == 2) LAUNCH_DENSE(2, 2, 1)
+        else LAUNCH_DENSE(1, 2, 1)
+#undef LAUNCH_DENSE
         return cov_check_launch("cov_traj_minmax");
     }
-#undef LAUNCH_DENSE
-    // pruned: seed the bounds on a strided sample, cull tiles against them, evaluate the listed tiles
+    // pruned: pose table + seed on a strided sample, cull + work list, evaluation of the listed tiles: 3 launches
     const TrajWorkspace t = carve_workspace(ws, n, W);
     const float4* boxes = boxes_for_call(xyz, n, boxes_dev, t, s);
-    cudaMemsetAsync(t.ints, 0, 256, s);
-    cov_pose_table_kernel<<<(W + 127) / 128, 128, 0, s>>>(poses, quats, W, K, C, nullptr, t.table, t.ints);
+    cudaMemsetAsync(t.ctrl, 0, t.ctrl_bytes, s);
     {
         const int64_t stride = (n + kSeedSamples - 1) / kSeedSamples;
         const int64_t nsamples = (n + stride - 1) / stride;
         const dim3 sgrid((unsigned)((nsamples + COV_THREADS - 1) / COV_THREADS), (unsigned)((W + 31) / 32));
-        cov_traj_seed_kernel<<<sgrid, COV_THREADS, 0, s>>>(xyz, nsamples, stride, t.table, W, C, gmin, gmax);
+        cov_traj_prepare_kernel<<<sgrid, COV_THREADS, 0, s>>>(xyz, nsamples, stride, poses, quats, W, K, C, t.table, t.enc);
     }
-    launch_cull(boxes, ppt, ntiles, t, W, gmin, gmax, 1.f / C.kd, 2.0, s);
-    unsigned long long* stats = cov_stats_device_ptr();
+    launch_cull(boxes, ppt, ntiles, t, W, t.enc, 1.f / C.kd, nullptr, 0, s);
+    unsigned long long* stats = opts ? opts->stats_dev : nullptr;
 #define LAUNCH_TILES(P)                                                                                             \
     {                                                                                                               \
         const size_t smem_t = minmax_tiles_smem_bytes(W, P);                                                        \
         const int grid = grid_for(cov_traj_minmax_tiles_kernel<P, 2>, smem_t, ntiles);                              \
         cov_traj_minmax_tiles_kernel<P, 2><<<grid, COV_THREADS, smem_t, s>>>(                                       \
-            xyz, n, t.table, W, C, gmin, gmax, boxes, t.amask, mask_stride_words(W), t.worklist, t.ints, ntiles, stats); \
+            xyz, n, t.table, W, C, t.enc, minmax, boxes, t.amask, mask_stride_words(W), t.worklist, t.ctrl, ntiles, stats); \
     }
     if (ppt == 8) LAUNCH_TILES(8) else if (ppt == 4) LAUNCH_TILES(4) else if (ppt == 2) LAUNCH_TILES(2) else LAUNCH_TILES(1)
 #undef LAUNCH_TILES
@@ -1583,8 +1643,8 @@ extern "C" int cov_traj_minmax(const float* xyz, int64_t n, const float* poses, 
 
 extern "C" int cov_traj_fused(const float* xyz, int64_t n, const float* poses, const float* quats, int W,
                               const float* K, const cov_camera* cam, const float* boxes_dev, const float* minmax,
-                              const float* upstream, const int32_t* reward_index, float* rewards, double* acc, void* ws,
-                              size_t ws_bytes, void* stream) {
+                              const float* upstream, const int32_t* reward_index, float* rewards, double* acc,
+                              const cov_traj_opts* opts, void* ws, size_t ws_bytes, void* stream) {
     int rc = check_traj_args("cov_traj_fused", xyz, n, poses, quats, W, K, cam, ws, ws_bytes);
     if (rc) return rc;
     if (!minmax || !rewards || !acc) {
@@ -1597,30 +1657,25 @@ extern "C" int cov_traj_fused(const float* xyz, int64_t n, const float* poses, c
     }
     cudaStream_t s = (cudaStream_t)stream;
     const CovConst C = cov_make_const(cam);
-    const bool prune = cov_pruning_enabled() != 0;
+    const bool prune = !(opts && opts->dense) && n >= kDenseBelow;
     const TrajWorkspace t = carve_workspace(ws, n, W);
-    cudaMemsetAsync(acc, 0, ((size_t)W * COV_ACC_STRIDE + 1) * sizeof(double), s);
-
-    // the dense kernel: the whole call when pruning is off, a stand-by launch behind the pruned kernel otherwise
-    // (it runs only if the cull found nothing to prune: run_flag = ints[2])
-    const int ppt_d = pick_ppt(n, W, true, false);
-    if (ppt_d == 0) {
-        cov_set_error("cov_traj_fused: %d poses do not fit in shared memory", W);
-        return COV_ERR_UNSUPPORTED;
-    }
-    auto launch_dense = [&](const int* run_flag) -> int {
+    if (!prune) {  // every pair evaluated: accumulators zeroed, one kernel
+        const int ppt_d = pick_ppt(n, W, true, false);
+        if (ppt_d == 0) {
+            cov_set_error("cov_traj_fused: %d poses do not fit in shared memory", W);
+            return COV_ERR_UNSUPPORTED;
+        }
+        cudaMemsetAsync(acc, 0, ((size_t)W * COV_ACC_STRIDE + 1) * sizeof(double), s);
         const size_t smem = fused_smem_bytes(W, ppt_d, false);
         const int64_t ntiles = (n + tile_points(ppt_d) - 1) / tile_points(ppt_d);
         // phase-2 parallelism: split each pose row over 2^seg_log2 lanes until there are >= 2 tasks per thread
         int seg_log2 = 0;
         while ((W << seg_log2) < 2 * COV_THREADS && (2 << seg_log2) <= bit_words(ppt_d) && seg_log2 < 5) ++seg_log2;
-        int grid = 1;
 #define LAUNCH_F(P, UP)                                                                                           \
     {                                                                                                             \
-        grid = grid_for(cov_traj_fused_kernel<P, UP, 2>, smem, ntiles);                                           \
+        const int grid = grid_for(cov_traj_fused_kernel<P, UP, 2>, smem, ntiles);                                 \
         cov_traj_fused_kernel<P, UP, 2><<<grid, COV_THREADS, smem, s>>>(xyz, n, poses, quats, W, K, C, minmax,    \
-                                                                        upstream, reward_index, rewards, t.partials, \
-                                                                        t.sumr, acc, seg_log2, run_flag);         \
+                                                                        upstream, reward_index, rewards, acc, seg_log2); \
     }
         if (upstream) {
             if (ppt_d == 4) LAUNCH_F(4, true) else if (ppt_d == 2) LAUNCH_F(2, true) else LAUNCH_F(1, true)
@@ -1628,58 +1683,45 @@ extern "C" int cov_traj_fused(const float* xyz, int64_t n, const float* poses, c
             if (ppt_d == 4) LAUNCH_F(4, false) else if (ppt_d == 2) LAUNCH_F(2, false) else LAUNCH_F(1, false)
         }
 #undef LAUNCH_F
-        return grid;
-    };
-    if (!prune) {
-        const int grid = launch_dense(nullptr);
-        cov_traj_reduce_kernel<<<((W * 8 + 1) * 8 + 255) / 256, 256, 0, s>>>(t.partials, t.sumr, grid, grid, W, 0.0, nullptr, acc);
         return cov_check_launch("cov_traj_fused");
     }
-    // pruned: rewards start at 1/2; cull tiles against the gate thresholds; evaluate the listed tiles
-    const int ppt = pick_ppt(n, W, true, true);
-    if (ppt == 0) {
-        cov_set_error("cov_traj_fused: %d poses do not fit in shared memory", W);
-        return COV_ERR_UNSUPPORTED;
-    }
-    const size_t smem = fused_smem_bytes(W, ppt, true);
+    // pruned: table (+ zeroing), cull + work list (+ rewards pre-fill), evaluation of the listed tiles: 3 launches
+    constexpr int ppt = kItemPpt * kItemsPerTile * 32 / COV_THREADS;  // tiles of 1024 points, eight 128-point items each
+    static_assert(ppt == 4 && tile_points(ppt) == kItemsPerTile * kItemPts, "tile = 8 items");
     const int64_t ntiles = (n + tile_points(ppt) - 1) / tile_points(ppt);
     const float4* boxes = boxes_for_call(xyz, n, boxes_dev, t, s);
-    cudaMemsetAsync(t.ints, 0, 256, s);
-    cov_pose_table_kernel<<<(W + 127) / 128, 128, 0, s>>>(poses, quats, W, K, C, minmax, t.table, t.ints);
+    cov_traj_table_kernel<<<1, 256, 0, s>>>(poses, quats, W, K, C, minmax, t.table, t.ctrl, (int)(t.ctrl_bytes / sizeof(int)),
+                                            acc, 0.5 * (double)n);
+    const bool prefilled = opts && opts->rewards_prefilled;
+    launch_cull(boxes, ppt, ntiles, t, W, nullptr, 0.f, prefilled ? nullptr : rewards, n, s);
+    unsigned long long* stats = opts ? opts->stats_dev : nullptr;
     {
-        const int fgrid = (int)std::min<int64_t>((n + 1023) / 1024, (int64_t)cov_sm_count_cached() * 16);
-        cov_fill_kernel<<<fgrid, 256, 0, s>>>(rewards, n, 0.5f);
+        // persistent warps: as many blocks as are resident; every warp draws 128-point items from a ticket counter
+        int64_t grid = 0;
+        if (upstream) grid = (int64_t)blocks_per_sm(cov_traj_fused_tiles_kernel<true>, COV_THREADS, 0) * cov_sm_count_cached();
+        else grid = (int64_t)blocks_per_sm(cov_traj_fused_tiles_kernel<false>, COV_THREADS, 0) * cov_sm_count_cached();
+        grid = std::max<int64_t>(1, std::min<int64_t>(grid, ntiles));
+        if (upstream)
+            cov_traj_fused_tiles_kernel<true><<<(unsigned)grid, COV_THREADS, 0, s>>>(
+                xyz, n, t.table, W, C, upstream, reward_index, rewards, acc, boxes, t.amask, mask_stride_words(W),
+                t.worklist, t.ctrl, ntiles, stats);
+        else
+            cov_traj_fused_tiles_kernel<false><<<(unsigned)grid, COV_THREADS, 0, s>>>(
+                xyz, n, t.table, W, C, upstream, reward_index, rewards, acc, boxes, t.amask, mask_stride_words(W),
+                t.worklist, t.ctrl, ntiles, stats);
     }
-    launch_cull(boxes, ppt, ntiles, t, W, nullptr, nullptr, 0.f, 0.25, s);
-    unsigned long long* stats = cov_stats_device_ptr();
-    int grid = 1;
-#define LAUNCH_FT(P, UP)                                                                                          \
-    {                                                                                                             \
-        grid = grid_for(cov_traj_fused_tiles_kernel<P, UP>, smem, ntiles);                                        \
-        cov_traj_fused_tiles_kernel<P, UP><<<grid, COV_THREADS, smem, s>>>(                                       \
-            xyz, n, t.table, W, C, upstream, reward_index, rewards, t.partials, t.sumr, acc, boxes, t.amask,      \
-            mask_stride_words(W), t.worklist, t.ints, ntiles, stats);                                             \
-    }
-    if (upstream) {
-        if (ppt == 4) LAUNCH_FT(4, true) else if (ppt == 2) LAUNCH_FT(2, true) else LAUNCH_FT(1, true)
-    } else {
-        if (ppt == 4) LAUNCH_FT(4, false) else if (ppt == 2) LAUNCH_FT(2, false) else LAUNCH_FT(1, false)
-    }
-#undef LAUNCH_FT
-    const int grid_dense = launch_dense(t.ints + 2);
-    cov_traj_reduce_kernel<<<((W * 8 + 1) * 8 + 255) / 256, 256, 0, s>>>(t.partials, t.sumr, grid, grid_dense, W, 0.5 * (double)n,
-                                                               t.ints + 2, acc);
     return cov_check_launch("cov_traj_fused");
 }
 
 extern "C" int cov_sweep_rewards(const float* xyz, int64_t n, const float* poses, const float* quats, int n_traj,
                                  int per_traj, const float* K, const cov_camera* cam, const float* boxes_dev,
-                                 const float* minmax, double* sum_rewards, void* ws, size_t ws_bytes, void* stream) {
+                                 const float* minmax, double* sum_rewards, const cov_traj_opts* opts, void* ws,
+                                 size_t ws_bytes, void* stream) {
     if (!xyz || n <= 0 || !poses || !quats || n_traj <= 0 || per_traj <= 0 || !K || !cam || !minmax || !sum_rewards) {
         cov_set_error("cov_sweep_rewards: bad argument");
         return COV_ERR_ARG;
     }
-    if (!cov_pruning_enabled())
+    if (opts && opts->dense)
         return cov_sweep_rewards_dense(xyz, n, poses, quats, n_traj, per_traj, K, cam, minmax, sum_rewards, stream);
     // trajectories per launch: pose table + two stages + per-trajectory sums within ~100 KB (two blocks per SM)
     constexpr int PPT = 4;
@@ -1693,9 +1735,10 @@ extern "C" int cov_sweep_rewards(const float* xyz, int64_t n, const float* poses
     int chunk = 1;
     while (chunk < n_traj && smem_for(chunk + 1) <= 100 * 1024 && (chunk + 1) * per_traj <= 32 * kMaskWords) ++chunk;
     const int Wc = chunk * per_traj;
-    if (!ws || ws_bytes < cov_traj_workspace_bytes(n, Wc) || (((uintptr_t)ws) & 255) || (((uintptr_t)xyz) & 15)) {
-        cov_set_error("cov_sweep_rewards: workspace missing, misaligned or smaller than cov_traj_workspace_bytes(n, %d) = %zu",
-                      Wc, cov_traj_workspace_bytes(n, Wc));
+    if (!ws || ws_bytes < cov_traj_workspace_bytes(n, Wc) + 2 * (size_t)Wc * sizeof(float) || (((uintptr_t)ws) & 255) ||
+        (((uintptr_t)xyz) & 15)) {
+        cov_set_error("cov_sweep_rewards: workspace missing, misaligned or smaller than cov_sweep_workspace_bytes(n, %d, %d) = %zu",
+                      n_traj, per_traj, cov_sweep_workspace_bytes(n, n_traj, per_traj));
         return COV_ERR_WORKSPACE;
     }
     cudaStream_t s = (cudaStream_t)stream;
@@ -1704,23 +1747,30 @@ extern "C" int cov_sweep_rewards(const float* xyz, int64_t n, const float* poses
     const float4* boxes = boxes_for_call(xyz, n, boxes_dev, t, s);
     const int W = n_traj * per_traj;
     const int64_t ntiles = (n + tile_points(PPT) - 1) / tile_points(PPT);
-    float* mm = reinterpret_cast<float*>(t.partials);  // the chunk's minima and maxima, contiguous (2 * Wc floats)
+    float* mm = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + t.bytes);  // the chunk's minima and maxima, contiguous
     for (int t0 = 0; t0 < n_traj; t0 += chunk) {
         const int nt = (n_traj - t0 < chunk) ? n_traj - t0 : chunk;
         const int w0 = t0 * per_traj, Wn = nt * per_traj;
         cudaMemcpyAsync(mm, minmax + w0, (size_t)Wn * sizeof(float), cudaMemcpyDeviceToDevice, s);
         cudaMemcpyAsync(mm + Wn, minmax + W + w0, (size_t)Wn * sizeof(float), cudaMemcpyDeviceToDevice, s);
-        cudaMemsetAsync(t.ints, 0, 256, s);
-        cov_pose_table_kernel<<<(Wn + 127) / 128, 128, 0, s>>>(poses + 3 * (size_t)w0, quats + 4 * (size_t)w0, Wn, K, C, mm,
-                                                              t.table, t.ints);
-        launch_cull(boxes, PPT, ntiles, t, Wn, nullptr, nullptr, 0.f, 2.0, s);
+        cov_traj_table_kernel<<<1, 256, 0, s>>>(poses + 3 * (size_t)w0, quats + 4 * (size_t)w0, Wn, K, C, mm, t.table, t.ctrl,
+                                                (int)(t.ctrl_bytes / sizeof(int)), nullptr, 0.0);
+        launch_cull(boxes, PPT, ntiles, t, Wn, nullptr, 0.f, nullptr, 0, s);
         const size_t smem = smem_for(nt);
         const int grid = grid_for(cov_sweep_tiles_kernel<PPT>, smem, ntiles);
         cov_sweep_tiles_kernel<PPT><<<grid, COV_THREADS, smem, s>>>(xyz, n, t.table, Wn, per_traj, nt, C, boxes, t.amask,
-                                                                   mask_stride_words(Wn), t.worklist, t.ints,
+                                                                   mask_stride_words(Wn), t.worklist, t.ctrl,
                                                                    sum_rewards + t0);
     }
     return cov_check_launch("cov_sweep_rewards");
+}
+
+extern "C" size_t cov_sweep_workspace_bytes(int64_t n, int n_traj, int per_traj) {
+    if (n < 1) n = 1;
+    int W = n_traj * per_traj;
+    if (W > 32 * kMaskWords) W = 32 * kMaskWords;
+    if (W < 1) W = 1;
+    return cov_traj_workspace_bytes(n, W) + align256(2 * (size_t)W * sizeof(float));
 }
 
 extern "C" int cov_traj_epilogue(const double* acc, const float* minmax, const float* quats, int W, int64_t n_total,

@@ -201,6 +201,7 @@ class ModelTraj(nn.Module):
         self._pts32 = None
         self._perm = None
         self._boxes = None
+        self._ws = None
         self.to(self.device)
 
     def _cloud(self):
@@ -240,6 +241,15 @@ class ModelTraj(nn.Module):
             self._boxes.copy_(new_boxes)
         self._pts32_key = (id(self.points), self.points._version)
 
+    def _workspace(self, cloud):
+        # one workspace per (cloud, pose count), kept across steps: nothing in it outlives a call
+        if not cloud.is_cuda:
+            return None
+        need = ops._BACKEND.traj_workspace_bytes(cloud, max(1, self.poses.shape[0]))
+        if self._ws is None or self._ws.numel() < need or self._ws.device != cloud.device:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=cloud.device)
+        return self._ws
+
     def _wps_step(self, vis_wps_dist):
         # src/model.py:214-215.  poses0 never changes, so the host sync happens once per distance
         key = float(vis_wps_dist)
@@ -256,7 +266,8 @@ class ModelTraj(nn.Module):
         rewards, mean = ops.coverage_traj(cloud, self.poses[::wps_step], self.quats[::wps_step], self.K,
                                           self.img_width, self.img_height, self.pc_clip_limits[0],
                                           self.pc_clip_limits[1], self.eps, n_total=self.n_total, group=self.group,
-                                          reward_index=self._perm, boxes=self._boxes)
+                                          reward_index=self._perm, boxes=self._boxes,
+                                          dense=None if self.spatial_sort else True, workspace=self._workspace(cloud))
         self.rewards = rewards
         self._mean = mean
         if debug:

@@ -7,7 +7,9 @@ Sharded use: each rank passes ITS slice of the cloud plus a `group`; the per-pos
 are all-reduced with MIN/MAX, the accumulators with SUM (a few KB), so every rank ends up with
 the same scalar and the same pose gradients, while per-point outputs stay sharded.
 """
+import contextlib
 import ctypes
+import threading
 
 import torch
 
@@ -50,6 +52,34 @@ def _dev_f32(t, device=None, what="tensor"):
     if t.data_ptr() % 16:
         t = t.clone()
     return t
+
+
+class _Mode(threading.local):
+    dense = False      # evaluate every (point, pose) pair (cov_traj_opts.dense)
+    stats = None       # CUDA int64 tensor of 8 work counters, or None (cov_traj_opts.stats_dev)
+
+
+_MODE = _Mode()
+
+
+@contextlib.contextmanager
+def evaluation(dense=None, stats=None):
+    """Per-thread defaults of the trajectory ops inside the block: `dense=True` switches the exact pruning off
+    (A/B measurements, unordered clouds); `stats` = a CUDA int64 tensor of 8 counters the kernels add to.  Python-side
+    only: the C ABI takes these per call (cov_traj_opts) and keeps no process-wide switch."""
+    old = (_MODE.dense, _MODE.stats)
+    if dense is not None:
+        _MODE.dense = bool(dense)
+    if stats is not None:
+        _MODE.stats = stats
+    try:
+        yield
+    finally:
+        _MODE.dense, _MODE.stats = old
+
+
+def _opts(dense=None, rewards_prefilled=False):
+    return _lib.traj_opts(_MODE.dense if dense is None else dense, rewards_prefilled, _MODE.stats)
 
 
 def _ptr(t):
@@ -107,26 +137,30 @@ class CudaBackend:
         _call("cov_pose_epilogue", acc, _ptr(acc), _ptr(t), _ptr(q), _ptr(out))
         return out
 
-    def traj_workspace(self, pts, W):
-        ws_bytes = _lib.lib().cov_traj_workspace_bytes(pts.shape[0], W)
-        return torch.empty(ws_bytes, dtype=torch.uint8, device=pts.device)
+    def traj_workspace_bytes(self, pts, W):
+        return _lib.lib().cov_traj_workspace_bytes(pts.shape[0], W)
 
-    def traj_minmax(self, pts, P, Q, Kd, cam, boxes=None, ws=None):
+    def traj_workspace(self, pts, W):
+        return torch.empty(self.traj_workspace_bytes(pts, W), dtype=torch.uint8, device=pts.device)
+
+    def traj_minmax(self, pts, P, Q, Kd, cam, boxes=None, ws=None, dense=None):
         W = P.shape[0]
         minmax = torch.empty(2 * W, dtype=torch.float32, device=pts.device)
         ws = self.traj_workspace(pts, W) if ws is None else ws
+        opts = _opts(dense)
         _call("cov_traj_minmax", pts, _ptr(pts), pts.shape[0], _ptr(P), _ptr(Q), W, _ptr(Kd), ctypes.byref(cam),
-                                              _ptr(boxes), _ptr(minmax), _ptr(ws), ws.numel())
+              _ptr(boxes), _ptr(minmax), ctypes.byref(opts), _ptr(ws), ws.numel())
         return minmax
 
-    def traj_fused(self, pts, P, Q, Kd, cam, minmax, upstream, rewards, reward_index=None, boxes=None, ws=None):
-        L = _lib.lib()
+    def traj_fused(self, pts, P, Q, Kd, cam, minmax, upstream, rewards, reward_index=None, boxes=None, ws=None,
+                   dense=None):
         W, n = P.shape[0], pts.shape[0]
         acc = torch.empty(W * _lib.ACC_STRIDE + 1, dtype=torch.float64, device=pts.device)
         ws = self.traj_workspace(pts, W) if ws is None else ws
+        opts = _opts(dense)
         _call("cov_traj_fused", pts, _ptr(pts), n, _ptr(P), _ptr(Q), W, _ptr(Kd), ctypes.byref(cam), _ptr(boxes),
-                                    _ptr(minmax), _ptr(upstream), _ptr(reward_index), _ptr(rewards), _ptr(acc), _ptr(ws),
-                                    ws.numel())
+              _ptr(minmax), _ptr(upstream), _ptr(reward_index), _ptr(rewards), _ptr(acc), ctypes.byref(opts), _ptr(ws),
+              ws.numel())
         return acc
 
     def traj_epilogue(self, acc, minmax, Q, n_total, upstream_mode):
@@ -193,7 +227,8 @@ class CoverageTrajFn(torch.autograd.Function):
     over the poses given (reference src/model.py:217-237, :246)."""
 
     @staticmethod
-    def forward(ctx, points, poses, quats, K, cam, n_total, group, reward_index=None, boxes=None):
+    def forward(ctx, points, poses, quats, K, cam, n_total, group, reward_index=None, boxes=None, dense=None,
+                workspace=None):
         B = _BACKEND
         dev = points.device
         pts = B.prepare(points, what="points")
@@ -207,20 +242,26 @@ class CoverageTrajFn(torch.autograd.Function):
         if Q.shape[0] != W:
             raise ValueError("poses and quats disagree on the number of waypoints")
         n_total = int(n if n_total is None else n_total)
-        ws = B.traj_workspace(pts, W)                        # shared by both passes (and the upstream backward)
-        minmax = B.traj_minmax(pts, P, Q, Kd, cam, boxes, ws)   # pass A on this shard
+        dense = _MODE.dense if dense is None else bool(dense)
+        ws = workspace                                       # shared by both passes; a caller may keep one per cloud
+        if ws is None or ws.numel() < B.traj_workspace_bytes(pts, W) or ws.device != dev:
+            ws = B.traj_workspace(pts, W)
+        minmax = B.traj_minmax(pts, P, Q, Kd, cam, boxes, ws, dense)   # pass A on this shard
         _all_reduce_minmax(minmax, W, group)                 # global normalisers: W minima, W maxima
         rewards = torch.empty(n, dtype=torch.float32, device=dev)
-        out = CoverageTrajFn._run(pts, P, Q, Kd, cam, minmax, None, rewards, n_total, group, reward_index, boxes, ws)
+        out = CoverageTrajFn._run(pts, P, Q, Kd, cam, minmax, None, rewards, n_total, group, reward_index, boxes, ws,
+                                  dense)
         ctx.cam, ctx.group, ctx.n_total, ctx.reward_index, ctx.boxes = cam, group, n_total, reward_index, boxes
+        ctx.dense = dense
         ctx.shapes = (poses.shape, quats.shape)
         ctx.save_for_backward(pts, P, Q, Kd, minmax, out)
         ctx.set_materialize_grads(False)
         return rewards, out[0].clone()
 
     @staticmethod
-    def _run(pts, P, Q, Kd, cam, minmax, upstream, rewards, n_total, group, reward_index=None, boxes=None, ws=None):
-        acc = _BACKEND.traj_fused(pts, P, Q, Kd, cam, minmax, upstream, rewards, reward_index, boxes, ws)   # pass B
+    def _run(pts, P, Q, Kd, cam, minmax, upstream, rewards, n_total, group, reward_index=None, boxes=None, ws=None,
+             dense=None):
+        acc = _BACKEND.traj_fused(pts, P, Q, Kd, cam, minmax, upstream, rewards, reward_index, boxes, ws, dense)   # pass B
         if group is not None:
             _all_reduce(acc, _reduce_ops()[2], group)
         return _BACKEND.traj_epilogue(acc, minmax, Q, n_total, 0 if upstream is None else 1)
@@ -237,12 +278,12 @@ class CoverageTrajFn(torch.autograd.Function):
             up = _BACKEND.prepare(g_rewards, pts.device, "grad_rewards").reshape(-1)
             scratch = torch.empty(pts.shape[0], dtype=torch.float32, device=pts.device)
             o2 = CoverageTrajFn._run(pts, P, Q, Kd, ctx.cam, minmax, up, scratch, ctx.n_total, ctx.group,
-                                     ctx.reward_index, ctx.boxes)
+                                     ctx.reward_index, ctx.boxes, None, ctx.dense)
             g_p = o2[1:1 + 3 * W] if g_p is None else g_p + o2[1:1 + 3 * W]
             g_q = o2[1 + 3 * W:] if g_q is None else g_q + o2[1 + 3 * W:]
         ps, qs = ctx.shapes
         return (None, None if g_p is None else g_p.reshape(ps), None if g_q is None else g_q.reshape(qs),
-                None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None)
 
 
 class TrajRegularizersFn(torch.autograd.Function):
@@ -283,13 +324,14 @@ def coverage_pose(points, trans, quat, intrins, img_width, img_height, min_dist=
 
 
 def coverage_traj(points, poses, quats, intrins, img_width, img_height, min_dist=1.0, max_dist=5.0, eps=1e-6,
-                  n_total=None, group=None, reward_index=None, boxes=None):
+                  n_total=None, group=None, reward_index=None, boxes=None, dense=None, workspace=None):
     """Fused ModelTraj visibility term over the W poses given.  Returns (rewards (N,), mean(rewards)).
     `reward_index` (int32, from `spatial_sort`): `points` is a reordered copy of the caller's cloud and
     rewards come back in the caller's order.  `boxes` (from `tile_boxes(points)`): built once per cloud so the
-    pruned kernels do not rebuild them on every call."""
+    pruned kernels do not rebuild them on every call.  `dense=True`: evaluate every pair (no pruning; what an unordered
+    cloud should ask for).  `workspace`: a uint8 CUDA tensor kept by the caller across calls (one per cloud)."""
     cam = _lib.camera(img_width, img_height, min_dist, max_dist, eps)
-    return CoverageTrajFn.apply(points, poses, quats, intrins, cam, n_total, group, reward_index, boxes)
+    return CoverageTrajFn.apply(points, poses, quats, intrins, cam, n_total, group, reward_index, boxes, dense, workspace)
 
 
 @torch.no_grad()
@@ -341,19 +383,20 @@ def sweep_rewards(points, poses, quats, intrins, img_width, img_height, min_dist
     minmax = torch.empty(2 * W, dtype=torch.float32, device=dev)
     chunk = L.cov_traj_max_poses()
     boxes = tile_boxes(pts) if boxes is None else boxes
-    ws_bytes = L.cov_traj_workspace_bytes(n, min(W, 2048))
+    ws_bytes = max(L.cov_traj_workspace_bytes(n, min(W, chunk)), L.cov_sweep_workspace_bytes(n, T, Pn))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    opts = _opts()
     for w0 in range(0, W, chunk):  # pass A reuses the trajectory kernel, one pose-table-full at a time
         w1 = min(W, w0 + chunk)
         mm = torch.empty(2 * (w1 - w0), dtype=torch.float32, device=dev)
         _call("cov_traj_minmax", pts, _ptr(pts), n, _ptr(P[w0:w1]), _ptr(Q[w0:w1]), w1 - w0, _ptr(Kd),
-                                     ctypes.byref(cam), _ptr(boxes), _ptr(mm), _ptr(ws), ws_bytes)
+              ctypes.byref(cam), _ptr(boxes), _ptr(mm), ctypes.byref(opts), _ptr(ws), ws_bytes)
         minmax[w0:w1] = mm[:w1 - w0]
         minmax[W + w0:W + w1] = mm[w1 - w0:]
     _all_reduce_minmax(minmax, W, group)
     sums = torch.zeros(T, dtype=torch.float64, device=dev)
     _call("cov_sweep_rewards", pts, _ptr(pts), n, _ptr(P), _ptr(Q), T, Pn, _ptr(Kd), ctypes.byref(cam), _ptr(boxes),
-                                   _ptr(minmax), _ptr(sums), _ptr(ws), ws_bytes)
+          _ptr(minmax), _ptr(sums), ctypes.byref(opts), _ptr(ws), ws_bytes)
     if group is not None:
         _all_reduce(sums, _reduce_ops()[2], group)
     return sums / float(n if n_total is None else n_total)
