@@ -115,9 +115,15 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_reference_rate(body, rig, steps, warmup, budget_s):
-    """evals/s of the torch-CPU port on a bounded sample of the same workload (all 320 poses, a
-    subsample of the cloud sized so the whole run takes about `budget_s` seconds)."""
+# fixed sample of the workload for the CPU arm: 20 000 points x all 320 poses per step (the env override exists for the
+# contract test in tests/, which only checks the line's shape)
+CPU_SAMPLE_POINTS = int(os.environ.get("COV_BENCH_REF_POINTS", "20000"))
+
+
+def cpu_reference_rate(body, rig, steps, warmup, n_points=CPU_SAMPLE_POINTS):
+    """evals/s of the torch-CPU port on a FIXED, stated sample of the same workload: all 320 poses, the first
+    `n_points` points of the seeded cloud generator (torch autograd keeps ~240 B per point per pose, which bounds the
+    sample).  Fixed so that the figure is reproducible from run to run."""
     from oracle import torch_port, coverage_oracle as orc
     from trajectory_optimization_b200 import multicam
     threads = os.cpu_count() or 1
@@ -129,28 +135,17 @@ def cpu_reference_rate(body, rig, steps, warmup, budget_s):
     W = P.shape[0]
     g = torch.Generator().manual_seed(1000)
     lo, hi = torch.tensor(BOX_LO), torch.tensor(BOX_HI)
-
-    def cloud(n):
-        return torch.rand(n, 3, generator=g) * (hi - lo) + lo
-
-    # calibrate on a small sample, then size the real one (autograd keeps ~240 B per point per pose)
-    n_cal = 8000
-    pts = cloud(n_cal)
-    t0 = time.perf_counter()
-    torch_port.traj_step(pts, P, Q, K, orc.IMG_WIDTH, orc.IMG_HEIGHT)
-    rate_cal = n_cal * W / (time.perf_counter() - t0)
-    n = int(rate_cal * budget_s / ((steps + warmup) * W))
-    n = max(2000, min(n, 60_000))
-    pts = cloud(n)
+    pts = torch.rand(n_points, 3, generator=g) * (hi - lo) + lo
     for _ in range(warmup):
         torch_port.traj_step(pts, P, Q, K, orc.IMG_WIDTH, orc.IMG_HEIGHT)
     t0 = time.perf_counter()
     for _ in range(steps):
         torch_port.traj_step(pts, P, Q, K, orc.IMG_WIDTH, orc.IMG_HEIGHT)
     dt = time.perf_counter() - t0
-    return dict(value=n * W * steps / dt, unit="point*pose evals/s", cores=threads, kind="port",
-                sample=f"{n} points x {W} poses, {steps} fwd+bwd steps of oracle/torch_port.py (torch {torch.__version__} "
-                       f"CPU autograd, {threads} threads), {dt / steps * 1e3:.0f} ms/step"), dt / steps
+    return dict(value=n_points * W * steps / dt, unit="point*pose evals/s", cores=threads, kind="port",
+                sample=f"{n_points} points x {W} poses (fixed sample of the c4 cloud generator), {steps} fwd+bwd steps of "
+                       f"oracle/torch_port.py (torch {torch.__version__} CPU autograd, {threads} threads), "
+                       f"{dt / steps * 1e3:.0f} ms/step"), dt / steps
 
 
 def config_dict(n_total, world):
@@ -166,12 +161,14 @@ def run_reference(args):
         return
     from trajectory_optimization_b200 import multicam
     body, rig = body_waypoints(), multicam.ring_rig(N_CAMS)
-    base, ms = cpu_reference_rate(body, rig, args.steps, args.warmup,
-                                  budget_s=float(os.environ.get("COV_BENCH_REF_BUDGET_S", "90")))
+    base, ms = cpu_reference_rate(body, rig, args.steps, args.warmup)
     line = {"impl": "reference", "metric": "coverage fwd+bwd point*pose evals/s", "value": base["value"],
             "unit": "point*pose evals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": config_dict(args.points, args.gpus),
+            "dtype": "f32", "data": "synthetic",
+            "config": dict(config_dict(args.points, args.gpus), same_config=False, n_points_timed=CPU_SAMPLE_POINTS,
+                           note="the CPU arm times a fixed 20 000-point sample of this workload per step and reports a RATE; "
+                                "a full c4 step at this rate would take hours"),
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": base["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -216,13 +213,16 @@ def main():
 
     rig7 = multicam.rig_tensor(rig, dev)
 
-    def step(points, perm, boxes):
+    ws_keep = torch.empty(L.cov_traj_workspace_bytes(n_local, W), dtype=torch.uint8, device=dev)  # one per cloud, as ModelTraj
+    def step(points, perm, boxes, keep=None):
         body.grad = None
         t, q = multicam.camera_poses_fused(body, rig7)          # (x, y, z, yaw) x rig -> 320 camera poses
         rewards, mean = ops.coverage_traj(points, t, q, K, img_w, img_h, n_total=n_total, group=group, reward_index=perm,
-                                          boxes=boxes)
+                                          boxes=boxes, workspace=ws_keep)
         loss = 1.0 / (mean + 1e-6)
         loss.backward()
+        if keep is not None:
+            keep["rewards"] = rewards
         return loss
 
     def barrier():
@@ -246,7 +246,6 @@ def main():
     # ---- device-resident throughput (value): the product's default path ----
     # ModelTraj orders its cloud once at construction (the reference builds one model per cloud and iterates the
     # optimiser on it); that one-off sort is timed separately below and is inside the e2e figure.
-    L.cov_set_pruning(1)
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     pts_sorted, perm = ops.spatial_sort(pts)
@@ -297,13 +296,30 @@ def main():
     if clocks is not None:
         clocks["note"] = ("sampled every 50 ms from the start of the timed region through %d further untimed repetitions of "
                           "the same step (the timed region itself lasts %.1f ms)" % (n_cont, ms_total))
-    # same step with pruning switched off: every (point, pose) pair fully evaluated (bit-identical rewards)
-    L.cov_set_pruning(0)
-    for _ in range(2):
-        step(pts_sorted, perm, boxes)
-    dense_steps = max(2, min(args.steps, 5))
-    ms_dense = timed(lambda: step(pts_sorted, perm, boxes), dense_steps) / dense_steps
-    L.cov_set_pruning(1)
+    # same step with pruning switched off: every (point, pose) pair fully evaluated.  PARITY CHECK on the bench
+    # configuration itself, in this run: the pruned step's per-point rewards and loss must equal the dense step's bit for
+    # bit, its gradients to fp32 summation order.
+    last = {}
+    loss_p = step(pts_sorted, perm, boxes, last).detach().clone()
+    rewards_p, grad_p = last.pop("rewards"), body.grad.detach().clone()
+    with ops.evaluation(dense=True):
+        for _ in range(2):
+            loss_d = step(pts_sorted, perm, boxes, last).detach().clone()
+        rewards_d, grad_d = last.pop("rewards"), body.grad.detach().clone()
+        parity = {"rewards_bit_equal_dense": bool(torch.equal(rewards_p, rewards_d)),
+                  "loss_rel_diff_vs_dense": abs(float(loss_p) - float(loss_d)) / abs(float(loss_d)),
+                  "grad_rel_diff_vs_dense": float((grad_p - grad_d).abs().max() / grad_d.abs().max()),
+                  "note": "pruned vs dense step on THIS configuration and shard, same run; rewards compared with torch.equal"}
+        if world > 1:
+            flags = torch.tensor([1.0 if parity["rewards_bit_equal_dense"] else 0.0, -parity["grad_rel_diff_vs_dense"]],
+                                 device=dev, dtype=torch.float64)
+            dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+            parity["rewards_bit_equal_dense"], parity["grad_rel_diff_vs_dense"] = bool(flags[0] > 0.5), float(-flags[1])
+        if not parity["rewards_bit_equal_dense"] or parity["grad_rel_diff_vs_dense"] > 1e-4 or parity["loss_rel_diff_vs_dense"] > 1e-6:
+            raise SystemExit("bench.py: pruned step does not reproduce the dense step: %r" % (parity,))
+        del rewards_p, rewards_d
+        dense_steps = max(2, min(args.steps, 5))
+        ms_dense = timed(lambda: step(pts_sorted, perm, boxes), dense_steps) / dense_steps
 
     # ---- end to end: host (pinned) inputs in, loss + gradients out, every step ----
     # Every step consumes a NEW cloud from pinned host memory (1.2 GB over PCIe at N=1) plus the 64x4 body parameters:
@@ -383,15 +399,19 @@ def main():
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
     stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
+    stats_dev = torch.zeros(8, dtype=torch.int64, device=dev)
+    call_opts = {"o": _lib.traj_opts(dense=False, stats=stats_dev)}
+
     def pass_a():
         _lib.check(L.cov_traj_minmax(pts_sorted.data_ptr(), n_local, P.data_ptr(), Q.data_ptr(), W, K.data_ptr(),
-                                     ctypes.byref(cam), boxes.data_ptr(), minmax.data_ptr(), ws.data_ptr(), wsb, stream),
-                   "cov_traj_minmax")
+                                     ctypes.byref(cam), boxes.data_ptr(), minmax.data_ptr(), ctypes.byref(call_opts["o"]),
+                                     ws.data_ptr(), wsb, stream), "cov_traj_minmax")
 
     def pass_b():
         _lib.check(L.cov_traj_fused(pts_sorted.data_ptr(), n_local, P.data_ptr(), Q.data_ptr(), W, K.data_ptr(),
                                     ctypes.byref(cam), boxes.data_ptr(), minmax.data_ptr(), None, perm.data_ptr(),
-                                    rewards.data_ptr(), acc.data_ptr(), ws.data_ptr(), wsb, stream), "cov_traj_fused")
+                                    rewards.data_ptr(), acc.data_ptr(), ctypes.byref(call_opts["o"]), ws.data_ptr(), wsb,
+                                    stream), "cov_traj_fused")
 
     def global_minmax():
         pass_a()
@@ -400,20 +420,24 @@ def main():
     global_minmax()
     pass_b()
     reps = max(3, min(args.steps, 10))
-    stats = (ctypes.c_ulonglong * 8)()
-    L.cov_stats(1, None)
+    stats_dev.zero_()
+    pass_a()
+    pass_b()
+    torch.cuda.synchronize()
+    st = [int(x) for x in stats_dev.tolist()]        # work counters of exactly one pass A + one pass B
+    call_opts["o"] = _lib.traj_opts(dense=False)     # timed without the counters' atomics
     ms_a = timed(pass_a, reps) / reps
     global_minmax()
     ms_b = timed(pass_b, reps) / reps
-    L.cov_stats(1, stats)
-    st = [int(x) for x in stats]
-    L.cov_set_pruning(0)
+    call_opts["o"] = _lib.traj_opts(dense=True)
     global_minmax()
     pass_b()
     ms_a_dense = timed(pass_a, reps) / reps
     global_minmax()
     ms_b_dense = timed(pass_b, reps) / reps
-    L.cov_set_pruning(1)
+    call_opts["o"] = _lib.traj_opts(dense=False)
+    global_minmax()
+    pass_b()
     gated = float((rewards != 0.5).float().mean().item())  # fraction of points with at least one gated pose
 
     # FP32 / MUFU probes (measured peak for the dense kernels' roofline denominator)
@@ -460,26 +484,41 @@ def main():
     # The product path's dominant call is pass B on the ordered cloud.  With the tile pruning the arithmetic left is
     # ~0.3 % of the pairs; the floor of the call is then streaming the cloud once: 12 B/point read + 4 B/point of rewards
     # written = 16 B/point, which is what `achieved` counts (algorithmic bytes / call time).  The call
-    # actually moves less (`traffic`: tiles no pose can reach are never read) and spends its time on irregular per-tile
-    # work, so `frac` says how far it still is from that floor.  The dense kernels (pruning off: every pair gets the
-    # 64-flop forward) are FP32-issue bound and are reported against the FMA probe under `dense`.
+    # actually moves less (`traffic`: tiles no pose can reach are never read) and spends its time on irregular per-item
+    # arithmetic, so `executed` reports the flops it really performs against the FP32 peak as well.  The dense kernels
+    # (pruning off: every pair gets the 64-flop forward) are FP32-issue bound and are reported under `dense`.
+    traffic, traffic_src = None, "no ncu summary found under profiles/"
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_pass_b_traffic.json")))
+        traffic = float(tr["dram_bytes_per_call_at_1e8_points"]) * n_local / 1e8
+        traffic_src = tr["source"] + "; scaled linearly to this shard's %d points" % n_local
+    except Exception:
+        pass
+    item_pts = 128                                   # one (warp, pose) pair = 128 point x pose evaluations
+    flops_b = (st[1] * FLOP_FWD + st[4] * (FLOP_FWD + FLOP_BWD)) * item_pts
+    flops_a = st[3] * FLOP_FWD * 256
     roofline = {
-        "kernel": "cov_traj_fused call = pass B on the Morton-ordered cloud, pruning on (pose table, cov_fill_kernel, "
-                  "cov_cull_kernel, cov_worklist_kernel, cov_traj_fused_tiles_kernel<4,0>, cov_traj_reduce_kernel); the "
-                  "tiles kernel is ~80 % of it",
+        "kernel": "cov_traj_fused call = pass B on the Morton-ordered cloud, pruning on: cov_traj_table_kernel, "
+                  "cov_cull_kernel (+ work list + rewards pre-fill), cov_traj_fused_tiles_kernel (persistent warps; ~85 % of "
+                  "the call)",
         "bound": "hbm", "achieved": gbs_b, "peak": hbm_peak, "unit": "GB/s", "frac": gbs_b / hbm_peak,
         "peak_source": hbm_src, "bytes_per_point": BYTES_PASS_B, "ms_per_launch": ms_b,
-        "traffic": 0.91e9 * n_local / 1e8,
-        "traffic_source": "ncu dram__bytes_read+write at 1e8 points (profiles/): tiles kernel 0.33e9 + 0.18e9 (it reads only "
-                          "the 27 % of tiles the cull lists), fill 0.34e9, cull 0.03e9, reduce 0.003e9; scaled by shard size",
-        "pass_a": {"kernel": "cov_traj_minmax call, pruning on (seed, pose table, cull, work list, "
-                             "cov_traj_minmax_tiles_kernel<8,2>)", "bound": "hbm",
+        "traffic": traffic, "traffic_source": traffic_src,
+        "executed": {
+            "note": "arithmetic the pruned call really performs, from the kernels' own work counters (one counted call): "
+                    "(warp, pose) pairs evaluated x 128 points x 64 flop + pairs differentiated x 128 x (64 + 86) flop, over the "
+                    "CALL time, against the nominal FP32 peak",
+            "flop_per_call": flops_b, "tflops": flops_b / (ms_b * 1e-3) / 1e12,
+            "frac_of_fp32_nominal": flops_b / (ms_b * 1e-3) / 1e12 / FP32_NOMINAL_TFLOPS,
+            "pairs_evaluated": st[1] * item_pts, "pairs_differentiated": st[4] * item_pts,
+            "pass_a_tflops": flops_a / (ms_a * 1e-3) / 1e12},
+        "pass_a": {"kernel": "cov_traj_minmax call, pruning on: memset, cov_traj_prepare_kernel (pose table + seed), "
+                             "cov_cull_kernel (+ work list), cov_traj_minmax_tiles_kernel<8,2>", "bound": "hbm",
                    "bytes_per_point": BYTES_PASS_A, "ms_per_launch": ms_a, "achieved": gbs_a, "frac": gbs_a / hbm_peak},
         "work_executed": {
-            "note": "(warp, pose) pairs, as fractions of all pairs: listed by the cull / ran the per-point pre-filter / "
-                    "fully evaluated",
-            "pass_b": {"tile_listed": frac(st[6], st[0]), "prefiltered": frac(st[4], st[0]), "full": frac(st[1], st[0])},
-            "pass_a": {"tile_listed": frac(st[7], st[2]), "prefiltered": frac(st[5], st[2]), "full": frac(st[3], st[2])}},
+            "note": "(warp, pose) pairs, as fractions of all pairs: listed by the cull / evaluated / (pass B) differentiated",
+            "pass_b": {"tile_listed": frac(st[6], st[0]), "evaluated": frac(st[1], st[0]), "differentiated": frac(st[4], st[0])},
+            "pass_a": {"tile_listed": frac(st[7], st[2]), "prefiltered": frac(st[5], st[2]), "evaluated": frac(st[3], st[2])}},
         "dense": {
             "note": "pruning off: every (point, pose) pair fully evaluated; FP32-issue bound; 64 flop per forward evaluation",
             "pass_b": {"kernel": "cov_traj_fused_kernel<4,0,2>", "bound": "fp32", "ms_per_launch": ms_b_dense,
@@ -495,10 +534,14 @@ def main():
     }
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu_baseline, _ = cpu_reference_rate(body0, rig, steps=3, warmup=1, budget_s=20.0)
+        cpu_baseline, _ = cpu_reference_rate(body0, rig, steps=3, warmup=1)
     line = {"metric": "coverage fwd+bwd point*pose evals/s", "value": value, "unit": "point*pose evals/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "value_is": "DENSE-EQUIVALENT rate: every one of the N x W (point, pose) pairs gets its exact result per step; the "
+                        "exact pruning arithmetically evaluates only `pairs_evaluated_frac` of them (see `dense` for the rate "
+                        "with every pair evaluated)",
+            "pairs_evaluated_frac": frac(st[1], st[0]),
             "config": dict(config_dict(n_total, world),
                            pruning="exact tile-level distance-bound pruning on a Morton-ordered cloud (default); see `dense`",
                            launch=graph_note,
@@ -508,7 +551,8 @@ def main():
             "eager": {"value": n_total * W * args.steps / (ms_eager * 1e-3), "unit": "point*pose evals/s",
                       "ms_per_step": ms_eager / args.steps, "note": "same step launched kernel by kernel from Python"},
             "dense": {"value": n_total * W / (ms_dense * 1e-3), "unit": "point*pose evals/s", "ms_per_step": ms_dense,
-                      "note": "same step with cov_set_pruning(0): every pair fully evaluated"},
+                      "note": "same step with cov_traj_opts.dense: every pair fully evaluated"},
+            "parity_check": parity,
             "e2e": {"value": e2e_value, "unit": "point*pose evals/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "note": "a NEW cloud from pinned host memory every step (copy + spatial ordering + objective + gradient + "
@@ -518,9 +562,8 @@ def main():
                                        "h2d_bytes_per_step": host_body.numel() * 4 * world, "d2h_bytes_per_step": d2h,
                                        "note": "the reference's usage: one cloud per model; per step only the body parameters "
                                                "go in and loss + gradients come back, eager launches, synchronous"}},
-            # own kernels per step: rig poses; pass A: init, seed, pose table, cull, work list, tiles; pass B: pose table,
-            # fill, cull, work list, tiles, dense stand-by, reduce; epilogue; rig backward
-            "gpu_launches": 16 * args.steps,
+            # own kernels per step: rig poses; pass A: prepare, cull, tiles; pass B: table, cull, tiles; epilogue; rig backward
+            "gpu_launches": 9 * args.steps,
             "roofline": roofline, "cpu_baseline": cpu_baseline}
     print(json.dumps(line))
     finish()

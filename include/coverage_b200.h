@@ -102,8 +102,9 @@ typedef struct cov_traj_opts {
     int dense;                     /* != 0: evaluate every (point, pose) pair (what an unordered cloud should ask for) */
     int rewards_prefilled;         /* cov_traj_fused: != 0: rewards_dev already holds 1/2 everywhere (skip the pre-fill) */
     unsigned long long* stats_dev; /* NULL, or 8 device counters the evaluation kernels ADD to, in (warp, pose) pairs:
-                                      [0] pass B all pairs, [1] fully evaluated, [2],[3] same for pass A, [4]/[5] pass
-                                      B/A pairs that ran the per-point pre-filter, [6]/[7] pass B/A pairs the cull listed
+                                      [0] pass B all pairs, [1] evaluated (forward), [2],[3] same for pass A, [4] pass B
+                                      pairs differentiated (evaluated again + gradient), [5] pass A pairs that ran the
+                                      per-point pre-filter, [6]/[7] pass B/A pairs the cull listed
                                       (benchmark reporting; NULL in production) */
 } cov_traj_opts;
 

@@ -157,10 +157,9 @@ print(json.dumps({"config": "c5: 1024 trajectories x 32 waypoints, 50M points, f
                   "mean_reward_range": [float(res.min()), float(res.max())]}), flush=True)
 # dense reference on a sample of 32 trajectories (the full dense sweep takes ~8 s)
 from trajectory_optimization_b200 import _lib  # noqa: E402
-_lib.lib().cov_set_pruning(0)
-ms_d = events(lambda: ops.sweep_rewards(spts, P[:32], Qs[:32], K, iw, ih, boxes=sboxes, presorted=True), 1)
-res_d = ops.sweep_rewards(spts, P[:32], Qs[:32], K, iw, ih, boxes=sboxes, presorted=True)
-_lib.lib().cov_set_pruning(1)
+with ops.evaluation(dense=True):
+    ms_d = events(lambda: ops.sweep_rewards(spts, P[:32], Qs[:32], K, iw, ih, boxes=sboxes, presorted=True), 1)
+    res_d = ops.sweep_rewards(spts, P[:32], Qs[:32], K, iw, ih, boxes=sboxes, presorted=True)
 print(json.dumps({"config": "c5 dense sample: 32 of the 1024 trajectories, pruning off", "ms": ms_d,
                   "pairs_per_s": 5e7 * 32 * 32 / (ms_d * 1e-3), "extrapolated_full_c5_s": ms_d * 1e-3 * 32,
                   "max_rel_diff_vs_pruned": float(((res[:32] - res_d).abs() / res_d.abs()).max())}), flush=True)

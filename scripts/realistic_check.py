@@ -50,14 +50,12 @@ def timed(fn, reps=5):
     return e0.elapsed_time(e1) / reps, out
 
 
-L.cov_set_pruning(1)
-stats = (__import__("ctypes").c_ulonglong * 8)()
-L.cov_stats(1, None)
-ms_p, (r1, m1, gp1, gq1) = timed(run)
-L.cov_stats(1, stats)
-L.cov_set_pruning(0)
-ms_d, (r0, m0, gp0, gq0) = timed(run, 2)
-L.cov_set_pruning(1)
+stats_dev = torch.zeros(8, dtype=torch.int64, device="cuda")
+with ops.evaluation(stats=stats_dev):
+    ms_p, (r1, m1, gp1, gq1) = timed(run)
+stats = stats_dev.tolist()
+with ops.evaluation(dense=True):
+    ms_d, (r0, m0, gp0, gq0) = timed(run, 2)
 rel = lambda a, b: float((a - b).abs().max() / b.abs().max())  # noqa: E731
 print(f"{n} points x {t.shape[0]} poses (sample cloud x{reps}, jittered, shuffled): pruned step {ms_p:.3f} ms, dense step {ms_d:.3f} ms "
       f"({ms_d / ms_p:.1f}x); rewards equal {torch.equal(r1, r0)}, mean equal {torch.equal(m1, m0)}, grad rel diff "

@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_prints_the_contract_line():
-    env = dict(os.environ, COV_BENCH_REF_BUDGET_S="3")
+    env = dict(os.environ, COV_BENCH_REF_POINTS="2000")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
                          capture_output=True, text=True, env=env, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
@@ -19,6 +19,7 @@ def test_reference_arm_prints_the_contract_line():
         assert key in line, key
     assert line["impl"] == "reference" and line["higher_is_better"] is True and line["vs_baseline"] is None
     assert line["unit"] == "point*pose evals/s" and "workload" in line["config"] and line["value"] > 0
+    assert line["config"]["same_config"] is False and line["config"]["n_points_timed"] == 2000
     cb = line["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "sample" in cb
     e2e = line["e2e"]
@@ -26,7 +27,7 @@ def test_reference_arm_prints_the_contract_line():
 
 
 def test_reference_arm_other_ranks_exit_quietly():
-    env = dict(os.environ, RANK="1", WORLD_SIZE="2", COV_BENCH_REF_BUDGET_S="3")
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", COV_BENCH_REF_POINTS="2000")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                          capture_output=True, text=True, env=env, timeout=300, cwd=ROOT)
     assert out.returncode == 0 and out.stdout.strip() == ""

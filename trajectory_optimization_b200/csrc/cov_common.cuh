@@ -128,6 +128,105 @@ __device__ __forceinline__ float cov_vis(float x, float y, float z, const float4
     return __fmul_rn(E, s);
 }
 
+// ---- packed fp32 pairs (sm_100: fma/mul/add/sub.rn.f32x2 -> FFMA2 / FMUL2 / FADD2) --------------------------------
+// One instruction does the IEEE round-to-nearest operation on both halves of a 64-bit register pair, at half the issue
+// rate of the scalar instruction: the same flop/s, HALF THE ISSUE SLOTS.  The evaluation is issue-bound (26 FP32-pipe
+// instructions next to 3 MUFU and the loop skeleton), so packing two evaluations into one instruction stream frees the
+// issue slots the FP32 pipe was waiting for.  Per half the results are bit-identical to the scalar __f*_rn intrinsics.
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t f2_pack(float lo, float hi) {
+    f2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(f2_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f2_t f2_fma(f2_t a, f2_t b, f2_t c) {
+    f2_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f2_t f2_mul(f2_t a, f2_t b) {
+    f2_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f2_t f2_add(f2_t a, f2_t b) {
+    f2_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f2_t f2_sub(f2_t a, f2_t b) {
+    f2_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f2_t f2_lo(const float4& v) { return f2_pack(v.x, v.y); }
+__device__ __forceinline__ f2_t f2_hi(const float4& v) { return f2_pack(v.z, v.w); }
+
+// Per-launch constants as broadcast pairs (built once per kernel).
+struct CovConst2 {
+    f2_t kd, zk, zc, c0, one;
+};
+__device__ __forceinline__ CovConst2 cov_make_const2(const CovConst& C) {
+    CovConst2 c;
+    c.kd = f2_pack(C.kd, C.kd);
+    c.zk = f2_pack(C.zk, C.zk);
+    c.zc = f2_pack(C.zc, C.zc);
+    c.c0 = f2_pack(C.c0, C.c0);
+    c.one = f2_pack(1.f, 1.f);
+    return c;
+}
+
+// Rows v0..v3 of TWO poses (A, B) interleaved component-wise, the layout the dense kernels keep in shared memory so
+// that one LDS.128 delivers two packed constants:  q[2i] = (v_i.x A, v_i.x B, v_i.y A, v_i.y B),
+// q[2i+1] = (v_i.z A, v_i.z B, v_i.w A, v_i.w B), i = 0..3.  A pose PAIR occupies COV_PAIR_F4 float4:
+// q[0..7], then v4 A, v4 B, v5 A, v5 B.
+#define COV_PAIR_F4 12
+__device__ __forceinline__ void cov_pair_store(float4* __restrict__ pair, int slot, const float4* __restrict__ row) {
+    float* f = reinterpret_cast<float*>(pair);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        f[(2 * i) * 4 + slot] = row[i].x;
+        f[(2 * i) * 4 + 2 + slot] = row[i].y;
+        f[(2 * i + 1) * 4 + slot] = row[i].z;
+        f[(2 * i + 1) * 4 + 2 + slot] = row[i].w;
+    }
+    pair[8 + slot] = row[4];
+    pair[10 + slot] = row[5];
+}
+// scalar row i (0..3) of the pose in `slot` out of the pair layout (rare paths: gradient walk, tie sets)
+__device__ __forceinline__ float4 cov_pair_row(const float4* __restrict__ pair, int slot, int i) {
+    const float* f = reinterpret_cast<const float*>(pair);
+    return make_float4(f[(2 * i) * 4 + slot], f[(2 * i) * 4 + 2 + slot], f[(2 * i + 1) * 4 + slot], f[(2 * i + 1) * 4 + 2 + slot]);
+}
+
+// m of ONE point against a pose PAIR: (m_A, m_B), each half bit-identical to cov_vis with that pose's rows.
+// X, Y, Z are the point's coordinates as broadcast pairs (built once per tile); q[0..7] as laid out above.
+__device__ __forceinline__ f2_t cov_vis2p(f2_t X, f2_t Y, f2_t Z, const float4& q0, const float4& q1, const float4& q2_,
+                                          const float4& q3, const float4& q4, const float4& q5, const float4& q6,
+                                          const float4& q7, const CovConst2& C) {
+    const f2_t ex = f2_sub(X, f2_lo(q6)), ey = f2_sub(Y, f2_hi(q6)), ez = f2_sub(Z, f2_lo(q7));
+    const f2_t q2 = f2_fma(ez, ez, f2_fma(ey, ey, f2_mul(ex, ex)));
+    const f2_t g0 = f2_fma(f2_lo(q1), Z, f2_fma(f2_hi(q0), Y, f2_fma(f2_lo(q0), X, f2_hi(q1))));
+    const f2_t g1 = f2_fma(f2_lo(q3), Z, f2_fma(f2_hi(q2_), Y, f2_fma(f2_lo(q2_), X, f2_hi(q3))));
+    const f2_t den = f2_fma(f2_lo(q5), Z, f2_fma(f2_hi(q4), Y, f2_fma(f2_lo(q4), X, f2_hi(q5))));
+    float ta, tb;
+    f2_unpack(f2_fma(den, C.zk, C.zc), ta, tb);
+    const f2_t e2z = f2_pack(cov_ex2(fminf(ta, 80.f)), cov_ex2(fminf(tb, 80.f)));  // exp(-h2), capped
+    const f2_t opz = f2_add(C.one, e2z);
+    float pa, pb;
+    f2_unpack(f2_mul(opz, den), pa, pb);
+    const f2_t r = f2_pack(cov_rcp(pa), cov_rcp(pb));
+    const f2_t zi = f2_mul(r, opz);   // 1/(h2+eps)
+    const f2_t s = f2_mul(r, den);    // sigmoid(h2)
+    const f2_t du = f2_fma(g0, zi, C.c0), dv = f2_fma(g1, zi, C.c0);
+    float Qa, Qb;
+    f2_unpack(f2_fma(q2, C.kd, f2_fma(dv, dv, f2_mul(du, du))), Qa, Qb);
+    return f2_mul(f2_pack(cov_ex2(-Qa), cov_ex2(-Qb)), s);
+}
+
 // dm/dx (world frame) from the intermediates; g = 0 when m is not a positive finite number.
 __device__ __forceinline__ void cov_vis_grad(float m, const CovEval& ev, const float4& v0, const float4& v1,
                                              const float4& v2, const CovConst& C, float& gx, float& gy, float& gz) {

@@ -64,7 +64,9 @@ __host__ __device__ inline int mask_stride_words(int W) { return (((W + 31) >> 5
 // one staged tile of the pruned kernels: points | boxes | pose mask (all 16-byte multiples, buffer 128-byte multiple)
 __host__ __device__ constexpr int stage_floats(int ppt) { return tile_points(ppt) * 3 + tile_boxes(ppt) * 8 + kMaskWords; }
 
-size_t minmax_smem_bytes(int W) { return (size_t)W * (COV_ROW_F4 * sizeof(float4) + 2 * sizeof(unsigned)); }
+size_t minmax_smem_bytes(int W) {  // pose pairs (COV_PAIR_F4 float4 each) + block minima and maxima
+    return (size_t)((W + 1) / 2) * (COV_PAIR_F4 * sizeof(float4) + 4 * sizeof(unsigned));
+}
 __host__ __device__ inline int minmax_tiles_stage_offset_floats(int W) {
     return (int)((((size_t)W * (COV_ROW_F4 * 16 + 12) + 127) & ~(size_t)127) / 4);
 }
@@ -72,8 +74,8 @@ size_t minmax_tiles_smem_bytes(int W, int ppt) {
     return (size_t)minmax_tiles_stage_offset_floats(W) * 4 + 2 * (size_t)stage_floats(ppt) * 4;
 }
 // fused pass: pose table, then (128-byte aligned) the tile stage(s), G_j, gate bits, accumulators, gated-pose list
-__host__ __device__ inline int fused_stage_offset_floats(int W) {
-    return (int)((((size_t)W * COV_ROW_F4 * 16 + 127) & ~(size_t)127) / 4);
+__host__ __device__ inline int fused_stage_offset_floats(int W) {  // W rounded up to whole pose pairs (dense kernel)
+    return (int)((((size_t)((W + 1) & ~1) * COV_ROW_F4 * 16 + 127) & ~(size_t)127) / 4);
 }
 size_t fused_smem_bytes(int W, int ppt, bool prune) {
     if (prune)  // 2 tile stages (the pose table stays in global memory, the accumulators are the caller's)
@@ -96,6 +98,28 @@ __device__ __noinline__ void tie_accumulate(float x, float y, float z, int w, Co
     float gx, gy, gz;
     cov_vis_grad(m, ev, row[0], row[1], row[2], C, gx, gy, gz);
     const float yx = x - row[5].x, yy = y - row[5].y, yz = z - row[5].z;
+    atomicAdd(dst + 0, (double)gx);
+    atomicAdd(dst + 1, (double)gy);
+    atomicAdd(dst + 2, (double)gz);
+    atomicAdd(dst + 3, (double)(gy * yz - gz * yy));
+    atomicAdd(dst + 4, (double)(gz * yx - gx * yz));
+    atomicAdd(dst + 5, (double)(gx * yy - gy * yx));
+    atomicAdd(dst + 6, 1.0);
+}
+
+// Same for the dense pass B, whose table is laid out in pose PAIRS (COV_PAIR_F4, cov_common.cuh).
+__device__ __noinline__ void tie_accumulate_pair(float x, float y, float z, int w, CovConst C, double* acc, int slot) {
+    extern __shared__ float4 smem4[];
+    const float4* pair = smem4 + (size_t)(w >> 1) * COV_PAIR_F4;
+    const int h = w & 1;
+    const float4 v0 = cov_pair_row(pair, h, 0), v1 = cov_pair_row(pair, h, 1), v2 = cov_pair_row(pair, h, 2),
+                 v3 = cov_pair_row(pair, h, 3), v5 = pair[10 + h];
+    double* dst = acc + slot;
+    CovEval ev;
+    const float m = cov_vis<true>(x, y, z, v0, v1, v2, v3, C, &ev);
+    float gx, gy, gz;
+    cov_vis_grad(m, ev, v0, v1, v2, C, gx, gy, gz);
+    const float yx = x - v5.x, yy = y - v5.y, yz = z - v5.z;
     atomicAdd(dst + 0, (double)gx);
     atomicAdd(dst + 1, (double)gy);
     atomicAdd(dst + 2, (double)gz);
@@ -211,75 +235,76 @@ __device__ __forceinline__ void stage_issue(float* stage, unsigned long long* ba
 }
 
 // =============================================== pass A, dense ===============================================
-// Also the SEED launch of the pruned pass (point_stride > 1: every point_stride-th point, n = number of samples).
-template <int PPT, int MINB, int U>
+// Every (point, pose) pair.  The evaluation runs on packed fp32 pairs (FFMA2): a thread evaluates each of its points
+// against TWO poses at a time, the pose rows interleaved pairwise in shared memory (COV_PAIR_F4) so that one LDS.128
+// brings two packed constants; the points are kept as broadcast pairs in registers.
+template <int PPT, int MINB>
 __global__ void __launch_bounds__(COV_THREADS, MINB)
-cov_traj_minmax_kernel(const float* __restrict__ xyz, int64_t n, int64_t point_stride, const float* __restrict__ poses,
+cov_traj_minmax_kernel(const float* __restrict__ xyz, int64_t n, const float* __restrict__ poses,
                        const float* __restrict__ quats, int W, const float* __restrict__ K9, CovConst C,
                        unsigned* __restrict__ gmin, unsigned* __restrict__ gmax) {
     extern __shared__ float4 smem4[];
     float4* ptab = smem4;
-    unsigned* smin = reinterpret_cast<unsigned*>(ptab + (size_t)W * COV_ROW_F4);
-    unsigned* smax = smin + W;
+    const int NP = (W + 1) >> 1;  // pose pairs; an odd W repeats its last pose in the spare slot
+    unsigned* smin = reinterpret_cast<unsigned*>(ptab + (size_t)NP * COV_PAIR_F4);
+    unsigned* smax = smin + 2 * NP;
     const int tid = threadIdx.x, lane = tid & 31;
-    for (int w = tid; w < W; w += COV_THREADS) {
-        cov_pose_row(poses + 3 * w, quats + 4 * w, K9, C, ptab + (size_t)w * COV_ROW_F4);
+    for (int w = tid; w < 2 * NP; w += COV_THREADS) {
+        const int ws = w < W ? w : W - 1;
+        float4 row[COV_ROW_F4];
+        cov_pose_row(poses + 3 * ws, quats + 4 * ws, K9, C, row);
+        cov_pair_store(ptab + (size_t)(w >> 1) * COV_PAIR_F4, w & 1, row);
         smin[w] = 0x7f800000u;
         smax[w] = 0u;
     }
     __syncthreads();
+    const CovConst2 C2 = cov_make_const2(C);
     constexpr int T = tile_points(PPT);
     const int64_t ntiles = (n + T - 1) / T;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        float px[PPT], py[PPT], pz[PPT];
+        f2_t X[PPT], Y[PPT], Z[PPT];
 #pragma unroll
         for (int s = 0; s < PPT; ++s) {
             int64_t j = tile * T + s * COV_THREADS + tid;
-            j = (j < n ? j : n - 1) * point_stride;  // a duplicate cannot change a min or a max
-            px[s] = __ldg(xyz + j * 3);
-            py[s] = __ldg(xyz + j * 3 + 1);
-            pz[s] = __ldg(xyz + j * 3 + 2);
+            j = j < n ? j : n - 1;  // a duplicate cannot change a min or a max
+            const float x = __ldg(xyz + j * 3), y = __ldg(xyz + j * 3 + 1), z = __ldg(xyz + j * 3 + 2);
+            X[s] = f2_pack(x, x);
+            Y[s] = f2_pack(y, y);
+            Z[s] = f2_pack(z, z);
         }
-        for (int w0 = 0; w0 < W; w0 += 32) {
-            // lane i keeps the warp-wide min/max of pose w0+i in registers; one shared atomic per 32 poses
+        for (int p0 = 0; p0 < NP; p0 += 16) {
+            // lane 2i (2i+1) keeps the warp-wide min/max of pose A (B) of pair p0+i; one shared atomic per 32 poses
             unsigned keep_mn = 0x7f800000u, keep_mx = 0u;
-            const int wn = (W - w0 < 32) ? (W - w0) : 32;
-            for (int i = 0; i < wn; i += U) {
-                float mn[U], mx[U];
-                int wi[U];
+            const int pn = (NP - p0 < 16) ? (NP - p0) : 16;
+            for (int i = 0; i < pn; ++i) {
+                const float4* q = ptab + (size_t)(p0 + i) * COV_PAIR_F4;
+                const float4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3], q4 = q[4], q5 = q[5], q6 = q[6], q7 = q[7];
+                float mnA, mxA, mnB, mxB;
+                f2_unpack(cov_vis2p(X[0], Y[0], Z[0], q0, q1, q2, q3, q4, q5, q6, q7, C2), mnA, mnB);
+                mxA = mnA;
+                mxB = mnB;
 #pragma unroll
-                for (int u = 0; u < U; ++u) {  // U poses in flight: U*PPT independent evaluation chains
-                    wi[u] = (i + u < wn) ? (i + u) : (wn - 1);  // odd remainder: re-evaluate the last pose (harmless)
-                    const float4* row = ptab + (size_t)(w0 + wi[u]) * COV_ROW_F4;
-                    const float4 v0 = row[0], v1 = row[1], v2 = row[2], v3 = row[3];
-                    float m[PPT];
-#pragma unroll
-                    for (int s = 0; s < PPT; ++s) m[s] = cov_vis<false>(px[s], py[s], pz[s], v0, v1, v2, v3, C, nullptr);
-                    mn[u] = m[0];
-                    mx[u] = m[0];
-#pragma unroll
-                    for (int s = 1; s + 1 < PPT; s += 2) {
-                        mn[u] = fminf(mn[u], fminf(m[s], m[s + 1]));
-                        mx[u] = fmaxf(mx[u], fmaxf(m[s], m[s + 1]));
-                    }
-                    if ((PPT & 1) == 0) {
-                        mn[u] = fminf(mn[u], m[PPT - 1]);
-                        mx[u] = fmaxf(mx[u], m[PPT - 1]);
-                    }
+                for (int s = 1; s < PPT; ++s) {
+                    float a, b;
+                    f2_unpack(cov_vis2p(X[s], Y[s], Z[s], q0, q1, q2, q3, q4, q5, q6, q7, C2), a, b);
+                    mnA = fminf(mnA, a); mxA = fmaxf(mxA, a);
+                    mnB = fminf(mnB, b); mxB = fmaxf(mxB, b);
                 }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const unsigned umn = __reduce_min_sync(kFull, __float_as_uint(mn[u]));
-                    const unsigned umx = __reduce_max_sync(kFull, __float_as_uint(mx[u]));
-                    if (lane == wi[u]) {
-                        keep_mn = umn;
-                        keep_mx = umx;
-                    }
+                const unsigned umnA = __reduce_min_sync(kFull, __float_as_uint(mnA));
+                const unsigned umxA = __reduce_max_sync(kFull, __float_as_uint(mxA));
+                const unsigned umnB = __reduce_min_sync(kFull, __float_as_uint(mnB));
+                const unsigned umxB = __reduce_max_sync(kFull, __float_as_uint(mxB));
+                if (lane == 2 * i) {
+                    keep_mn = umnA;
+                    keep_mx = umxA;
+                } else if (lane == 2 * i + 1) {
+                    keep_mn = umnB;
+                    keep_mx = umxB;
                 }
             }
-            if (lane < wn) {
-                atomicMin(smin + w0 + lane, keep_mn);
-                atomicMax(smax + w0 + lane, keep_mx);
+            if (lane < 2 * pn) {
+                atomicMin(smin + 2 * p0 + lane, keep_mn);
+                atomicMax(smax + 2 * p0 + lane, keep_mx);
             }
         }
     }
@@ -775,6 +800,91 @@ __device__ __forceinline__ bool fused_pose_iter(int w, unsigned ptab, unsigned* 
     return anyb != 0u;
 }
 
+__device__ __forceinline__ float4 lds_f4(unsigned saddr) {
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
+
+// Phase 1 of the dense pass B for NP consecutive pose PAIRS (2 NP poses): every point of the thread against the poses
+// on packed fp32 pairs (cov_vis2p; PPT * NP independent chains in flight), then per pose the conservative warp vote and
+// — only when some lane may pass — the exact gate, the ballots and the log-odds.  Ballot words go to the gate bit
+// matrix.  The spare slot of an odd W is skipped.  Returns whether this warp gated a pair (warp-uniform).
+template <int PPT, int NPAIR, bool AMIN>
+__device__ __forceinline__ bool dense_pair_iter(int pair0, int W, unsigned ptab_s, unsigned* __restrict__ bits, int warp,
+                                                const f2_t (&X)[PPT], const f2_t (&Y)[PPT], const f2_t (&Z)[PPT],
+                                                float (&L)[PPT], const CovConst& C, const CovConst2& C2,
+                                                double* __restrict__ acc, int lane) {
+    float m[NPAIR][2][PPT];
+    float thr[NPAIR][2];
+    unsigned anyb = 0u;
+#pragma unroll
+    for (int k = 0; k < NPAIR; ++k) {
+        const unsigned base = ptab_s + (unsigned)(pair0 + k) * (COV_PAIR_F4 * 16u);
+        const float4 q0 = lds_f4(base), q1 = lds_f4(base + 16u), q2 = lds_f4(base + 32u), q3 = lds_f4(base + 48u),
+                     q4 = lds_f4(base + 64u), q5 = lds_f4(base + 80u), q6 = lds_f4(base + 96u), q7 = lds_f4(base + 112u);
+#pragma unroll
+        for (int s = 0; s < PPT; ++s)
+            f2_unpack(cov_vis2p(X[s], Y[s], Z[s], q0, q1, q2, q3, q4, q5, q6, q7, C2), m[k][0][s], m[k][1][s]);
+        thr[k][0] = q7.z;  // conservative gate thresholds (v3.w of the two poses)
+        thr[k][1] = q7.w;
+    }
+#pragma unroll
+    for (int k = 0; k < NPAIR; ++k) {
+        const unsigned base = ptab_s + (unsigned)(pair0 + k) * (COV_PAIR_F4 * 16u);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int w = 2 * (pair0 + k) + h;
+            if (w >= W) break;  // the spare slot of an odd pose count
+            float mmax = m[k][h][0];
+#pragma unroll
+            for (int s = 1; s < PPT; ++s) mmax = fmaxf(mmax, m[k][h][s]);
+            unsigned bal[PPT];
+#pragma unroll
+            for (int s = 0; s < PPT; ++s) bal[s] = 0u;
+            if (__any_sync(kFull, mmax >= thr[k][h])) {  // warp-uniform; a few % of (warp, pose) iterations
+                const float4 v4 = lds_f4(base + (8u + h) * 16u);
+#pragma unroll
+                for (int s = 0; s < PPT; ++s) {
+                    const float d = __fsub_rn(m[k][h][s], v4.w);
+                    const bool act = d >= v4.x;  // exactly p >= 0.5
+                    bal[s] = __ballot_sync(kFull, act);
+                    anyb |= bal[s];
+                    if (act) {
+                        const float p = __fmul_rn(d, v4.z);
+                        const float qc = (p > C.hi) ? C.hi : p;  // upper clip; a NaN p (pose that sees nothing: 0/0) stays NaN, as torch.clip
+                        L[s] += COV_LN2_F * cov_lg2(qc * cov_rcp(1.f - qc));
+                        if (d == v4.y) {
+                            float x, y, z, t;
+                            f2_unpack(X[s], x, t); f2_unpack(Y[s], y, t); f2_unpack(Z[s], z, t);
+                            tie_accumulate_pair(x, y, z, w, C, acc, w * COV_ACC_STRIDE + 8);
+                        }
+                    }
+                }
+            }
+            if (lane == 0) {
+                unsigned* brow = bit_row_group<PPT>(bits, w, warp);
+                if (PPT == 4) *reinterpret_cast<uint4*>(brow) = make_uint4(bal[0], bal[1 % PPT], bal[2 % PPT], bal[3 % PPT]);
+                else if (PPT == 2) *reinterpret_cast<uint2*>(brow) = make_uint2(bal[0], bal[1 % PPT]);
+                else brow[0] = bal[0];
+            }
+            if (AMIN) {  // only compact clouds whose minimum did not underflow to 0 (block-uniform choice of the loop)
+                const float a = lds_f4(base + (8u + h) * 16u).w;
+                if (a > 0.f) {
+#pragma unroll
+                    for (int s = 0; s < PPT; ++s)
+                        if (m[k][h][s] == a) {
+                            float x, y, z, t;
+                            f2_unpack(X[s], x, t); f2_unpack(Y[s], y, t); f2_unpack(Z[s], z, t);
+                            tie_accumulate_pair(x, y, z, w, C, acc, w * COV_ACC_STRIDE + 15);
+                        }
+                }
+            }
+        }
+    }
+    return anyb != 0u;
+}
+
 // Forward of one listed pose for a warp of the pruned kernel: m for the warp's points, log-odds of the gated ones added to
 // L; returns whether the warp has a gated pair for the pose.  `row` = the pose's 6 float4 in the global table (L1 hits:
 // a tile touches a handful of rows).  The conservative threshold lives in v5.w (v3.w holds qthr); the exact gate test
@@ -836,8 +946,10 @@ __device__ __forceinline__ void fused_phase2(const float4* __restrict__ ptab, co
         const bool live = task < ntask;
         const int w = live ? (task >> seg_log2) : 0;
         const int seg = task & (nseg - 1);
-        const float4* row = ptab + (size_t)w * COV_ROW_F4;
-        const float4 v0 = row[0], v1 = row[1], v2 = row[2], v3 = row[3], v4 = row[4], v5 = row[5];
+        const float4* pair = ptab + (size_t)(w >> 1) * COV_PAIR_F4;
+        const int hslot = w & 1;
+        const float4 v0 = cov_pair_row(pair, hslot, 0), v1 = cov_pair_row(pair, hslot, 1), v2 = cov_pair_row(pair, hslot, 2),
+                     v3 = cov_pair_row(pair, hslot, 3), v4 = pair[8 + hslot], v5 = pair[10 + hslot];
         const unsigned* brow = bits + (size_t)w * RS;
         int k = seg * wps;
         const int kend = live ? k + wps : k;
@@ -925,14 +1037,17 @@ cov_traj_fused_kernel(const float* __restrict__ xyz, int64_t n, const float* __r
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) amin_pos = 0;
     __syncthreads();
-    for (int w = tid; w < W; w += COV_THREADS) {
-        float4* row = ptab + (size_t)w * COV_ROW_F4;
-        cov_pose_row(poses + 3 * w, quats + 4 * w, K9, C, row);
-        const float a = minmax[w];
-        const float b = __fsub_rn(minmax[W + w], a);
+    const int NP = (W + 1) >> 1;  // pose pairs; an odd W repeats its last pose in the spare slot (never used)
+    for (int w = tid; w < 2 * NP; w += COV_THREADS) {
+        const int ws = w < W ? w : W - 1;
+        float4 row[COV_ROW_F4];
+        cov_pose_row(poses + 3 * ws, quats + 4 * ws, K9, C, row);
+        const float a = minmax[ws];
+        const float b = __fsub_rn(minmax[W + ws], a);
         const float hb = 0.5f * b;
         row[3].w = (a + hb) * (1.f - 9.5367431640625e-07f);  // conservative gate threshold (exact test in the rare path)
         row[4] = make_float4(hb, b, __frcp_rn(b), a);
+        cov_pair_store(ptab + (size_t)(w >> 1) * COV_PAIR_F4, w & 1, row);
         if (a > 0.f) amin_pos = 1;  // benign race: every writer stores 1
     }
     for (int i = tid; i < W * 8; i += COV_THREADS) accs[i] = 0.f;
@@ -942,8 +1057,10 @@ cov_traj_fused_kernel(const float* __restrict__ xyz, int64_t n, const float* __r
     const int64_t ntiles = (n + T - 1) / T;
     const bool check_amin = amin_pos != 0;
     const unsigned ptab_s = smem_u32(ptab);
+    const CovConst2 C2 = cov_make_const2(C);
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        float px[PPT], py[PPT], pz[PPT], L[PPT];
+        f2_t X[PPT], Y[PPT], Z[PPT];   // the thread's points as broadcast pairs
+        float L[PPT];
         bool valid[PPT];
         const int lbase = warp * (32 * PPT) + lane;
 #pragma unroll
@@ -951,22 +1068,24 @@ cov_traj_fused_kernel(const float* __restrict__ xyz, int64_t n, const float* __r
             const int64_t j = tile * T + lbase + s * 32;
             valid[s] = j < n;
             // a point past the end sits 3e18 m away: m = 0 exactly, never gated, never a tie
-            px[s] = valid[s] ? __ldg(xyz + j * 3) : 3.0e18f;
-            py[s] = valid[s] ? __ldg(xyz + j * 3 + 1) : 3.0e18f;
-            pz[s] = valid[s] ? __ldg(xyz + j * 3 + 2) : 3.0e18f;
-            pt[(lbase + s * 32) * 3] = px[s];
-            pt[(lbase + s * 32) * 3 + 1] = py[s];
-            pt[(lbase + s * 32) * 3 + 2] = pz[s];
+            const float x = valid[s] ? __ldg(xyz + j * 3) : 3.0e18f;
+            const float y = valid[s] ? __ldg(xyz + j * 3 + 1) : 3.0e18f;
+            const float z = valid[s] ? __ldg(xyz + j * 3 + 2) : 3.0e18f;
+            pt[(lbase + s * 32) * 3] = x;
+            pt[(lbase + s * 32) * 3 + 1] = y;
+            pt[(lbase + s * 32) * 3 + 2] = z;
+            X[s] = f2_pack(x, x);
+            Y[s] = f2_pack(y, y);
+            Z[s] = f2_pack(z, z);
             L[s] = 0.f;
         }
-        {
-            int w = 0;
-            if (check_amin) {  // arg-min points carry gradient: every pair must be looked at
-                for (; w < W; ++w) fused_pose_iter<PPT, 1, true, false>(w, ptab_s, bits, warp, px, py, pz, L, C, acc, lane);
-            } else {
-                for (; w + U <= W; w += U) fused_pose_iter<PPT, U, false, false>(w, ptab_s, bits, warp, px, py, pz, L, C, acc, lane);
-                for (; w < W; ++w) fused_pose_iter<PPT, 1, false, false>(w, ptab_s, bits, warp, px, py, pz, L, C, acc, lane);
-            }
+        bool any_gate = false;  // warp-uniform
+        if (check_amin) {  // arg-min points carry gradient: every pair must be looked at
+            for (int pr = 0; pr < NP; ++pr) any_gate |= dense_pair_iter<PPT, 1, true>(pr, W, ptab_s, bits, warp, X, Y, Z, L, C, C2, acc, lane);
+        } else {
+            int pr = 0;
+            for (; pr + U <= NP; pr += U) any_gate |= dense_pair_iter<PPT, U, false>(pr, W, ptab_s, bits, warp, X, Y, Z, L, C, C2, acc, lane);
+            for (; pr < NP; ++pr) any_gate |= dense_pair_iter<PPT, 1, false>(pr, W, ptab_s, bits, warp, X, Y, Z, L, C, C2, acc, lane);
         }
 #pragma unroll
         for (int s = 0; s < PPT; ++s) {
@@ -981,9 +1100,11 @@ cov_traj_fused_kernel(const float* __restrict__ xyz, int64_t n, const float* __r
             }
             Gs[lbase + s * 32] = g;
         }
-        __syncthreads();
-        fused_phase2<PPT>(ptab, bits, pt, Gs, accs, W, seg_log2, C, tid);
-        __syncthreads();
+        // one barrier per tile; the gradient walk (and its closing barrier) only when somebody gated a pair
+        if (__syncthreads_or(any_gate ? 1 : 0)) {
+            fused_phase2<PPT>(ptab, bits, pt, Gs, accs, W, seg_log2, C, tid);
+            __syncthreads();
+        }
     }
     fused_block_flush(accs, W, acc, sum_r, red, tid);
 }
@@ -1053,7 +1174,7 @@ cov_traj_fused_tiles_kernel(const float* __restrict__ xyz, int64_t n, const floa
     };
 
     double sum_r = 0.0;
-    unsigned n_box = 0, n_full = 0;
+    unsigned n_box = 0, n_full = 0, n_bwd = 0;
     unsigned uses0 = 0, uses1 = 0;
     int cur = 0;
     if (lane == 0) {
@@ -1154,6 +1275,7 @@ cov_traj_fused_tiles_kernel(const float* __restrict__ xyz, int64_t n, const floa
                 while (word) {
                     const int w = c * 32 + __ffs(word) - 1;
                     word &= word - 1;
+                    ++n_bwd;
                     const float4* row = table + (size_t)w * COV_ROW_F4;
                     const float4 v0 = __ldg(row), v1 = __ldg(row + 1), v2 = __ldg(row + 2), v3 = __ldg(row + 3),
                                  v4 = __ldg(row + 4), v5 = __ldg(row + 5);
@@ -1224,7 +1346,7 @@ cov_traj_fused_tiles_kernel(const float* __restrict__ xyz, int64_t n, const floa
     if (stats && lane == 0) {
         if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(stats + 0, (unsigned long long)ntiles * kWarps * W);
         atomicAdd(stats + 1, (unsigned long long)n_full);
-        atomicAdd(stats + 4, (unsigned long long)n_full);
+        atomicAdd(stats + 4, (unsigned long long)n_bwd);
         atomicAdd(stats + 6, (unsigned long long)n_box);
     }
 }
@@ -1605,15 +1727,15 @@ extern "C" int cov_traj_minmax(const float* xyz, int64_t n, const float* poses, 
         unsigned* gmax = gmin + W;
         const size_t smem = minmax_smem_bytes(W);
         cov_minmax_init_kernel<<<(W + 255) / 256, 256, 0, s>>>(gmin, gmax, W);
-#define LAUNCH_DENSE(P, B, U)                                                                                        \
-    {                                                                                                                \
-        const int grid = grid_for(cov_traj_minmax_kernel<P, B, U>, smem, ntiles);                                    \
-        cov_traj_minmax_kernel<P, B, U><<<grid, COV_THREADS, smem, s>>>(xyz, n, 1, poses, quats, W, K, C, gmin, gmax); \
+#define LAUNCH_DENSE(P, B)                                                                                       \
+    {                                                                                                            \
+        const int grid = grid_for(cov_traj_minmax_kernel<P, B>, smem, ntiles);                                   \
+        cov_traj_minmax_kernel<P, B><<<grid, COV_THREADS, smem, s>>>(xyz, n, poses, quats, W, K, C, gmin, gmax); \
     }
-        if (ppt == 8) LAUNCH_DENSE(8, 2, 2)
-        else if (ppt == 4) LAUNCH_DENSE(4, 2, 1)
-        else if (ppt == 2) LAUNCH_DENSE(2, 2, 1)
-        else LAUNCH_DENSE(1, 2, 1)
+        if (ppt == 8) LAUNCH_DENSE(8, 2)
+        else if (ppt == 4) LAUNCH_DENSE(4, 2)
+        else if (ppt == 2) LAUNCH_DENSE(2, 2)
+        else LAUNCH_DENSE(1, 2)
 #undef LAUNCH_DENSE
         return cov_check_launch("cov_traj_minmax");
     }
@@ -1673,8 +1795,8 @@ extern "C" int cov_traj_fused(const float* xyz, int64_t n, const float* poses, c
         while ((W << seg_log2) < 2 * COV_THREADS && (2 << seg_log2) <= bit_words(ppt_d) && seg_log2 < 5) ++seg_log2;
 #define LAUNCH_F(P, UP)                                                                                           \
     {                                                                                                             \
-        const int grid = grid_for(cov_traj_fused_kernel<P, UP, 2>, smem, ntiles);                                 \
-        cov_traj_fused_kernel<P, UP, 2><<<grid, COV_THREADS, smem, s>>>(xyz, n, poses, quats, W, K, C, minmax,    \
+        const int grid = grid_for(cov_traj_fused_kernel<P, UP, 1>, smem, ntiles);                                 \
+        cov_traj_fused_kernel<P, UP, 1><<<grid, COV_THREADS, smem, s>>>(xyz, n, poses, quats, W, K, C, minmax,    \
                                                                         upstream, reward_index, rewards, acc, seg_log2); \
     }
         if (upstream) {
