@@ -148,6 +148,172 @@ def cpu_reference_rate(body, rig, steps, warmup, n_points=CPU_SAMPLE_POINTS):
                        f"{dt / steps * 1e3:.0f} ms/step"), dt / steps
 
 
+N_POINTS_C5, N_TRAJ_C5, N_WPS_C5 = 50_000_000, 1024, 32
+
+
+def c5_trajectories(n_traj=N_TRAJ_C5, n_wps=N_WPS_C5):
+    """1024 candidate trajectories = the base S-curve + N(0, 1 m) lateral offsets and N(0, 0.2 rad) yaw jitter, seed 2
+    (SURVEY.md 8d); one camera per waypoint.  Returns poses (T, P, 3), quats (T, P, 4) as fp32 torch tensors."""
+    gen = np.random.default_rng(2)
+    base = body_waypoints(n_wps, 20.0).numpy()
+    poses = np.repeat(base[None, :, :3], n_traj, 0) + gen.normal(0, 1.0, (n_traj, 1, 3)) * np.array([1, 1, 0])
+    yaw = base[None, :, 3] + gen.normal(0, 0.2, (n_traj, n_wps))
+    quats = np.stack([np.cos(yaw / 2), 0 * yaw, 0 * yaw, np.sin(yaw / 2)], -1)
+    return torch.tensor(poses, dtype=torch.float32), torch.tensor(quats, dtype=torch.float32)
+
+
+def run_c5(args):
+    """BASELINE config 5: batched candidate-trajectory sweep, 1024 trajectories x 32 waypoints on a 50M-point cloud,
+    forward only (two passes: per-pose normalisers, then per-trajectory log-odds fusion), at 1/2/4/8 GPUs.
+    Sharding: the cloud fits one GPU (600 MB), so every rank holds the WHOLE cloud and evaluates its own
+    block of trajectories: no collective on the data path, one all-gather of 1024 doubles.  Strong scaling."""
+    from oracle import coverage_oracle as orc
+    n_total, T, Pn = args.points, N_TRAJ_C5, N_WPS_C5
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg = {"workload": "c5: candidate-trajectory sweep, %d trajectories x %d waypoints (one camera each), forward only, "
+                       "%gM-point synthetic box cloud; trajectories sharded over %d GPU(s), whole cloud on every GPU"
+                       % (T, Pn, n_total / 1e6, world),
+           "n_points": n_total, "n_trajectories": T, "poses_per_trajectory": Pn, "parallelism": f"trajectories/{world}",
+           "l2_policy": "inputs larger than L2 (600 MB of points streamed by every pass)"}
+    poses, quats = c5_trajectories()
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from oracle import torch_port
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        K = torch.from_numpy(orc.K_DEFAULT.copy())
+        g = torch.Generator().manual_seed(1000)
+        n_s, t_s = CPU_SAMPLE_POINTS, 8
+        pts = torch.rand(n_s, 3, generator=g) * (torch.tensor(BOX_HI) - torch.tensor(BOX_LO)) + torch.tensor(BOX_LO)
+
+        def cpu_step():
+            with torch.no_grad():
+                return [torch_port.traj_vis_loss(pts, poses[t], quats[t], K, orc.IMG_WIDTH, orc.IMG_HEIGHT)[0] for t in range(t_s)]
+
+        for _ in range(args.warmup):
+            cpu_step()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            cpu_step()
+        dt = (time.perf_counter() - t0) / args.steps
+        val = n_s * t_s * Pn / dt
+        base = dict(value=val, unit="point*pose evals/s", cores=threads, kind="port",
+                    sample=f"{n_s} points x {t_s} of the {T} trajectories x {Pn} poses per step, forward only, "
+                           f"oracle/torch_port.py on {threads} threads, {dt * 1e3:.0f} ms/step")
+        print(json.dumps({"impl": "reference", "metric": "candidate sweep fwd point*pose evals/s", "value": val,
+                          "unit": "point*pose evals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                          "dtype": "f32", "data": "synthetic", "config": dict(cfg, same_config=False), "cpu_baseline": base,
+                          "e2e": {"value": val, "unit": "point*pose evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}))
+        return
+
+    import torch.distributed as dist
+    from trajectory_optimization_b200 import _lib, ops, tools
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    _lib.lib()
+    K, img_w, img_h = tools.load_intrinsics(dev)
+    pts = make_cloud_shard(n_total, 0, 1, dev)             # the WHOLE cloud on every rank (identical seeds)
+    spts, _ = ops.spatial_sort(pts)
+    del pts
+    boxes = ops.tile_boxes(spts)
+    P, Q = poses.to(dev), quats.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def sweep(Pd, Qd):
+        return ops.sweep_rewards(spts, Pd, Qd, K, img_w, img_h, boxes=boxes, presorted=True, group=group, shard="trajectories")
+
+    for _ in range(args.warmup):
+        res = sweep(P, Q)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(lambda: sweep(P, Q), args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    pairs = float(n_total) * T * Pn
+    value = pairs * args.steps / (ms_total * 1e-3)
+    # end to end: the candidate poses come from pinned host memory every step, the T means go back to the host
+    host_P = torch.empty(poses.shape, dtype=torch.float32, pin_memory=True).copy_(poses)
+    host_Q = torch.empty(quats.shape, dtype=torch.float32, pin_memory=True).copy_(quats)
+    host_out = torch.empty(T, dtype=torch.float64, pin_memory=True)
+
+    def e2e_step():
+        P.copy_(host_P, non_blocking=True)
+        Q.copy_(host_Q, non_blocking=True)
+        host_out.copy_(sweep(P, Q), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    # every pair evaluated (pruning off) on a sample of 32 trajectories; same means required
+    t_s = 32
+    with ops.evaluation(dense=True):
+        res_d = ops.sweep_rewards(spts, P[:t_s], Q[:t_s], K, img_w, img_h, boxes=boxes, presorted=True)
+        ms_d = timed(lambda: ops.sweep_rewards(spts, P[:t_s], Q[:t_s], K, img_w, img_h, boxes=boxes, presorted=True), 1)
+    rel = float(((res[:t_s] - res_d).abs() / res_d.abs()).max())
+    if rel > 1e-9:
+        raise SystemExit("bench.py c5: pruned sweep differs from the dense sweep by %.2e" % rel)
+    dense_tf = 2.0 * n_total * t_s * Pn * FLOP_FWD / (ms_d * 1e-3) / 1e12   # two forward passes per pair
+    if rank != 0:
+        sys.stdout.flush()
+        if world > 1:
+            torch.cuda.synchronize()
+            os._exit(0)
+        return
+    line = {"metric": "candidate sweep fwd point*pose evals/s", "value": value, "unit": "point*pose evals/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "value_is": "DENSE-EQUIVALENT rate: N x T x P (point, pose) pairs per sweep / sweep time; the exact pruning skips "
+                        "pairs that provably cannot matter (see `dense`)",
+            "config": cfg, "clocks": clocks,
+            "dense": {"ms_for_sample": ms_d, "sample": "%d of the %d trajectories, every pair evaluated in both passes" % (t_s, T),
+                      "value": float(n_total) * t_s * Pn / (ms_d * 1e-3), "unit": "point*pose evals/s",
+                      "extrapolated_full_sweep_s": ms_d * 1e-3 * T / t_s},
+            "parity_check": {"max_rel_diff_pruned_vs_dense_means": rel, "trajectories_compared": t_s},
+            "e2e": {"value": pairs * args.steps / (ms_e2e * 1e-3), "unit": "point*pose evals/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": (host_P.numel() + host_Q.numel()) * 4 * world, "d2h_bytes_per_step": T * 8 * world,
+                    "note": "candidate poses from pinned host memory in, per-trajectory means out, every step; the cloud is resident"},
+            "gpu_launches": None,
+            "roofline": {"kernel": "dense sweep kernels on the 32-trajectory sample (cov_traj_minmax_kernel + cov_sweep_kernel)",
+                         "bound": "fp32", "unit": "TFLOP/s", "achieved": dense_tf, "peak": FP32_NOMINAL_TFLOPS,
+                         "frac": dense_tf / FP32_NOMINAL_TFLOPS, "traffic": None,
+                         "note": "FP32 CUDA-core bound (no tensor-core work: the transform is 3x4); peak = nominal FP32 "
+                                 "148 SM x 128 lanes x 2 x 1.965 GHz; 64 flop per forward evaluation, two passes"},
+            "cpu_baseline": None, "mean_reward_range": [float(res.min()), float(res.max())]}
+    print(json.dumps(line))
+    sys.stdout.flush()
+    if world > 1:
+        torch.cuda.synchronize()
+        os._exit(0)
+
+
 def config_dict(n_total, world):
     return {"workload": "c4: trajectory optimisation fwd+bwd, 64 waypoints x 5 cams = 320 poses, "
                         f"{n_total / 1e6:g}M-point synthetic box cloud, point-sharded over {world} GPU(s)",
@@ -181,10 +347,18 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--points", type=int, default=N_POINTS_C4, help="total cloud size (default: config 4)")
+    ap.add_argument("--points", type=int, default=None, help="total cloud size (default: the workload's)")
+    ap.add_argument("--workload", default="c4", choices=["c4", "c5"],
+                    help="c4 (default, the headline): trajectory optimisation fwd+bwd; c5: candidate-trajectory sweep")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong (default): --points is the TOTAL cloud, sharded over the ranks; weak: --points PER RANK")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.points is None:
+        args.points = N_POINTS_C4 if args.workload == "c4" else N_POINTS_C5
+    if args.workload == "c5":
+        return run_c5(args)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -202,7 +376,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
     L = _lib.lib()
-    n_total = args.points
+    n_total = args.points * (world if args.scaling == "weak" else 1)
     W = N_WAYPOINTS * N_CAMS
     K, img_w, img_h = tools.load_intrinsics(dev)
     rig = multicam.ring_rig(N_CAMS)
@@ -537,7 +711,7 @@ def main():
         cpu_baseline, _ = cpu_reference_rate(body0, rig, steps=3, warmup=1)
     line = {"metric": "coverage fwd+bwd point*pose evals/s", "value": value, "unit": "point*pose evals/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "value_is": "DENSE-EQUIVALENT rate: every one of the N x W (point, pose) pairs gets its exact result per step; the "
                         "exact pruning arithmetically evaluates only `pairs_evaluated_frac` of them (see `dense` for the rate "
                         "with every pair evaluated)",

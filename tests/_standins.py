@@ -90,6 +90,22 @@ class OracleBackend:
         acc[W * ACC] = r.sum()
         return torch.from_numpy(acc)
 
+    def sweep_minmax(self, pts, P, Q, Kd, cam, boxes=None):
+        return self.traj_minmax(pts, P, Q, Kd, cam)
+
+    def sweep_sums(self, pts, P, Q, T, Pn, Kd, cam, boxes, minmax):
+        W, hi = len(P), float(np.float32(1.0 - cam.eps))
+        sums = np.zeros(T)
+        for t in range(T):
+            L = np.zeros(len(pts))
+            for w in range(t * Pn, (t + 1) * Pn):
+                m = self._vis(pts, P[w], Q[w], Kd, cam)[0]
+                a, b = float(minmax[w]), float(minmax[W + w]) - float(minmax[w])
+                qc = np.clip((m - a) / b, 0.5, hi)
+                L += np.log(qc / (1 - qc))
+            sums[t] = (1 / (1 + np.exp(-L))).sum()
+        return torch.from_numpy(sums)
+
     def traj_epilogue(self, acc, minmax, Q, n_total, upstream_mode):
         a, W = acc.numpy(), len(Q)
         out = np.zeros(1 + 7 * W)

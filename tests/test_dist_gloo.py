@@ -93,3 +93,63 @@ def test_two_rank_sharded_objective_matches_unsharded_oracle():
         assert rel_err(gt.ravel() * 1.0, refp["g_trans"]) < 1e-5 and rel_err(gqp.ravel(), refp["g_quat"]) < 1e-5
         assert g_loss < 0
     assert np.allclose(results[0][2], results[1][2]) and np.allclose(results[0][3], results[1][3])  # replicas agree
+
+
+def _sweep_case():
+    gen = np.random.default_rng(5)
+    pts = (gen.random((1200, 3)) * np.array([16, 16, 4]) + np.array([-4, -4, -1])).astype(np.float32)
+    T, Pn = 5, 3   # 5 trajectories over 2 ranks: an uneven split
+    base = np.stack([np.linspace(0, 6, Pn), np.linspace(0, 3, Pn), np.zeros(Pn)], 1)
+    poses = (base[None] + gen.normal(0, 0.8, (T, 1, 3)) * np.array([1, 1, 0])).astype(np.float32)
+    quats = (gen.normal(0, 0.3, (T, Pn, 4)) + np.array([1.0, 0, 0, 0])).astype(np.float32)
+    return pts, poses, quats
+
+
+def _sweep_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import coverage_oracle as orc
+        from trajectory_optimization_b200 import ops
+        ops._BACKEND = OracleBackend()
+        pts, poses, quats = _sweep_case()
+        n = len(pts)
+        K = torch.from_numpy(orc.K_DEFAULT.copy())
+        P, Q = torch.from_numpy(poses), torch.from_numpy(quats)
+        by_traj = ops.sweep_rewards(torch.from_numpy(pts), P, Q, K, orc.IMG_WIDTH, orc.IMG_HEIGHT, group=dist.group.WORLD,
+                                    shard="trajectories", presorted=True)
+        lo, hi = rank * n // world, (rank + 1) * n // world
+        by_pts = ops.sweep_rewards(torch.from_numpy(pts[lo:hi].copy()), P, Q, K, orc.IMG_WIDTH, orc.IMG_HEIGHT, n_total=n,
+                                   group=dist.group.WORLD, shard="points", presorted=True)
+        q.put((rank, by_traj.numpy(), by_pts.numpy()))
+    except Exception as e:
+        q.put((rank, repr(e)))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_sweep_trajectory_and_point_sharding_match_the_oracle():
+    """BASELINE config 5 on N > 1 ranks: trajectories sharded (whole cloud per rank, no data-path
+    collective, one all-gather) and points sharded (MAX + SUM all-reduces) both give the unsharded per-trajectory means."""
+    from oracle import coverage_oracle as orc
+    from tests.conftest import rel_err
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sweep_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted([q.get(timeout=240) for _ in range(world)], key=lambda t: t[0])
+    assert all(len(r) == 3 for r in results), results
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    pts, poses, quats = _sweep_case()
+    K, W, H = orc.load_intrinsics()
+    ref = np.array([orc.traj_objective(pts, poses[t], quats[t], K, W, H, dtype=np.float64, want_grad=False)["mean"]
+                    for t in range(len(poses))])
+    for rank, by_traj, by_pts in results:
+        assert by_traj.shape == ref.shape and by_pts.shape == ref.shape
+        assert rel_err(by_traj, ref) < 1e-9 and rel_err(by_pts, ref) < 1e-9

@@ -269,3 +269,36 @@ def test_pointcloud2_builders_take_numpy_like_the_reference(dev):
         assert back.dtype == np.float64 and np.array_equal(back, xyz64.astype(np.float32).astype(np.float64))
     finally:
         sys.path.remove(shims)
+
+
+def test_multi_camera_visibility_matches_per_camera_oracle(dev, tools):
+    """transform -> cull -> HPR for 5 cameras in one call (reference src/pc_processor.py:158-182 per camera): index sets
+    equal the oracle's cull + Qhull HPR run on the SAME camera-frame points (bit-exact sets on a non-degenerate cloud)."""
+    gen = np.random.default_rng(17)
+    d = gen.normal(size=(60_000, 3))
+    pts = (d / np.linalg.norm(d, axis=1, keepdims=True) * gen.uniform(1.5, 9.0, (60_000, 1))).astype(np.float32)
+    yaws = np.deg2rad([0, 72, -72, 144, -144])
+    # camera optical frames looking outwards around the vertical axis
+    from trajectory_optimization_b200 import multicam
+    R0 = multicam.R_BODY_OPTICAL.double()
+    quats, trans = [], []
+    for i, y in enumerate(yaws):
+        Rz = torch.tensor([[np.cos(y), -np.sin(y), 0.0], [np.sin(y), np.cos(y), 0.0], [0.0, 0.0, 1.0]], dtype=torch.float64)
+        quats.append(multicam.matrix_to_quat_wxyz((Rz @ R0)[None])[0])
+        trans.append(torch.tensor([0.1 * i, -0.05 * i, 0.02 * i], dtype=torch.float64))
+    K, W, H = tools.load_intrinsics(dev)
+    res = tools.multi_camera_visibility(torch.from_numpy(pts), torch.stack(trans), torch.stack(quats), K, H, W, 1.0, 10.0,
+                                        device=dev)
+    assert [r["camera"] for r in res] == [0, 1, 2, 3, 4]
+    from trajectory_optimization_b200.model import to_camera_frame
+    for r in res:
+        c = r["camera"]
+        cam = to_camera_frame(torch.from_numpy(pts).to(dev), quats[c][None].float().to(dev), trans[c][None].float().to(dev))
+        cam_np = cam.cpu().numpy()
+        culled, dm, fm = orc.frustum_cull(cam_np.T, IMG_H, IMG_W, K_np, 1.0, 10.0)
+        ref_idx = np.flatnonzero(dm & fm)
+        assert np.array_equal(r["frustum_idx"].cpu().numpy(), ref_idx) and len(ref_idx) > 1000
+        assert np.array_equal(r["frustum_points"].cpu().numpy(), culled)
+        vis, _ = orc.hidden_pts_removal(culled, 2)
+        assert np.array_equal(r["visible_idx"].cpu().numpy(), ref_idx[vis])
+        assert np.array_equal(r["visible_points"].cpu().numpy(), culled[vis])

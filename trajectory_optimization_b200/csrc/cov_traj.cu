@@ -67,12 +67,6 @@ __host__ __device__ constexpr int stage_floats(int ppt) { return tile_points(ppt
 size_t minmax_smem_bytes(int W) {  // pose pairs (COV_PAIR_F4 float4 each) + block minima and maxima
     return (size_t)((W + 1) / 2) * (COV_PAIR_F4 * sizeof(float4) + 4 * sizeof(unsigned));
 }
-__host__ __device__ inline int minmax_tiles_stage_offset_floats(int W) {
-    return (int)((((size_t)W * (COV_ROW_F4 * 16 + 12) + 127) & ~(size_t)127) / 4);
-}
-size_t minmax_tiles_smem_bytes(int W, int ppt) {
-    return (size_t)minmax_tiles_stage_offset_floats(W) * 4 + 2 * (size_t)stage_floats(ppt) * 4;
-}
 // fused pass: pose table, then (128-byte aligned) the tile stage(s), G_j, gate bits, accumulators, gated-pose list
 __host__ __device__ inline int fused_stage_offset_floats(int W) {  // W rounded up to whole pose pairs (dense kernel)
     return (int)((((size_t)((W + 1) & ~1) * COV_ROW_F4 * 16 + 127) & ~(size_t)127) / 4);
@@ -394,37 +388,41 @@ cov_traj_prepare_kernel(const float* __restrict__ xyz, int64_t nsamples, int64_t
     }
 }
 
-// Pass B, first launch (one block): zero the control words, the look-back descriptors and the caller's accumulator
-// rows (acc[W * STRIDE] starts at `sum_base` = 0.5 * n: what the unlisted points add to the reward sum), then build
-// the pose table with the normalisation constants: v3.w = qthr, v4 = (b/2, b, 1/b, a), v5.w = thr.
-__global__ void __launch_bounds__(256)
+// Pass B, first launch: block 0 zeroes the control words, the look-back descriptors and the caller's accumulator rows
+// (acc[W * STRIDE] starts at `sum_base` = 0.5 * n: what the unlisted points add to the reward sum) and sets ctrl[1] when
+// some pose has min_j m > 0; every block builds 64 rows of the pose table with the normalisation constants:
+// v3.w = qthr, v4 = (b/2, b, 1/b, a), v5.w = thr.
+__global__ void __launch_bounds__(64)
 cov_traj_table_kernel(const float* __restrict__ poses, const float* __restrict__ quats, int W,
                       const float* __restrict__ K9, CovConst C, const float* __restrict__ minmax,
                       float4* __restrict__ table, int* __restrict__ ctrl, int ctrl_words, double* __restrict__ acc,
                       double sum_base) {
     const int tid = threadIdx.x;
-    for (int i = tid; i < ctrl_words; i += blockDim.x) ctrl[i] = 0;
-    if (acc) {
-        for (int i = tid; i < W * COV_ACC_STRIDE; i += blockDim.x) acc[i] = 0.0;
-        if (tid == 0) acc[(size_t)W * COV_ACC_STRIDE] = sum_base;
+    if (blockIdx.x == 0) {
+        int amin = 0;
+        for (int w = tid; w < W; w += blockDim.x) amin |= minmax[w] > 0.f;
+        amin = __syncthreads_or(amin);
+        for (int i = tid; i < ctrl_words; i += blockDim.x) ctrl[i] = (i == 1) ? amin : 0;
+        if (acc) {
+            for (int i = tid; i < W * COV_ACC_STRIDE; i += blockDim.x) acc[i] = 0.0;
+            if (tid == 0) acc[(size_t)W * COV_ACC_STRIDE] = sum_base;
+        }
     }
-    __syncthreads();
-    for (int w = tid; w < W; w += blockDim.x) {
-        float4 row[COV_ROW_F4];
-        cov_pose_row(poses + 3 * w, quats + 4 * w, K9, C, row);
-        const float a = minmax[w];
-        const float b = __fsub_rn(minmax[W + w], a);
-        const float hb = 0.5f * b;
-        const float thr = (a + hb) * (1.f - 9.5367431640625e-07f);  // conservative gate threshold
-        row[5].w = thr;
-        // q2 above qthr cannot reach thr (thr <= 0 or NaN, or a > 0 — arg-min points carry gradient: never prune)
-        row[3].w = (thr > 0.f && !(a > 0.f)) ? (float)((1e-4 - log2((double)thr)) / (double)C.kd * 1.000001)
-                                             : __uint_as_float(0x7f800000u);
-        row[4] = make_float4(hb, b, __frcp_rn(b), a);
-        if (a > 0.f) atomicOr(ctrl + 1, 1);
+    const int w = blockIdx.x * blockDim.x + tid;
+    if (w >= W) return;
+    float4 row[COV_ROW_F4];
+    cov_pose_row(poses + 3 * w, quats + 4 * w, K9, C, row);
+    const float a = minmax[w];
+    const float b = __fsub_rn(minmax[W + w], a);
+    const float hb = 0.5f * b;
+    const float thr = (a + hb) * (1.f - 9.5367431640625e-07f);  // conservative gate threshold
+    row[5].w = thr;
+    // q2 above qthr cannot reach thr (thr <= 0 or NaN, or a > 0 — arg-min points carry gradient: never prune)
+    row[3].w = (thr > 0.f && !(a > 0.f)) ? (float)((1e-4 - log2((double)thr)) / (double)C.kd * 1.000001)
+                                         : __uint_as_float(0x7f800000u);
+    row[4] = make_float4(hb, b, __frcp_rn(b), a);
 #pragma unroll
-        for (int i = 0; i < COV_ROW_F4; ++i) table[(size_t)w * COV_ROW_F4 + i] = row[i];
-    }
+    for (int i = 0; i < COV_ROW_F4; ++i) table[(size_t)w * COV_ROW_F4 + i] = row[i];
 }
 
 // Bounding boxes of runs of kBoxPts consecutive points: boxes[2b] = (lo, 0), boxes[2b+1] = (hi, 0); boxes past the
@@ -458,19 +456,23 @@ __global__ void __launch_bounds__(256) cov_tile_boxes_kernel(const float* __rest
 // consecutive tiles: every pose is tested against the group's box first (one lane per pose), and only the few that
 // pass are tested against the 8 tile boxes (one lane per tile).  Pass A passes `enc` (after the prepare launch) and the
 // cap is derived here; pass B reads qthr from the table.
-// A block iteration covers a CHUNK of 64 consecutive tiles and appends the chunk's listed tiles to the work list in
-// ascending order: the chunk's offset is the exclusive prefix sum of the chunks' counts, obtained with a decoupled
-// look-back over per-chunk descriptors (publish the own aggregate, then sum predecessors until one carries an
-// inclusive prefix).  The list is a pure function of the masks (deterministic).  Grid <= resident capacity, so every
-// predecessor a block waits for is running.  `fill_dst` (pass B): the same blocks write 1/2 to every reward.
+// A block iteration covers a CHUNK of 64 consecutive tiles; the block first culls ALL its chunks (warps independent, no
+// barrier), then appends each chunk's listed tiles to the work list in ascending order: the chunk's offset is the
+// exclusive prefix sum of the chunks' counts, obtained with a decoupled look-back over per-chunk descriptors (publish
+// the own aggregates, then sum predecessors until one carries an inclusive prefix).  The list is a pure function of the
+// masks (deterministic).  Grid <= resident capacity, and every block publishes its aggregates before it waits for
+// anybody's, so every predecessor a block waits for has been (or is being) published.  `fill_dst` (pass B): the same
+// blocks write 1/2 to every reward.
+constexpr int kCullMaxIter = 32;  // chunks per block at most (the host sizes the grid accordingly)
+
 __global__ void __launch_bounds__(256)
 cov_cull_kernel(const float4* __restrict__ boxes, int boxes_per_tile, int64_t ntiles, const float4* __restrict__ table,
                 int W, const unsigned* __restrict__ enc, float inv_kd, unsigned* __restrict__ amask_g, int mask_stride,
                 int* __restrict__ worklist, int* __restrict__ ctrl, unsigned long long* __restrict__ desc,
                 float* __restrict__ fill_dst, int64_t fill_n) {
     extern __shared__ float4 v3s[];
-    __shared__ unsigned warp_listed[8];
-    __shared__ int warp_base[8];
+    __shared__ unsigned char listed_s[kCullMaxIter][8];  // per own chunk and warp: which of the warp's 8 tiles are listed
+    __shared__ int chunk_base[kCullMaxIter];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int w = tid; w < W; w += blockDim.x) {
         float4 v3 = table[(size_t)w * COV_ROW_F4 + 3];
@@ -493,7 +495,8 @@ cov_cull_kernel(const float4* __restrict__ boxes, int boxes_per_tile, int64_t nt
     const int64_t nchunks = (ntiles + kChunkTiles - 1) / kChunkTiles;
     const int sub = lane >> 3, tl = lane & 7;  // box loads: lane = (pass-local box slot, tile of the group)
     unsigned long long npairs = 0;
-    for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    int it = 0;
+    for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x, ++it) {
         // lane -> tile tl of this warp's group; the 4 lanes with the same tl share the tile's boxes_per_tile boxes (<= 16)
         const int64_t tile_l = (chunk * 8 + warp) * 8 + tl;
         float4 lo = make_float4(inf, inf, inf, 0.f), hi = make_float4(-inf, -inf, -inf, 0.f);
@@ -542,21 +545,27 @@ cov_cull_kernel(const float4* __restrict__ boxes, int boxes_per_tile, int64_t nt
         const bool listed = lane < 8 && tile_l < ntiles && any != 0u;
         if (listed) npairs += any;
         const unsigned listed8 = __ballot_sync(kFull, listed);
-        if (lane == 0) warp_listed[warp] = listed8;
-        __syncthreads();
-        if (warp == 0) {
-            const unsigned mine = lane < 8 ? warp_listed[lane] : 0u;
-            const int cnt = __popc(mine);
-            int incl = cnt;
+        if (lane == 0) listed_s[it][warp] = (unsigned char)listed8;
+    }
+    const int n_it = it;
+    __syncthreads();
+    if (warp == 0) {
+        // own chunk `k` is chunk blockIdx.x + k * gridDim.x; lane l < 8 holds warp l's listed bits
+        for (int k = lane; k < n_it; k += 32) {  // publish every own aggregate first
+            int total = 0;
 #pragma unroll
-            for (int o = 1; o < 8; o <<= 1) {
-                const int v = __shfl_up_sync(kFull, incl, o);
-                if (lane >= o) incl += v;
-            }
-            const unsigned long long total = (unsigned long long)__shfl_sync(kFull, incl, 7);
+            for (int q = 0; q < 8; ++q) total += __popc((unsigned)listed_s[k][q]);
+            const int64_t chunk = blockIdx.x + (int64_t)k * gridDim.x;
+            if (chunk > 0) st_release_u64(desc + chunk, kDescAgg | (unsigned long long)total);
+        }
+        __syncwarp();
+        for (int k = 0; k < n_it; ++k) {
+            const int64_t chunk = blockIdx.x + (int64_t)k * gridDim.x;
+            unsigned long long total = 0ull;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) total += (unsigned long long)__popc((unsigned)listed_s[k][q]);
             unsigned long long excl = 0ull;
             if (chunk > 0) {
-                if (lane == 0) st_release_u64(desc + chunk, kDescAgg | total);
                 int64_t look = chunk - 1;
                 while (true) {  // windows of 32 predecessors, nearest first
                     const int64_t idx = look - lane;
@@ -578,126 +587,160 @@ cov_cull_kernel(const float4* __restrict__ boxes, int boxes_per_tile, int64_t nt
             if (lane == 0) {
                 st_release_u64(desc + chunk, kDescPrefix | (excl + total));
                 if (chunk == nchunks - 1) ctrl[0] = (int)(excl + total);
+                chunk_base[k] = (int)excl;
             }
-            if (lane < 8) warp_base[lane] = (int)excl + incl - cnt;
         }
-        __syncthreads();
-        if (listed) worklist[warp_base[warp] + __popc(listed8 & ((1u << lane) - 1u))] = (int)tile_l;
+    }
+    __syncthreads();
+    for (int k = 0; k < n_it; ++k) {
+        const int64_t chunk = blockIdx.x + (int64_t)k * gridDim.x;
+        const int64_t tile_l = (chunk * 8 + warp) * 8 + tl;
+        const unsigned listed8 = listed_s[k][warp];
+        int before = 0;  // listed tiles of the chunk in the warps ahead of this one
+        for (int q = 0; q < warp; ++q) before += __popc((unsigned)listed_s[k][q]);
+        if (lane < 8 && ((listed8 >> lane) & 1u))
+            worklist[chunk_base[k] + before + __popc(listed8 & ((1u << lane) - 1u))] = (int)tile_l;
     }
     npairs = __reduce_add_sync(kFull, (unsigned)npairs);
     if (lane == 0 && npairs) atomicAdd(reinterpret_cast<unsigned long long*>(ctrl + 4), npairs);
 }
 
 // =============================================== pass A, pruned ===============================================
-template <int PPT, int MINB>
-__global__ void __launch_bounds__(COV_THREADS, MINB)
+// Persistent WARPS over the work list, like pass B below: the unit of work is one box of 128 consecutive points of a
+// listed tile, drawn by a warp from a global ticket counter; lane 0 stages the next item (points, box, the tile's pose
+// mask) by TMA into the warp's other private stage while the warp works on the current one.  A listed pose is evaluated
+// when the cap ball (from the seed's extrema; any later value is tighter and valid) meets the warp's box and one of its
+// points.  Extrema meet per block in shared memory, then in the zero-initialised encoded arrays; the last block decodes
+// them into the caller's floats.
+constexpr int kItemPts = 128;                 // points per work item = one warp's registers = one precomputed box
+constexpr int kItemsPerTile = 8;              // a listed tile (1024 points) is eight items
+constexpr int kItemPpt = kItemPts / 32;
+constexpr int kItemStageWordsA = kItemPts * 3 + 8 + kMaskWords;               // points | box | pose mask
+constexpr int kItemStageWords = kItemStageWordsA + kItemPts;                  // ... | permutation (pass B)
+
+__global__ void __launch_bounds__(COV_THREADS, 3)
 cov_traj_minmax_tiles_kernel(const float* __restrict__ xyz, int64_t n, const float4* __restrict__ table, int W, CovConst C,
                              unsigned* __restrict__ enc, float* __restrict__ minmax_out, const float4* __restrict__ boxes,
                              const unsigned* __restrict__ amask_g, int mask_stride, const int* __restrict__ worklist,
                              int* __restrict__ ctrl, int64_t ntiles, unsigned long long* __restrict__ stats) {
-    constexpr int T = tile_points(PPT);
-    constexpr int NB = tile_boxes(PPT);
-    constexpr int SF = stage_floats(PPT);
-    constexpr int WB = (32 * PPT >= kBoxPts) ? (32 * PPT / kBoxPts) : 1;  // boxes covering one warp's points
-    extern __shared__ float4 smem4[];
-    float4* ptab = smem4;
-    unsigned* smin = reinterpret_cast<unsigned*>(ptab + (size_t)W * COV_ROW_F4);
+    constexpr int PPT = kItemPpt;
+    extern __shared__ float4 smem4[];                      // block minima | maxima (uint) | per-pose caps
+    unsigned* smin = reinterpret_cast<unsigned*>(smem4);
     unsigned* smax = smin + W;
     float* sqcap = reinterpret_cast<float*>(smax + W);
-    float* stage = reinterpret_cast<float*>(smem4) + minmax_tiles_stage_offset_floats(W);  // [2][SF]
-    __shared__ __align__(8) unsigned long long mbar[2];
+    __shared__ __align__(128) float stages[kWarps][2][kItemStageWordsA];
+    __shared__ __align__(8) unsigned long long mbar[kWarps][2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float inv_kd = 1.f / C.kd;
-    unsigned n_box = 0, n_pre = 0, n_full = 0;
-    if (tid == 0) {
-        mbar_init(&mbar[0], 1);
-        mbar_init(&mbar[1], 1);
+    unsigned long long* bar = mbar[warp];
+    if (lane == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
         mbar_fence_init();
     }
-    for (int i = tid; i < W * COV_ROW_F4; i += COV_THREADS) ptab[i] = table[i];
     for (int w = tid; w < W; w += COV_THREADS) {
         smin[w] = 0x7f800000u;
         smax[w] = 0u;
         sqcap[w] = minmax_qcap(~enc[w], enc[W + w], inv_kd);  // from the seed (any later value is tighter and valid)
     }
     __syncthreads();
-    const int count = ctrl[0];
-    const int64_t nfull = n / T;
+    const int n_items = ctrl[0] * kItemsPerTile;
     const int nwords = (W + 31) >> 5;
+    int* ticket = ctrl + 3;
+    auto issue = [&](int it, int b) {
+        if (it >= n_items) return;
+        const int64_t tile = worklist[it >> 3];
+        const int64_t j0 = tile * (kItemsPerTile * kItemPts) + (int64_t)(it & 7) * kItemPts;
+        float* st = stages[warp][b];
+        const bool whole = j0 + kItemPts <= n;
+        mbar_expect_tx(&bar[b], (whole ? kItemPts * 12u : 0u) + 32u + (unsigned)mask_stride * 4u);
+        if (whole) tma_copy(st, xyz + j0 * 3, kItemPts * 12u, &bar[b]);
+        tma_copy(st + kItemPts * 3, boxes + (j0 / kBoxPts) * 2, 32u, &bar[b]);
+        tma_copy(st + kItemPts * 3 + 8, amask_g + tile * mask_stride, (unsigned)mask_stride * 4u, &bar[b]);
+    };
+    unsigned n_box = 0, n_pre = 0, n_full = 0;
     unsigned uses0 = 0, uses1 = 0;
-    if (tid == 0 && (int)blockIdx.x < count)
-        stage_issue<PPT>(stage, &mbar[0], xyz, boxes, amask_g, mask_stride, (int64_t)worklist[blockIdx.x], nfull);
+    int cur = 0;
+    if (lane == 0) {
+        cur = atomicAdd(ticket, 1);
+        issue(cur, 0);
+    }
+    cur = __shfl_sync(kFull, cur, 0);
     int buf = 0;
-    for (int i = blockIdx.x; i < count; i += gridDim.x, buf ^= 1) {
-        const int64_t tile = worklist[i];
-        if (tid == 0 && i + (int)gridDim.x < count)  // the other stage was last read before the previous barrier
-            stage_issue<PPT>(stage + (buf ^ 1) * SF, &mbar[buf ^ 1], xyz, boxes, amask_g, mask_stride,
-                             (int64_t)worklist[i + gridDim.x], nfull);
-        if (buf == 0) mbar_wait(&mbar[0], uses0++ & 1u);
-        else mbar_wait(&mbar[1], uses1++ & 1u);
-        const float* st = stage + buf * SF;
+    while (cur < n_items) {
+        int nxt = 0;
+        if (lane == 0) {  // the other stage was last read before the __syncwarp that ended the previous item
+            nxt = atomicAdd(ticket, 1);
+            issue(nxt, buf ^ 1);
+        }
+        nxt = __shfl_sync(kFull, nxt, 0);
+        if (buf == 0) mbar_wait(&bar[0], uses0++ & 1u);
+        else mbar_wait(&bar[1], uses1++ & 1u);
+        const float* st = stages[warp][buf];
+        const int64_t tile = worklist[cur >> 3];
+        const int64_t j0 = tile * (kItemsPerTile * kItemPts) + (int64_t)(cur & 7) * kItemPts;
         float px[PPT], py[PPT], pz[PPT];
-        if (tile < nfull) {
-            const float* src = st + (warp * (32 * PPT) + lane) * 3;
+        if (j0 + kItemPts <= n) {
 #pragma unroll
             for (int s = 0; s < PPT; ++s) {
-                px[s] = src[s * 96];
-                py[s] = src[s * 96 + 1];
-                pz[s] = src[s * 96 + 2];
+                px[s] = st[(s * 32 + lane) * 3];
+                py[s] = st[(s * 32 + lane) * 3 + 1];
+                pz[s] = st[(s * 32 + lane) * 3 + 2];
             }
         } else {
 #pragma unroll
             for (int s = 0; s < PPT; ++s) {
-                int64_t j = tile * T + warp * (32 * PPT) + s * 32 + lane;
-                j = j < n ? j : n - 1;  // a duplicate cannot change a min or a max
+                int64_t j = j0 + s * 32 + lane;
+                j = j < n ? j : n - 1;  // a duplicate cannot change a min or a max (j0 < n: the item holds a real point)
                 px[s] = __ldg(xyz + j * 3);
                 py[s] = __ldg(xyz + j * 3 + 1);
                 pz[s] = __ldg(xyz + j * 3 + 2);
             }
         }
-        // box of this warp's points = union of the precomputed boxes that cover them
-        const float4* tb = reinterpret_cast<const float4*>(st + T * 3);
-        const int b0 = (warp * 32 * PPT) / kBoxPts;
-        float4 wlo = tb[2 * b0], whi = tb[2 * b0 + 1];
+        const float4* tb = reinterpret_cast<const float4*>(st + kItemPts * 3);
+        const float4 wlo = tb[0], whi = tb[1];
+        const unsigned* am = reinterpret_cast<const unsigned*>(st + kItemPts * 3 + 8);
+        if (j0 < n) {
+            for (int c = 0; c < nwords; ++c) {
+                unsigned word = am[c];
+                while (word) {
+                    const int w = c * 32 + __ffs(word) - 1;
+                    word &= word - 1;
+                    const float4* row = table + (size_t)w * COV_ROW_F4;
+                    const float4 v3 = __ldg(row + 3);
+                    const float cap = sqcap[w];
+                    ++n_box;
+                    if (box_q2lb(wlo, whi, v3) > cap) continue;
+                    ++n_pre;
+                    float qmin = cov_q2(px[0], py[0], pz[0], v3);
 #pragma unroll
-        for (int k = 1; k < WB; ++k) box_union(wlo, whi, tb[2 * (b0 + k)], tb[2 * (b0 + k) + 1]);
-        const unsigned* am = reinterpret_cast<const unsigned*>(st + T * 3 + NB * 8);
-        for (int c = 0; c < nwords; ++c) {
-            unsigned word = am[c];
-            while (word) {
-                const int w = c * 32 + __ffs(word) - 1;
-                word &= word - 1;
-                const float4* row = ptab + (size_t)w * COV_ROW_F4;
-                const float4 v3 = row[3];
-                const float cap = sqcap[w];
-                ++n_box;
-                if (box_q2lb(wlo, whi, v3) > cap) continue;
-                ++n_pre;
-                float qmin = cov_q2(px[0], py[0], pz[0], v3);
+                    for (int s = 1; s < PPT; ++s) qmin = fminf(qmin, cov_q2(px[s], py[s], pz[s], v3));
+                    if (!__any_sync(kFull, !(qmin > cap))) continue;
+                    ++n_full;
+                    const float4 v0 = __ldg(row), v1 = __ldg(row + 1), v2 = __ldg(row + 2);
+                    float m[PPT];
 #pragma unroll
-                for (int s = 1; s < PPT; ++s) qmin = fminf(qmin, cov_q2(px[s], py[s], pz[s], v3));
-                if (!__any_sync(kFull, !(qmin > cap))) continue;
-                ++n_full;
-                const float4 v0 = row[0], v1 = row[1], v2 = row[2];
-                float m[PPT];
+                    for (int s = 0; s < PPT; ++s) m[s] = cov_vis<false>(px[s], py[s], pz[s], v0, v1, v2, v3, C, nullptr);
+                    float mn = m[0], mx = m[0];
 #pragma unroll
-                for (int s = 0; s < PPT; ++s) m[s] = cov_vis<false>(px[s], py[s], pz[s], v0, v1, v2, v3, C, nullptr);
-                float mn = m[0], mx = m[0];
-#pragma unroll
-                for (int s = 1; s < PPT; ++s) {
-                    mn = fminf(mn, m[s]);
-                    mx = fmaxf(mx, m[s]);
-                }
-                const unsigned umn = __reduce_min_sync(kFull, __float_as_uint(mn));
-                const unsigned umx = __reduce_max_sync(kFull, __float_as_uint(mx));
-                if (lane == 0) {
-                    atomicMin(smin + w, umn);
-                    atomicMax(smax + w, umx);
+                    for (int s = 1; s < PPT; ++s) {
+                        mn = fminf(mn, m[s]);
+                        mx = fmaxf(mx, m[s]);
+                    }
+                    const unsigned umn = __reduce_min_sync(kFull, __float_as_uint(mn));
+                    const unsigned umx = __reduce_max_sync(kFull, __float_as_uint(mx));
+                    if (lane == 0) {
+                        atomicMin(smin + w, umn);
+                        atomicMax(smax + w, umx);
+                    }
                 }
             }
         }
-        __syncthreads();  // every warp is done with this stage before it is refilled
+        __syncwarp();  // every lane is done with this stage before lane 0 refills it
+        cur = nxt;
+        buf ^= 1;
     }
+    __syncthreads();
     for (int w = tid; w < W; w += COV_THREADS) {
         if (smax[w] != 0u || smin[w] != 0x7f800000u) {
             atomicMax(enc + w, ~smin[w]);
@@ -1125,10 +1168,6 @@ cov_traj_fused_kernel(const float* __restrict__ xyz, int64_t n, const float* __r
 // re-evaluation keeps most lanes busy.  The pose table stays in global memory (a box touches ~5 rows: L1 hits).
 // `rewards` was pre-filled with 1/2, only other values are stored; the warps add sum_j (r_j - 1/2) of the listed
 // tiles to acc[W * STRIDE], which starts at 0.5 * n.
-constexpr int kItemPts = 128;                 // points per work item = one warp's registers = one precomputed box
-constexpr int kItemsPerTile = 8;              // a listed tile (1024 points) is eight items
-constexpr int kItemPpt = kItemPts / 32;
-constexpr int kItemStageWords = kItemPts * 3 + 8 + kMaskWords + kItemPts;  // points | box | pose mask | permutation
 constexpr int kTilesMinBlocks = 3;            // resident blocks per SM the register allocation aims at
 
 template <bool HAS_UP>
@@ -1563,8 +1602,7 @@ int pick_ppt(int64_t n, int W, bool fused, bool prune) {
     const int cand[3] = {4, 2, 1};
     for (int i = 0; i < 3; ++i) {
         const int ppt = cand[i];
-        const size_t sm = fused ? fused_smem_bytes(W, ppt, prune)
-                                : (prune ? minmax_tiles_smem_bytes(W, ppt) : minmax_smem_bytes(W));
+        const size_t sm = fused ? fused_smem_bytes(W, ppt, prune) : minmax_smem_bytes(W);
         if (sm > kSmemCap) continue;
         const int64_t ntiles = (n + tile_points(ppt) - 1) / tile_points(ppt);
         if (ntiles >= 2 * (int64_t)sms || ppt == 1) return ppt;
@@ -1649,16 +1687,23 @@ const float4* boxes_for_call(const float* xyz, int64_t n, const float* boxes_dev
 }
 
 // cull + work list in one launch; every block must be resident (the blocks wait on one another's descriptors)
-void launch_cull(const float4* boxes, int ppt, int64_t ntiles, const TrajWorkspace& t, int W, const unsigned* enc,
-                 float inv_kd, float* fill_dst, int64_t fill_n, cudaStream_t s) {
+int launch_cull(const float4* boxes, int ppt, int64_t ntiles, const TrajWorkspace& t, int W, const unsigned* enc,
+                float inv_kd, float* fill_dst, int64_t fill_n, cudaStream_t s) {
     const size_t smem = (size_t)W * sizeof(float4);
     const int64_t nchunks = (ntiles + kChunkTiles - 1) / kChunkTiles;
     const int64_t resident = (int64_t)blocks_per_sm(cov_cull_kernel, 256, smem) * cov_sm_count_cached();
     int64_t want = nchunks;
     if (fill_dst) want = std::max<int64_t>(want, (int64_t)cov_sm_count_cached() * 4);  // enough stores in flight for the fill
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, resident));
+    int64_t g = std::max<int64_t>(1, std::min<int64_t>(want, resident));
+    if ((nchunks + g - 1) / g > kCullMaxIter) {
+        cov_set_error("cov_cull: %lld tiles exceed what one launch can list (%lld blocks x %d chunks)", (long long)ntiles,
+                      (long long)g, kCullMaxIter);
+        return COV_ERR_UNSUPPORTED;
+    }
+    const int grid = (int)g;
     cov_cull_kernel<<<grid, 256, smem, s>>>(boxes, tile_boxes(ppt), ntiles, t.table, W, enc, inv_kd, t.amask,
                                             mask_stride_words(W), t.worklist, t.ctrl, t.desc, fill_dst, fill_n);
+    return COV_OK;
 }
 
 }  // namespace
@@ -1667,8 +1712,8 @@ extern "C" int cov_traj_max_poses(void) {
     static int cached = 0;
     if (cached) return cached;
     int w = 1;
-    while (w < 32 * kMaskWords && fused_smem_bytes(w + 1, 1, false) <= kSmemCap && fused_smem_bytes(w + 1, 1, true) <= kSmemCap &&
-           minmax_tiles_smem_bytes(w + 1, 1) <= kSmemCap && (size_t)(w + 1) * sizeof(float4) <= 48 * 1024)
+    while (w < 32 * kMaskWords && fused_smem_bytes(w + 1, 1, false) <= kSmemCap && minmax_smem_bytes(w + 1) <= kSmemCap &&
+           (size_t)(w + 1) * sizeof(float4) <= 48 * 1024)
         ++w;
     cached = w;
     return w;
@@ -1713,10 +1758,8 @@ extern "C" int cov_traj_minmax(const float* xyz, int64_t n, const float* poses, 
     cudaStream_t s = (cudaStream_t)stream;
     const CovConst C = cov_make_const(cam);
     const bool prune = !(opts && opts->dense) && n >= kDenseBelow;
-    int ppt = pick_ppt(n, W, false, prune);
-    if (ppt == 4 && (n + tile_points(8) - 1) / tile_points(8) >= 4 * (int64_t)cov_sm_count_cached() &&
-        (!prune || minmax_tiles_smem_bytes(W, 8) <= kSmemCap))
-        ppt = 8;
+    int ppt = pick_ppt(n, W, false, false);
+    if (ppt == 4 && (n + tile_points(8) - 1) / tile_points(8) >= 4 * (int64_t)cov_sm_count_cached()) ppt = 8;
     if (ppt == 0) {
         cov_set_error("cov_traj_minmax: %d poses do not fit in shared memory", W);
         return COV_ERR_UNSUPPORTED;
@@ -1742,6 +1785,8 @@ extern "C" int cov_traj_minmax(const float* xyz, int64_t n, const float* poses, 
     // pruned: pose table + seed on a strided sample, cull + work list, evaluation of the listed tiles: 3 launches
     const TrajWorkspace t = carve_workspace(ws, n, W);
     const float4* boxes = boxes_for_call(xyz, n, boxes_dev, t, s);
+    constexpr int ppt_t = 4;  // tiles of 1024 points, eight 128-point items each (as pass B)
+    const int64_t ntiles_t = (n + tile_points(ppt_t) - 1) / tile_points(ppt_t);
     cudaMemsetAsync(t.ctrl, 0, t.ctrl_bytes, s);
     {
         const int64_t stride = (n + kSeedSamples - 1) / kSeedSamples;
@@ -1749,17 +1794,15 @@ extern "C" int cov_traj_minmax(const float* xyz, int64_t n, const float* poses, 
         const dim3 sgrid((unsigned)((nsamples + COV_THREADS - 1) / COV_THREADS), (unsigned)((W + 31) / 32));
         cov_traj_prepare_kernel<<<sgrid, COV_THREADS, 0, s>>>(xyz, nsamples, stride, poses, quats, W, K, C, t.table, t.enc);
     }
-    launch_cull(boxes, ppt, ntiles, t, W, t.enc, 1.f / C.kd, nullptr, 0, s);
-    unsigned long long* stats = opts ? opts->stats_dev : nullptr;
-#define LAUNCH_TILES(P)                                                                                             \
-    {                                                                                                               \
-        const size_t smem_t = minmax_tiles_smem_bytes(W, P);                                                        \
-        const int grid = grid_for(cov_traj_minmax_tiles_kernel<P, 2>, smem_t, ntiles);                              \
-        cov_traj_minmax_tiles_kernel<P, 2><<<grid, COV_THREADS, smem_t, s>>>(                                       \
-            xyz, n, t.table, W, C, t.enc, minmax, boxes, t.amask, mask_stride_words(W), t.worklist, t.ctrl, ntiles, stats); \
+    if ((rc = launch_cull(boxes, ppt_t, ntiles_t, t, W, t.enc, 1.f / C.kd, nullptr, 0, s)) != COV_OK) return rc;
+    {
+        const size_t smem_t = (size_t)W * 12;
+        int64_t grid = (int64_t)blocks_per_sm(cov_traj_minmax_tiles_kernel, COV_THREADS, smem_t) * cov_sm_count_cached();
+        grid = std::max<int64_t>(1, std::min<int64_t>(grid, ntiles_t));
+        cov_traj_minmax_tiles_kernel<<<(unsigned)grid, COV_THREADS, smem_t, s>>>(
+            xyz, n, t.table, W, C, t.enc, minmax, boxes, t.amask, mask_stride_words(W), t.worklist, t.ctrl, ntiles_t,
+            opts ? opts->stats_dev : nullptr);
     }
-    if (ppt == 8) LAUNCH_TILES(8) else if (ppt == 4) LAUNCH_TILES(4) else if (ppt == 2) LAUNCH_TILES(2) else LAUNCH_TILES(1)
-#undef LAUNCH_TILES
     return cov_check_launch("cov_traj_minmax");
 }
 
@@ -1812,10 +1855,10 @@ extern "C" int cov_traj_fused(const float* xyz, int64_t n, const float* poses, c
     static_assert(ppt == 4 && tile_points(ppt) == kItemsPerTile * kItemPts, "tile = 8 items");
     const int64_t ntiles = (n + tile_points(ppt) - 1) / tile_points(ppt);
     const float4* boxes = boxes_for_call(xyz, n, boxes_dev, t, s);
-    cov_traj_table_kernel<<<1, 256, 0, s>>>(poses, quats, W, K, C, minmax, t.table, t.ctrl, (int)(t.ctrl_bytes / sizeof(int)),
-                                            acc, 0.5 * (double)n);
+    cov_traj_table_kernel<<<(W + 63) / 64, 64, 0, s>>>(poses, quats, W, K, C, minmax, t.table, t.ctrl,
+                                                       (int)(t.ctrl_bytes / sizeof(int)), acc, 0.5 * (double)n);
     const bool prefilled = opts && opts->rewards_prefilled;
-    launch_cull(boxes, ppt, ntiles, t, W, nullptr, 0.f, prefilled ? nullptr : rewards, n, s);
+    if ((rc = launch_cull(boxes, ppt, ntiles, t, W, nullptr, 0.f, prefilled ? nullptr : rewards, n, s)) != COV_OK) return rc;
     unsigned long long* stats = opts ? opts->stats_dev : nullptr;
     {
         // persistent warps: as many blocks as are resident; every warp draws 128-point items from a ticket counter
@@ -1875,9 +1918,9 @@ extern "C" int cov_sweep_rewards(const float* xyz, int64_t n, const float* poses
         const int w0 = t0 * per_traj, Wn = nt * per_traj;
         cudaMemcpyAsync(mm, minmax + w0, (size_t)Wn * sizeof(float), cudaMemcpyDeviceToDevice, s);
         cudaMemcpyAsync(mm + Wn, minmax + W + w0, (size_t)Wn * sizeof(float), cudaMemcpyDeviceToDevice, s);
-        cov_traj_table_kernel<<<1, 256, 0, s>>>(poses + 3 * (size_t)w0, quats + 4 * (size_t)w0, Wn, K, C, mm, t.table, t.ctrl,
-                                                (int)(t.ctrl_bytes / sizeof(int)), nullptr, 0.0);
-        launch_cull(boxes, PPT, ntiles, t, Wn, nullptr, 0.f, nullptr, 0, s);
+        cov_traj_table_kernel<<<(Wn + 63) / 64, 64, 0, s>>>(poses + 3 * (size_t)w0, quats + 4 * (size_t)w0, Wn, K, C, mm, t.table,
+                                                            t.ctrl, (int)(t.ctrl_bytes / sizeof(int)), nullptr, 0.0);
+        if (launch_cull(boxes, PPT, ntiles, t, Wn, nullptr, 0.f, nullptr, 0, s) != COV_OK) return COV_ERR_UNSUPPORTED;
         const size_t smem = smem_for(nt);
         const int grid = grid_for(cov_sweep_tiles_kernel<PPT>, smem, ntiles);
         cov_sweep_tiles_kernel<PPT><<<grid, COV_THREADS, smem, s>>>(xyz, n, t.table, Wn, per_traj, nt, C, boxes, t.amask,

@@ -148,7 +148,43 @@ HULL_HD int hull_lp_add(HullLP& L, double a, double b, double c, int cid) {
     return HULL_UNDECIDED;
 }
 
-// sign of det[a;b;c] with a forward error bound: +1 / -1 when certain, 0 when not.
+// ---- double-double arithmetic for the determinant signs the fp64 filter cannot settle ----
+// (hi, lo) with hi = fl(hi + lo); products by an error-free fma split, sums by the two-sum.  Relative error of a
+// dd product or sum <= 2^-104.
+struct HullDD { double hi, lo; };
+HULL_HD HullDD hull_two_prod(double a, double b) {
+    HullDD r;
+    r.hi = a * b;
+    r.lo = fma(a, b, -r.hi);
+    return r;
+}
+HULL_HD HullDD hull_two_sum(double a, double b) {
+    HullDD r;
+    r.hi = a + b;
+    const double bb = r.hi - a;
+    r.lo = (a - (r.hi - bb)) + (b - bb);
+    return r;
+}
+HULL_HD HullDD hull_dd_add(HullDD a, HullDD b) {
+    HullDD s = hull_two_sum(a.hi, b.hi);
+    s.lo += a.lo + b.lo;
+    return hull_two_sum(s.hi, s.lo);
+}
+HULL_HD HullDD hull_dd_neg(HullDD a) { HullDD r; r.hi = -a.hi; r.lo = -a.lo; return r; }
+HULL_HD HullDD hull_dd_mul_d(HullDD a, double b) {
+    HullDD p = hull_two_prod(a.hi, b);
+    p.lo += a.lo * b;
+    return hull_two_sum(p.hi, p.lo);
+}
+// b_i c_j - b_k c_l in double-double (each product is error-free)
+HULL_HD HullDD hull_dd_minor(double bi, double cj, double bk, double cl) {
+    return hull_dd_add(hull_two_prod(bi, cj), hull_dd_neg(hull_two_prod(bk, cl)));
+}
+
+// sign of det[a;b;c]: +1 / -1 when certain, 0 when not.  Stage 1 is an fp64 evaluation with a forward error bound;
+// when that is inconclusive the determinant is recomputed in double-double (error < 2^-96 of the permanent, i.e.
+// 13 orders of magnitude finer): what still comes out as 0 is degenerate at ~100 bits — for fp32-valued input that
+// means exactly coplanar with the origin (duplicate points, points on a common plane through 0).
 HULL_HD int hull_det_sign(const double* a, const double* b, const double* c) {
     const double m0 = b[1] * c[2] - b[2] * c[1], m1 = b[2] * c[0] - b[0] * c[2], m2 = b[0] * c[1] - b[1] * c[0];
     const double det = a[0] * m0 + a[1] * m1 + a[2] * m2;
@@ -156,7 +192,14 @@ HULL_HD int hull_det_sign(const double* a, const double* b, const double* c) {
                         fabs(a[1]) * (fabs(b[2] * c[0]) + fabs(b[0] * c[2])) +
                         fabs(a[2]) * (fabs(b[0] * c[1]) + fabs(b[1] * c[0]));
     const double bound = 1.0e-15 * perm;  // > 8 * 2^-53 * perm
-    return det > bound ? 1 : (det < -bound ? -1 : 0);
+    if (det > bound) return 1;
+    if (det < -bound) return -1;
+    if (!(perm > 0.0)) return 0;
+    const HullDD d = hull_dd_add(hull_dd_add(hull_dd_mul_d(hull_dd_minor(b[1], c[2], b[2], c[1]), a[0]),
+                                             hull_dd_mul_d(hull_dd_minor(b[2], c[0], b[0], c[2]), a[1])),
+                                 hull_dd_mul_d(hull_dd_minor(b[0], c[1], b[1], c[0]), a[2]));
+    const double bound2 = 1.3e-29 * perm;  // 2^-96 * perm, far above the ~12 * 2^-104 * perm the dd evaluation can lose
+    return d.hi > bound2 ? 1 : (d.hi < -bound2 ? -1 : 0);
 }
 
 // Is p inside conv(0, s1, s2, s3)?  1 = certified inside (closed, non-degenerate), 0 = cannot certify.

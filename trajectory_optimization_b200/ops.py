@@ -163,6 +163,36 @@ class CudaBackend:
               ws.numel())
         return acc
 
+    def sweep_minmax(self, pts, P, Q, Kd, cam, boxes=None):
+        """Per-pose minima and maxima of all T*P poses of a sweep (pass A, one pose-table-full at a time)."""
+        L = _lib.lib()
+        W, n, dev = P.shape[0], pts.shape[0], pts.device
+        minmax = torch.empty(2 * W, dtype=torch.float32, device=dev)
+        chunk = L.cov_traj_max_poses()
+        ws_bytes = L.cov_traj_workspace_bytes(n, min(W, chunk))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        opts = _opts()
+        for w0 in range(0, W, chunk):
+            w1 = min(W, w0 + chunk)
+            mm = torch.empty(2 * (w1 - w0), dtype=torch.float32, device=dev)
+            _call("cov_traj_minmax", pts, _ptr(pts), n, _ptr(P[w0:w1]), _ptr(Q[w0:w1]), w1 - w0, _ptr(Kd),
+                  ctypes.byref(cam), _ptr(boxes), _ptr(mm), ctypes.byref(opts), _ptr(ws), ws_bytes)
+            minmax[w0:w1] = mm[:w1 - w0]
+            minmax[W + w0:W + w1] = mm[w1 - w0:]
+        return minmax
+
+    def sweep_sums(self, pts, P, Q, T, Pn, Kd, cam, boxes, minmax):
+        """sum_j rewards_j(t) over this cloud for every trajectory t (fp64)."""
+        L = _lib.lib()
+        n, dev = pts.shape[0], pts.device
+        ws_bytes = L.cov_sweep_workspace_bytes(n, T, Pn)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        sums = torch.zeros(T, dtype=torch.float64, device=dev)
+        opts = _opts()
+        _call("cov_sweep_rewards", pts, _ptr(pts), n, _ptr(P), _ptr(Q), T, Pn, _ptr(Kd), ctypes.byref(cam), _ptr(boxes),
+              _ptr(minmax), _ptr(sums), ctypes.byref(opts), _ptr(ws), ws_bytes)
+        return sums
+
     def traj_epilogue(self, acc, minmax, Q, n_total, upstream_mode):
         W = Q.shape[0]
         out = torch.empty(1 + 7 * W, dtype=torch.float32, device=acc.device)
@@ -365,38 +395,48 @@ def spatial_sort(points):
 
 @torch.no_grad()
 def sweep_rewards(points, poses, quats, intrins, img_width, img_height, min_dist=1.0, max_dist=5.0, eps=1e-6,
-                  n_total=None, group=None, boxes=None, presorted=False):
-    """Forward-only mean reward of many candidate trajectories: poses (T, P, 3), quats (T, P, 4) -> (T,) fp64.
+                  n_total=None, group=None, boxes=None, presorted=False, shard="points"):
+    """Forward-only mean reward of many candidate trajectories: poses (T, P, 3), quats (T, P, 4) -> (T,) fp64
+    (semantics: ModelTraj.forward per trajectory with every pose evaluated, reference src/model.py:217-237).
     The cloud is Morton-ordered first (no per-point output exists, so the order is free) unless `presorted`;
-    callers that sweep the same cloud repeatedly order it once (`spatial_sort`, `tile_boxes`) and pass both."""
-    L = _lib.lib()
-    pts = _dev_f32(points, what="points")
+    callers that sweep the same cloud repeatedly order it once (`spatial_sort`, `tile_boxes`) and pass both.
+
+    With a `group` (one process per GPU) there are two ways to split the work:
+      shard="points"        `points` is THIS RANK'S slice of the cloud; the per-pose normalisers are all-reduced (MAX of
+                            2 T P floats) and the per-trajectory sums are all-reduced (SUM of T doubles);
+      shard="trajectories"  every rank holds the WHOLE cloud (it fits: 50 M points = 600 MB) and evaluates its own
+                            contiguous block of T / world trajectories — no collective on the data path, one all-gather
+                            of T doubles at the end.  The choice when the cloud fits one GPU."""
+    B = _BACKEND
+    if shard not in ("points", "trajectories"):
+        raise ValueError("shard must be 'points' or 'trajectories'")
+    pts = B.prepare(points, what="points")
     if not presorted and boxes is None and pts.shape[0] > 0:
-        pts, _ = spatial_sort(pts)
+        pts, _, boxes = B.order_cloud(pts, True)
     dev = pts.device
     T, Pn = poses.shape[0], poses.shape[1]
-    P = _dev_f32(poses, dev, "poses").reshape(-1, 3)
-    Q = _dev_f32(quats, dev, "quats").reshape(-1, 4)
-    Kd = _dev_f32(intrins, dev, "intrins").reshape(9)
+    n = pts.shape[0]
+    Kd = B.prepare(intrins, dev, "intrins").reshape(9)
     cam = _lib.camera(img_width, img_height, min_dist, max_dist, eps)
-    W, n = T * Pn, pts.shape[0]
-    minmax = torch.empty(2 * W, dtype=torch.float32, device=dev)
-    chunk = L.cov_traj_max_poses()
-    boxes = tile_boxes(pts) if boxes is None else boxes
-    ws_bytes = max(L.cov_traj_workspace_bytes(n, min(W, chunk)), L.cov_sweep_workspace_bytes(n, T, Pn))
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    opts = _opts()
-    for w0 in range(0, W, chunk):  # pass A reuses the trajectory kernel, one pose-table-full at a time
-        w1 = min(W, w0 + chunk)
-        mm = torch.empty(2 * (w1 - w0), dtype=torch.float32, device=dev)
-        _call("cov_traj_minmax", pts, _ptr(pts), n, _ptr(P[w0:w1]), _ptr(Q[w0:w1]), w1 - w0, _ptr(Kd),
-              ctypes.byref(cam), _ptr(boxes), _ptr(mm), ctypes.byref(opts), _ptr(ws), ws_bytes)
-        minmax[w0:w1] = mm[:w1 - w0]
-        minmax[W + w0:W + w1] = mm[w1 - w0:]
-    _all_reduce_minmax(minmax, W, group)
-    sums = torch.zeros(T, dtype=torch.float64, device=dev)
-    _call("cov_sweep_rewards", pts, _ptr(pts), n, _ptr(P), _ptr(Q), T, Pn, _ptr(Kd), ctypes.byref(cam), _ptr(boxes),
-          _ptr(minmax), _ptr(sums), ctypes.byref(opts), _ptr(ws), ws_bytes)
+    if group is not None and shard == "trajectories":
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        per = (T + world - 1) // world
+        t0, t1 = min(T, rank * per), min(T, (rank + 1) * per)
+        mine = torch.zeros(per, dtype=torch.float64, device=dev)
+        if t1 > t0:
+            P = B.prepare(poses[t0:t1], dev, "poses").reshape(-1, 3)
+            Q = B.prepare(quats[t0:t1], dev, "quats").reshape(-1, 4)
+            minmax = B.sweep_minmax(pts, P, Q, Kd, cam, boxes)
+            mine[:t1 - t0] = B.sweep_sums(pts, P, Q, t1 - t0, Pn, Kd, cam, boxes, minmax)
+        out = torch.empty(world * per, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(out, mine, group=group)
+        return out[:T] / float(n)
+    P = B.prepare(poses, dev, "poses").reshape(-1, 3)
+    Q = B.prepare(quats, dev, "quats").reshape(-1, 4)
+    minmax = B.sweep_minmax(pts, P, Q, Kd, cam, boxes)
+    _all_reduce_minmax(minmax, T * Pn, group)
+    sums = B.sweep_sums(pts, P, Q, T, Pn, Kd, cam, boxes, minmax)
     if group is not None:
         _all_reduce(sums, _reduce_ops()[2], group)
     return sums / float(n if n_total is None else n_total)

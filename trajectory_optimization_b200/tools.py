@@ -39,16 +39,61 @@ def convexHull(points, device):
 def hidden_pts_removal(pts: torch.Tensor, device, R_param: int = 2):
     """src/tools.py:67-85.  Returns (visible points (M,3), visibility mask float32 (N,)).
     Keeps the reference's `vertices[:-1]`: the origin is dropped when it is a hull vertex,
-    otherwise the highest-index visible point is."""
+    otherwise the highest-index visible point is.  Decisions the hull stage could not certify (exactly coplanar or
+    duplicate points: degenerate input, where Qhull's own answer depends on its joggle options) raise a warning."""
     pts = pts.to(device)
     flipped, _ = ops.spherical_flip(pts, R_param)
-    mask, origin_is_vertex, _ = ops.hpr_hull_mask(flipped)
+    mask, origin_is_vertex, n_uncertified = ops.hpr_hull_mask(flipped)
+    if n_uncertified:
+        import warnings
+        warnings.warn(f"hidden_pts_removal: {n_uncertified} hull decision(s) could not be certified even at ~100 bits "
+                      "(degenerate input: duplicate or exactly coplanar points); the visible set may differ from Qhull's "
+                      "on those points", RuntimeWarning, stacklevel=2)
     idx = torch.nonzero(mask, as_tuple=False).reshape(-1)
     if not origin_is_vertex:
         idx = idx[:-1]
     visible_mask = torch.zeros(pts.size()[0], device=device)
     visible_mask[idx] = 1
     return pts[idx, :], visible_mask
+
+
+@torch.no_grad()
+def multi_camera_visibility(points, cam_trans, cam_quats, intrins, img_height, img_width, min_dist=1.0, max_dist=10.0,
+                            R_param=2, device=None, group=None):
+    """The per-camera visibility pipeline of the reference's point-cloud processor for C cameras in one call:
+    ego -> camera frame (src/pc_processor.py:64-70), binary frustum cull (:72-83), Katz hidden-point removal
+    (:178 -> src/tools.py:67-85), all on the device.  `cam_trans` (C,3), `cam_quats` (C,4) (w,x,y,z) are the camera poses
+    in the cloud's frame (what `tf.lookupTransform(pc_frame, cam_frame)` returns, reordered); `intrins` (3,3) or (C,3,3).
+
+    Cameras are independent, so with a `group` (one process per GPU, every rank holding the cloud) they are REPLICATED
+    work: rank r takes cameras r, r + world, ....  Returns a list with one dict per LOCAL camera:
+    camera (index), frustum_idx (int64 indices into `points`, ascending), frustum_points (M,3) camera frame,
+    visible_idx (int64 indices into `points`), visible_points (V,3) camera frame."""
+    from .model import to_camera_frame
+    device = torch.device(device) if device is not None else (points.device if isinstance(points, torch.Tensor) and points.is_cuda
+                                                               else torch.device("cuda", torch.cuda.current_device()))
+    pts = torch.as_tensor(points, dtype=torch.float32).to(device)
+    T = torch.as_tensor(cam_trans, dtype=torch.float32).to(device).reshape(-1, 3)
+    Q = torch.as_tensor(cam_quats, dtype=torch.float32).to(device).reshape(-1, 4)
+    K = torch.as_tensor(intrins, dtype=torch.float32).to(device)
+    C = T.shape[0]
+    rank, world = 0, 1
+    if group is not None:
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+    out = []
+    for c in range(rank, C, world):
+        cam = to_camera_frame(pts, Q[c:c + 1], T[c:c + 1]).contiguous()
+        Kc = K if K.dim() == 2 else K[c]
+        idx, _, _ = ops.frustum_cull(cam, Kc, img_width, img_height, min_dist, max_dist)
+        fr = cam[idx]
+        if fr.shape[0] >= 4:
+            vis_pts, vis_mask = hidden_pts_removal(fr, device, R_param)
+            vis_local = torch.nonzero(vis_mask, as_tuple=False).reshape(-1)
+        else:  # fewer than a tetrahedron: Qhull raises in the reference; nothing can occlude anything
+            vis_pts, vis_local = fr, torch.arange(fr.shape[0], device=device)
+        out.append(dict(camera=c, frustum_idx=idx, frustum_points=fr, visible_idx=idx[vis_local], visible_points=vis_pts))
+    return out
 
 
 def hidden_pts_removal_o3d(pts):
