@@ -314,6 +314,35 @@ def run_c5(args):
         os._exit(0)
 
 
+def pin_to_gpu_numa_node(local):
+    """Bind this process (and the pinned host buffers it allocates from now on) to the CPUs of the NUMA node the GPU
+    hangs off, so that the host->device copies of several ranks do not all cross the same socket interconnect.
+    Best effort: returns a short description, or the reason nothing was done."""
+    try:
+        bus = torch.cuda.get_device_properties(local).pci_bus_id if hasattr(torch.cuda.get_device_properties(local), "pci_bus_id") else None
+        if bus is None:
+            out = subprocess.run(["nvidia-smi", "-i", str(local), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                                 capture_output=True, text=True, timeout=10).stdout.strip()
+            bus = out[-12:].lower() if out else None
+        else:
+            bus = "%04x:%02x:%02x.0" % (torch.cuda.get_device_properties(local).pci_domain_id, bus,
+                                         torch.cuda.get_device_properties(local).pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return "GPU reports no NUMA node"
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.extend(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return f"no allowed CPU on NUMA node {node}"
+        os.sched_setaffinity(0, allowed)
+        return f"bound to NUMA node {node} ({len(allowed)} CPUs) of GPU {bus}"
+    except Exception as exc:
+        return "not bound (%s)" % (str(exc).splitlines()[0][:80],)
+
+
 def config_dict(n_total, world):
     return {"workload": "c4: trajectory optimisation fwd+bwd, 64 waypoints x 5 cams = 320 poses, "
                         f"{n_total / 1e6:g}M-point synthetic box cloud, point-sharded over {world} GPU(s)",
@@ -371,6 +400,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_note = pin_to_gpu_numa_node(local)
     group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -731,6 +761,7 @@ def main():
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "note": "a NEW cloud from pinned host memory every step (copy + spatial ordering + objective + gradient + "
                             "read-back); bound by the PCIe copy",
+                    "host_affinity": numa_note,
                     "resident_cloud": {"value": n_total * W * args.steps / (ms_params * 1e-3), "unit": "point*pose evals/s",
                                        "ms_per_step": ms_params / args.steps,
                                        "h2d_bytes_per_step": host_body.numel() * 4 * world, "d2h_bytes_per_step": d2h,

@@ -4,7 +4,9 @@
       ModelPose kernel at 1e8 points against the HBM roofline;
   c3  5-camera trajectory evaluation, 20 waypoints, 10M points (fwd+bwd evals/s);
   c5  candidate sweep sample: 64 of the 1024 trajectories x 32 waypoints on a 50M-point cloud (fwd evals/s).
-c2 (HPR) is scripts/hpr_bench.py.  Not the driver's bench; numbers are quoted in DESIGN.md/profiles."""
+c2 (HPR) is scripts/hpr_bench.py.  Every GPU figure is followed by the same work through oracle/torch_port.py (the
+torch port of the reference) on the host cores AND on the GPU in eager mode (what a user of the reference gets today
+on this machine).  Not the driver's bench; numbers are quoted in DESIGN.md/profiles."""
 import json
 import os
 import sys
@@ -163,3 +165,75 @@ with ops.evaluation(dense=True):
 print(json.dumps({"config": "c5 dense sample: 32 of the 1024 trajectories, pruning off", "ms": ms_d,
                   "pairs_per_s": 5e7 * 32 * 32 / (ms_d * 1e-3), "extrapolated_full_c5_s": ms_d * 1e-3 * 32,
                   "max_rel_diff_vs_pruned": float(((res[:32] - res_d).abs() / res_d.abs()).max())}), flush=True)
+
+
+# ---- the reference's own arithmetic (oracle/torch_port.py) on the host cores and on the GPU in eager mode ----
+from oracle import torch_port  # noqa: E402
+
+threads = os.cpu_count() or 1
+torch.set_num_threads(threads)
+
+
+def port_pose_step(points, device, reps):
+    T = torch.tensor([[6.0, 2.0, 0.0]], device=device, requires_grad=True)
+    Qp = torch.tensor([[0.92, 0.0, 0.0, 0.39]], device=device, requires_grad=True)
+    o = torch.optim.Adam([{"params": [T], "lr": 0.02}, {"params": [Qp], "lr": 0.02}])
+    Kd = K.to(device)
+
+    def one():
+        o.zero_grad()
+        loss, _ = torch_port.pose_loss(points, T, Qp, Kd, iw, ih)
+        loss.backward()
+        o.step()
+
+    for _ in range(2):
+        one()
+    if device.type == "cuda":
+        torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        one()
+    if device.type == "cuda":
+        torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / reps * 1e3
+
+
+def port_traj_step(points, P, Q, device, reps):
+    Kd = K.to(device)
+    P, Q, points = P.to(device), Q.to(device), points.to(device)
+    for _ in range(1):
+        torch_port.traj_step(points, P, Q, Kd, iw, ih)
+    if device.type == "cuda":
+        torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        torch_port.traj_step(points, P, Q, Kd, iw, ih)
+    if device.type == "cuda":
+        torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / reps * 1e3
+
+
+cpu = torch.device("cpu")
+pts1 = box(100_000, 0)
+ms_cpu = port_pose_step(pts1.cpu(), cpu, 10)
+ms_gpu = port_pose_step(pts1, dev, 50)
+print(json.dumps({"config": "c1 reference arithmetic (oracle/torch_port.py): ModelPose opt step, 100k points",
+                  "cpu_ms_per_step": ms_cpu, "cpu_threads": threads, "torch_cuda_eager_ms_per_step": ms_gpu}), flush=True)
+sel = slice(0, None, 2)   # wps_step = 2 on the sample path (src/model.py:214-217)
+sample_pts = torch.from_numpy(sample["pts"]).float()   # (`spts` was reused for the c5 cloud above)
+ms_cpu = port_traj_step(sample_pts, sposes[sel], squats[sel], cpu, 3)
+ms_gpu = port_traj_step(sample_pts, sposes[sel], squats[sel], dev, 10)
+print(json.dumps({"config": "reference arithmetic: trajectory visibility fwd+bwd on the reference's sample cloud (40k points, 14 of 27 "
+                            "waypoints)", "cpu_ms_per_step": ms_cpu, "cpu_threads": threads,
+                  "torch_cuda_eager_ms_per_step": ms_gpu}), flush=True)
+with torch.no_grad():
+    t3, q3 = multicam.camera_poses_from_body(bench.body_waypoints(20, 12.0), multicam.ring_rig(5))
+P3, Q3 = t3.reshape(-1, 3).contiguous(), q3.reshape(-1, 4).contiguous()
+n3 = 100_000   # torch autograd keeps ~240 B per (point, pose): 1e7 x 100 would need 240 GB
+pts3 = box(n3, 2)
+ms_cpu = port_traj_step(pts3.cpu(), P3, Q3, cpu, 2)
+ms_gpu = port_traj_step(pts3, P3, Q3, dev, 5)
+print(json.dumps({"config": "c3 reference arithmetic on a 100k-point sample (100 poses; 1e7 points do not fit torch autograd)",
+                  "cpu_ms_per_step": ms_cpu, "cpu_evals_per_s": n3 * 100 / (ms_cpu * 1e-3), "cpu_threads": threads,
+                  "torch_cuda_eager_ms_per_step": ms_gpu, "torch_cuda_eager_evals_per_s": n3 * 100 / (ms_gpu * 1e-3),
+                  "extrapolated_cpu_s_per_c3_step": ms_cpu * 1e-3 * 1e7 / n3}), flush=True)
