@@ -35,6 +35,8 @@ struct HullWs {  // carve-up of the caller's workspace
     unsigned long long* rho_max_bits;  // 1
     int* n_occ;           // 1
     int* n_valid;         // 1
+    int* n_far;           // 1: points handed to the warp-per-point sweep (their sorted ids reuse `key`)
+    int* block_tot;       // ceil(G^3 / 4096): chunk totals / offsets of the histogram scan
 };
 
 size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
@@ -53,6 +55,8 @@ size_t hull_carve(void* base, int64_t n, int G, HullWs* w) {
     t.rho_max_bits = (unsigned long long*)take(16);
     t.n_occ = (int*)take(16);
     t.n_valid = (int*)take(16);
+    t.n_far = (int*)take(16);
+    t.block_tot = (int*)take(((ncell + 4095) / 4096 + 1) * sizeof(int));
     if (w) *w = t;
     return off;
 }
@@ -78,49 +82,78 @@ hull_prep_kernel(const float* __restrict__ f, int64_t n, int G, int* __restrict_
 
 // exclusive scan in place over ncell+1 entries (entry ncell receives the total).  One block walks the histogram in
 // chunks of 4096 consecutive cells (4 per thread, so a warp touches 512 contiguous bytes) and carries the running total.
-__global__ void __launch_bounds__(1024) hull_scan_kernel(int* __restrict__ cnt, int64_t ncell, int* __restrict__ n_valid) {
-    __shared__ int wtot[32];
-    __shared__ int chunk_total;
+// Exclusive scan of the cell histogram in three small launches (a single block walking 2 M cells took 1 ms):
+// per-block totals of 4096-cell chunks, a one-block scan of those totals, then each block scans its chunk from its offset.
+constexpr int kScanChunk = 4096;
+
+__device__ __forceinline__ int hull_block_exclusive_scan(int s, int* wtot, int& total) {  // 1024 threads; s = thread's sum
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    int carry = 0;
-    for (int64_t base = 0; base < ncell; base += 4096) {
-        const int64_t i = base + (int64_t)t * 4;
-        int v[4];
+    int incl = s;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = (i + k < ncell) ? cnt[i + k] : 0;
-        const int s = v[0] + v[1] + v[2] + v[3];
-        int incl = s;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+    }
+    if (lane == 31) wtot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const int w = wtot[lane];
+        int sc = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const int u = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += u;
+            const int u = __shfl_up_sync(0xffffffffu, sc, o);
+            if (lane >= o) sc += u;
         }
-        if (lane == 31) wtot[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            const int w = wtot[lane];
-            int sc = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int u = __shfl_up_sync(0xffffffffu, sc, o);
-                if (lane >= o) sc += u;
-            }
-            wtot[lane] = sc - w;  // exclusive over warps
-            if (lane == 31) chunk_total = sc;
-        }
-        __syncthreads();
-        int run = carry + wtot[warp] + incl - s;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (i + k < ncell) cnt[i + k] = run;
-            run += v[k];
-        }
-        carry += chunk_total;
-        __syncthreads();  // wtot / chunk_total are rewritten by the next chunk
+        wtot[lane] = sc - w;  // exclusive over warps
+        if (lane == 31) wtot[32] = sc;
     }
-    if (t == 0) {
+    __syncthreads();
+    total = wtot[32];
+    return wtot[warp] + incl - s;
+}
+
+__global__ void __launch_bounds__(1024) hull_scan_totals_kernel(const int* __restrict__ cnt, int64_t ncell, int* __restrict__ block_tot) {
+    __shared__ int wtot[33];
+    const int64_t i = (int64_t)blockIdx.x * kScanChunk + (int64_t)threadIdx.x * 4;
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s += (i + k < ncell) ? cnt[i + k] : 0;
+    int total;
+    hull_block_exclusive_scan(s, wtot, total);
+    if (threadIdx.x == 0) block_tot[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) hull_scan_offsets_kernel(int* __restrict__ block_tot, int nblocks, int* __restrict__ cnt,
+                                                                 int64_t ncell, int* __restrict__ n_valid) {
+    __shared__ int wtot[33];
+    int carry = 0;
+    for (int base = 0; base < nblocks; base += 1024) {  // one round up to 1024 chunks = 4 M cells
+        const int i = base + threadIdx.x;
+        const int v = i < nblocks ? block_tot[i] : 0;
+        int total;
+        const int ex = hull_block_exclusive_scan(v, wtot, total);
+        if (i < nblocks) block_tot[i] = carry + ex;
+        carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
         cnt[ncell] = carry;
         *n_valid = carry;
+    }
+}
+
+__global__ void __launch_bounds__(1024) hull_scan_apply_kernel(int* __restrict__ cnt, int64_t ncell, const int* __restrict__ block_off) {
+    __shared__ int wtot[33];
+    const int64_t i = (int64_t)blockIdx.x * kScanChunk + (int64_t)threadIdx.x * 4;
+    int v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = (i + k < ncell) ? cnt[i + k] : 0;
+    int total;
+    int run = block_off[blockIdx.x] + hull_block_exclusive_scan(v[0] + v[1] + v[2] + v[3], wtot, total);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (i + k < ncell) cnt[i + k] = run;
+        run += v[k];
     }
 }
 
@@ -146,7 +179,7 @@ __global__ void __launch_bounds__(128)
 hull_classify_kernel(int G, const int* __restrict__ cell_start, const float4* __restrict__ sorted,
                      const int* __restrict__ occ, const int* __restrict__ n_occ,
                      const unsigned long long* __restrict__ rho_max_bits, const int* __restrict__ n_valid,
-                     uint8_t* __restrict__ mask, int* __restrict__ info) {
+                     uint8_t* __restrict__ mask, int* __restrict__ info, int* __restrict__ far_list, int* __restrict__ n_far) {
     const int k = blockIdx.x * 128 + threadIdx.x;
     if (k >= *n_valid) return;
     HullGrid g;
@@ -158,14 +191,114 @@ hull_classify_kernel(int G, const int* __restrict__ cell_start, const float4* __
     g.n_occ = *n_occ;
     g.rho_max = __longlong_as_double((long long)*rho_max_bits);
     int cert[3];
-    const int rc = hull_classify_point(g, k, cert);
-    const bool vertex = (rc == HULL_EXTREME || rc == HULL_EXTREME_UNCERT);  // OVERFLOW: the LP ran away, no feasible region in reach
+    // near phase only (one thread per point); a point that needs the all-voxel sweep, a wider tilt box or a bigger
+    // active set goes on the far list and gets a whole warp (hull_far_kernel)
+    const int rc = hull_classify_attempt(g, k, HULL_TILT_NEAR, cert, false);
+    if (rc == HULL_UNDECIDED || rc == HULL_EXTREME_UNCERT || rc == HULL_OVERFLOW) {
+        far_list[atomicAdd(n_far, 1)] = k;
+        return;
+    }
+    const bool vertex = rc == HULL_EXTREME;
     mask[__float_as_int(sorted[k].w)] = vertex ? 1 : 0;
-    if (rc != HULL_EXTREME && rc != HULL_INSIDE) atomicAdd(info + 1, 1);  // decided by the LP but not certified in fp64
+    if (rc != HULL_EXTREME && rc != HULL_INSIDE) atomicAdd(info + 1, 1);  // decided by the LP but not certified
     if (vertex) atomicAdd(info + 2, 1);
 }
 
-// One block: GJK on conv(F).  info[0] = 1 when the origin is outside conv(F) (i.e. a vertex of conv(F U {0})).
+// The all-voxel sweep for the points of the far list (silhouette points of a cloud that does not surround the camera:
+// large tilt), ONE WARP PER POINT.  Every lane keeps the same LP (the updates are deterministic, so the 32 copies never
+// diverge); per round the lanes scan disjoint subsets of the occupied voxels, culled by the bound on n.f over a voxel,
+// for the MOST VIOLATED half-plane, the warp agrees on one, and every lane adds it.  The answer (feasible / infeasible)
+// does not depend on the pivot order; certificates as in hull_core.h.
+__global__ void __launch_bounds__(128)
+hull_far_kernel(int G, const int* __restrict__ cell_start, const float4* __restrict__ sorted, const int* __restrict__ occ,
+                const int* __restrict__ n_occ_p, const unsigned long long* __restrict__ rho_max_bits,
+                const int* __restrict__ far_list, const int* __restrict__ n_far, uint8_t* __restrict__ mask,
+                int* __restrict__ info) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const int n_occ = *n_occ_p;
+    const double h = 2.0 / G;
+    const double rho_max = __longlong_as_double((long long)*rho_max_bits);
+    for (int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < *n_far; item += warps) {
+        const int self = far_list[item];
+        const float4 ps = sorted[self];
+        HullFrame F;
+        hull_frame_init(F, (double)ps.x, (double)ps.y, (double)ps.z);
+        int rc = HULL_UNDECIDED;
+        int cert[3] = {-1, -1, -1};
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            const double tilt = attempt == 0 ? HULL_TILT_NEAR : HULL_TILT_MAX;
+            HullLP L;
+            hull_lp_init(L, tilt);
+            rc = HULL_UNDECIDED;
+            for (int round = 0; round < 4096 && rc == HULL_UNDECIDED; ++round) {
+                const double n0 = F.u[0] + L.x0 * F.e1[0] + L.x1 * F.e2[0];
+                const double n1 = F.u[1] + L.x0 * F.e1[1] + L.x1 * F.e2[1];
+                const double n2 = F.u[2] + L.x0 * F.e1[2] + L.x1 * F.e2[2];
+                const double nn = sqrt(n0 * n0 + n1 * n1 + n2 * n2);
+                const double np = (n0 * F.p[0] + n1 * F.p[1] + n2 * F.p[2]) * (1.0 - 1e-12);
+                const double slack = nn * h * 0.8660254037844387;
+                double best = 0.0, ba = 0.0, bb = 0.0, bc = 0.0;  // most violated half-plane this lane has seen (score < 0)
+                int bid = -1;
+                for (int k = lane; k < n_occ; k += 32) {
+                    const int cell = occ[k];
+                    const int iz = cell % G, iy = (cell / G) % G, ix = cell / (G * G);
+                    const double c0 = (ix + 0.5) * h - 1.0, c1 = (iy + 0.5) * h - 1.0, c2 = (iz + 0.5) * h - 1.0;
+                    if (rho_max * (n0 * c0 + n1 * c1 + n2 * c2 + slack) < np) continue;
+                    const int b = cell_start[cell], e = cell_start[cell + 1];
+                    for (int j = b; j < e; ++j) {
+                        if (j == self) continue;
+                        const float4 sp = sorted[j];
+                        double a, bq, c;
+                        hull_constraint(F, tilt, (double)sp.x, (double)sp.y, (double)sp.z, a, bq, c);
+                        if (!hull_violated(L, a, bq, c)) continue;
+                        bool active = false;
+                        for (int q = 0; q < L.n; ++q) active |= L.id[q] == j;
+                        if (active) continue;  // the residual is evaluation noise of an optimum that sits on its line
+                        const double score = (a * L.x0 + bq * L.x1 + c) / (fabs(a * L.x0) + fabs(bq * L.x1) + fabs(c));
+                        if (score < best || (score == best && (bid < 0 || j < bid))) { best = score; ba = a; bb = bq; bc = c; bid = j; }
+                    }
+                }
+                // the warp's most violated half-plane (ties: smallest id) — the same on every lane
+                double wbest = best;
+                int wid = bid;
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ob = __shfl_xor_sync(0xffffffffu, wbest, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, wid, o);
+                    if (oi >= 0 && (wid < 0 || ob < wbest || (ob == wbest && oi < wid))) { wbest = ob; wid = oi; }
+                }
+                if (wid < 0) {  // clean sweep over everything the bound could not exclude
+                    rc = (fabs(L.x0) > L.tilt || fabs(L.x1) > L.tilt) ? HULL_EXTREME_UNCERT : HULL_EXTREME;
+                    break;
+                }
+                const int src = __ffs(__ballot_sync(0xffffffffu, bid == wid && best == wbest)) - 1;
+                const double a = __shfl_sync(0xffffffffu, ba, src), bq = __shfl_sync(0xffffffffu, bb, src),
+                             c = __shfl_sync(0xffffffffu, bc, src);
+                const int r = hull_lp_add(L, a, bq, c, wid);
+                if (r == HULL_INSIDE || r == HULL_OVERFLOW) rc = r;
+            }
+            if (rc == HULL_UNDECIDED) rc = HULL_OVERFLOW;  // round limit
+            if (rc == HULL_INSIDE) { cert[0] = L.cert[0]; cert[1] = L.cert[1]; cert[2] = L.cert[2]; }
+            if (rc != HULL_EXTREME_UNCERT && rc != HULL_OVERFLOW) break;  // settled within this tilt box
+        }
+        if (lane == 0) {
+            if (rc == HULL_INSIDE) {
+                bool ok = cert[0] >= 0 && cert[1] >= 0 && cert[2] >= 0 && cert[0] != cert[1] && cert[1] != cert[2] && cert[0] != cert[2];
+                if (ok) {
+                    const float4 s1 = sorted[cert[0]], s2 = sorted[cert[1]], s3 = sorted[cert[2]];
+                    const double a1[3] = {s1.x, s1.y, s1.z}, a2[3] = {s2.x, s2.y, s2.z}, a3[3] = {s3.x, s3.y, s3.z};
+                    ok = hull_certify_inside(F.p, a1, a2, a3) != 0;
+                }
+                if (!ok) rc = HULL_INSIDE_UNCERT;
+            }
+            const bool vertex = (rc == HULL_EXTREME || rc == HULL_EXTREME_UNCERT);
+            mask[__float_as_int(ps.w)] = vertex ? 1 : 0;
+            if (rc != HULL_EXTREME && rc != HULL_INSIDE) atomicAdd(info + 1, 1);
+            if (vertex) atomicAdd(info + 2, 1);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(1024)
 hull_origin_kernel(const float* __restrict__ f, int64_t n, int* __restrict__ info) {
     __shared__ HullSimplex S;
@@ -260,17 +393,26 @@ extern "C" int cov_hpr_hull(const float* flipped, int64_t n, uint8_t* vertex_mas
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t ncell = (int64_t)G * G * G;
     // one memset clears histogram, cursors, occupied list and the three scalars (contiguous in the carve-up)
-    cudaMemsetAsync(w.cell_count, 0, (size_t)((char*)w.n_valid + 16 - (char*)w.cell_count), s);
+    cudaMemsetAsync(w.cell_count, 0, (size_t)((char*)w.n_far + 16 - (char*)w.cell_count), s);
     cudaMemsetAsync(info, 0, 4 * sizeof(int32_t), s);
     int64_t nb = (n + 255) / 256;
     const int64_t cap = (int64_t)cov_sm_count_cached() * 16;
     if (nb > cap) nb = cap;
     hull_prep_kernel<<<(unsigned)nb, 256, 0, s>>>(flipped, n, G, w.key, w.cell_count, w.rho_max_bits);
-    hull_scan_kernel<<<1, 1024, 0, s>>>(w.cell_count, ncell, w.n_valid);
+    {
+        // `cursor` (zero until the scatter below) lends its head to the chunk totals
+        const int nchunk = (int)((ncell + kScanChunk - 1) / kScanChunk);
+        hull_scan_totals_kernel<<<nchunk, 1024, 0, s>>>(w.cell_count, ncell, w.block_tot);
+        hull_scan_offsets_kernel<<<1, 1024, 0, s>>>(w.block_tot, nchunk, w.cell_count, ncell, w.n_valid);
+        hull_scan_apply_kernel<<<nchunk, 1024, 0, s>>>(w.cell_count, ncell, w.block_tot);
+    }
     hull_occupied_kernel<<<(unsigned)((ncell + 255) / 256), 256, 0, s>>>(w.cell_count, ncell, w.occ, w.n_occ);
     hull_scatter_kernel<<<(unsigned)nb, 256, 0, s>>>(flipped, n, w.key, w.cell_count, w.cursor, w.sorted, vertex_mask);
+    // `key` is free once the points are scattered: it becomes the list of the points that need the all-voxel sweep
     hull_classify_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(G, w.cell_count, w.sorted, w.occ, w.n_occ,
-                                                                    w.rho_max_bits, w.n_valid, vertex_mask, info);
+                                                                    w.rho_max_bits, w.n_valid, vertex_mask, info, w.key, w.n_far);
+    hull_far_kernel<<<(unsigned)(cov_sm_count_cached() * 8), 128, 0, s>>>(G, w.cell_count, w.sorted, w.occ, w.n_occ, w.rho_max_bits,
+                                                                         w.key, w.n_far, vertex_mask, info);
     hull_origin_kernel<<<1, 1024, 0, s>>>(flipped, n, info);
     return cov_check_launch("cov_hpr_hull");
 }

@@ -281,7 +281,9 @@ HULL_HD int hull_sweep_cell(const HullGrid& g, int cell, int self, const HullFra
 #define HULL_R_NEAR 6
 
 // Classify sorted point `self`.  cert_out receives the three sorted-array ids of an INSIDE certificate.
-HULL_HD int hull_classify_attempt(const HullGrid& g, int self, double tilt, int* cert_out) {
+// far_ok = false: stop after the near phase and return HULL_UNDECIDED when the point needs the all-voxel sweep (the
+// CUDA path hands those points to a kernel that runs that sweep with a whole warp per point).
+HULL_HD int hull_classify_attempt(const HullGrid& g, int self, double tilt, int* cert_out, bool far_ok = true) {
     const float4 ps = g.sorted[self];
     HullFrame F;
     hull_frame_init(F, (double)ps.x, (double)ps.y, (double)ps.z);
@@ -317,6 +319,7 @@ HULL_HD int hull_classify_attempt(const HullGrid& g, int self, double tilt, int*
         if (whole || hull_coverage_ok(L, F.rho, g.rho_max, r * g.h)) { rc = HULL_EXTREME; break; }
         ++r;
     }
+    if (rc == HULL_UNDECIDED && !far_ok) return HULL_UNDECIDED;
     // far phase (large tilt, e.g. silhouette points of a half-space cloud): every occupied voxel, culled by a
     // bound on n.f over the voxel: rho_max (n.c + |n| h sqrt(3)/2), c = voxel centre.
     while (rc == HULL_UNDECIDED) {
