@@ -604,17 +604,18 @@ def main():
     stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
     stats_dev = torch.zeros(8, dtype=torch.int64, device=dev)
-    call_opts = {"o": _lib.traj_opts(dense=False, stats=stats_dev)}
+    # as the product path calls them (ops.CoverageTrajFn): pass A pre-fills pass B's rewards under its idle bandwidth
+    call_opts = {"a": _lib.traj_opts(stats=stats_dev, prefill=rewards), "b": _lib.traj_opts(stats=stats_dev, rewards_prefilled=True)}
 
     def pass_a():
         _lib.check(L.cov_traj_minmax(pts_sorted.data_ptr(), n_local, P.data_ptr(), Q.data_ptr(), W, K.data_ptr(),
-                                     ctypes.byref(cam), boxes.data_ptr(), minmax.data_ptr(), ctypes.byref(call_opts["o"]),
+                                     ctypes.byref(cam), boxes.data_ptr(), minmax.data_ptr(), ctypes.byref(call_opts["a"]),
                                      ws.data_ptr(), wsb, stream), "cov_traj_minmax")
 
     def pass_b():
         _lib.check(L.cov_traj_fused(pts_sorted.data_ptr(), n_local, P.data_ptr(), Q.data_ptr(), W, K.data_ptr(),
                                     ctypes.byref(cam), boxes.data_ptr(), minmax.data_ptr(), None, perm.data_ptr(),
-                                    rewards.data_ptr(), acc.data_ptr(), ctypes.byref(call_opts["o"]), ws.data_ptr(), wsb,
+                                    rewards.data_ptr(), acc.data_ptr(), ctypes.byref(call_opts["b"]), ws.data_ptr(), wsb,
                                     stream), "cov_traj_fused")
 
     def global_minmax():
@@ -629,17 +630,17 @@ def main():
     pass_b()
     torch.cuda.synchronize()
     st = [int(x) for x in stats_dev.tolist()]        # work counters of exactly one pass A + one pass B
-    call_opts["o"] = _lib.traj_opts(dense=False)     # timed without the counters' atomics
+    call_opts["a"], call_opts["b"] = _lib.traj_opts(prefill=rewards), _lib.traj_opts(rewards_prefilled=True)  # no counters
     ms_a = timed(pass_a, reps) / reps
     global_minmax()
     ms_b = timed(pass_b, reps) / reps
-    call_opts["o"] = _lib.traj_opts(dense=True)
+    call_opts["a"] = call_opts["b"] = _lib.traj_opts(dense=True)
     global_minmax()
     pass_b()
     ms_a_dense = timed(pass_a, reps) / reps
     global_minmax()
     ms_b_dense = timed(pass_b, reps) / reps
-    call_opts["o"] = _lib.traj_opts(dense=False)
+    call_opts["a"], call_opts["b"] = _lib.traj_opts(prefill=rewards), _lib.traj_opts(rewards_prefilled=True)
     global_minmax()
     pass_b()
     gated = float((rewards != 0.5).float().mean().item())  # fraction of points with at least one gated pose
@@ -703,8 +704,9 @@ def main():
     flops_a = st[3] * FLOP_FWD * 256
     roofline = {
         "kernel": "cov_traj_fused call = pass B on the Morton-ordered cloud, pruning on: cov_traj_table_kernel, "
-                  "cov_cull_kernel (+ work list + rewards pre-fill), cov_traj_fused_tiles_kernel (persistent warps; ~85 % of "
-                  "the call)",
+                  "cov_cull_kernel (+ work list), cov_traj_fused_tiles_kernel (persistent warps; ~90 % of the call); the "
+                  "rewards were pre-filled with 1/2 by the pass-A call before it (its 4 B/point are in BOTH calls' byte counts "
+                  "below: bytes_per_point 16 here, 12 for pass A, as SURVEY 8d defines them)",
         "bound": "hbm", "achieved": gbs_b, "peak": hbm_peak, "unit": "GB/s", "frac": gbs_b / hbm_peak,
         "peak_source": hbm_src, "bytes_per_point": BYTES_PASS_B, "ms_per_launch": ms_b,
         "traffic": traffic, "traffic_source": traffic_src,

@@ -100,13 +100,21 @@ size_t cov_traj_workspace_bytes(int64_t n, int n_poses);
  * consecutive points (cov_spatial_sort).  Clouds below 65536 points always take the dense kernels. */
 typedef struct cov_traj_opts {
     int dense;                     /* != 0: evaluate every (point, pose) pair (what an unordered cloud should ask for) */
-    int rewards_prefilled;         /* cov_traj_fused: != 0: rewards_dev already holds 1/2 everywhere (skip the pre-fill) */
+    int rewards_prefilled;         /* cov_traj_fused: != 0: rewards_dev already holds 1/2 everywhere (skip the pre-fill);
+                                      ignored by the dense path, which writes every reward itself */
+    float* prefill_dev;            /* cov_traj_minmax: NULL, or the (n) rewards buffer of the cov_traj_fused call that
+                                      follows: the pruned pass A fills it with 1/2 under its idle memory bandwidth
+                                      (then pass rewards_prefilled = 1 to cov_traj_fused).  Honoured only when the call
+                                      takes the pruned path (dense == 0 and n >= 65536): cov_traj_prefill_applies() */
     unsigned long long* stats_dev; /* NULL, or 8 device counters the evaluation kernels ADD to, in (warp, pose) pairs:
                                       [0] pass B all pairs, [1] evaluated (forward), [2],[3] same for pass A, [4] pass B
                                       pairs differentiated (evaluated again + gradient), [5] pass A pairs that ran the
                                       per-point pre-filter, [6]/[7] pass B/A pairs the cull listed
                                       (benchmark reporting; NULL in production) */
 } cov_traj_opts;
+
+/* != 0 when cov_traj_minmax with these options and this n honours prefill_dev (i.e. takes the pruned path). */
+int cov_traj_prefill_applies(int64_t n, const cov_traj_opts* opts);
 
 /* boxes_dev: NULL, or the bounding boxes cov_tile_boxes made for this cloud (built once per cloud; with NULL the
  * pruned kernels rebuild them into the workspace on every call).  workspace_dev: cov_traj_workspace_bytes(n, n_poses)

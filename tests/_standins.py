@@ -60,13 +60,16 @@ class OracleBackend:
     def traj_workspace_bytes(self, pts, W):
         return 0
 
-    def traj_minmax(self, pts, P, Q, Kd, cam, boxes=None, ws=None, dense=None):
+    def prefill_applies(self, pts, dense=None):
+        return False
+
+    def traj_minmax(self, pts, P, Q, Kd, cam, boxes=None, ws=None, dense=None, prefill=None):
         mm = [self._vis(pts, P[w], Q[w], Kd, cam)[0] for w in range(len(P))]
         # fp64 so that the stand-in's second pass can find its arg-min/arg-max by exact comparison
         return torch.tensor([m.min() for m in mm] + [m.max() for m in mm], dtype=torch.float64)
 
     def traj_fused(self, pts, P, Q, Kd, cam, minmax, upstream, rewards, reward_index=None, boxes=None, ws=None,
-                   dense=None):
+                   dense=None, prefilled=False):
         W, hi = len(P), float(np.float32(1.0 - cam.eps))
         acc, L, keep = np.zeros(W * ACC + 1), np.zeros(len(pts)), []
         for w in range(W):

@@ -25,7 +25,7 @@ class Camera(C.Structure):
 
 class TrajOpts(C.Structure):
     """struct cov_traj_opts (per-call options; all zero = defaults)."""
-    _fields_ = [("dense", C.c_int), ("rewards_prefilled", C.c_int), ("stats_dev", C.c_void_p)]
+    _fields_ = [("dense", C.c_int), ("rewards_prefilled", C.c_int), ("prefill_dev", C.c_void_p), ("stats_dev", C.c_void_p)]
 
 
 _vp, _i64, _int, _f, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_size_t
@@ -42,6 +42,7 @@ PROTOTYPES = {
     "cov_pose_epilogue": (_int, [_vp, _vp, _vp, _vp, _vp]),
     "cov_traj_max_poses": (_int, []),
     "cov_traj_workspace_bytes": (_sz, [_i64, _int]),
+    "cov_traj_prefill_applies": (_int, [_i64, _opts]),
     "cov_traj_minmax": (_int, [_vp, _i64, _vp, _vp, _int, _vp, _cam, _vp, _vp, _opts, _vp, _sz, _vp]),
     "cov_traj_fused": (_int, [_vp, _i64, _vp, _vp, _int, _vp, _cam, _vp, _vp, _vp, _vp, _vp, _vp, _opts, _vp, _sz, _vp]),
     "cov_traj_epilogue": (_int, [_vp, _vp, _vp, _int, _i64, _int, _vp, _vp]),
@@ -98,6 +99,8 @@ def camera(img_width, img_height, min_dist, max_dist, eps):
     return Camera(float(img_width), float(img_height), float(min_dist), float(max_dist), float(eps))
 
 
-def traj_opts(dense=False, rewards_prefilled=False, stats=None):
-    """cov_traj_opts; `stats`: None or a CUDA int64/uint64 tensor of 8 counters the evaluation kernels add to."""
-    return TrajOpts(1 if dense else 0, 1 if rewards_prefilled else 0, None if stats is None else stats.data_ptr())
+def traj_opts(dense=False, rewards_prefilled=False, stats=None, prefill=None):
+    """cov_traj_opts; `stats`: None or a CUDA int64/uint64 tensor of 8 counters the evaluation kernels add to;
+    `prefill`: None or the fp32 rewards tensor pass A should fill with 1/2 for the pass B that follows."""
+    return TrajOpts(1 if dense else 0, 1 if rewards_prefilled else 0, None if prefill is None else prefill.data_ptr(),
+                    None if stats is None else stats.data_ptr())

@@ -622,7 +622,8 @@ __global__ void __launch_bounds__(COV_THREADS, 3)
 cov_traj_minmax_tiles_kernel(const float* __restrict__ xyz, int64_t n, const float4* __restrict__ table, int W, CovConst C,
                              unsigned* __restrict__ enc, float* __restrict__ minmax_out, const float4* __restrict__ boxes,
                              const unsigned* __restrict__ amask_g, int mask_stride, const int* __restrict__ worklist,
-                             int* __restrict__ ctrl, int64_t ntiles, unsigned long long* __restrict__ stats) {
+                             int* __restrict__ ctrl, int64_t ntiles, unsigned long long* __restrict__ stats,
+                             float* __restrict__ fill_dst, int64_t fill_n) {
     constexpr int PPT = kItemPpt;
     extern __shared__ float4 smem4[];                      // block minima | maxima (uint) | per-pose caps
     unsigned* smin = reinterpret_cast<unsigned*>(smem4);
@@ -647,6 +648,22 @@ cov_traj_minmax_tiles_kernel(const float* __restrict__ xyz, int64_t n, const flo
     const int n_items = ctrl[0] * kItemsPerTile;
     const int nwords = (W + 31) >> 5;
     int* ticket = ctrl + 3;
+    // Pre-fill of pass B's rewards with 1/2 under this kernel's idle memory bandwidth (cov_traj_opts.prefill_dev): the
+    // warp that takes item i also writes slice i of the buffer (fire-and-forget streaming stores), in 16-byte units.
+    const int64_t fill_q = (fill_n + 3) / 4;                                          // float4 slots (tail handled below)
+    const int64_t fill_per_item = fill_dst ? (fill_q + (n_items > 0 ? n_items : 1) - 1) / (n_items > 0 ? n_items : 1) : 0;
+    auto fill_slice = [&](int64_t q0, int64_t q1) {
+        if (q1 > fill_q) q1 = fill_q;
+        for (int64_t q = q0 + lane; q < q1; q += 32) {
+            if (q * 4 + 4 <= fill_n) __stcs(reinterpret_cast<float4*>(fill_dst) + q, make_float4(0.5f, 0.5f, 0.5f, 0.5f));
+            else for (int64_t k = q * 4; k < fill_n; ++k) fill_dst[k] = 0.5f;
+        }
+    };
+    if (fill_dst && n_items == 0) {  // nothing listed: the warps of the grid share the whole buffer
+        const int64_t gw = (int64_t)blockIdx.x * kWarps + warp, nw = (int64_t)gridDim.x * kWarps;
+        const int64_t per = (fill_q + nw - 1) / nw;
+        fill_slice(gw * per, (gw + 1) * per);
+    }
     auto issue = [&](int it, int b) {
         if (it >= n_items) return;
         const int64_t tile = worklist[it >> 3];
@@ -674,6 +691,7 @@ cov_traj_minmax_tiles_kernel(const float* __restrict__ xyz, int64_t n, const flo
             issue(nxt, buf ^ 1);
         }
         nxt = __shfl_sync(kFull, nxt, 0);
+        if (fill_dst) fill_slice((int64_t)cur * fill_per_item, (int64_t)(cur + 1) * fill_per_item);
         if (buf == 0) mbar_wait(&bar[0], uses0++ & 1u);
         else mbar_wait(&bar[1], uses1++ & 1u);
         const float* st = stages[warp][buf];
@@ -1727,6 +1745,10 @@ extern "C" size_t cov_traj_workspace_bytes(int64_t n, int n_poses) {
 
 extern "C" int64_t cov_tile_boxes_count(int64_t n) { return n > 0 ? boxes_padded(n) : 0; }
 
+extern "C" int cov_traj_prefill_applies(int64_t n, const cov_traj_opts* opts) {
+    return (!(opts && opts->dense) && n >= kDenseBelow) ? 1 : 0;
+}
+
 extern "C" int cov_tile_boxes(const float* xyz, int64_t n, float* boxes, void* stream) {
     if (!xyz || !boxes || n <= 0) {
         cov_set_error("cov_tile_boxes: null pointer or empty cloud (n=%lld)", (long long)n);
@@ -1766,6 +1788,7 @@ extern "C" int cov_traj_minmax(const float* xyz, int64_t n, const float* poses, 
     }
     const int64_t ntiles = (n + tile_points(ppt) - 1) / tile_points(ppt);
     if (!prune) {
+        // (prefill_dev is not honoured here: the dense pass B writes every reward itself)
         unsigned* gmin = reinterpret_cast<unsigned*>(minmax);
         unsigned* gmax = gmin + W;
         const size_t smem = minmax_smem_bytes(W);
@@ -1801,7 +1824,7 @@ extern "C" int cov_traj_minmax(const float* xyz, int64_t n, const float* poses, 
         grid = std::max<int64_t>(1, std::min<int64_t>(grid, ntiles_t));
         cov_traj_minmax_tiles_kernel<<<(unsigned)grid, COV_THREADS, smem_t, s>>>(
             xyz, n, t.table, W, C, t.enc, minmax, boxes, t.amask, mask_stride_words(W), t.worklist, t.ctrl, ntiles_t,
-            opts ? opts->stats_dev : nullptr);
+            opts ? opts->stats_dev : nullptr, opts ? opts->prefill_dev : nullptr, n);
     }
     return cov_check_launch("cov_traj_minmax");
 }

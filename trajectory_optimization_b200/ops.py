@@ -78,8 +78,8 @@ def evaluation(dense=None, stats=None):
         _MODE.dense, _MODE.stats = old
 
 
-def _opts(dense=None, rewards_prefilled=False):
-    return _lib.traj_opts(_MODE.dense if dense is None else dense, rewards_prefilled, _MODE.stats)
+def _opts(dense=None, rewards_prefilled=False, prefill=None):
+    return _lib.traj_opts(_MODE.dense if dense is None else dense, rewards_prefilled, _MODE.stats, prefill)
 
 
 def _ptr(t):
@@ -143,21 +143,26 @@ class CudaBackend:
     def traj_workspace(self, pts, W):
         return torch.empty(self.traj_workspace_bytes(pts, W), dtype=torch.uint8, device=pts.device)
 
-    def traj_minmax(self, pts, P, Q, Kd, cam, boxes=None, ws=None, dense=None):
+    def prefill_applies(self, pts, dense=None):
+        """Will pass A on this cloud honour a `prefill` buffer (pruned path)?"""
+        opts = _opts(dense)
+        return bool(_lib.lib().cov_traj_prefill_applies(pts.shape[0], ctypes.byref(opts)))
+
+    def traj_minmax(self, pts, P, Q, Kd, cam, boxes=None, ws=None, dense=None, prefill=None):
         W = P.shape[0]
         minmax = torch.empty(2 * W, dtype=torch.float32, device=pts.device)
         ws = self.traj_workspace(pts, W) if ws is None else ws
-        opts = _opts(dense)
+        opts = _opts(dense, prefill=prefill)
         _call("cov_traj_minmax", pts, _ptr(pts), pts.shape[0], _ptr(P), _ptr(Q), W, _ptr(Kd), ctypes.byref(cam),
               _ptr(boxes), _ptr(minmax), ctypes.byref(opts), _ptr(ws), ws.numel())
         return minmax
 
     def traj_fused(self, pts, P, Q, Kd, cam, minmax, upstream, rewards, reward_index=None, boxes=None, ws=None,
-                   dense=None):
+                   dense=None, prefilled=False):
         W, n = P.shape[0], pts.shape[0]
         acc = torch.empty(W * _lib.ACC_STRIDE + 1, dtype=torch.float64, device=pts.device)
         ws = self.traj_workspace(pts, W) if ws is None else ws
-        opts = _opts(dense)
+        opts = _opts(dense, rewards_prefilled=prefilled)
         _call("cov_traj_fused", pts, _ptr(pts), n, _ptr(P), _ptr(Q), W, _ptr(Kd), ctypes.byref(cam), _ptr(boxes),
               _ptr(minmax), _ptr(upstream), _ptr(reward_index), _ptr(rewards), _ptr(acc), ctypes.byref(opts), _ptr(ws),
               ws.numel())
@@ -276,11 +281,13 @@ class CoverageTrajFn(torch.autograd.Function):
         ws = workspace                                       # shared by both passes; a caller may keep one per cloud
         if ws is None or ws.numel() < B.traj_workspace_bytes(pts, W) or ws.device != dev:
             ws = B.traj_workspace(pts, W)
-        minmax = B.traj_minmax(pts, P, Q, Kd, cam, boxes, ws, dense)   # pass A on this shard
-        _all_reduce_minmax(minmax, W, group)                 # global normalisers: W minima, W maxima
         rewards = torch.empty(n, dtype=torch.float32, device=dev)
+        # the pruned pass A pre-fills pass B's rewards with 1/2 under its idle memory bandwidth
+        prefill = rewards if B.prefill_applies(pts, dense) else None
+        minmax = B.traj_minmax(pts, P, Q, Kd, cam, boxes, ws, dense, prefill)   # pass A on this shard
+        _all_reduce_minmax(minmax, W, group)                 # global normalisers: W minima, W maxima
         out = CoverageTrajFn._run(pts, P, Q, Kd, cam, minmax, None, rewards, n_total, group, reward_index, boxes, ws,
-                                  dense)
+                                  dense, prefill is not None)
         ctx.cam, ctx.group, ctx.n_total, ctx.reward_index, ctx.boxes = cam, group, n_total, reward_index, boxes
         ctx.dense = dense
         ctx.shapes = (poses.shape, quats.shape)
@@ -290,8 +297,9 @@ class CoverageTrajFn(torch.autograd.Function):
 
     @staticmethod
     def _run(pts, P, Q, Kd, cam, minmax, upstream, rewards, n_total, group, reward_index=None, boxes=None, ws=None,
-             dense=None):
-        acc = _BACKEND.traj_fused(pts, P, Q, Kd, cam, minmax, upstream, rewards, reward_index, boxes, ws, dense)   # pass B
+             dense=None, prefilled=False):
+        acc = _BACKEND.traj_fused(pts, P, Q, Kd, cam, minmax, upstream, rewards, reward_index, boxes, ws, dense,
+                                  prefilled)   # pass B
         if group is not None:
             _all_reduce(acc, _reduce_ops()[2], group)
         return _BACKEND.traj_epilogue(acc, minmax, Q, n_total, 0 if upstream is None else 1)
