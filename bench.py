@@ -751,6 +751,10 @@ def main():
             "config": dict(config_dict(n_total, world),
                            pruning="exact tile-level distance-bound pruning on a Morton-ordered cloud (default); see `dense`",
                            launch=graph_note,
+                           collectives=("none (one GPU)" if world == 1 else
+                                        "in-kernel NVLink exchange: cov_peer_allreduce (peer stores + flags, csrc/cov_peer.cu), "
+                                        "one launch per exchange step" if ops.peer_exchange(group, dev, W) is not None else
+                                        "NCCL all_reduce (MAX of 2W floats, SUM of 22W+1 doubles)"),
                            cloud_order="ordered once per cloud by cov_spatial_sort (%.2f ms for this rank's shard, outside "
                                        "`value`, inside `e2e`)" % ms_sort),
             "clocks": clocks,

@@ -152,6 +152,31 @@ int cov_sweep_rewards(const float* xyz_dev, int64_t n, const float* poses_dev, c
                       size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * The two exchange steps of the point-sharded objective (MAX of the 2 W normalisers, SUM of the 22 W + 1 accumulator
+ * doubles) as ONE small kernel each over NVLink peer memory, in place of a collective-library launch.
+ * ref: no reference code (the reference is single-process); replaces the dist.all_reduce calls of SURVEY.md 8e.
+ * Every rank (one process per GPU of one NVLink domain) owns an exchange buffer that all peers can address — the host
+ * allocates it as symmetric memory and passes the world's pointers; it must be ZERO-INITIALISED once and then belongs
+ * to the library.  Every rank issues the same sequence of calls.  The kernel pushes its vector into every peer's buffer,
+ * raises per-slice flags, waits for the world's flags in its own buffer and reduces in rank order (bit-identical
+ * results on all ranks); capturable in CUDA graphs (the call epoch is a device-side counter).
+ *   kind: COV_PEER_MAX_F32 / COV_PEER_MINMAX_F32 (data_dev = n floats) or COV_PEER_SUM_F64 (n doubles), reduced IN PLACE.
+ *   region_offset: where this call site's region starts inside the exchange buffers (256-byte aligned; one region of
+ *   cov_peer_region_bytes(kind, n, world) bytes per call site and vector length).
+ * ------------------------------------------------------------------------------------------ */
+#define COV_MAX_PEERS 16
+#define COV_PEER_MAX_F32 0
+#define COV_PEER_SUM_F64 1
+#define COV_PEER_MINMAX_F32 2 /* n floats: MIN over the first n/2, MAX over the rest (the 2 W normalisers) */
+typedef struct cov_peers {
+    void* ptr[COV_MAX_PEERS]; /* rank r's exchange buffer as addressable from THIS device */
+    int world;
+    int rank;
+} cov_peers;
+size_t cov_peer_region_bytes(int kind, int64_t n, int world);
+int cov_peer_allreduce(int kind, void* data_dev, int64_t n, const cov_peers* peers, size_t region_offset, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Multi-camera front end: n_body waypoints (x, y, z, yaw) x n_cams fixed extrinsics -> camera poses in the layout
  * cov_traj_* / cov_sweep_rewards take (pose index = body*n_cams + cam), and the chain rule back.
  * ref: no reference implementation (BASELINE north_star item 3); the camera rig is the tf extrinsics of

@@ -772,3 +772,21 @@ def test_ops_follow_the_tensors_device_not_the_current_device(mod):
         out.append((float(loss), m.rewards.cpu(), m.poses.grad.cpu()))
     assert torch.cuda.current_device() == 0
     assert out[0][0] == out[1][0] and torch.equal(out[0][1], out[1][1]) and torch.equal(out[0][2], out[1][2])
+
+
+def test_two_gpu_sharded_objective_with_in_kernel_exchange():
+    """scripts/dist_check.py on two GPUs (NCCL group): the point-sharded models reproduce the unsharded loss, rewards and
+    gradients, once through the in-kernel NVLink exchange (cov_peer_allreduce) and once through NCCL all-reduces."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for peer, port in (("1", "29631"), ("0", "29632")):
+        env = dict(os.environ, COV_PEER_EXCHANGE=peer)
+        out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                              "--master-addr", "127.0.0.1", "--master-port", port, os.path.join(root, "scripts", "dist_check.py")],
+                             capture_output=True, text=True, env=env, timeout=600, cwd=root)
+        assert out.returncode == 0 and "dist_check OK" in out.stdout, (out.stdout[-2000:], out.stderr[-2000:])
+        assert ("unavailable" not in out.stderr) or peer == "0"

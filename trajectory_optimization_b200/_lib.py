@@ -28,6 +28,15 @@ class TrajOpts(C.Structure):
     _fields_ = [("dense", C.c_int), ("rewards_prefilled", C.c_int), ("prefill_dev", C.c_void_p), ("stats_dev", C.c_void_p)]
 
 
+MAX_PEERS = 16          # COV_MAX_PEERS
+PEER_MAX_F32, PEER_SUM_F64, PEER_MINMAX_F32 = 0, 1, 2
+
+
+class Peers(C.Structure):
+    """struct cov_peers: the world's exchange buffers as addressable from this device."""
+    _fields_ = [("ptr", C.c_void_p * MAX_PEERS), ("world", C.c_int), ("rank", C.c_int)]
+
+
 _vp, _i64, _int, _f, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_size_t
 _cam = C.POINTER(Camera)
 _opts = C.POINTER(TrajOpts)
@@ -49,6 +58,8 @@ PROTOTYPES = {
     "cov_traj_regularizers": (_int, [_vp, _vp, _int, _f, _f, _f, _vp, _vp]),
     "cov_sweep_workspace_bytes": (_sz, [_i64, _int, _int]),
     "cov_sweep_rewards": (_int, [_vp, _i64, _vp, _vp, _int, _int, _vp, _cam, _vp, _vp, _vp, _opts, _vp, _sz, _vp]),
+    "cov_peer_region_bytes": (_sz, [_int, _i64, _int]),
+    "cov_peer_allreduce": (_int, [_int, _vp, _i64, C.POINTER(Peers), _sz, _vp]),
     "cov_rig_poses": (_int, [_vp, _int, _vp, _int, _vp, _vp, _vp]),
     "cov_rig_poses_backward": (_int, [_vp, _int, _vp, _int, _vp, _vp, _f, _vp, _vp]),
     "cov_cull_workspace_bytes": (_sz, [_i64]),

@@ -9,6 +9,7 @@ the same scalar and the same pose gradients, while per-point outputs stay sharde
 """
 import contextlib
 import ctypes
+import os
 import threading
 
 import torch
@@ -97,14 +98,88 @@ def _reduce_ops():
     return dist.ReduceOp.MIN, dist.ReduceOp.MAX, dist.ReduceOp.SUM
 
 
+class PeerExchange:
+    """The world's exchange buffers for the in-kernel NVLink all-reduces of one (group, device, pose count): symmetric
+    memory allocated and rendezvoused ONCE (outside any graph capture), then used by `cov_peer_allreduce`
+    (csrc/cov_peer.cu) for the 2 W normalisers and the 22 W + 1 accumulator doubles of every step."""
+
+    def __init__(self, group, device, W):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        L = _lib.lib()
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > _lib.MAX_PEERS:
+            raise RuntimeError(f"peer exchange supports up to {_lib.MAX_PEERS} ranks")
+        self.n_mm, self.n_acc = 2 * W, W * _lib.ACC_STRIDE + 1
+        b_mm = (L.cov_peer_region_bytes(_lib.PEER_MINMAX_F32, self.n_mm, self.world) + 255) // 256 * 256
+        b_acc = (L.cov_peer_region_bytes(_lib.PEER_SUM_F64, self.n_acc, self.world) + 255) // 256 * 256
+        self.off_mm, self.off_acc = 0, b_mm
+        with torch.cuda.device(device):
+            self.buf = symm.empty(b_mm + b_acc, dtype=torch.uint8, device=device)
+            self.buf.zero_()
+            self.handle = symm.rendezvous(self.buf, group)
+            torch.cuda.synchronize(device)
+        dist.barrier(group)      # every rank's buffer is zeroed before anybody pushes into it
+        self.peers = _lib.Peers()
+        for r, ptr in enumerate(self.handle.buffer_ptrs):
+            self.peers.ptr[r] = ptr
+        self.peers.world, self.peers.rank = self.world, self.rank
+
+    def reduce(self, kind, t, offset):
+        _call("cov_peer_allreduce", t, kind, _ptr(t), t.numel(), ctypes.byref(self.peers), offset)
+
+
+_PEER_CACHE = {}
+_PEER_STATE = {"enabled": os.environ.get("COV_PEER_EXCHANGE", "1") != "0", "warned": False}
+
+
+def peer_exchange(group, device, W):
+    """The PeerExchange for (group, device, W), or None when the in-kernel exchange is off or unavailable (then the
+    collectives are NCCL all-reduces).  Created on first use, which must happen outside CUDA-graph capture (any eager
+    warm-up step does it)."""
+    if group is None or not _PEER_STATE["enabled"] or device.type != "cuda" or W > 2048:
+        return None
+    key = (id(group), device.index, W)
+    if key not in _PEER_CACHE:
+        try:
+            import torch.distributed as dist
+            if dist.get_backend(group) != "nccl":
+                raise RuntimeError("peer exchange needs one CUDA device per rank (nccl group)")
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("first use inside a CUDA-graph capture")
+            _PEER_CACHE[key] = PeerExchange(group, device, W)
+        except Exception as exc:   # no P2P / symmetric memory on this box: the NCCL path is equivalent
+            _PEER_CACHE[key] = None
+            if not _PEER_STATE["warned"]:
+                _PEER_STATE["warned"] = True
+                import warnings
+                warnings.warn(f"in-kernel NVLink exchange unavailable ({str(exc).splitlines()[0][:160]}); using NCCL all-reduces")
+    return _PEER_CACHE[key]
+
+
 def _all_reduce_minmax(minmax, W, group):
-    """Global per-pose minima (first W) and maxima (last W) in ONE collective: MIN(x) = -MAX(-x), and negation is exact
-    (+0 minima come back as +0).  One latency-bound all-reduce less per step."""
+    """Global per-pose minima (first W) and maxima (last W) in ONE exchange: the in-kernel NVLink all-reduce
+    (MIN | MAX halves) when available, else one NCCL MAX with the minima negated (MIN(x) = -MAX(-x), exact)."""
     if group is None:
+        return
+    px = peer_exchange(group, minmax.device, W) if minmax.is_cuda and minmax.dtype == torch.float32 else None
+    if px is not None and px.n_mm == minmax.numel():
+        px.reduce(_lib.PEER_MINMAX_F32, minmax, px.off_mm)
         return
     minmax[:W].neg_()
     _all_reduce(minmax, _reduce_ops()[1], group)
     minmax[:W].neg_()
+
+
+def _all_reduce_acc(acc, W, group):
+    """SUM of the 22 W + 1 accumulator doubles over the ranks (in rank order: identical on every rank)."""
+    if group is None:
+        return
+    px = peer_exchange(group, acc.device, W) if acc.is_cuda and acc.dtype == torch.float64 else None
+    if px is not None and px.n_acc == acc.numel():
+        px.reduce(_lib.PEER_SUM_F64, acc, px.off_acc)
+        return
+    _all_reduce(acc, _reduce_ops()[2], group)
 
 
 class CudaBackend:
@@ -300,8 +375,7 @@ class CoverageTrajFn(torch.autograd.Function):
              dense=None, prefilled=False):
         acc = _BACKEND.traj_fused(pts, P, Q, Kd, cam, minmax, upstream, rewards, reward_index, boxes, ws, dense,
                                   prefilled)   # pass B
-        if group is not None:
-            _all_reduce(acc, _reduce_ops()[2], group)
+        _all_reduce_acc(acc, P.shape[0], group)
         return _BACKEND.traj_epilogue(acc, minmax, Q, n_total, 0 if upstream is None else 1)
 
     @staticmethod
