@@ -867,79 +867,73 @@ __device__ __forceinline__ float4 lds_f4(unsigned saddr) {
     return v;
 }
 
-// Phase 1 of the dense pass B for NP consecutive pose PAIRS (2 NP poses): every point of the thread against the poses
-// on packed fp32 pairs (cov_vis2p; PPT * NP independent chains in flight), then per pose the conservative warp vote and
-// — only when some lane may pass — the exact gate, the ballots and the log-odds.  Ballot words go to the gate bit
-// matrix.  The spare slot of an odd W is skipped.  Returns whether this warp gated a pair (warp-uniform).
-template <int PPT, int NPAIR, bool AMIN>
-__device__ __forceinline__ bool dense_pair_iter(int pair0, int W, unsigned ptab_s, unsigned* __restrict__ bits, int warp,
+// Phase 1 of the dense pass B for one pose PAIR: every point of the thread against both poses on packed fp32 pairs
+// (cov_vis2p), then ONE conservative warp vote for the pair and — only when some lane may pass for either pose — the
+// exact gate, the ballots and the log-odds per pose.  Non-zero ballot words go to the gate bit matrix (which is all zero
+// otherwise: zeroed at kernel start, and the gradient walk clears what it consumed).  The spare slot of an odd W repeats
+// the last pose and is skipped after the vote.  Returns whether this warp gated a pair (warp-uniform).
+template <int PPT, bool AMIN>
+__device__ __forceinline__ bool dense_pair_iter(int pair, int W, unsigned ptab_s, unsigned* __restrict__ bits, int warp,
                                                 const f2_t (&X)[PPT], const f2_t (&Y)[PPT], const f2_t (&Z)[PPT],
                                                 float (&L)[PPT], const CovConst& C, const CovConst2& C2,
                                                 double* __restrict__ acc, int lane) {
-    float m[NPAIR][2][PPT];
-    float thr[NPAIR][2];
+    const unsigned base = ptab_s + (unsigned)pair * (COV_PAIR_F4 * 16u);
+    const float4 q0 = lds_f4(base), q1 = lds_f4(base + 16u), q2 = lds_f4(base + 32u), q3 = lds_f4(base + 48u),
+                 q4 = lds_f4(base + 64u), q5 = lds_f4(base + 80u), q6 = lds_f4(base + 96u), q7 = lds_f4(base + 112u);
+    float m[2][PPT];
+#pragma unroll
+    for (int s = 0; s < PPT; ++s) f2_unpack(cov_vis2p(X[s], Y[s], Z[s], q0, q1, q2, q3, q4, q5, q6, q7, C2), m[0][s], m[1][s]);
+    float mxa = m[0][0], mxb = m[1][0];
+#pragma unroll
+    for (int s = 1; s < PPT; ++s) {
+        mxa = fmaxf(mxa, m[0][s]);
+        mxb = fmaxf(mxb, m[1][s]);
+    }
+    // conservative gate thresholds (v3.w of the two poses): one vote for the pair; a few % of the iterations pass
+    bool hot = __any_sync(kFull, (mxa >= q7.z) | (mxb >= q7.w));
+    if (AMIN) hot = true;  // arg-min points carry gradient: every pair is looked at (block-uniform)
+    if (!hot) return false;
     unsigned anyb = 0u;
 #pragma unroll
-    for (int k = 0; k < NPAIR; ++k) {
-        const unsigned base = ptab_s + (unsigned)(pair0 + k) * (COV_PAIR_F4 * 16u);
-        const float4 q0 = lds_f4(base), q1 = lds_f4(base + 16u), q2 = lds_f4(base + 32u), q3 = lds_f4(base + 48u),
-                     q4 = lds_f4(base + 64u), q5 = lds_f4(base + 80u), q6 = lds_f4(base + 96u), q7 = lds_f4(base + 112u);
+    for (int h = 0; h < 2; ++h) {
+        const int w = 2 * pair + h;
+        if (w >= W) break;  // the spare slot of an odd pose count
+        const float4 v4 = lds_f4(base + (8u + h) * 16u);
+        unsigned bal[PPT];
+        unsigned any_h = 0u;
 #pragma unroll
-        for (int s = 0; s < PPT; ++s)
-            f2_unpack(cov_vis2p(X[s], Y[s], Z[s], q0, q1, q2, q3, q4, q5, q6, q7, C2), m[k][0][s], m[k][1][s]);
-        thr[k][0] = q7.z;  // conservative gate thresholds (v3.w of the two poses)
-        thr[k][1] = q7.w;
-    }
+        for (int s = 0; s < PPT; ++s) {
+            const float d = __fsub_rn(m[h][s], v4.w);
+            const bool act = d >= v4.x;  // exactly p >= 0.5
+            bal[s] = __ballot_sync(kFull, act);
+            any_h |= bal[s];
+            if (act) {
+                const float p = __fmul_rn(d, v4.z);
+                const float qc = (p > C.hi) ? C.hi : p;  // upper clip; a NaN p (pose that sees nothing: 0/0) stays NaN, as torch.clip
+                L[s] += COV_LN2_F * cov_lg2(qc * cov_rcp(1.f - qc));
+                if (d == v4.y) {
+                    float x, y, z, t;
+                    f2_unpack(X[s], x, t); f2_unpack(Y[s], y, t); f2_unpack(Z[s], z, t);
+                    tie_accumulate_pair(x, y, z, w, C, acc, w * COV_ACC_STRIDE + 8);
+                }
+            }
+        }
+        anyb |= any_h;
+        if (any_h != 0u && lane == 0) {
+            unsigned* brow = bit_row_group<PPT>(bits, w, warp);
+            if (PPT == 4) *reinterpret_cast<uint4*>(brow) = make_uint4(bal[0], bal[1 % PPT], bal[2 % PPT], bal[3 % PPT]);
+            else if (PPT == 2) *reinterpret_cast<uint2*>(brow) = make_uint2(bal[0], bal[1 % PPT]);
+            else brow[0] = bal[0];
+        }
+        if (AMIN) {  // only compact clouds whose minimum did not underflow to 0
+            if (v4.w > 0.f) {
 #pragma unroll
-    for (int k = 0; k < NPAIR; ++k) {
-        const unsigned base = ptab_s + (unsigned)(pair0 + k) * (COV_PAIR_F4 * 16u);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int w = 2 * (pair0 + k) + h;
-            if (w >= W) break;  // the spare slot of an odd pose count
-            float mmax = m[k][h][0];
-#pragma unroll
-            for (int s = 1; s < PPT; ++s) mmax = fmaxf(mmax, m[k][h][s]);
-            unsigned bal[PPT];
-#pragma unroll
-            for (int s = 0; s < PPT; ++s) bal[s] = 0u;
-            if (__any_sync(kFull, mmax >= thr[k][h])) {  // warp-uniform; a few % of (warp, pose) iterations
-                const float4 v4 = lds_f4(base + (8u + h) * 16u);
-#pragma unroll
-                for (int s = 0; s < PPT; ++s) {
-                    const float d = __fsub_rn(m[k][h][s], v4.w);
-                    const bool act = d >= v4.x;  // exactly p >= 0.5
-                    bal[s] = __ballot_sync(kFull, act);
-                    anyb |= bal[s];
-                    if (act) {
-                        const float p = __fmul_rn(d, v4.z);
-                        const float qc = (p > C.hi) ? C.hi : p;  // upper clip; a NaN p (pose that sees nothing: 0/0) stays NaN, as torch.clip
-                        L[s] += COV_LN2_F * cov_lg2(qc * cov_rcp(1.f - qc));
-                        if (d == v4.y) {
-                            float x, y, z, t;
-                            f2_unpack(X[s], x, t); f2_unpack(Y[s], y, t); f2_unpack(Z[s], z, t);
-                            tie_accumulate_pair(x, y, z, w, C, acc, w * COV_ACC_STRIDE + 8);
-                        }
+                for (int s = 0; s < PPT; ++s)
+                    if (m[h][s] == v4.w) {
+                        float x, y, z, t;
+                        f2_unpack(X[s], x, t); f2_unpack(Y[s], y, t); f2_unpack(Z[s], z, t);
+                        tie_accumulate_pair(x, y, z, w, C, acc, w * COV_ACC_STRIDE + 15);
                     }
-                }
-            }
-            if (lane == 0) {
-                unsigned* brow = bit_row_group<PPT>(bits, w, warp);
-                if (PPT == 4) *reinterpret_cast<uint4*>(brow) = make_uint4(bal[0], bal[1 % PPT], bal[2 % PPT], bal[3 % PPT]);
-                else if (PPT == 2) *reinterpret_cast<uint2*>(brow) = make_uint2(bal[0], bal[1 % PPT]);
-                else brow[0] = bal[0];
-            }
-            if (AMIN) {  // only compact clouds whose minimum did not underflow to 0 (block-uniform choice of the loop)
-                const float a = lds_f4(base + (8u + h) * 16u).w;
-                if (a > 0.f) {
-#pragma unroll
-                    for (int s = 0; s < PPT; ++s)
-                        if (m[k][h][s] == a) {
-                            float x, y, z, t;
-                            f2_unpack(X[s], x, t); f2_unpack(Y[s], y, t); f2_unpack(Z[s], z, t);
-                            tie_accumulate_pair(x, y, z, w, C, acc, w * COV_ACC_STRIDE + 15);
-                        }
-                }
             }
         }
     }
@@ -994,7 +988,7 @@ __device__ __forceinline__ bool tiles_pose_iter(const float4* __restrict__ row, 
 // its set bits in ascending point order, recomputes m (bit-identical) and dm/dx, and accumulates in registers;
 // segments are combined with xor-shuffles; one owner lane adds into accs.
 template <int PPT>
-__device__ __forceinline__ void fused_phase2(const float4* __restrict__ ptab, const unsigned* __restrict__ bits,
+__device__ __forceinline__ void fused_phase2(const float4* __restrict__ ptab, unsigned* __restrict__ bits,
                                              const float* __restrict__ pt, const float* __restrict__ Gs,
                                              float* __restrict__ accs, int W, int seg_log2, const CovConst& C, int tid) {
     constexpr int NW = bit_words(PPT);
@@ -1011,13 +1005,17 @@ __device__ __forceinline__ void fused_phase2(const float4* __restrict__ ptab, co
         const int hslot = w & 1;
         const float4 v0 = cov_pair_row(pair, hslot, 0), v1 = cov_pair_row(pair, hslot, 1), v2 = cov_pair_row(pair, hslot, 2),
                      v3 = cov_pair_row(pair, hslot, 3), v4 = pair[8 + hslot], v5 = pair[10 + hslot];
-        const unsigned* brow = bits + (size_t)w * RS;
+        unsigned* brow = bits + (size_t)w * RS;  // every word of a row belongs to exactly one lane: it is cleared once read
         int k = seg * wps;
         const int kend = live ? k + wps : k;
         unsigned word = live ? brow[k] : 0u;
+        if (word != 0u) brow[k] = 0u;
         float f0 = 0.f, f1 = 0.f, f2 = 0.f, t0 = 0.f, t1 = 0.f, t2 = 0.f, se = 0.f, sep = 0.f;
         while (true) {
-            while (word == 0u && k + 1 < kend) word = brow[++k];
+            while (word == 0u && k + 1 < kend) {
+                word = brow[++k];
+                if (word != 0u) brow[k] = 0u;
+            }
             if (!__any_sync(kFull, word != 0u)) break;
             if (word != 0u) {
                 const int bit = __ffs(word) - 1;
@@ -1112,6 +1110,7 @@ cov_traj_fused_kernel(const float* __restrict__ xyz, int64_t n, const float* __r
         if (a > 0.f) amin_pos = 1;  // benign race: every writer stores 1
     }
     for (int i = tid; i < W * 8; i += COV_THREADS) accs[i] = 0.f;
+    for (int i = tid; i < W * RS; i += COV_THREADS) bits[i] = 0u;  // phase 1 stores non-zero ballots only; phase 2 clears what it reads
     __syncthreads();
 
     double sum_r = 0.0;
@@ -1142,11 +1141,9 @@ cov_traj_fused_kernel(const float* __restrict__ xyz, int64_t n, const float* __r
         }
         bool any_gate = false;  // warp-uniform
         if (check_amin) {  // arg-min points carry gradient: every pair must be looked at
-            for (int pr = 0; pr < NP; ++pr) any_gate |= dense_pair_iter<PPT, 1, true>(pr, W, ptab_s, bits, warp, X, Y, Z, L, C, C2, acc, lane);
+            for (int pr = 0; pr < NP; ++pr) any_gate |= dense_pair_iter<PPT, true>(pr, W, ptab_s, bits, warp, X, Y, Z, L, C, C2, acc, lane);
         } else {
-            int pr = 0;
-            for (; pr + U <= NP; pr += U) any_gate |= dense_pair_iter<PPT, U, false>(pr, W, ptab_s, bits, warp, X, Y, Z, L, C, C2, acc, lane);
-            for (; pr < NP; ++pr) any_gate |= dense_pair_iter<PPT, 1, false>(pr, W, ptab_s, bits, warp, X, Y, Z, L, C, C2, acc, lane);
+            for (int pr = 0; pr < NP; ++pr) any_gate |= dense_pair_iter<PPT, false>(pr, W, ptab_s, bits, warp, X, Y, Z, L, C, C2, acc, lane);
         }
 #pragma unroll
         for (int s = 0; s < PPT; ++s) {
