@@ -314,6 +314,9 @@ def run_c5(args):
         os._exit(0)
 
 
+ORIGINAL_AFFINITY = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else set()
+
+
 def pin_to_gpu_numa_node(local):
     """Bind this process (and the pinned host buffers it allocates from now on) to the CPUs of the NUMA node the GPU
     hangs off, so that the host->device copies of several ranks do not all cross the same socket interconnect.
@@ -740,6 +743,10 @@ def main():
     }
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
+        try:
+            os.sched_setaffinity(0, ORIGINAL_AFFINITY)   # the CPU arm gets every host core back
+        except Exception:
+            pass
         cpu_baseline, _ = cpu_reference_rate(body0, rig, steps=3, warmup=1)
     line = {"metric": "coverage fwd+bwd point*pose evals/s", "value": value, "unit": "point*pose evals/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,

@@ -509,7 +509,12 @@ def test_graphed_optimisation_step_matches_eager(dev, mod):
         m = model.ModelTraj(pts, torch.from_numpy(poses), torch.from_numpy(quats), K, Wd, Hd, device=dev)
         opt = torch.optim.Adam([{"params": [m.poses], "lr": 0.02}, {"params": [m.quats], "lr": 0.01}], capturable=True)
         if graphed:
-            g = GraphedStep(m, opt, warmup=2)        # 2 eager warm-up steps, then 3 replays
+            # one eager step on the default stream first: the autograd graph it leaves behind (model.loss[...]) must not
+            # tie the capture to the default stream (GraphedStep detaches the model's state)
+            opt.zero_grad()
+            m().backward()
+            opt.step()
+            g = GraphedStep(m, opt, warmup=1)        # 1 more eager warm-up step, then 3 replays
             for _ in range(3):
                 loss = g.step()
         else:

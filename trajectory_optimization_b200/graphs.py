@@ -21,6 +21,12 @@ class GraphedStep:
             raise RuntimeError("GraphedStep needs a CUDA device")
         self.model, self.optimizer = model, optimizer
         self.kwargs = dict(forward_kwargs or {})
+        # A model that already ran eagerly on the default stream keeps its last autograd graph alive (ModelTraj.loss[...],
+        # ModelPose._total); the AccumulateGrad nodes of that graph are bound to the default stream and would make the
+        # capture depend on it ("operation would make the legacy stream depend on a capturing blocking stream").
+        if hasattr(model, "detach_state"):
+            model.detach_state()
+        optimizer.zero_grad(set_to_none=True)
         side = stream or torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):                      # warm-up off the default stream, as capture requires

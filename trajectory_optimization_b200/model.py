@@ -111,6 +111,14 @@ class ModelPose(nn.Module):
         self.points = points.to(self.device)
         self._pts32 = None
 
+    def detach_state(self):
+        """Drop the references this model keeps into the last autograd graph (`_total`) so that the graph — and the
+        gradient-accumulation nodes bound to the stream it ran on — can be freed (graphs.GraphedStep calls this before
+        it warms up on its capture stream)."""
+        self._total = None
+        if self.observations is not None:
+            self.observations = self.observations.detach()
+
     def forward(self, debug=False, hpr=False):
         t0 = time()
         weight = None
@@ -220,6 +228,17 @@ class ModelTraj(nn.Module):
         captured CUDA graph use `refresh_points_()` instead (same shapes, buffers rewritten in place)."""
         self.points = torch.as_tensor(points, dtype=torch.float32).to(self.device)
         self._pts32 = None
+
+    def detach_state(self):
+        """Drop the references this model keeps into the last autograd graph (`loss[...]`, `_mean`) so that the graph —
+        and the gradient-accumulation nodes bound to the stream it ran on — can be freed (graphs.GraphedStep calls this
+        before it warms up on its capture stream)."""
+        self._mean = None
+        for k, v in list(self.loss.items()):
+            if isinstance(v, torch.Tensor):
+                self.loss[k] = v.detach()
+        if self.rewards is not None:
+            self.rewards = self.rewards.detach()
 
     @torch.no_grad()
     def refresh_points_(self, points):

@@ -30,11 +30,17 @@ def _guard(t):
 
 def _call(name, on, *args):
     """One C-ABI call on the device of tensor `on` and on that device's current stream (every entry point takes the
-    stream last); raises RuntimeError with the library's message on a non-zero return code."""
-    L = _lib.lib()
-    with _guard(on):
-        rc = getattr(L, name)(*args, _stream(on.device))
-    _lib.check(rc, name)
+    stream last); raises RuntimeError with the library's message on a non-zero return code.  The device guard is only
+    entered when the tensor's device is not the current one (the common case pays two cheap queries)."""
+    fn = getattr(_lib.lib(), name)
+    dev = on.device
+    if dev.index == torch.cuda.current_device():
+        rc = fn(*args, ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    else:
+        with torch.cuda.device(dev):
+            rc = fn(*args, ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    if rc:
+        _lib.check(rc, name)
 
 
 def _dev_f32(t, device=None, what="tensor"):
