@@ -9,16 +9,18 @@
 //
 // Each pass exists in two forms that give bit-identical normalisers and rewards:
 //
-// DENSE (cov_set_pruning(0)): every (point, pose) pair is evaluated.  FP32-issue bound.
+// DENSE (cov_traj_opts.dense, and every cloud below 65 536 points): every (point, pose) pair is evaluated, on packed
+//   fp32 pairs — one point against TWO poses per instruction stream (cov_vis2p, FFMA2); bound by the FP32 and MUFU pipes.
 //   pass A: thread-local fmin/fmax over the thread's points, one integer REDUX per warp (m >= 0, so the float order
 //           is the uint order), one shared atomic per warp and 32 poses, one global atomic per block and pose.
 //   pass B, per tile of 256*PPT points:
-//     phase 1  every pair: m, gate (m - a >= b/2  <=>  p >= 0.5, exact), warp ballot of the gate into a pose-major
-//              bit matrix in shared memory; gated lanes add their log-odds to the point's running sum in pose order.
+//     phase 1  every pair: m, one conservative vote per pose pair; when it passes: the exact gate (m - a >= b/2  <=>
+//              p >= 0.5), warp ballots of the gate into a pose-major bit matrix in shared memory (non-zero words only),
+//              gated lanes add their log-odds to the point's running sum in pose order.
 //     phase 2  the bit matrix is walked pose-major: a lane owns (pose, row segment), pops its set bits, re-evaluates
-//              m and dm/dx for that pair and accumulates the 8 weighted sums in registers — no atomics, fixed order.
+//              m and dm/dx for that pair and accumulates the 8 weighted sums in registers — fixed order within a block.
 //
-// PRUNED (default): cull -> compact -> evaluate, on boxes of 128 consecutive points (cov_tile_boxes; tight when the
+// PRUNED (default): cull -> list -> evaluate, on boxes of 128 consecutive points (cov_tile_boxes; tight when the
 //   cloud is Morton-ordered by cov_spatial_sort, valid for any order).  A pair whose distance Gaussian alone bounds m
 //   below what can matter is never evaluated:  m <= 2^-(kd q2)(1+1.3e-5)  and  q2 >= box bound > qcap  =>  m < bound.
 //     pass A: bound = a lower bound of max_j m from a strided sample of the cloud (seed launch), valid once the
@@ -79,29 +81,10 @@ size_t fused_smem_bytes(int W, int ppt, bool prune) {
            (size_t)W * bit_stride(ppt) * sizeof(unsigned) + (size_t)W * 8 * sizeof(float);
 }
 
-// Unweighted dm/dy and dm/dy x y of one (point, pose) into a tie-set accumulator (7 doubles).  Rare (one point per
-// pose and step), so it is a real call; it takes the pose INDEX and finds the row in the pose table at the start of
-// dynamic shared memory (where every kernel of this file keeps it) — passing a row pointer would make the callers
-// compute a generic shared-memory address on every iteration of their hot loops.
-__device__ __noinline__ void tie_accumulate(float x, float y, float z, int w, CovConst C, double* acc, int slot) {
-    extern __shared__ float4 smem4[];
-    const float4* row = smem4 + (size_t)w * COV_ROW_F4;
-    double* dst = acc + slot;
-    CovEval ev;
-    const float m = cov_vis<true>(x, y, z, row[0], row[1], row[2], row[3], C, &ev);
-    float gx, gy, gz;
-    cov_vis_grad(m, ev, row[0], row[1], row[2], C, gx, gy, gz);
-    const float yx = x - row[5].x, yy = y - row[5].y, yz = z - row[5].z;
-    atomicAdd(dst + 0, (double)gx);
-    atomicAdd(dst + 1, (double)gy);
-    atomicAdd(dst + 2, (double)gz);
-    atomicAdd(dst + 3, (double)(gy * yz - gz * yy));
-    atomicAdd(dst + 4, (double)(gz * yx - gx * yz));
-    atomicAdd(dst + 5, (double)(gx * yy - gy * yx));
-    atomicAdd(dst + 6, 1.0);
-}
-
-// Same for the dense pass B, whose table is laid out in pose PAIRS (COV_PAIR_F4, cov_common.cuh).
+// Unweighted dm/dy and dm/dy x y of one (point, pose) into a tie-set accumulator (7 doubles: F, T, count).  Rare (one
+// point per pose and step), so these are real calls; they take the pose INDEX (or its row in the global table) and find
+// the constants themselves — passing loaded rows would keep them live across the callers' hot loops.
+// The dense pass B keeps its table in pose PAIRS at the start of dynamic shared memory (COV_PAIR_F4, cov_common.cuh).
 __device__ __noinline__ void tie_accumulate_pair(float x, float y, float z, int w, CovConst C, double* acc, int slot) {
     extern __shared__ float4 smem4[];
     const float4* pair = smem4 + (size_t)(w >> 1) * COV_PAIR_F4;
@@ -796,69 +779,35 @@ __device__ __forceinline__ unsigned* bit_row_group(unsigned* bits, int w, int gr
     return bits + (size_t)w * bit_stride(PPT) + group * PPT;
 }
 
-// Phase-1 body for U consecutive poses starting at w (U*PPT independent chains).  Dense kernel: the ballots go to
-// the gate bit matrix.  TILES = pruned kernel: the conservative threshold lives in v5.w (v3.w holds qthr), nothing
-// is stored, and the return value says whether this warp has a gated pair for the pose (U = 1).
-template <int PPT, int U, bool AMIN, bool TILES>
-__device__ __forceinline__ bool fused_pose_iter(int w, unsigned ptab, unsigned* __restrict__ bits,
-                                                int warp, const float (&px)[PPT], const float (&py)[PPT],
-                                                const float (&pz)[PPT], float (&L)[PPT], const CovConst& C,
-                                                double* __restrict__ acc, int lane) {
-    float m[U][PPT];
-    float mmax[U];
-    unsigned anyb = 0u;
+// Forward of one listed pose for a warp of the candidate sweep (pose table in shared memory, row layout): m for the
+// warp's points, log-odds of the gated ones added to L; returns whether the warp gated a pair.  The conservative
+// threshold lives in v5.w (v3.w holds qthr); the exact gate test runs only when some lane may pass.
+template <int PPT>
+__device__ __forceinline__ bool sweep_pose_iter(int w, unsigned ptab, const float (&px)[PPT], const float (&py)[PPT],
+                                                const float (&pz)[PPT], float (&L)[PPT], const CovConst& C) {
+    const float4 v0 = lds_row(ptab, w, 0), v1 = lds_row(ptab, w, 1), v2 = lds_row(ptab, w, 2), v3 = lds_row(ptab, w, 3);
+    float m[PPT];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-        const float4 v0 = lds_row(ptab, w + u, 0), v1 = lds_row(ptab, w + u, 1), v2 = lds_row(ptab, w + u, 2),
-                     v3 = lds_row(ptab, w + u, 3);
+    for (int s = 0; s < PPT; ++s) m[s] = cov_vis<false>(px[s], py[s], pz[s], v0, v1, v2, v3, C, nullptr);
+    float mmax = m[0];
 #pragma unroll
-        for (int s = 0; s < PPT; ++s) m[u][s] = cov_vis<false>(px[s], py[s], pz[s], v0, v1, v2, v3, C, nullptr);
-        mmax[u] = m[u][0];
+    for (int s = 1; s < PPT; ++s) mmax = fmaxf(mmax, m[s]);
+    bool any = false;
+    if (__any_sync(kFull, mmax >= lds_row(ptab, w, 5).w)) {  // warp-uniform; a few % of (warp, pose) iterations
+        const float4 v4 = lds_row(ptab, w, 4);
 #pragma unroll
-        for (int s = 1; s + 1 < PPT; s += 2) mmax[u] = fmaxf(mmax[u], fmaxf(m[u][s], m[u][s + 1]));
-        if ((PPT & 1) == 0) mmax[u] = fmaxf(mmax[u], m[u][PPT - 1]);
-        // >= 0  <=>  some point of this lane may pass the gate (conservative threshold)
-        mmax[u] -= TILES ? lds_row(ptab, w + u, 5).w : v3.w;
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        unsigned bal[PPT];
-#pragma unroll
-        for (int s = 0; s < PPT; ++s) bal[s] = 0u;
-        if (__any_sync(kFull, mmax[u] >= 0.f)) {  // warp-uniform; a few % of (warp, pose) iterations
-            const float4 v4 = lds_row(ptab, w + u, 4);
-#pragma unroll
-            for (int s = 0; s < PPT; ++s) {
-                const float d = __fsub_rn(m[u][s], v4.w);
-                const bool act = d >= v4.x;  // exactly p >= 0.5
-                bal[s] = __ballot_sync(kFull, act);
-                if (act) {
-                    const float p = __fmul_rn(d, v4.z);
-                    const float qc = (p > C.hi) ? C.hi : p;  // upper clip; a NaN p (pose that sees nothing: 0/0) stays NaN, as torch.clip
-                    L[s] += COV_LN2_F * cov_lg2(qc * cov_rcp(1.f - qc));
-                    if (acc && d == v4.y) tie_accumulate(px[s], py[s], pz[s], w + u, C, acc, (w + u) * COV_ACC_STRIDE + 8);
-                }
+        for (int s = 0; s < PPT; ++s) {
+            const float d = __fsub_rn(m[s], v4.w);
+            if (d >= v4.x) {  // exactly p >= 0.5
+                const float p = __fmul_rn(d, v4.z);
+                const float qc = (p > C.hi) ? C.hi : p;  // upper clip; a NaN p (pose that sees nothing: 0/0) stays NaN, as torch.clip
+                L[s] += COV_LN2_F * cov_lg2(qc * cov_rcp(1.f - qc));
+                any = true;
             }
         }
-        if (TILES) {
-#pragma unroll
-            for (int s = 0; s < PPT; ++s) anyb |= bal[s];
-        } else if (lane == 0) {
-            unsigned* brow = bit_row_group<PPT>(bits, w + u, warp);
-            if (PPT == 4) *reinterpret_cast<uint4*>(brow) = make_uint4(bal[0], bal[1 % PPT], bal[2 % PPT], bal[3 % PPT]);
-            else if (PPT == 2) *reinterpret_cast<uint2*>(brow) = make_uint2(bal[0], bal[1 % PPT]);
-            else brow[0] = bal[0];
-        }
-        if (AMIN) {  // only compact clouds whose minimum did not underflow to 0 (block-uniform choice of the loop)
-            const float a = lds_row(ptab, w + u, 4).w;
-            if (a > 0.f) {
-#pragma unroll
-                for (int s = 0; s < PPT; ++s)
-                    if (m[u][s] == a) tie_accumulate(px[s], py[s], pz[s], w + u, C, acc, (w + u) * COV_ACC_STRIDE + 15);
-            }
-        }
+        any = __any_sync(kFull, any);
     }
-    return anyb != 0u;
+    return any;
 }
 
 __device__ __forceinline__ float4 lds_f4(unsigned saddr) {
@@ -1508,7 +1457,7 @@ cov_sweep_tiles_kernel(const float* __restrict__ xyz, int64_t n, const float4* _
 #pragma unroll
                     for (int s = 0; s < PPT; ++s) L[s] = 0.f;
                 }
-                touched |= fused_pose_iter<PPT, 1, false, true>(w, ptab_s, nullptr, warp, px, py, pz, L, C, nullptr, lane);
+                touched |= sweep_pose_iter<PPT>(w, ptab_s, px, py, pz, L, C);
             }
         }
         flush();
