@@ -63,8 +63,6 @@ __host__ __device__ constexpr int bit_words(int ppt) { return kWarps * ppt; }   
 __host__ __device__ constexpr int bit_stride(int ppt) { return bit_words(ppt) + 4; }  // dense rows: padded, 16-byte aligned
 __host__ __device__ constexpr int tile_boxes(int ppt) { return tile_points(ppt) / kBoxPts; }
 __host__ __device__ inline int mask_stride_words(int W) { return (((W + 31) >> 5) + 3) & ~3; }  // 16-byte multiple
-// one staged tile of the pruned kernels: points | boxes | pose mask (all 16-byte multiples, buffer 128-byte multiple)
-__host__ __device__ constexpr int stage_floats(int ppt) { return tile_points(ppt) * 3 + tile_boxes(ppt) * 8 + kMaskWords; }
 
 size_t minmax_smem_bytes(int W) {  // pose pairs (COV_PAIR_F4 float4 each) + block minima and maxima
     return (size_t)((W + 1) / 2) * (COV_PAIR_F4 * sizeof(float4) + 4 * sizeof(unsigned));
@@ -73,10 +71,7 @@ size_t minmax_smem_bytes(int W) {  // pose pairs (COV_PAIR_F4 float4 each) + blo
 __host__ __device__ inline int fused_stage_offset_floats(int W) {  // W rounded up to whole pose pairs (dense kernel)
     return (int)((((size_t)((W + 1) & ~1) * COV_ROW_F4 * 16 + 127) & ~(size_t)127) / 4);
 }
-size_t fused_smem_bytes(int W, int ppt, bool prune) {
-    if (prune)  // 2 tile stages (the pose table stays in global memory, the accumulators are the caller's)
-        return 2 * (size_t)(stage_floats(ppt) + tile_points(ppt)) * 4;
-    // pose table | tile points | G_j | gate bits | block accumulators
+size_t fused_smem_bytes(int W, int ppt) {  // dense pass B: pose table | tile points | G_j | gate bits | block accumulators
     return (size_t)fused_stage_offset_floats(W) * 4 + (size_t)tile_points(ppt) * 12 + (size_t)tile_points(ppt) * 4 +
            (size_t)W * bit_stride(ppt) * sizeof(unsigned) + (size_t)W * 8 * sizeof(float);
 }
@@ -155,16 +150,6 @@ __device__ __forceinline__ float minmax_qcap(unsigned mn, unsigned mx, float inv
     return cap;
 }
 
-// Pose-table row loads by 32-bit shared address (the address is formed once per kernel; with generic pointers the
-// compiler re-derives the shared window base inside the hot loops).  The table is constant after the prologue barrier.
-__device__ __forceinline__ float4 lds_row(unsigned table_saddr, int w, int i) {
-    float4 v;
-    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-        : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-        : "r"(table_saddr + (unsigned)(w * COV_ROW_F4 + i) * 16u));
-    return v;
-}
-
 // ---- TMA bulk copies (global -> shared) completing on an mbarrier ------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
@@ -192,23 +177,6 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         "}\n" ::"r"(smem_u32(bar)),
         "r"(parity)
         : "memory");
-}
-
-// One staged tile: points (unless the tile is the ragged last one), its boxes and its pose mask — and, for pass B on an
-// ordered cloud, the tile's slice of the permutation — on one mbarrier.
-template <int PPT>
-__device__ __forceinline__ void stage_issue(float* stage, unsigned long long* bar, const float* __restrict__ xyz,
-                                            const float4* __restrict__ boxes, const unsigned* __restrict__ amask_g,
-                                            int mask_stride, int64_t tile, int64_t nfull,
-                                            const int32_t* __restrict__ perm = nullptr) {
-    constexpr int T = tile_points(PPT);
-    constexpr int NB = tile_boxes(PPT);
-    const bool whole = tile < nfull;
-    mbar_expect_tx(bar, (whole ? T * 12u : 0u) + NB * 32u + (unsigned)mask_stride * 4u + ((whole && perm) ? T * 4u : 0u));
-    if (whole) tma_copy(stage, xyz + tile * (T * 3), T * 12u, bar);
-    tma_copy(stage + T * 3, boxes + tile * (NB * 2), NB * 32u, bar);
-    tma_copy(stage + T * 3 + NB * 8, amask_g + tile * mask_stride, (unsigned)mask_stride * 4u, bar);
-    if (whole && perm) tma_copy(stage + stage_floats(PPT), perm + tile * T, T * 4u, bar);
 }
 
 // =============================================== pass A, dense ===============================================
@@ -779,37 +747,6 @@ __device__ __forceinline__ unsigned* bit_row_group(unsigned* bits, int w, int gr
     return bits + (size_t)w * bit_stride(PPT) + group * PPT;
 }
 
-// Forward of one listed pose for a warp of the candidate sweep (pose table in shared memory, row layout): m for the
-// warp's points, log-odds of the gated ones added to L; returns whether the warp gated a pair.  The conservative
-// threshold lives in v5.w (v3.w holds qthr); the exact gate test runs only when some lane may pass.
-template <int PPT>
-__device__ __forceinline__ bool sweep_pose_iter(int w, unsigned ptab, const float (&px)[PPT], const float (&py)[PPT],
-                                                const float (&pz)[PPT], float (&L)[PPT], const CovConst& C) {
-    const float4 v0 = lds_row(ptab, w, 0), v1 = lds_row(ptab, w, 1), v2 = lds_row(ptab, w, 2), v3 = lds_row(ptab, w, 3);
-    float m[PPT];
-#pragma unroll
-    for (int s = 0; s < PPT; ++s) m[s] = cov_vis<false>(px[s], py[s], pz[s], v0, v1, v2, v3, C, nullptr);
-    float mmax = m[0];
-#pragma unroll
-    for (int s = 1; s < PPT; ++s) mmax = fmaxf(mmax, m[s]);
-    bool any = false;
-    if (__any_sync(kFull, mmax >= lds_row(ptab, w, 5).w)) {  // warp-uniform; a few % of (warp, pose) iterations
-        const float4 v4 = lds_row(ptab, w, 4);
-#pragma unroll
-        for (int s = 0; s < PPT; ++s) {
-            const float d = __fsub_rn(m[s], v4.w);
-            if (d >= v4.x) {  // exactly p >= 0.5
-                const float p = __fmul_rn(d, v4.z);
-                const float qc = (p > C.hi) ? C.hi : p;  // upper clip; a NaN p (pose that sees nothing: 0/0) stays NaN, as torch.clip
-                L[s] += COV_LN2_F * cov_lg2(qc * cov_rcp(1.f - qc));
-                any = true;
-            }
-        }
-        any = __any_sync(kFull, any);
-    }
-    return any;
-}
-
 __device__ __forceinline__ float4 lds_f4(unsigned saddr) {
     float4 v;
     asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
@@ -917,7 +854,7 @@ __device__ __forceinline__ bool tiles_pose_iter(const float4* __restrict__ row, 
                 const float p = __fmul_rn(d, v4.z);
                 const float qc = (p > C.hi) ? C.hi : p;  // upper clip; a NaN p (pose that sees nothing: 0/0) stays NaN, as torch.clip
                 L[s] += COV_LN2_F * cov_lg2(qc * cov_rcp(1.f - qc));
-                if (d == v4.y) tie_accumulate_g(px[s], py[s], pz[s], row, C, acc_row + 8);
+                if (acc_row && d == v4.y) tie_accumulate_g(px[s], py[s], pz[s], row, C, acc_row + 8);
             }
         }
         any = __any_sync(kFull, any);
@@ -1355,77 +1292,88 @@ cov_traj_fused_tiles_kernel(const float* __restrict__ xyz, int64_t n, const floa
 }
 
 // ---- candidate sweep, pruned (BASELINE config 5): forward only, per-trajectory sum_j r_j ----
-// Poses are trajectory-major (pose = traj * per_traj + i), so walking a tile's pose mask in ascending order visits the
-// trajectories one after the other: a warp keeps the log-odds sums of its points for the current trajectory, and when
-// the trajectory changes it adds sum_j (sigmoid(L_j) - 1/2) to that trajectory's total (fp64 shared atomic).
-// Trajectories no pose of which is listed for a tile contribute exactly 1/2 per point: 0.5 * n is added once.
-template <int PPT>
-__global__ void __launch_bounds__(COV_THREADS, 2)
+// Persistent warps as in the two passes above (128-point items from a ticket counter, private double-buffered TMA
+// stages, pose table read through L1).  Poses are trajectory-major (pose = traj * per_traj + i), so walking a tile's pose
+// mask in ascending order visits the trajectories one after the other: a warp keeps the log-odds sums of its points for
+// the current trajectory, and when the trajectory changes it adds sum_j (sigmoid(L_j) - 1/2) to that trajectory's total
+// (fp64 shared atomic; the block adds its totals to the output at the end).  Trajectories no pose of which is listed for
+// an item contribute exactly 1/2 per point: 0.5 * n is added once.
+__global__ void __launch_bounds__(COV_THREADS, 3)
 cov_sweep_tiles_kernel(const float* __restrict__ xyz, int64_t n, const float4* __restrict__ table, int W, int per_traj,
                        int n_traj, CovConst C, const float4* __restrict__ boxes, const unsigned* __restrict__ amask_g,
-                       int mask_stride, const int* __restrict__ worklist, const int* __restrict__ count_ptr,
+                       int mask_stride, const int* __restrict__ worklist, int* __restrict__ ctrl,
                        double* __restrict__ sum_out) {
-    constexpr int T = tile_points(PPT);
-    constexpr int NB = tile_boxes(PPT);
-    constexpr int SF = stage_floats(PPT);
-    constexpr int WB = (32 * PPT >= kBoxPts) ? (32 * PPT / kBoxPts) : 1;
+    constexpr int PPT = kItemPpt;
     extern __shared__ float4 smem4[];
-    float4* ptab = smem4;
-    float* stage = reinterpret_cast<float*>(smem4) + fused_stage_offset_floats(W);
-    double* ssum = reinterpret_cast<double*>(stage + 2 * SF);
-    __shared__ __align__(8) unsigned long long mbar[2];
+    double* ssum = reinterpret_cast<double*>(smem4);   // per-trajectory totals of this block
+    __shared__ __align__(128) float stages[kWarps][2][kItemStageWordsA];
+    __shared__ __align__(8) unsigned long long mbar[kWarps][2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) {
-        mbar_init(&mbar[0], 1);
-        mbar_init(&mbar[1], 1);
+    unsigned long long* bar = mbar[warp];
+    if (lane == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
         mbar_fence_init();
     }
-    for (int i = tid; i < W * COV_ROW_F4; i += COV_THREADS) ptab[i] = table[i];
     for (int t = tid; t < n_traj; t += COV_THREADS) ssum[t] = 0.0;
     __syncthreads();
-    const int count = count_ptr[0];
-    const int64_t nfull = n / T;
+    const int n_items = ctrl[0] * kItemsPerTile;
     const int nwords = (W + 31) >> 5;
-    const unsigned ptab_s = smem_u32(ptab);
+    int* ticket = ctrl + 3;
+    auto issue = [&](int it, int b) {
+        if (it >= n_items) return;
+        const int64_t tile = worklist[it >> 3];
+        const int64_t j0 = tile * (kItemsPerTile * kItemPts) + (int64_t)(it & 7) * kItemPts;
+        float* st = stages[warp][b];
+        const bool whole = j0 + kItemPts <= n;
+        mbar_expect_tx(&bar[b], (whole ? kItemPts * 12u : 0u) + 32u + (unsigned)mask_stride * 4u);
+        if (whole) tma_copy(st, xyz + j0 * 3, kItemPts * 12u, &bar[b]);
+        tma_copy(st + kItemPts * 3, boxes + (j0 / kBoxPts) * 2, 32u, &bar[b]);
+        tma_copy(st + kItemPts * 3 + 8, amask_g + tile * mask_stride, (unsigned)mask_stride * 4u, &bar[b]);
+    };
     unsigned uses0 = 0, uses1 = 0;
-    if (tid == 0 && (int)blockIdx.x < count)
-        stage_issue<PPT>(stage, &mbar[0], xyz, boxes, amask_g, mask_stride, (int64_t)worklist[blockIdx.x], nfull);
+    int cur_it = 0;
+    if (lane == 0) {
+        cur_it = atomicAdd(ticket, 1);
+        issue(cur_it, 0);
+    }
+    cur_it = __shfl_sync(kFull, cur_it, 0);
     int buf = 0;
-    for (int i = blockIdx.x; i < count; i += gridDim.x, buf ^= 1) {
-        const int64_t tile = worklist[i];
-        if (tid == 0 && i + (int)gridDim.x < count)
-            stage_issue<PPT>(stage + (buf ^ 1) * SF, &mbar[buf ^ 1], xyz, boxes, amask_g, mask_stride,
-                             (int64_t)worklist[i + gridDim.x], nfull);
-        if (buf == 0) mbar_wait(&mbar[0], uses0++ & 1u);
-        else mbar_wait(&mbar[1], uses1++ & 1u);
-        const float* st = stage + buf * SF;
+    while (cur_it < n_items) {
+        int nxt = 0;
+        if (lane == 0) {
+            nxt = atomicAdd(ticket, 1);
+            issue(nxt, buf ^ 1);
+        }
+        nxt = __shfl_sync(kFull, nxt, 0);
+        if (buf == 0) mbar_wait(&bar[0], uses0++ & 1u);
+        else mbar_wait(&bar[1], uses1++ & 1u);
+        const float* st = stages[warp][buf];
+        const int64_t tile = worklist[cur_it >> 3];
+        const int64_t j0 = tile * (kItemsPerTile * kItemPts) + (int64_t)(cur_it & 7) * kItemPts;
         float px[PPT], py[PPT], pz[PPT], L[PPT];
         bool valid[PPT];
-        const int lbase = warp * (32 * PPT) + lane;
-        if (tile < nfull) {
+        if (j0 + kItemPts <= n) {
 #pragma unroll
             for (int s = 0; s < PPT; ++s) {
                 valid[s] = true;
-                px[s] = st[(lbase + s * 32) * 3];
-                py[s] = st[(lbase + s * 32) * 3 + 1];
-                pz[s] = st[(lbase + s * 32) * 3 + 2];
+                px[s] = st[(s * 32 + lane) * 3];
+                py[s] = st[(s * 32 + lane) * 3 + 1];
+                pz[s] = st[(s * 32 + lane) * 3 + 2];
             }
         } else {
 #pragma unroll
             for (int s = 0; s < PPT; ++s) {
-                const int64_t j = tile * T + lbase + s * 32;
+                const int64_t j = j0 + s * 32 + lane;
                 valid[s] = j < n;
                 px[s] = valid[s] ? __ldg(xyz + j * 3) : 3.0e18f;  // past the end: m = 0 exactly, never gated
                 py[s] = valid[s] ? __ldg(xyz + j * 3 + 1) : 3.0e18f;
                 pz[s] = valid[s] ? __ldg(xyz + j * 3 + 2) : 3.0e18f;
             }
         }
-        const float4* tb = reinterpret_cast<const float4*>(st + T * 3);
-        const int b0 = (warp * 32 * PPT) / kBoxPts;
-        float4 wlo = tb[2 * b0], whi = tb[2 * b0 + 1];
-#pragma unroll
-        for (int k = 1; k < WB; ++k) box_union(wlo, whi, tb[2 * (b0 + k)], tb[2 * (b0 + k) + 1]);
-        const unsigned* am = reinterpret_cast<const unsigned*>(st + T * 3 + NB * 8);
+        const float4* tb = reinterpret_cast<const float4*>(st + kItemPts * 3);
+        const float4 wlo = tb[0], whi = tb[1];
+        const unsigned* am = reinterpret_cast<const unsigned*>(st + kItemPts * 3 + 8);
         int cur = -1;      // trajectory whose log-odds sums are in L
         bool touched = false;
         auto flush = [&]() {
@@ -1443,12 +1391,9 @@ cov_sweep_tiles_kernel(const float* __restrict__ xyz, int64_t n, const float4* _
             while (word) {
                 const int w = c * 32 + __ffs(word) - 1;
                 word &= word - 1;
-                const float4 v3 = ptab[(size_t)w * COV_ROW_F4 + 3];
+                const float4* row = table + (size_t)w * COV_ROW_F4;
+                const float4 v3 = __ldg(row + 3);
                 if (box_q2lb(wlo, whi, v3) > v3.w) continue;
-                float qmin = cov_q2(px[0], py[0], pz[0], v3);
-#pragma unroll
-                for (int s = 1; s < PPT; ++s) qmin = fminf(qmin, cov_q2(px[s], py[s], pz[s], v3));
-                if (!__any_sync(kFull, !(qmin > v3.w))) continue;
                 const int t = w / per_traj;
                 if (t != cur) {
                     flush();
@@ -1457,11 +1402,13 @@ cov_sweep_tiles_kernel(const float* __restrict__ xyz, int64_t n, const float4* _
 #pragma unroll
                     for (int s = 0; s < PPT; ++s) L[s] = 0.f;
                 }
-                touched |= sweep_pose_iter<PPT>(w, ptab_s, px, py, pz, L, C);
+                touched |= tiles_pose_iter<PPT, false>(row, v3, px, py, pz, L, C, nullptr);
             }
         }
         flush();
-        __syncthreads();  // every warp is done with this stage before it is refilled
+        __syncwarp();  // every lane is done with this stage before lane 0 refills it
+        cur_it = nxt;
+        buf ^= 1;
     }
     __syncthreads();
     for (int t = tid; t < n_traj; t += COV_THREADS) {
@@ -1561,12 +1508,13 @@ int grid_for(Kern kern, size_t smem, int64_t ntiles) {
     return g < 1 ? 1 : (int)g;
 }
 
-int pick_ppt(int64_t n, int W, bool fused, bool prune) {
+// points per thread of the DENSE kernels: the largest tile that still gives every SM two tiles and fits shared memory
+int pick_ppt(int64_t n, int W, bool fused) {
     const int sms = cov_sm_count_cached();
     const int cand[3] = {4, 2, 1};
     for (int i = 0; i < 3; ++i) {
         const int ppt = cand[i];
-        const size_t sm = fused ? fused_smem_bytes(W, ppt, prune) : minmax_smem_bytes(W);
+        const size_t sm = fused ? fused_smem_bytes(W, ppt) : minmax_smem_bytes(W);
         if (sm > kSmemCap) continue;
         const int64_t ntiles = (n + tile_points(ppt) - 1) / tile_points(ppt);
         if (ntiles >= 2 * (int64_t)sms || ppt == 1) return ppt;
@@ -1676,7 +1624,7 @@ extern "C" int cov_traj_max_poses(void) {
     static int cached = 0;
     if (cached) return cached;
     int w = 1;
-    while (w < 32 * kMaskWords && fused_smem_bytes(w + 1, 1, false) <= kSmemCap && minmax_smem_bytes(w + 1) <= kSmemCap &&
+    while (w < 32 * kMaskWords && fused_smem_bytes(w + 1, 1) <= kSmemCap && minmax_smem_bytes(w + 1) <= kSmemCap &&
            (size_t)(w + 1) * sizeof(float4) <= 48 * 1024)
         ++w;
     cached = w;
@@ -1726,7 +1674,7 @@ extern "C" int cov_traj_minmax(const float* xyz, int64_t n, const float* poses, 
     cudaStream_t s = (cudaStream_t)stream;
     const CovConst C = cov_make_const(cam);
     const bool prune = !(opts && opts->dense) && n >= kDenseBelow;
-    int ppt = pick_ppt(n, W, false, false);
+    int ppt = pick_ppt(n, W, false);
     if (ppt == 4 && (n + tile_points(8) - 1) / tile_points(8) >= 4 * (int64_t)cov_sm_count_cached()) ppt = 8;
     if (ppt == 0) {
         cov_set_error("cov_traj_minmax: %d poses do not fit in shared memory", W);
@@ -1794,13 +1742,13 @@ extern "C" int cov_traj_fused(const float* xyz, int64_t n, const float* poses, c
     const bool prune = !(opts && opts->dense) && n >= kDenseBelow;
     const TrajWorkspace t = carve_workspace(ws, n, W);
     if (!prune) {  // every pair evaluated: accumulators zeroed, one kernel
-        const int ppt_d = pick_ppt(n, W, true, false);
+        const int ppt_d = pick_ppt(n, W, true);
         if (ppt_d == 0) {
             cov_set_error("cov_traj_fused: %d poses do not fit in shared memory", W);
             return COV_ERR_UNSUPPORTED;
         }
         cudaMemsetAsync(acc, 0, ((size_t)W * COV_ACC_STRIDE + 1) * sizeof(double), s);
-        const size_t smem = fused_smem_bytes(W, ppt_d, false);
+        const size_t smem = fused_smem_bytes(W, ppt_d);
         const int64_t ntiles = (n + tile_points(ppt_d) - 1) / tile_points(ppt_d);
         // phase-2 parallelism: split each pose row over 2^seg_log2 lanes until there are >= 2 tasks per thread
         int seg_log2 = 0;
@@ -1857,20 +1805,16 @@ extern "C" int cov_sweep_rewards(const float* xyz, int64_t n, const float* poses
     }
     if (opts && opts->dense)
         return cov_sweep_rewards_dense(xyz, n, poses, quats, n_traj, per_traj, K, cam, minmax, sum_rewards, stream);
-    // trajectories per launch: pose table + two stages + per-trajectory sums within ~100 KB (two blocks per SM)
-    constexpr int PPT = 4;
-    auto smem_for = [&](int nt) {
-        return (size_t)fused_stage_offset_floats(nt * per_traj) * 4 + 2 * (size_t)stage_floats(PPT) * 4 + (size_t)nt * sizeof(double);
-    };
-    if (smem_for(1) > kSmemCap || per_traj > 32 * kMaskWords) {
-        cov_set_error("cov_sweep_rewards: %d poses per trajectory do not fit in shared memory", per_traj);
+    // trajectories per launch: as many as the per-tile pose mask holds (32 * kMaskWords poses); the pose table stays in
+    // global memory, the block keeps one fp64 total per trajectory in shared memory
+    if (per_traj > 32 * kMaskWords) {
+        cov_set_error("cov_sweep_rewards: %d poses per trajectory exceed the pose mask (%d)", per_traj, 32 * kMaskWords);
         return COV_ERR_UNSUPPORTED;
     }
-    int chunk = 1;
-    while (chunk < n_traj && smem_for(chunk + 1) <= 100 * 1024 && (chunk + 1) * per_traj <= 32 * kMaskWords) ++chunk;
+    int chunk = (32 * kMaskWords) / per_traj;
+    if (chunk > n_traj) chunk = n_traj;
     const int Wc = chunk * per_traj;
-    if (!ws || ws_bytes < cov_traj_workspace_bytes(n, Wc) + 2 * (size_t)Wc * sizeof(float) || (((uintptr_t)ws) & 255) ||
-        (((uintptr_t)xyz) & 15)) {
+    if (!ws || ws_bytes < cov_sweep_workspace_bytes(n, n_traj, per_traj) || (((uintptr_t)ws) & 255) || (((uintptr_t)xyz) & 15)) {
         cov_set_error("cov_sweep_rewards: workspace missing, misaligned or smaller than cov_sweep_workspace_bytes(n, %d, %d) = %zu",
                       n_traj, per_traj, cov_sweep_workspace_bytes(n, n_traj, per_traj));
         return COV_ERR_WORKSPACE;
@@ -1880,7 +1824,8 @@ extern "C" int cov_sweep_rewards(const float* xyz, int64_t n, const float* poses
     const TrajWorkspace t = carve_workspace(ws, n, Wc);
     const float4* boxes = boxes_for_call(xyz, n, boxes_dev, t, s);
     const int W = n_traj * per_traj;
-    const int64_t ntiles = (n + tile_points(PPT) - 1) / tile_points(PPT);
+    constexpr int ppt = 4;  // tiles of 1024 points, eight 128-point items each
+    const int64_t ntiles = (n + tile_points(ppt) - 1) / tile_points(ppt);
     float* mm = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + t.bytes);  // the chunk's minima and maxima, contiguous
     for (int t0 = 0; t0 < n_traj; t0 += chunk) {
         const int nt = (n_traj - t0 < chunk) ? n_traj - t0 : chunk;
@@ -1889,12 +1834,13 @@ extern "C" int cov_sweep_rewards(const float* xyz, int64_t n, const float* poses
         cudaMemcpyAsync(mm + Wn, minmax + W + w0, (size_t)Wn * sizeof(float), cudaMemcpyDeviceToDevice, s);
         cov_traj_table_kernel<<<(Wn + 63) / 64, 64, 0, s>>>(poses + 3 * (size_t)w0, quats + 4 * (size_t)w0, Wn, K, C, mm, t.table,
                                                             t.ctrl, (int)(t.ctrl_bytes / sizeof(int)), nullptr, 0.0);
-        if (launch_cull(boxes, PPT, ntiles, t, Wn, nullptr, 0.f, nullptr, 0, s) != COV_OK) return COV_ERR_UNSUPPORTED;
-        const size_t smem = smem_for(nt);
-        const int grid = grid_for(cov_sweep_tiles_kernel<PPT>, smem, ntiles);
-        cov_sweep_tiles_kernel<PPT><<<grid, COV_THREADS, smem, s>>>(xyz, n, t.table, Wn, per_traj, nt, C, boxes, t.amask,
-                                                                   mask_stride_words(Wn), t.worklist, t.ctrl,
-                                                                   sum_rewards + t0);
+        if (launch_cull(boxes, ppt, ntiles, t, Wn, nullptr, 0.f, nullptr, 0, s) != COV_OK) return COV_ERR_UNSUPPORTED;
+        const size_t smem = (size_t)nt * sizeof(double);
+        int64_t grid = (int64_t)blocks_per_sm(cov_sweep_tiles_kernel, COV_THREADS, smem) * cov_sm_count_cached();
+        grid = std::max<int64_t>(1, std::min<int64_t>(grid, ntiles));
+        cov_sweep_tiles_kernel<<<(unsigned)grid, COV_THREADS, smem, s>>>(xyz, n, t.table, Wn, per_traj, nt, C, boxes, t.amask,
+                                                                        mask_stride_words(Wn), t.worklist, t.ctrl,
+                                                                        sum_rewards + t0);
     }
     return cov_check_launch("cov_sweep_rewards");
 }
