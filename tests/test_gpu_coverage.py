@@ -795,3 +795,43 @@ def test_two_gpu_sharded_objective_with_in_kernel_exchange():
                              capture_output=True, text=True, env=env, timeout=600, cwd=root)
         assert out.returncode == 0 and "dist_check OK" in out.stdout, (out.stdout[-2000:], out.stderr[-2000:])
         assert ("unavailable" not in out.stderr) or peer == "0"
+
+
+def test_peer_exchange_kernel_single_rank(dev, mod):
+    """cov_peer_allreduce with a world of one (the exchange buffer is a plain zeroed device buffer): the in-place result
+    equals the input for all three kinds, over several calls (the slot parity alternates with the device-side epoch) and
+    when replayed from a CUDA graph.  The multi-rank behaviour is covered by scripts/dist_check.py on >= 2 GPUs."""
+    import ctypes
+    from trajectory_optimization_b200 import _lib
+    model, tools, ops = mod
+    L = _lib.lib()
+    W = 321
+    n_mm, n_acc = 2 * W, W * _lib.ACC_STRIDE + 1
+    b_mm = (L.cov_peer_region_bytes(_lib.PEER_MINMAX_F32, n_mm, 1) + 255) // 256 * 256
+    b_acc = (L.cov_peer_region_bytes(_lib.PEER_SUM_F64, n_acc, 1) + 255) // 256 * 256
+    buf = torch.zeros(b_mm + b_acc, dtype=torch.uint8, device=dev)
+    peers = _lib.Peers()
+    peers.ptr[0] = buf.data_ptr()
+    peers.world, peers.rank = 1, 0
+    g = torch.Generator(device=dev).manual_seed(1)
+    for it in range(5):
+        mm = torch.rand(n_mm, device=dev, generator=g) - 0.5
+        acc = torch.randn(n_acc, device=dev, generator=g, dtype=torch.float64)
+        mm0, acc0 = mm.clone(), acc.clone()
+        ops._call("cov_peer_allreduce", mm, _lib.PEER_MINMAX_F32, mm.data_ptr(), n_mm, ctypes.byref(peers), 0)
+        ops._call("cov_peer_allreduce", acc, _lib.PEER_SUM_F64, acc.data_ptr(), n_acc, ctypes.byref(peers), b_mm)
+        assert torch.equal(mm, mm0) and torch.equal(acc, acc0)
+    # graph replays draw fresh epochs from the device-side ticket
+    acc = torch.randn(n_acc, device=dev, generator=g, dtype=torch.float64)
+    acc0 = acc.clone()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        ops._call("cov_peer_allreduce", acc, _lib.PEER_SUM_F64, acc.data_ptr(), n_acc, ctypes.byref(peers), b_mm)
+    for _ in range(4):
+        graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(acc, acc0)
+    with pytest.raises(RuntimeError):
+        ops._call("cov_peer_allreduce", acc, 7, acc.data_ptr(), n_acc, ctypes.byref(peers), b_mm)

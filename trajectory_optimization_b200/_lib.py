@@ -9,7 +9,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcovb200.so")
+# COV_B200_LIB: another build of the same library (A/B experiments with kernel variants); default: the in-tree build
+LIB_PATH = os.environ.get("COV_B200_LIB") or os.path.join(_HERE, "libcovb200.so")
 _lock = threading.Lock()
 _lib = None
 
