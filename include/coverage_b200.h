@@ -87,7 +87,8 @@ int cov_pose_epilogue(const double* acc_dev, const float* trans_dev, const float
  *   reward_index_dev: NULL, or (n) int32: point j of xyz_dev is point reward_index_dev[j] of the caller's cloud
  *   (the permutation cov_spatial_sort returns); rewards_dev and upstream_dev are then indexed in the caller's order.
  * ------------------------------------------------------------------------------------------ */
-int cov_traj_max_poses(void);
+int cov_traj_max_poses(void);        /* poses one call takes on ANY path (the dense kernels' shared-memory pose table) */
+int cov_traj_max_poses_pruned(void); /* ... when the call takes the pruned path (cov_traj_prefill_applies): the tile masks' width */
 size_t cov_traj_workspace_bytes(int64_t n, int n_poses);
 
 /* Per-call options of cov_traj_minmax / cov_traj_fused / cov_sweep_rewards; NULL = all zero = the defaults.

@@ -835,3 +835,32 @@ def test_peer_exchange_kernel_single_rank(dev, mod):
     assert torch.equal(acc, acc0)
     with pytest.raises(RuntimeError):
         ops._call("cov_peer_allreduce", acc, 7, acc.data_ptr(), n_acc, ctypes.byref(peers), b_mm)
+
+
+def test_pruned_path_takes_up_to_2048_poses_per_call(dev, mod):
+    """The pruned kernels keep no pose table in shared memory: one call takes 32 x 64 = 2048 poses (the dense kernels
+    1233).  A sweep of 1500 one-pose trajectories runs as ONE pruned pass A and one sweep launch and must agree with the
+    dense sweep (which chunks the poses)."""
+    from trajectory_optimization_b200 import _lib
+    model, tools, ops = mod
+    L = _lib.lib()
+    assert L.cov_traj_max_poses_pruned() == 2048 and L.cov_traj_max_poses() < 2048
+    gen = np.random.default_rng(23)
+    pts = torch.from_numpy(_box(gen, 120_000)).to(dev)
+    T = 1500
+    poses = (gen.random((T, 1, 3)) * np.array([30, 30, 2]) + np.array([-5, -5, -0.5])).astype(np.float32)
+    quats = gen.normal(0, 1, (T, 1, 4)).astype(np.float32)
+    K, Wd, Hd = tools.load_intrinsics(dev)
+    P, Q = torch.from_numpy(poses), torch.from_numpy(quats)
+    means = ops.sweep_rewards(pts, P, Q, K, Wd, Hd)
+    with ops.evaluation(dense=True):
+        means_dense = ops.sweep_rewards(pts, P, Q, K, Wd, Hd)
+    assert means.shape == (T,) and rel_err(means.cpu().numpy(), means_dense.cpu().numpy()) < 1e-9
+    # and the trajectory objective itself with 1500 poses in one pruned call
+    Pg = P.reshape(T, 3).to(dev).requires_grad_(True)
+    Qg = Q.reshape(T, 4).to(dev).requires_grad_(True)
+    rewards, mean = ops.coverage_traj(pts, Pg, Qg, K, Wd, Hd)
+    mean.backward()
+    assert torch.isfinite(rewards).all() and float(rewards.min()) >= 0.5 and torch.isfinite(Pg.grad).all()
+    with pytest.raises(RuntimeError):          # the dense path cannot take them in one call, and says so
+        ops.coverage_traj(pts, Pg, Qg, K, Wd, Hd, dense=True)

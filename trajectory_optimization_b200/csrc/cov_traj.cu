@@ -1561,13 +1561,15 @@ TrajWorkspace carve_workspace(void* ws, int64_t n, int W) {
 }
 
 int check_traj_args(const char* who, const float* xyz, int64_t n, const float* poses, const float* quats, int W,
-                    const float* K, const cov_camera* cam, const void* ws, size_t ws_bytes) {
+                    const float* K, const cov_camera* cam, const void* ws, size_t ws_bytes, bool pruned) {
     if (!xyz || n <= 0 || !poses || !quats || W <= 0 || !K || !cam) {
         cov_set_error("%s: null pointer, empty cloud or no poses (n=%lld, W=%d)", who, (long long)n, W);
         return COV_ERR_ARG;
     }
-    if (W > cov_traj_max_poses()) {
-        cov_set_error("%s: %d poses exceed the shared-memory pose table (max %d)", who, W, cov_traj_max_poses());
+    // the dense kernels keep the pose table in shared memory; the pruned ones only a bit per pose in the tile masks
+    const int max_w = pruned ? cov_traj_max_poses_pruned() : cov_traj_max_poses();
+    if (W > max_w) {
+        cov_set_error("%s: %d poses exceed what one call takes on this path (max %d)", who, W, max_w);
         return COV_ERR_UNSUPPORTED;
     }
     if (n >= ((int64_t)1 << 31) * 256) {
@@ -1631,6 +1633,8 @@ extern "C" int cov_traj_max_poses(void) {
     return w;
 }
 
+extern "C" int cov_traj_max_poses_pruned(void) { return 32 * kMaskWords; }
+
 extern "C" size_t cov_traj_workspace_bytes(int64_t n, int n_poses) {
     if (n < 1) n = 1;
     if (n_poses < 1) n_poses = 1;
@@ -1661,7 +1665,8 @@ extern "C" int cov_tile_boxes(const float* xyz, int64_t n, float* boxes, void* s
 extern "C" int cov_traj_minmax(const float* xyz, int64_t n, const float* poses, const float* quats, int W,
                                const float* K, const cov_camera* cam, const float* boxes_dev, float* minmax,
                                const cov_traj_opts* opts, void* ws, size_t ws_bytes, void* stream) {
-    int rc = check_traj_args("cov_traj_minmax", xyz, n, poses, quats, W, K, cam, ws, ws_bytes);
+    const bool prune = !(opts && opts->dense) && n >= kDenseBelow;
+    int rc = check_traj_args("cov_traj_minmax", xyz, n, poses, quats, W, K, cam, ws, ws_bytes, prune);
     if (rc) return rc;
     if (!minmax) {
         cov_set_error("cov_traj_minmax: null minmax");
@@ -1673,8 +1678,7 @@ extern "C" int cov_traj_minmax(const float* xyz, int64_t n, const float* poses, 
     }
     cudaStream_t s = (cudaStream_t)stream;
     const CovConst C = cov_make_const(cam);
-    const bool prune = !(opts && opts->dense) && n >= kDenseBelow;
-    int ppt = pick_ppt(n, W, false);
+    int ppt = prune ? 4 : pick_ppt(n, W, false);
     if (ppt == 4 && (n + tile_points(8) - 1) / tile_points(8) >= 4 * (int64_t)cov_sm_count_cached()) ppt = 8;
     if (ppt == 0) {
         cov_set_error("cov_traj_minmax: %d poses do not fit in shared memory", W);
@@ -1727,7 +1731,8 @@ extern "C" int cov_traj_fused(const float* xyz, int64_t n, const float* poses, c
                               const float* K, const cov_camera* cam, const float* boxes_dev, const float* minmax,
                               const float* upstream, const int32_t* reward_index, float* rewards, double* acc,
                               const cov_traj_opts* opts, void* ws, size_t ws_bytes, void* stream) {
-    int rc = check_traj_args("cov_traj_fused", xyz, n, poses, quats, W, K, cam, ws, ws_bytes);
+    const bool prune = !(opts && opts->dense) && n >= kDenseBelow;
+    int rc = check_traj_args("cov_traj_fused", xyz, n, poses, quats, W, K, cam, ws, ws_bytes, prune);
     if (rc) return rc;
     if (!minmax || !rewards || !acc) {
         cov_set_error("cov_traj_fused: null minmax/rewards/acc");
@@ -1739,7 +1744,6 @@ extern "C" int cov_traj_fused(const float* xyz, int64_t n, const float* poses, c
     }
     cudaStream_t s = (cudaStream_t)stream;
     const CovConst C = cov_make_const(cam);
-    const bool prune = !(opts && opts->dense) && n >= kDenseBelow;
     const TrajWorkspace t = carve_workspace(ws, n, W);
     if (!prune) {  // every pair evaluated: accumulators zeroed, one kernel
         const int ppt_d = pick_ppt(n, W, true);

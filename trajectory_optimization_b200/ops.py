@@ -254,7 +254,7 @@ class CudaBackend:
         L = _lib.lib()
         W, n, dev = P.shape[0], pts.shape[0], pts.device
         minmax = torch.empty(2 * W, dtype=torch.float32, device=dev)
-        chunk = L.cov_traj_max_poses()
+        chunk = L.cov_traj_max_poses_pruned() if self.prefill_applies(pts) else L.cov_traj_max_poses()
         ws_bytes = L.cov_traj_workspace_bytes(n, min(W, chunk))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         opts = _opts()
