@@ -13,6 +13,8 @@
 //   hull_scatter   counting-sort scatter into (x, y, z, original index) records
 //   hull_classify  one thread per point: hull_classify_point -> vertex mask, counters
 //   hull_origin    GJK distance from the origin to conv(F) in one block (is the origin a vertex?)
+#include <cstdlib>
+
 #include "cov_common.cuh"
 #include "hull_core.h"
 #include "../../include/coverage_b200.h"
@@ -20,6 +22,9 @@
 namespace {
 
 constexpr int kHullMaxG = 128;
+// one-thread-per-point near phase: radius and evaluation budget after which a point is handed to the warp-per-point kernel
+constexpr int kNearRadius = HULL_R_NEAR;
+constexpr int kNearBudget = 0;
 
 int hull_grid_size(int64_t n) {
     int G = (int)lround(sqrt((double)n / (12.0 * 3.141592653589793)));
@@ -179,7 +184,8 @@ __global__ void __launch_bounds__(128)
 hull_classify_kernel(int G, const int* __restrict__ cell_start, const float4* __restrict__ sorted,
                      const int* __restrict__ occ, const int* __restrict__ n_occ,
                      const unsigned long long* __restrict__ rho_max_bits, const int* __restrict__ n_valid,
-                     uint8_t* __restrict__ mask, int* __restrict__ info, int* __restrict__ far_list, int* __restrict__ n_far) {
+                     uint8_t* __restrict__ mask, int* __restrict__ info, int* __restrict__ far_list, int* __restrict__ n_far,
+                     int r_near, int budget) {
     const int k = blockIdx.x * 128 + threadIdx.x;
     if (k >= *n_valid) return;
     HullGrid g;
@@ -193,7 +199,7 @@ hull_classify_kernel(int G, const int* __restrict__ cell_start, const float4* __
     int cert[3];
     // near phase only (one thread per point); a point that needs the all-voxel sweep, a wider tilt box or a bigger
     // active set goes on the far list and gets a whole warp (hull_far_kernel)
-    const int rc = hull_classify_attempt(g, k, HULL_TILT_NEAR, cert, false);
+    const int rc = hull_classify_attempt(g, k, HULL_TILT_NEAR, cert, false, r_near, budget);
     if (rc == HULL_UNDECIDED || rc == HULL_EXTREME_UNCERT || rc == HULL_OVERFLOW) {
         far_list[atomicAdd(n_far, 1)] = k;
         return;
@@ -409,8 +415,14 @@ extern "C" int cov_hpr_hull(const float* flipped, int64_t n, uint8_t* vertex_mas
     hull_occupied_kernel<<<(unsigned)((ncell + 255) / 256), 256, 0, s>>>(w.cell_count, ncell, w.occ, w.n_occ);
     hull_scatter_kernel<<<(unsigned)nb, 256, 0, s>>>(flipped, n, w.key, w.cell_count, w.cursor, w.sorted, vertex_mask);
     // `key` is free once the points are scattered: it becomes the list of the points that need the all-voxel sweep
+    int r_near = kNearRadius, budget = kNearBudget;
+#ifdef COV_HULL_KNOBS
+    if (const char* e = getenv("COV_HULL_R_NEAR")) r_near = atoi(e);
+    if (const char* e = getenv("COV_HULL_BUDGET")) budget = atoi(e);
+#endif
     hull_classify_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(G, w.cell_count, w.sorted, w.occ, w.n_occ,
-                                                                    w.rho_max_bits, w.n_valid, vertex_mask, info, w.key, w.n_far);
+                                                                    w.rho_max_bits, w.n_valid, vertex_mask, info, w.key, w.n_far,
+                                                                    r_near, budget);
     hull_far_kernel<<<(unsigned)(cov_sm_count_cached() * 8), 128, 0, s>>>(G, w.cell_count, w.sorted, w.occ, w.n_occ, w.rho_max_bits,
                                                                          w.key, w.n_far, vertex_mask, info);
     hull_origin_kernel<<<1, 1024, 0, s>>>(flipped, n, info);

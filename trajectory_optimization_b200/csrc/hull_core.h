@@ -283,7 +283,10 @@ HULL_HD int hull_sweep_cell(const HullGrid& g, int cell, int self, const HullFra
 // Classify sorted point `self`.  cert_out receives the three sorted-array ids of an INSIDE certificate.
 // far_ok = false: stop after the near phase and return HULL_UNDECIDED when the point needs the all-voxel sweep (the
 // CUDA path hands those points to a kernel that runs that sweep with a whole warp per point).
-HULL_HD int hull_classify_attempt(const HullGrid& g, int self, double tilt, int* cert_out, bool far_ok = true) {
+// r_near / budget (far_ok = false only): give up the near phase beyond Chebyshev radius r_near or after `budget` constraint
+// evaluations (0 = no limit) — the point is deferred, not decided, so the answer does not depend on either.
+HULL_HD int hull_classify_attempt(const HullGrid& g, int self, double tilt, int* cert_out, bool far_ok = true,
+                                  int r_near = HULL_R_NEAR, int budget = 0) {
     const float4 ps = g.sorted[self];
     HullFrame F;
     hull_frame_init(F, (double)ps.x, (double)ps.y, (double)ps.z);
@@ -293,7 +296,9 @@ HULL_HD int hull_classify_attempt(const HullGrid& g, int self, double tilt, int*
     const int cx = hull_cell_coord(F.u[0], G), cy = hull_cell_coord(F.u[1], G), cz = hull_cell_coord(F.u[2], G);
     int clean = -1;  // every voxel within Chebyshev radius `clean` has been swept without moving the LP
     int rc = HULL_UNDECIDED;
-    for (int r = 0; r <= HULL_R_NEAR && rc == HULL_UNDECIDED;) {
+    int work = 0;
+    if (far_ok) { r_near = HULL_R_NEAR; budget = 0; }
+    for (int r = 0; r <= r_near && rc == HULL_UNDECIDED;) {
         bool changed = false;
         for (int dx = -r; dx <= r && rc == HULL_UNDECIDED; ++dx) {
             const int ix = cx + dx;
@@ -307,7 +312,12 @@ HULL_HD int hull_classify_attempt(const HullGrid& g, int self, double tilt, int*
                     const int ad = (dx < 0 ? -dx : dx), bd = (dy < 0 ? -dy : dy), cd = (dz < 0 ? -dz : dz);
                     const int cheb = ad > bd ? (ad > cd ? ad : cd) : (bd > cd ? bd : cd);
                     if (cheb <= clean) continue;
-                    rc = hull_sweep_cell(g, (ix * G + iy) * G + iz, self, F, L, changed);
+                    const int cell = (ix * G + iy) * G + iz;
+                    if (budget > 0) {
+                        work += g.cell_start[cell + 1] - g.cell_start[cell];
+                        if (work > budget) return HULL_UNDECIDED;
+                    }
+                    rc = hull_sweep_cell(g, cell, self, F, L, changed);
                     if (rc != HULL_UNDECIDED) break;
                 }
             }
