@@ -270,6 +270,13 @@ int cov_tile_boxes(const float* xyz_dev, int64_t n, float* boxes_dev, void* stre
 int cov_spatial_sort(const float* xyz_dev, int64_t n, float* xyz_sorted_dev, int32_t* perm_dev, void* workspace_dev,
                      size_t workspace_bytes, void* stream);
 
+/* The stable radix sort of (uint32 key, int32 value) pairs that cov_spatial_sort and cov_voxel_grid are built on (own
+ * kernels, csrc/cov_radix.cuh), on its own: sorts in place by key bits [begin_bit, end_bit), equal keys keep their order.
+ * No reference counterpart (torch.sort / pcl's std::sort would be the nearest); exported for tests and tools. */
+size_t cov_sort_pairs_workspace_bytes(int64_t n);
+int cov_sort_pairs(uint32_t* keys_dev, int32_t* vals_dev, int64_t n, int begin_bit, int end_bit, void* workspace_dev,
+                   size_t workspace_bytes, void* stream);
+
 /* FP32 FMA / MUFU.EX2 throughput probes used by bench.py for the roofline denominators.
  * Each runs `iters` dependent-chain iterations on a full grid and writes a checksum; the caller
  * times them with CUDA events.  Returns the number of FMA (or ex2) operations issued. */

@@ -41,12 +41,13 @@ for kind in ("shell", "halfspace"):
     P = torch.from_numpy(cloud(kind)).to(dev)
     flipped, _ = ops.spherical_flip(P, 2)
     base = None
-    for r_near, budget in [(6, 0), (4, 0), (3, 0), (2, 0), (1, 0), (6, 4000), (6, 2000), (6, 1000), (6, 500), (6, 250),
-                           (3, 1000), (2, 500), (2, 250)]:
+    for r_near, budget, r_mid in [(6, 0, 6), (1, 0, 6), (1, 1000, 6), (1, 2000, 6), (0, 0, 6), (0, 500, 6), (1, 1000, 3), (1, 1000, 4),
+                                  (1, 1000, 8), (1, 1000, 12), (1, 1000, 16), (2, 1000, 8)]:
         os.environ["COV_HULL_R_NEAR"] = str(r_near)
         os.environ["COV_HULL_BUDGET"] = str(budget)
-        ms, (mask, origin, n_unc) = timed(lambda: ops.hpr_hull_mask(flipped))
+        os.environ["COV_HULL_R_MID"] = str(r_mid)
+        ms, (mask, origin, n_unc, info) = timed(lambda: ops.hpr_hull_mask(flipped, return_info=True))
         if base is None:
             base = mask.clone()
-        print(f"{kind:9s} r_near {r_near} budget {budget:5d}: {ms:7.3f} ms  vertices {int(mask.sum())} uncertified {n_unc} "
-              f"same set {bool(torch.equal(mask, base))}", flush=True)
+        print(f"{kind:9s} r_near {r_near} budget {budget:5d} r_mid {r_mid:2d}: {ms:7.3f} ms  vertices {int(mask.sum())} uncertified {n_unc} "
+              f"same set {bool(torch.equal(mask, base))} handed to the warp stage {info[3]}, to the all-voxel stage {info[2]}", flush=True)

@@ -360,7 +360,7 @@ def test_pruned_evaluation_is_bit_identical_to_dense(dev, mod):
 def test_spatial_sort_is_a_stable_morton_permutation(dev, mod):
     model, tools, ops = mod
     gen = np.random.default_rng(3)
-    for n in (1, 5, 1000, 250_007):
+    for n in (1, 5, 1000, 250_007, 3_000_001):   # the last: several 4096-key tiles per block and a ragged end
         pts_np = _box(gen, n)
         if n >= 1000:
             pts_np[10] = pts_np[500]  # duplicate points keep their input order (stable sort)
@@ -380,6 +380,24 @@ def test_spatial_sort_is_a_stable_morton_permutation(dev, mod):
                 key |= ((cell[:, a].astype(np.uint64) >> b) & 1) << (3 * b + a)
         order = np.argsort(key, kind="stable")
         assert np.array_equal(order, perm.cpu().numpy())
+
+
+@pytest.mark.parametrize("n,bits", [(1, (0, 32)), (31, (0, 32)), (4096, (0, 32)), (4097, (0, 32)), (100_003, (0, 32)),
+                                    (100_003, (5, 19)), (2_500_001, (0, 30)), (5_000_000, (0, 8)), (5_000_000, (24, 32))])
+def test_sort_pairs_is_a_stable_unsigned_radix_sort(n, bits, dev, mod):
+    """The library's own pair sort (csrc/cov_radix.cuh) against numpy's stable argsort on the selected key bits."""
+    model, tools, ops = mod
+    gen = np.random.default_rng(n + bits[0])
+    keys = gen.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    if n > 1000:
+        keys[::7] = keys[3]            # many equal keys: their values must keep the input order
+        keys[5::11] &= 0xff            # small keys: high digits all zero
+    vals = np.arange(n, dtype=np.int32)
+    k, v = ops.sort_pairs(torch.from_numpy(keys.view(np.int32)).to(dev), torch.from_numpy(vals).to(dev), *bits)
+    digit = (keys.astype(np.uint64) >> bits[0]) & ((1 << (bits[1] - bits[0])) - 1)
+    order = np.argsort(digit, kind="stable")
+    assert np.array_equal(v.cpu().numpy(), vals[order])
+    assert np.array_equal(k.cpu().numpy().view(np.uint32), keys[order])
 
 
 def test_model_traj_sorted_cloud_equals_caller_order(dev, mod):

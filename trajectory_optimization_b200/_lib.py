@@ -76,6 +76,8 @@ PROTOTYPES = {
     "cov_voxel_grid": (_int, [_vp, _i64, _f, _int, _f, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
     "cov_spatial_sort_workspace_bytes": (_sz, [_i64]),
     "cov_spatial_sort": (_int, [_vp, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "cov_sort_pairs_workspace_bytes": (_sz, [_i64]),
+    "cov_sort_pairs": (_int, [_vp, _vp, _i64, _int, _int, _vp, _sz, _vp]),
     "cov_tile_boxes_count": (_i64, [_i64]),
     "cov_tile_boxes": (_int, [_vp, _i64, _vp, _vp]),
     "cov_probe_fma": (_i64, [_int, _vp, _vp]),

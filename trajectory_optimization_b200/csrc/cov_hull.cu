@@ -22,9 +22,13 @@
 namespace {
 
 constexpr int kHullMaxG = 128;
-// one-thread-per-point near phase: radius and evaluation budget after which a point is handed to the warp-per-point kernel
-constexpr int kNearRadius = HULL_R_NEAR;
-constexpr int kNearBudget = 0;
+// one-thread-per-point near phase: radius and evaluation budget after which a point is handed to the warp-per-point
+// stage.  Measured on 1 M-point clouds (scripts/hull_knobs.py): radius 6 / no budget 6.5 ms (shell) and 27.5 ms (half
+// space: the warp waits for its slowest lane); radius 1: 6.0 and 14.7 ms.  The budget bounds what one lane can cost
+// when a direction voxel is crowded.
+constexpr int kNearRadius = 1;
+constexpr int kNearBudget = 1000;
+constexpr int kMidRadius = 16;   // warp-per-point stage: largest Chebyshev radius before the all-voxel sweep (half-space cloud: radius 6 leaves 747 points for it = 4.6 ms, radius 16 none)
 
 int hull_grid_size(int64_t n) {
     int G = (int)lround(sqrt((double)n / (12.0 * 3.141592653589793)));
@@ -40,7 +44,9 @@ struct HullWs {  // carve-up of the caller's workspace
     unsigned long long* rho_max_bits;  // 1
     int* n_occ;           // 1
     int* n_valid;         // 1
-    int* n_far;           // 1: points handed to the warp-per-point sweep (their sorted ids reuse `key`)
+    int* n_far;           // 1: points handed on to the all-voxel sweep (their sorted ids: `far`)
+    int* n_mid;           // 1: points the near phase gave up on (their sorted ids reuse `key`)
+    int* far;             // n
     int* block_tot;       // ceil(G^3 / 4096): chunk totals / offsets of the histogram scan
 };
 
@@ -54,6 +60,7 @@ size_t hull_carve(void* base, int64_t n, int G, HullWs* w) {
     HullWs t;
     t.sorted = (float4*)take((size_t)n * sizeof(float4));
     t.key = (int*)take((size_t)n * sizeof(int));
+    t.far = (int*)take((size_t)n * sizeof(int));
     t.cell_count = (int*)take((ncell + 1) * sizeof(int));
     t.cursor = (int*)take(ncell * sizeof(int));
     t.occ = (int*)take(ncell * sizeof(int));
@@ -61,6 +68,7 @@ size_t hull_carve(void* base, int64_t n, int G, HullWs* w) {
     t.n_occ = (int*)take(16);
     t.n_valid = (int*)take(16);
     t.n_far = (int*)take(16);
+    t.n_mid = (int*)take(16);
     t.block_tot = (int*)take(((ncell + 4095) / 4096 + 1) * sizeof(int));
     if (w) *w = t;
     return off;
@@ -184,7 +192,7 @@ __global__ void __launch_bounds__(128)
 hull_classify_kernel(int G, const int* __restrict__ cell_start, const float4* __restrict__ sorted,
                      const int* __restrict__ occ, const int* __restrict__ n_occ,
                      const unsigned long long* __restrict__ rho_max_bits, const int* __restrict__ n_valid,
-                     uint8_t* __restrict__ mask, int* __restrict__ info, int* __restrict__ far_list, int* __restrict__ n_far,
+                     uint8_t* __restrict__ mask, int* __restrict__ info, int* __restrict__ mid_list, int* __restrict__ n_mid,
                      int r_near, int budget) {
     const int k = blockIdx.x * 128 + threadIdx.x;
     if (k >= *n_valid) return;
@@ -197,11 +205,11 @@ hull_classify_kernel(int G, const int* __restrict__ cell_start, const float4* __
     g.n_occ = *n_occ;
     g.rho_max = __longlong_as_double((long long)*rho_max_bits);
     int cert[3];
-    // near phase only (one thread per point); a point that needs the all-voxel sweep, a wider tilt box or a bigger
-    // active set goes on the far list and gets a whole warp (hull_far_kernel)
+    // near phase only (one thread per point); a point that exhausts its evaluation budget or needs a wider search, a
+    // wider tilt box or a bigger active set goes on the list of the cooperative stages (hull_mid_kernel, hull_far_kernel)
     const int rc = hull_classify_attempt(g, k, HULL_TILT_NEAR, cert, false, r_near, budget);
     if (rc == HULL_UNDECIDED || rc == HULL_EXTREME_UNCERT || rc == HULL_OVERFLOW) {
-        far_list[atomicAdd(n_far, 1)] = k;
+        mid_list[atomicAdd(n_mid, 1)] = k;
         return;
     }
     const bool vertex = rc == HULL_EXTREME;
@@ -210,22 +218,143 @@ hull_classify_kernel(int G, const int* __restrict__ cell_start, const float4* __
     if (vertex) atomicAdd(info + 2, 1);
 }
 
-// The all-voxel sweep for the points of the far list (silhouette points of a cloud that does not surround the camera:
-// large tilt), ONE WARP PER POINT.  Every lane keeps the same LP (the updates are deterministic, so the 32 copies never
-// diverge); per round the lanes scan disjoint subsets of the occupied voxels, culled by the bound on n.f over a voxel,
-// for the MOST VIOLATED half-plane, the warp agrees on one, and every lane adds it.  The answer (feasible / infeasible)
-// does not depend on the pivot order; certificates as in hull_core.h.
+// ---- cooperative stages for the points the one-thread near phase gives up on ----
+// Every participating thread keeps the same LP (the updates are deterministic, so the copies never diverge); per round
+// the threads scan disjoint candidates for the MOST VIOLATED half-plane, agree on one, and every thread adds it.  The
+// answer (feasible / infeasible) does not depend on the pivot order; certificates as in hull_core.h.
+struct HullPick {
+    double score, a, b, c;   // most violated half-plane seen so far (score < 0), none: id < 0
+    int id;
+};
+
+__device__ __forceinline__ void hull_pick_init(HullPick& pk) {
+    pk.score = 0.0; pk.a = 0.0; pk.b = 0.0; pk.c = 0.0; pk.id = -1;
+}
+
+__device__ __forceinline__ void hull_consider(const HullFrame& F, const HullLP& L, const float4& sp, int j, HullPick& pk) {
+    double a, bq, c;
+    hull_constraint(F, L.tilt, (double)sp.x, (double)sp.y, (double)sp.z, a, bq, c);
+    if (!hull_violated(L, a, bq, c)) return;
+    bool active = false;
+    for (int q = 0; q < L.n; ++q) active |= L.id[q] == j;
+    if (active) return;  // the residual is evaluation noise of an optimum that sits on its line
+    const double score = (a * L.x0 + bq * L.x1 + c) / (fabs(a * L.x0) + fabs(bq * L.x1) + fabs(c));
+    if (score < pk.score || (score == pk.score && (pk.id < 0 || j < pk.id))) { pk.score = score; pk.a = a; pk.b = bq; pk.c = c; pk.id = j; }
+}
+
+// the warp's most violated half-plane (ties: smallest id) — the same on every lane afterwards
+__device__ __forceinline__ void hull_warp_pick(HullPick& pk) {
+    double wbest = pk.score;
+    int wid = pk.id;
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, wbest, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, wid, o);
+        if (oi >= 0 && (wid < 0 || ob < wbest || (ob == wbest && oi < wid))) { wbest = ob; wid = oi; }
+    }
+    const int src = __ffs(__ballot_sync(0xffffffffu, pk.id == wid && pk.score == wbest)) - 1;
+    pk.a = __shfl_sync(0xffffffffu, pk.a, src);
+    pk.b = __shfl_sync(0xffffffffu, pk.b, src);
+    pk.c = __shfl_sync(0xffffffffu, pk.c, src);
+    pk.score = wbest;
+    pk.id = wid;
+}
+
+// one thread writes the decision for sorted point `ps` (certifying an INSIDE answer first)
+__device__ __forceinline__ void hull_finalize(int rc, const int* cert, const HullFrame& F, const float4& ps,
+                                              const float4* __restrict__ sorted, uint8_t* __restrict__ mask, int* __restrict__ info) {
+    if (rc == HULL_INSIDE) {
+        bool ok = cert[0] >= 0 && cert[1] >= 0 && cert[2] >= 0 && cert[0] != cert[1] && cert[1] != cert[2] && cert[0] != cert[2];
+        if (ok) {
+            const float4 s1 = sorted[cert[0]], s2 = sorted[cert[1]], s3 = sorted[cert[2]];
+            const double a1[3] = {s1.x, s1.y, s1.z}, a2[3] = {s2.x, s2.y, s2.z}, a3[3] = {s3.x, s3.y, s3.z};
+            ok = hull_certify_inside(F.p, a1, a2, a3) != 0;
+        }
+        if (!ok) rc = HULL_INSIDE_UNCERT;
+    }
+    const bool vertex = (rc == HULL_EXTREME || rc == HULL_EXTREME_UNCERT);
+    mask[__float_as_int(ps.w)] = vertex ? 1 : 0;
+    if (rc != HULL_EXTREME && rc != HULL_INSIDE) atomicAdd(info + 1, 1);
+    if (vertex) atomicAdd(info + 2, 1);
+}
+
+// Middle stage, ONE WARP PER POINT: the near phase's neighbourhood search (Chebyshev cubes of growing radius around the
+// point's direction voxel, coverage bound after a clean sweep) with the candidates of a cube spread over the lanes.  The
+// voxels of a (dx, dy) column are consecutive in the counting sort, so a column is one contiguous run of records.
+// A point that needs a wider tilt box, a bigger active set or a radius beyond r_max goes on to the all-voxel stage.
 __global__ void __launch_bounds__(128)
+hull_mid_kernel(int G, const int* __restrict__ cell_start, const float4* __restrict__ sorted,
+                const unsigned long long* __restrict__ rho_max_bits, const int* __restrict__ mid_list,
+                const int* __restrict__ n_mid, uint8_t* __restrict__ mask, int* __restrict__ info, int* __restrict__ far_list,
+                int* __restrict__ n_far, int r_max) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const double h = 2.0 / G;
+    const double rho_max = __longlong_as_double((long long)*rho_max_bits);
+    for (int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < *n_mid; item += warps) {
+        const int self = mid_list[item];
+        const float4 ps = sorted[self];
+        HullFrame F;
+        hull_frame_init(F, (double)ps.x, (double)ps.y, (double)ps.z);
+        const int cx = hull_cell_coord(F.u[0], G), cy = hull_cell_coord(F.u[1], G), cz = hull_cell_coord(F.u[2], G);
+        HullLP L;
+        hull_lp_init(L, HULL_TILT_NEAR);
+        int rc = HULL_UNDECIDED;
+        bool defer = false;
+        int r = 1;
+        for (int round = 0; round < 4096 && rc == HULL_UNDECIDED && !defer; ++round) {
+            HullPick pk;
+            hull_pick_init(pk);
+            const int side = 2 * r + 1;
+            const int izlo = max(cz - r, 0), izhi = min(cz + r, G - 1);
+            for (int col = 0; col < side * side; ++col) {
+                const int ix = cx + col / side - r, iy = cy + col % side - r;
+                if (ix < 0 || ix >= G || iy < 0 || iy >= G) continue;
+                const int cbase = (ix * G + iy) * G;
+                const int b = cell_start[cbase + izlo], e = cell_start[cbase + izhi + 1];
+                for (int j = b + lane; j < e; j += 32)
+                    if (j != self) hull_consider(F, L, sorted[j], j, pk);
+            }
+            hull_warp_pick(pk);
+            if (pk.id < 0) {  // clean sweep of the cube of radius r
+                const bool whole = (cx - r <= 0 && cx + r >= G - 1 && cy - r <= 0 && cy + r >= G - 1 && cz - r <= 0 && cz + r >= G - 1);
+                if (whole || hull_coverage_ok(L, F.rho, rho_max, r * h)) {
+                    if (fabs(L.x0) > L.tilt || fabs(L.x1) > L.tilt) defer = true;  // the rounding margin needs the wide tilt box
+                    else rc = HULL_EXTREME;
+                } else if (++r > r_max) {
+                    defer = true;
+                }
+                continue;
+            }
+            const int ra = hull_lp_add(L, pk.a, pk.b, pk.c, pk.id);
+            if (ra == HULL_INSIDE) rc = HULL_INSIDE;
+            else if (ra == HULL_OVERFLOW) defer = true;
+        }
+        if (rc == HULL_UNDECIDED) defer = true;  // round limit
+        if (lane == 0) {
+            if (defer) far_list[atomicAdd(n_far, 1)] = self;
+            else hull_finalize(rc, L.cert, F, ps, sorted, mask, info);
+        }
+    }
+}
+
+// The all-voxel sweep for what is left (silhouette points of a cloud that does not surround the camera: large tilt), ONE
+// BLOCK PER POINT: per round the threads scan disjoint subsets of the occupied voxels, culled by the bound on n.f over
+// a voxel; warps agree by shuffles, the block through shared memory.  (One warp per point left the GPU idle: a single
+// point takes a warp milliseconds, and there are only hundreds of such points.)
+constexpr int kFarThreads = 256;
+
+__global__ void __launch_bounds__(kFarThreads)
 hull_far_kernel(int G, const int* __restrict__ cell_start, const float4* __restrict__ sorted, const int* __restrict__ occ,
                 const int* __restrict__ n_occ_p, const unsigned long long* __restrict__ rho_max_bits,
                 const int* __restrict__ far_list, const int* __restrict__ n_far, uint8_t* __restrict__ mask,
                 int* __restrict__ info) {
-    const int lane = threadIdx.x & 31;
-    const int warps = (gridDim.x * blockDim.x) >> 5;
+    __shared__ double s_score[kFarThreads / 32], s_abc[kFarThreads / 32][3];
+    __shared__ int s_id[kFarThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n_occ = *n_occ_p;
     const double h = 2.0 / G;
     const double rho_max = __longlong_as_double((long long)*rho_max_bits);
-    for (int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < *n_far; item += warps) {
+    for (int item = blockIdx.x; item < *n_far; item += gridDim.x) {  // block-uniform control flow from here on
         const int self = far_list[item];
         const float4 ps = sorted[self];
         HullFrame F;
@@ -233,9 +362,8 @@ hull_far_kernel(int G, const int* __restrict__ cell_start, const float4* __restr
         int rc = HULL_UNDECIDED;
         int cert[3] = {-1, -1, -1};
         for (int attempt = 0; attempt < 2; ++attempt) {
-            const double tilt = attempt == 0 ? HULL_TILT_NEAR : HULL_TILT_MAX;
             HullLP L;
-            hull_lp_init(L, tilt);
+            hull_lp_init(L, attempt == 0 ? HULL_TILT_NEAR : HULL_TILT_MAX);
             rc = HULL_UNDECIDED;
             for (int round = 0; round < 4096 && rc == HULL_UNDECIDED; ++round) {
                 const double n0 = F.u[0] + L.x0 * F.e1[0] + L.x1 * F.e2[0];
@@ -244,64 +372,45 @@ hull_far_kernel(int G, const int* __restrict__ cell_start, const float4* __restr
                 const double nn = sqrt(n0 * n0 + n1 * n1 + n2 * n2);
                 const double np = (n0 * F.p[0] + n1 * F.p[1] + n2 * F.p[2]) * (1.0 - 1e-12);
                 const double slack = nn * h * 0.8660254037844387;
-                double best = 0.0, ba = 0.0, bb = 0.0, bc = 0.0;  // most violated half-plane this lane has seen (score < 0)
-                int bid = -1;
-                for (int k = lane; k < n_occ; k += 32) {
+                HullPick pk;
+                hull_pick_init(pk);
+                for (int k = threadIdx.x; k < n_occ; k += kFarThreads) {
                     const int cell = occ[k];
                     const int iz = cell % G, iy = (cell / G) % G, ix = cell / (G * G);
                     const double c0 = (ix + 0.5) * h - 1.0, c1 = (iy + 0.5) * h - 1.0, c2 = (iz + 0.5) * h - 1.0;
                     if (rho_max * (n0 * c0 + n1 * c1 + n2 * c2 + slack) < np) continue;
                     const int b = cell_start[cell], e = cell_start[cell + 1];
-                    for (int j = b; j < e; ++j) {
-                        if (j == self) continue;
-                        const float4 sp = sorted[j];
-                        double a, bq, c;
-                        hull_constraint(F, tilt, (double)sp.x, (double)sp.y, (double)sp.z, a, bq, c);
-                        if (!hull_violated(L, a, bq, c)) continue;
-                        bool active = false;
-                        for (int q = 0; q < L.n; ++q) active |= L.id[q] == j;
-                        if (active) continue;  // the residual is evaluation noise of an optimum that sits on its line
-                        const double score = (a * L.x0 + bq * L.x1 + c) / (fabs(a * L.x0) + fabs(bq * L.x1) + fabs(c));
-                        if (score < best || (score == best && (bid < 0 || j < bid))) { best = score; ba = a; bb = bq; bc = c; bid = j; }
-                    }
+                    for (int j = b; j < e; ++j)
+                        if (j != self) hull_consider(F, L, sorted[j], j, pk);
                 }
-                // the warp's most violated half-plane (ties: smallest id) — the same on every lane
-                double wbest = best;
-                int wid = bid;
-                for (int o = 16; o > 0; o >>= 1) {
-                    const double ob = __shfl_xor_sync(0xffffffffu, wbest, o);
-                    const int oi = __shfl_xor_sync(0xffffffffu, wid, o);
-                    if (oi >= 0 && (wid < 0 || ob < wbest || (ob == wbest && oi < wid))) { wbest = ob; wid = oi; }
+                hull_warp_pick(pk);
+                if (lane == 0) {
+                    s_score[warp] = pk.score; s_id[warp] = pk.id;
+                    s_abc[warp][0] = pk.a; s_abc[warp][1] = pk.b; s_abc[warp][2] = pk.c;
                 }
-                if (wid < 0) {  // clean sweep over everything the bound could not exclude
+                __syncthreads();
+                double best = 0.0;
+                int bid = -1, bw = 0;
+#pragma unroll
+                for (int w = 0; w < kFarThreads / 32; ++w) {
+                    const int oi = s_id[w];
+                    const double ob = s_score[w];
+                    if (oi >= 0 && (bid < 0 || ob < best || (ob == best && oi < bid))) { best = ob; bid = oi; bw = w; }
+                }
+                const double a = s_abc[bw][0], bq = s_abc[bw][1], c = s_abc[bw][2];
+                __syncthreads();  // everybody has read the picks before the next round overwrites them
+                if (bid < 0) {  // clean sweep over everything the bound could not exclude
                     rc = (fabs(L.x0) > L.tilt || fabs(L.x1) > L.tilt) ? HULL_EXTREME_UNCERT : HULL_EXTREME;
                     break;
                 }
-                const int src = __ffs(__ballot_sync(0xffffffffu, bid == wid && best == wbest)) - 1;
-                const double a = __shfl_sync(0xffffffffu, ba, src), bq = __shfl_sync(0xffffffffu, bb, src),
-                             c = __shfl_sync(0xffffffffu, bc, src);
-                const int r = hull_lp_add(L, a, bq, c, wid);
+                const int r = hull_lp_add(L, a, bq, c, bid);
                 if (r == HULL_INSIDE || r == HULL_OVERFLOW) rc = r;
             }
             if (rc == HULL_UNDECIDED) rc = HULL_OVERFLOW;  // round limit
             if (rc == HULL_INSIDE) { cert[0] = L.cert[0]; cert[1] = L.cert[1]; cert[2] = L.cert[2]; }
             if (rc != HULL_EXTREME_UNCERT && rc != HULL_OVERFLOW) break;  // settled within this tilt box
         }
-        if (lane == 0) {
-            if (rc == HULL_INSIDE) {
-                bool ok = cert[0] >= 0 && cert[1] >= 0 && cert[2] >= 0 && cert[0] != cert[1] && cert[1] != cert[2] && cert[0] != cert[2];
-                if (ok) {
-                    const float4 s1 = sorted[cert[0]], s2 = sorted[cert[1]], s3 = sorted[cert[2]];
-                    const double a1[3] = {s1.x, s1.y, s1.z}, a2[3] = {s2.x, s2.y, s2.z}, a3[3] = {s3.x, s3.y, s3.z};
-                    ok = hull_certify_inside(F.p, a1, a2, a3) != 0;
-                }
-                if (!ok) rc = HULL_INSIDE_UNCERT;
-            }
-            const bool vertex = (rc == HULL_EXTREME || rc == HULL_EXTREME_UNCERT);
-            mask[__float_as_int(ps.w)] = vertex ? 1 : 0;
-            if (rc != HULL_EXTREME && rc != HULL_INSIDE) atomicAdd(info + 1, 1);
-            if (vertex) atomicAdd(info + 2, 1);
-        }
+        if (threadIdx.x == 0) hull_finalize(rc, cert, F, ps, sorted, mask, info);
     }
 }
 
@@ -399,7 +508,7 @@ extern "C" int cov_hpr_hull(const float* flipped, int64_t n, uint8_t* vertex_mas
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t ncell = (int64_t)G * G * G;
     // one memset clears histogram, cursors, occupied list and the three scalars (contiguous in the carve-up)
-    cudaMemsetAsync(w.cell_count, 0, (size_t)((char*)w.n_far + 16 - (char*)w.cell_count), s);
+    cudaMemsetAsync(w.cell_count, 0, (size_t)((char*)w.n_mid + 16 - (char*)w.cell_count), s);
     cudaMemsetAsync(info, 0, 4 * sizeof(int32_t), s);
     int64_t nb = (n + 255) / 256;
     const int64_t cap = (int64_t)cov_sm_count_cached() * 16;
@@ -414,17 +523,25 @@ extern "C" int cov_hpr_hull(const float* flipped, int64_t n, uint8_t* vertex_mas
     }
     hull_occupied_kernel<<<(unsigned)((ncell + 255) / 256), 256, 0, s>>>(w.cell_count, ncell, w.occ, w.n_occ);
     hull_scatter_kernel<<<(unsigned)nb, 256, 0, s>>>(flipped, n, w.key, w.cell_count, w.cursor, w.sorted, vertex_mask);
-    // `key` is free once the points are scattered: it becomes the list of the points that need the all-voxel sweep
-    int r_near = kNearRadius, budget = kNearBudget;
+    // `key` is free once the points are scattered: it becomes the list of the points the near phase hands on
+    int r_near = kNearRadius, budget = kNearBudget, r_mid = kMidRadius;
 #ifdef COV_HULL_KNOBS
     if (const char* e = getenv("COV_HULL_R_NEAR")) r_near = atoi(e);
     if (const char* e = getenv("COV_HULL_BUDGET")) budget = atoi(e);
+    if (const char* e = getenv("COV_HULL_R_MID")) r_mid = atoi(e);
 #endif
+    const int sms = cov_sm_count_cached();
     hull_classify_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(G, w.cell_count, w.sorted, w.occ, w.n_occ,
-                                                                    w.rho_max_bits, w.n_valid, vertex_mask, info, w.key, w.n_far,
+                                                                    w.rho_max_bits, w.n_valid, vertex_mask, info, w.key, w.n_mid,
                                                                     r_near, budget);
-    hull_far_kernel<<<(unsigned)(cov_sm_count_cached() * 8), 128, 0, s>>>(G, w.cell_count, w.sorted, w.occ, w.n_occ, w.rho_max_bits,
-                                                                         w.key, w.n_far, vertex_mask, info);
+    hull_mid_kernel<<<(unsigned)(sms * 8), 128, 0, s>>>(G, w.cell_count, w.sorted, w.rho_max_bits, w.key, w.n_mid, vertex_mask,
+                                                       info, w.far, w.n_far, r_mid);
+    hull_far_kernel<<<(unsigned)(sms * 4), kFarThreads, 0, s>>>(G, w.cell_count, w.sorted, w.occ, w.n_occ, w.rho_max_bits,
+                                                               w.far, w.n_far, vertex_mask, info);
     hull_origin_kernel<<<1, 1024, 0, s>>>(flipped, n, info);
+#ifdef COV_HULL_KNOBS
+    cudaMemcpyAsync(info + 3, w.n_mid, sizeof(int), cudaMemcpyDeviceToDevice, s);  // probe builds report the list lengths
+    cudaMemcpyAsync(info + 2, w.n_far, sizeof(int), cudaMemcpyDeviceToDevice, s);
+#endif
     return cov_check_launch("cov_hpr_hull");
 }

@@ -6,13 +6,13 @@
 // the tile-level pruning of cov_traj.cu feeds on.  Pipeline (all on the caller's stream, workspace from the caller):
 //   1. bounding box of the cloud           (block reduce + integer atomics on order-preserving keys)
 //   2. 30-bit Morton key per point         (cubic cells: 1024 along the longest extent)
-//   3. stable LSD radix sort of (key, index) pairs — cub::DeviceRadixSort (CUDA toolkit header library; this is
-//      set-up work outside the per-step hot path)
+//   3. stable LSD radix sort of (key, index) pairs — covradix::sort_pairs (cov_radix.cuh: own kernels, 8 bits per
+//      pass, MATCH.ANY ranking, tiles reordered in shared memory; 4 passes for the 30 key bits)
 //   4. gather xyz_sorted[j] = xyz[perm[j]]
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
+#include <algorithm>
 
 #include "cov_common.cuh"
+#include "cov_radix.cuh"
 #include "../../include/coverage_b200.h"
 
 namespace {
@@ -82,30 +82,34 @@ __global__ void __launch_bounds__(256) sort_key_kernel(const float* __restrict__
 
 __global__ void __launch_bounds__(256) sort_gather_kernel(const float* __restrict__ xyz, int64_t n, const int32_t* __restrict__ perm,
                                                           float* __restrict__ out) {
-    // 3 consecutive threads move one point, so the writes are fully coalesced
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 3 * n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t j = i / 3;
-        const int k = (int)(i - 3 * j);
-        out[i] = __ldg(xyz + (int64_t)perm[j] * 3 + k);
+    // 3 consecutive threads move one point, so the writes are fully coalesced; four independent (index, coordinate) load
+    // chains per thread keep enough of the scattered reads in flight
+    const int64_t total = 3 * n, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
+        int64_t src[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t i = i0 + u * stride;
+            const int64_t j = i / 3;
+            src[u] = i < total ? (int64_t)__ldg(perm + j) * 3 + (i - 3 * j) : -1;
+        }
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = src[u] >= 0 ? __ldg(xyz + src[u]) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (src[u] >= 0) out[i0 + u * stride] = v[u];
     }
 }
 
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
-size_t cub_temp_bytes(int64_t n) {
-    size_t bytes = 0;
-    cub::DoubleBuffer<unsigned> k(nullptr, nullptr);
-    cub::DoubleBuffer<int32_t> v(nullptr, nullptr);
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, k, v, (int)n, 0, 30, (cudaStream_t)0);
-    return bytes;
-}
-
 }  // namespace
 
-// workspace: [box 256 B][keys A n u32][keys B n u32][idx B n i32][cub temp]
+// workspace: [box 256 B][keys A n u32][keys B n u32][idx B n i32][digit counts]
 extern "C" size_t cov_spatial_sort_workspace_bytes(int64_t n) {
     if (n < 1) n = 1;
-    return 256 + 3 * align256((size_t)n * 4) + align256(cub_temp_bytes(n)) + 256;
+    return 256 + 3 * align256((size_t)n * 4) + align256(covradix::temp_bytes()) + 256;
 }
 
 extern "C" int cov_spatial_sort(const float* xyz, int64_t n, float* xyz_sorted, int32_t* perm, void* ws, size_t ws_bytes,
@@ -122,8 +126,8 @@ extern "C" int cov_spatial_sort(const float* xyz, int64_t n, float* xyz_sorted, 
         cov_set_error("cov_spatial_sort: workspace %zu < %zu bytes", ws_bytes, cov_spatial_sort_workspace_bytes(n));
         return COV_ERR_WORKSPACE;
     }
-    if (((uintptr_t)ws) & 255) {
-        cov_set_error("cov_spatial_sort: workspace must be 256-byte aligned");
+    if ((((uintptr_t)ws) & 255) || (((uintptr_t)perm) & 15)) {
+        cov_set_error("cov_spatial_sort: workspace must be 256-byte aligned, perm 16-byte aligned (TMA bulk copies)");
         return COV_ERR_ALIGN;
     }
     cudaStream_t s = (cudaStream_t)stream;
@@ -134,18 +138,15 @@ extern "C" int cov_spatial_sort(const float* xyz, int64_t n, float* xyz_sorted, 
     unsigned* keys_b = reinterpret_cast<unsigned*>(base + 256 + col);
     int32_t* idx_b = reinterpret_cast<int32_t*>(base + 256 + 2 * col);
     void* temp = base + 256 + 3 * col;
-    size_t temp_bytes = cub_temp_bytes(n);
 
-    const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)cov_sm_count_cached() * 16);
+    const int sms = cov_sm_count_cached();
+    const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)sms * 16);
     sort_box_init_kernel<<<1, 32, 0, s>>>(box);
     sort_box_kernel<<<grid, 256, 0, s>>>(xyz, n, box);
     sort_key_kernel<<<grid, 256, 0, s>>>(xyz, n, box, keys_a, perm);
-    cub::DoubleBuffer<unsigned> k(keys_a, keys_b);
-    cub::DoubleBuffer<int32_t> v(perm, idx_b);
-    if (cub::DeviceRadixSort::SortPairs(temp, temp_bytes, k, v, (int)n, 0, 30, s) != cudaSuccess)
-        return cov_check_launch("cov_spatial_sort (radix sort)") ? COV_ERR_CUDA : COV_ERR_CUDA;
-    if (v.Current() != perm)
-        cudaMemcpyAsync(perm, v.Current(), (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToDevice, s);
+    // 30 key bits = 4 passes (8, 8, 8, 6): the pairs end where they started, in (keys_a, perm)
+    if (covradix::sort_pairs(keys_a, perm, keys_b, idx_b, n, 0, 30, temp, sms, s) != 0)
+        cudaMemcpyAsync(perm, idx_b, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToDevice, s);
     const int ggrid = (int)std::min<int64_t>((3 * n + 255) / 256, (int64_t)cov_sm_count_cached() * 32);
     sort_gather_kernel<<<ggrid, 256, 0, s>>>(xyz, n, perm, xyz_sorted);
     return cov_check_launch("cov_spatial_sort");
@@ -292,18 +293,11 @@ __global__ void __launch_bounds__(256) vox_centroid_kernel(const float* __restri
     }
 }
 
-size_t vox_sort_temp_bytes(int64_t n) {
-    size_t a = 0, b = 0;
-    cub::DoubleBuffer<unsigned> k(nullptr, nullptr);
-    cub::DoubleBuffer<int32_t> v(nullptr, nullptr);
-    cub::DeviceRadixSort::SortPairs(nullptr, a, k, v, (int)n, 0, 32, (cudaStream_t)0);
-    cub::DeviceScan::ExclusiveSum(nullptr, b, (const int*)nullptr, (int*)nullptr, (int)n, (cudaStream_t)0);
-    return a > b ? a : b;
-}
+size_t vox_sort_temp_bytes(int64_t) { return std::max(covradix::temp_bytes(), covradix::scan_temp_bytes()); }
 
 }  // namespace
 
-// workspace: [header 256 B][keys A][keys B][idx A][idx B][head][pos][cub temp]
+// workspace: [header 256 B][keys A][keys B][idx A][idx B][head][pos][digit counts / scan partials]
 extern "C" size_t cov_voxel_grid_workspace_bytes(int64_t n) {
     if (n < 1) n = 1;
     return 256 + 6 * align256((size_t)n * 4) + align256(vox_sort_temp_bytes(n)) + 256;
@@ -334,24 +328,58 @@ extern "C" int cov_voxel_grid(const float* xyz, int64_t n, float leaf, int filte
     int* head = reinterpret_cast<int*>(base + 256 + 4 * col);
     int* pos = reinterpret_cast<int*>(base + 256 + 5 * col);
     void* temp = base + 256 + 6 * col;
-    size_t temp_bytes = vox_sort_temp_bytes(n);
-    const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)cov_sm_count_cached() * 16);
+    const int sms = cov_sm_count_cached();
+    const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)sms * 16);
     vox_init_kernel<<<1, 32, 0, s>>>(h);
     vox_box_kernel<<<grid, 256, 0, s>>>(xyz, n, filter_axis, limit_min, limit_max, h);
     vox_dims_kernel<<<1, 32, 0, s>>>(h, leaf);
     vox_key_kernel<<<grid, 256, 0, s>>>(xyz, n, leaf, filter_axis, limit_min, limit_max, h, keys_a, idx_a);
-    cub::DoubleBuffer<unsigned> k(keys_a, keys_b);
-    cub::DoubleBuffer<int32_t> v(idx_a, idx_b);
-    if (cub::DeviceRadixSort::SortPairs(temp, temp_bytes, k, v, (int)n, 0, 32, s) != cudaSuccess) {
-        cov_check_launch("cov_voxel_grid (radix sort)");
-        return COV_ERR_CUDA;
-    }
-    vox_head_kernel<<<grid, 256, 0, s>>>(k.Current(), n, head);
-    if (cub::DeviceScan::ExclusiveSum(temp, temp_bytes, head, pos, (int)n, s) != cudaSuccess) {
-        cov_check_launch("cov_voxel_grid (scan)");
-        return COV_ERR_CUDA;
-    }
-    vox_centroid_kernel<<<grid, 256, 0, s>>>(xyz, k.Current(), v.Current(), head, pos, n, xyz_out, count, h);
+    // stable sort by the full 32-bit voxel index (dropped points carry 0xffffffff and end up last): 4 passes, so the
+    // sorted pairs are back in (keys_a, idx_a)
+    const int where = covradix::sort_pairs(keys_a, idx_a, keys_b, idx_b, n, 0, 32, temp, sms, s);
+    const unsigned* keys_sorted = where ? keys_b : keys_a;
+    const int32_t* idx_sorted = where ? idx_b : idx_a;
+    vox_head_kernel<<<grid, 256, 0, s>>>(keys_sorted, n, head);
+    covradix::exclusive_sum(head, pos, n, temp, sms, s);
+    vox_centroid_kernel<<<grid, 256, 0, s>>>(xyz, keys_sorted, idx_sorted, head, pos, n, xyz_out, count, h);
     cudaMemcpyAsync(info, &h->min_b[0], 8 * sizeof(int), cudaMemcpyDeviceToDevice, s);  // min_b, div_b, overflow, n_voxels
     return cov_check_launch("cov_voxel_grid");
+}
+
+// ================================= the pair sort on its own (tests, tools) =================================
+// workspace: [keys B n u32][vals B n i32][digit counts]
+extern "C" size_t cov_sort_pairs_workspace_bytes(int64_t n) {
+    if (n < 1) n = 1;
+    return 2 * align256((size_t)n * 4) + align256(covradix::temp_bytes()) + 256;
+}
+
+extern "C" int cov_sort_pairs(uint32_t* keys, int32_t* vals, int64_t n, int begin_bit, int end_bit, void* ws, size_t ws_bytes,
+                              void* stream) {
+    if (!keys || !vals || !ws || n <= 0 || begin_bit < 0 || end_bit > 32 || begin_bit >= end_bit) {
+        cov_set_error("cov_sort_pairs: bad argument (n=%lld, bits [%d, %d))", (long long)n, begin_bit, end_bit);
+        return COV_ERR_ARG;
+    }
+    if (n >= ((int64_t)1 << 31)) {
+        cov_set_error("cov_sort_pairs: %lld pairs exceed the 32-bit position range", (long long)n);
+        return COV_ERR_UNSUPPORTED;
+    }
+    if (ws_bytes < cov_sort_pairs_workspace_bytes(n) || (((uintptr_t)ws) & 255)) {
+        cov_set_error("cov_sort_pairs: workspace too small or not 256-byte aligned");
+        return COV_ERR_WORKSPACE;
+    }
+    if ((((uintptr_t)keys) | ((uintptr_t)vals)) & 15) {
+        cov_set_error("cov_sort_pairs: keys and vals must be 16-byte aligned (TMA bulk copies)");
+        return COV_ERR_ALIGN;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    char* base = reinterpret_cast<char*>(ws);
+    const size_t col = align256((size_t)n * 4);
+    unsigned* keys_b = reinterpret_cast<unsigned*>(base);
+    int32_t* vals_b = reinterpret_cast<int32_t*>(base + col);
+    void* temp = base + 2 * col;
+    if (covradix::sort_pairs(keys, vals, keys_b, vals_b, n, begin_bit, end_bit, temp, cov_sm_count_cached(), s) != 0) {
+        cudaMemcpyAsync(keys, keys_b, (size_t)n * 4, cudaMemcpyDeviceToDevice, s);
+        cudaMemcpyAsync(vals, vals_b, (size_t)n * 4, cudaMemcpyDeviceToDevice, s);
+    }
+    return cov_check_launch("cov_sort_pairs");
 }

@@ -482,6 +482,24 @@ def spatial_sort(points):
 
 
 @torch.no_grad()
+def sort_pairs(keys, vals, begin_bit=0, end_bit=32):
+    """Stable radix sort of (keys int32/uint32 bit patterns, vals int32) CUDA tensors by key bits [begin_bit, end_bit)
+    (include/coverage_b200.h: cov_sort_pairs); returns sorted copies.  Keys compare as UNSIGNED 32-bit values."""
+    L = _lib.lib()
+    if not (keys.is_cuda and vals.is_cuda and keys.dtype == torch.int32 and vals.dtype == torch.int32 and keys.shape == vals.shape
+            and keys.dim() == 1):
+        raise RuntimeError("sort_pairs: keys and vals must be 1-D int32 CUDA tensors of equal length")
+    k, v = keys.clone(), vals.clone()
+    n = k.shape[0]
+    if n == 0:
+        return k, v
+    ws_bytes = L.cov_sort_pairs_workspace_bytes(n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=k.device)
+    _call("cov_sort_pairs", k, _ptr(k), _ptr(v), n, int(begin_bit), int(end_bit), _ptr(ws), ws_bytes)
+    return k, v
+
+
+@torch.no_grad()
 def sweep_rewards(points, poses, quats, intrins, img_width, img_height, min_dist=1.0, max_dist=5.0, eps=1e-6,
                   n_total=None, group=None, boxes=None, presorted=False, shard="points"):
     """Forward-only mean reward of many candidate trajectories: poses (T, P, 3), quats (T, P, 4) -> (T,) fp64
@@ -564,9 +582,9 @@ def spherical_flip(points, param):
 
 
 @torch.no_grad()
-def hpr_hull_mask(flipped):
+def hpr_hull_mask(flipped, return_info=False):
     """Vertex mask of conv(flipped U {origin}) (reference src/tools.py:56-64 + the vertex set of :79).
-    Returns (mask uint8 (N,), origin_is_vertex bool, n_exact_fallback int)."""
+    Returns (mask uint8 (N,), origin_is_vertex bool, n_exact_fallback int) [+ the raw 4-int info when `return_info`]."""
     L = _lib.lib()
     f = _dev_f32(flipped, what="flipped points")
     n = f.shape[0]
@@ -576,4 +594,6 @@ def hpr_hull_mask(flipped):
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=f.device)
     _call("cov_hpr_hull", f, _ptr(f), n, _ptr(mask), _ptr(info), _ptr(ws), ws_bytes)
     info_h = info.tolist()
+    if return_info:
+        return mask, bool(info_h[0]), int(info_h[1]), info_h
     return mask, bool(info_h[0]), int(info_h[1])
