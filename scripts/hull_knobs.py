@@ -41,8 +41,8 @@ for kind in ("shell", "halfspace"):
     P = torch.from_numpy(cloud(kind)).to(dev)
     flipped, _ = ops.spherical_flip(P, 2)
     base = None
-    for r_near, budget, r_mid in [(6, 0, 6), (1, 0, 6), (1, 1000, 6), (1, 2000, 6), (0, 0, 6), (0, 500, 6), (1, 1000, 3), (1, 1000, 4),
-                                  (1, 1000, 8), (1, 1000, 12), (1, 1000, 16), (2, 1000, 8)]:
+    for r_near, budget, r_mid in [(1, 1000, 16), (1, 0, 16), (1, 500, 16), (1, 2000, 16), (1, 4000, 16), (2, 0, 16), (2, 2000, 16),
+                                  (2, 4000, 16), (3, 0, 16), (3, 4000, 16), (6, 0, 16), (0, 0, 16)]:
         os.environ["COV_HULL_R_NEAR"] = str(r_near)
         os.environ["COV_HULL_BUDGET"] = str(budget)
         os.environ["COV_HULL_R_MID"] = str(r_mid)

@@ -121,8 +121,12 @@ HULL_HD int hull_lp_add(HullLP& L, double a, double b, double c, int cid) {
     // the new optimum lies on the line a x + b y + c = 0: q + s t, q = closest point to the origin
     const double inv = 1.0 / nn, rn = sqrt(inv);
     const double q0 = -c * a * inv, q1 = -c * b * inv, t0 = -b * rn, t1 = a * rn;
-    double lo = -1e300, hi = 1e300;
+    // The feasible interval [lo, hi] of the line parameter.  Each constraint bounds it by -h/g; the running bounds are
+    // kept as fractions with positive denominators and compared by cross-multiplication, so the loop has no division
+    // (an fp64 division is ~30 instructions on the GPU and this loop is most of what the near phase executes).
+    double lo_n = -1e300, lo_d = 1.0, hi_n = 1e300, hi_d = 1.0;
     int ilo = -1, ihi = -1;
+    bool empty = false;
     // LP bounding box (ids -2: hitting it is not a proof of infeasibility -> HULL_OVERFLOW).  It is much wider than
     // the tilt the rounding margin covers; a solution beyond L.tilt is re-done with the wider margin by the caller.
     const double bx[4][3] = {{1, 0, HULL_BOX}, {-1, 0, HULL_BOX}, {0, 1, HULL_BOX}, {0, -1, HULL_BOX}};
@@ -132,10 +136,11 @@ HULL_HD int hull_lp_add(HullLP& L, double a, double b, double c, int cid) {
         if (k < 4) { ai = bx[k][0]; bi = bx[k][1]; ci = bx[k][2]; idk = -2; }
         else { ai = L.a[k - 4]; bi = L.b[k - 4]; ci = L.c[k - 4]; idk = L.id[k - 4]; }
         const double g = ai * t0 + bi * t1, h = ai * q0 + bi * q1 + ci;
-        if (g > 0.0) { const double s = -h / g; if (s > lo) { lo = s; ilo = idk; } }
-        else if (g < 0.0) { const double s = -h / g; if (s < hi) { hi = s; ihi = idk; } }
-        else if (h < 0.0) { lo = 1e300; hi = -1e300; ilo = idk; ihi = idk; break; }
+        if (g > 0.0) { if (-h * lo_d > lo_n * g) { lo_n = -h; lo_d = g; ilo = idk; } }        // -h/g > lo
+        else if (g < 0.0) { if (h * hi_d < hi_n * -g) { hi_n = h; hi_d = -g; ihi = idk; } }   // -h/g = h/(-g) < hi
+        else if (h < 0.0) { empty = true; ilo = idk; ihi = idk; break; }
     }
+    const double lo = empty ? 1e300 : lo_n / lo_d, hi = empty ? -1e300 : hi_n / hi_d;
     if (lo > hi) {
         if (ilo == -2 || ihi == -2) return HULL_OVERFLOW;
         L.cert[0] = cid; L.cert[1] = ilo; L.cert[2] = ihi;
