@@ -2,6 +2,7 @@
 """Times the once-per-cloud ordering (`cov_spatial_sort` = bounding box, Morton keys, pair sort, gather) and the voxel-grid
 filter on one GPU.  COV_B200_LIB selects another build of the library for A/B runs (e.g. round 2's CUB-based sort).
 usage: sort_bench.py [tag [n ...]]"""
+import ctypes
 import json
 import os
 import sys
@@ -38,21 +39,40 @@ def timed(fn, reps=5):
 
 
 sizes = [int(a) for a in sys.argv[2:]] or [12_500_000, 100_000_000]
+L = _lib.lib()
 for n in sizes:
     gen = torch.Generator(device=dev).manual_seed(n)
     pts = torch.rand(n, 3, device=dev, generator=gen) * torch.tensor([40.0, 40.0, 5.0], device=dev)
-    ms, (out, perm) = timed(lambda: ops.spatial_sort(pts))
+    # the C ABI with buffers allocated once: no allocator traffic inside the timed region
+    out = torch.empty_like(pts)
+    perm = torch.empty(n, dtype=torch.int32, device=dev)
+    wsb = L.cov_spatial_sort_workspace_bytes(n)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def run_sort():
+        _lib.check(L.cov_spatial_sort(pts.data_ptr(), n, out.data_ptr(), perm.data_ptr(), ws.data_ptr(), wsb, stream), "sort")
+
+    best = min(timed(run_sort, reps=5)[0] for _ in range(3))
     chk = int(perm[:: max(n // 1000, 1)].long().sum())
     ok = bool(torch.equal(out[:1000], pts[perm[:1000].long()]))
-    print(json.dumps({"lib": tag, "what": "cov_spatial_sort", "n": n, "ms": ms, "GB_per_s_of_20B_per_point": n * 20 / ms / 1e6,
+    print(json.dumps({"lib": tag, "what": "cov_spatial_sort (C ABI, preallocated; best of 3 x 5 calls)", "n": n, "ms": best,
                       "perm_checksum": chk, "gather_ok": ok}), flush=True)
-    if hasattr(ops, "sort_pairs") and "cov_sort_pairs" in _lib.PROTOTYPES:
-        keys = torch.randint(-2**31, 2**31 - 1, (n,), device=dev, dtype=torch.int32, generator=gen)
-        vals = torch.arange(n, device=dev, dtype=torch.int32)
-        ms2, _ = timed(lambda: ops.sort_pairs(keys, vals, 0, 32))
-        print(json.dumps({"lib": tag, "what": "cov_sort_pairs 32 bits (incl. two clones)", "n": n, "ms": ms2}), flush=True)
-        del keys, vals
-    del pts, out, perm
+    if "cov_sort_pairs" in _lib.PROTOTYPES:
+        keys0 = torch.randint(-2**31, 2**31 - 1, (n,), device=dev, dtype=torch.int32, generator=gen)
+        keys, vals = keys0.clone(), torch.arange(n, device=dev, dtype=torch.int32)
+        wsb2 = L.cov_sort_pairs_workspace_bytes(n)
+        ws2 = ws if wsb2 <= wsb else torch.empty(wsb2, dtype=torch.uint8, device=dev)
+
+        def run_pairs():  # re-sorting sorted keys moves the same bytes through the same kernels
+            _lib.check(L.cov_sort_pairs(keys.data_ptr(), vals.data_ptr(), n, 0, 32, ws2.data_ptr(), wsb2, stream), "pairs")
+
+        keys.copy_(keys0)
+        first = timed(lambda: (keys.copy_(keys0), run_pairs()), reps=3)[0]
+        copy_ms = timed(lambda: keys.copy_(keys0), reps=3)[0]
+        print(json.dumps({"lib": tag, "what": "cov_sort_pairs, 32 random key bits", "n": n, "ms": first - copy_ms}), flush=True)
+        del keys0, keys, vals, ws2
+    del pts, out, perm, ws
     torch.cuda.empty_cache()
 
 n = 10_000_000
