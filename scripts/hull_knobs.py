@@ -41,8 +41,8 @@ for kind in ("shell", "halfspace"):
     P = torch.from_numpy(cloud(kind)).to(dev)
     flipped, _ = ops.spherical_flip(P, 2)
     base = None
-    for r_near, budget, r_mid in [(1, 1000, 16), (1, 0, 16), (1, 500, 16), (1, 2000, 16), (1, 4000, 16), (2, 0, 16), (2, 2000, 16),
-                                  (2, 4000, 16), (3, 0, 16), (3, 4000, 16), (6, 0, 16), (0, 0, 16)]:
+    for r_near, budget, r_mid in [(1, 1000, 16), (1, 1000, 16), (1, 600, 16), (1, 400, 16), (1, 300, 16), (1, 200, 16), (1, 150, 16),
+                                  (1, 100, 16), (1, 60, 16), (2, 300, 16), (2, 600, 16), (0, 0, 16)]:
         os.environ["COV_HULL_R_NEAR"] = str(r_near)
         os.environ["COV_HULL_BUDGET"] = str(budget)
         os.environ["COV_HULL_R_MID"] = str(r_mid)

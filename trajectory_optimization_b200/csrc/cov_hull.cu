@@ -188,36 +188,6 @@ hull_scatter_kernel(const float* __restrict__ f, int64_t n, const int* __restric
     }
 }
 
-__global__ void __launch_bounds__(128)
-hull_classify_kernel(int G, const int* __restrict__ cell_start, const float4* __restrict__ sorted,
-                     const int* __restrict__ occ, const int* __restrict__ n_occ,
-                     const unsigned long long* __restrict__ rho_max_bits, const int* __restrict__ n_valid,
-                     uint8_t* __restrict__ mask, int* __restrict__ info, int* __restrict__ mid_list, int* __restrict__ n_mid,
-                     int r_near, int budget) {
-    const int k = blockIdx.x * 128 + threadIdx.x;
-    if (k >= *n_valid) return;
-    HullGrid g;
-    g.G = G;
-    g.h = 2.0 / G;
-    g.cell_start = cell_start;
-    g.sorted = sorted;
-    g.occ = occ;
-    g.n_occ = *n_occ;
-    g.rho_max = __longlong_as_double((long long)*rho_max_bits);
-    int cert[3];
-    // near phase only (one thread per point); a point that exhausts its evaluation budget or needs a wider search, a
-    // wider tilt box or a bigger active set goes on the list of the cooperative stages (hull_mid_kernel, hull_far_kernel)
-    const int rc = hull_classify_attempt(g, k, HULL_TILT_NEAR, cert, false, r_near, budget);
-    if (rc == HULL_UNDECIDED || rc == HULL_EXTREME_UNCERT || rc == HULL_OVERFLOW) {
-        mid_list[atomicAdd(n_mid, 1)] = k;
-        return;
-    }
-    const bool vertex = rc == HULL_EXTREME;
-    mask[__float_as_int(sorted[k].w)] = vertex ? 1 : 0;
-    if (rc != HULL_EXTREME && rc != HULL_INSIDE) atomicAdd(info + 1, 1);  // decided by the LP but not certified
-    if (vertex) atomicAdd(info + 2, 1);
-}
-
 // ---- cooperative stages for the points the one-thread near phase gives up on ----
 // Every participating thread keeps the same LP (the updates are deterministic, so the copies never diverge); per round
 // the threads scan disjoint candidates for the MOST VIOLATED half-plane, agree on one, and every thread adds it.  The
@@ -275,6 +245,102 @@ __device__ __forceinline__ void hull_finalize(int rc, const int* cert, const Hul
     mask[__float_as_int(ps.w)] = vertex ? 1 : 0;
     if (rc != HULL_EXTREME && rc != HULL_INSIDE) atomicAdd(info + 1, 1);
     if (vertex) atomicAdd(info + 2, 1);
+}
+
+// Stage 1, one THREAD per point: hull_classify_attempt's near phase (hull_core.h; same candidates in the same order, so
+// every point takes the same decisions as there) unrolled into ONE flat loop in which a lane handles one candidate per
+// iteration and the whole warp meets again at the top: [advance the lane's cursor over voxels and rings] -> [evaluate
+// the candidate's half-plane] -> [hull_lp_add if violated].  In the nested-loop form the lanes of a warp fell out of
+// step at their first LP update and never met again (ncu: 3.0 active threads per instruction in the candidate loop,
+// 1.0 in the LP update); here the evaluation runs with every undecided lane and lanes that are violated in the same
+// iteration update together.  A point that exhausts its evaluation budget or needs a wider search, a wider tilt box or a
+// bigger active set goes on the list of the cooperative stages (hull_mid_kernel, hull_far_kernel).
+__global__ void __launch_bounds__(128)
+hull_classify_kernel(int G, const int* __restrict__ cell_start, const float4* __restrict__ sorted,
+                     const unsigned long long* __restrict__ rho_max_bits, const int* __restrict__ n_valid,
+                     uint8_t* __restrict__ mask, int* __restrict__ info, int* __restrict__ mid_list, int* __restrict__ n_mid,
+                     int r_near, int budget) {
+    const int self = blockIdx.x * 128 + threadIdx.x;
+    const bool mine = self < *n_valid;
+    const double h = 2.0 / G;
+    const double rho_max = __longlong_as_double((long long)*rho_max_bits);
+    const float4 ps = mine ? sorted[self] : make_float4(1.f, 0.f, 0.f, 0.f);
+    HullFrame F;
+    hull_frame_init(F, (double)ps.x, (double)ps.y, (double)ps.z);
+    HullLP L;
+    hull_lp_init(L, HULL_TILT_NEAR);
+    const int cx = hull_cell_coord(F.u[0], G), cy = hull_cell_coord(F.u[1], G), cz = hull_cell_coord(F.u[2], G);
+    int r = 0, clean = -1;      // current radius; every voxel within Chebyshev radius `clean` was swept without moving the LP
+    int dx = 0, dy = 0, dz = 0; // next voxel of the cube of radius r (counters, no divisions: the cursor runs one lane at a time)
+    int k = 0, e = 0;           // remaining records of the current voxel
+    int work = 0;
+    bool changed = false;       // the LP moved during the current sweep
+    bool alive = mine, defer = false;
+    int rc = HULL_UNDECIDED;
+    while (__any_sync(0xffffffffu, alive)) {
+        int cand = -1;
+        if (alive) {
+            while (k >= e) {  // advance to the next non-empty voxel that still has to be swept, or end the sweep
+                if (dx <= r) {
+                    const int ix = cx + dx, iy = cy + dy, iz = cz + dz;
+                    const int ad = dx < 0 ? -dx : dx, bd = dy < 0 ? -dy : dy, cd = dz < 0 ? -dz : dz;
+                    if (++dz > r) {
+                        dz = -r;
+                        if (++dy > r) { dy = -r; ++dx; }
+                    }
+                    if (ix < 0 || ix >= G || iy < 0 || iy >= G || iz < 0 || iz >= G) continue;
+                    if (max(ad, max(bd, cd)) <= clean) continue;
+                    const int cell = (ix * G + iy) * G + iz;
+                    const int b = cell_start[cell], e2 = cell_start[cell + 1];
+                    if (budget > 0) {
+                        work += e2 - b;
+                        if (work > budget) { defer = true; alive = false; break; }
+                    }
+                    k = b;
+                    e = e2;
+                    continue;
+                }
+                // the sweep of radius r is complete
+                if (changed) {  // the LP moved: everything swept so far must be re-checked
+                    changed = false;
+                    clean = -1;
+                } else {
+                    clean = r;
+                    const bool whole = (cx - r <= 0 && cx + r >= G - 1 && cy - r <= 0 && cy + r >= G - 1 && cz - r <= 0 && cz + r >= G - 1);
+                    if (whole || hull_coverage_ok(L, F.rho, rho_max, r * h)) {
+                        if (fabs(L.x0) > L.tilt || fabs(L.x1) > L.tilt) defer = true;  // the rounding margin needs the wide tilt box
+                        else rc = HULL_EXTREME;
+                        alive = false;
+                        break;
+                    }
+                    if (++r > r_near) { defer = true; alive = false; break; }
+                }
+                dx = dy = dz = -r;
+            }
+            if (alive) {
+                cand = k++;
+                if (cand == self) cand = -1;
+            }
+        }
+        __syncwarp();
+        double a = 0.0, bq = 0.0, c = 0.0;
+        bool viol = false;
+        if (cand >= 0) {
+            const float4 sp = sorted[cand];
+            hull_constraint(F, L.tilt, (double)sp.x, (double)sp.y, (double)sp.z, a, bq, c);
+            viol = hull_violated(L, a, bq, c);
+        }
+        __syncwarp();
+        if (viol) {
+            const int ra = hull_lp_add(L, a, bq, c, cand);
+            if (ra == HULL_UNDECIDED) changed = true;
+            else if (ra == HULL_INSIDE) { rc = HULL_INSIDE; alive = false; }
+            else if (ra == HULL_OVERFLOW) { defer = true; alive = false; }
+        }
+    }
+    if (!mine) return;
+    if (defer) mid_list[atomicAdd(n_mid, 1)] = self;
+    else hull_finalize(rc, L.cert, F, ps, sorted, mask, info);
 }
 
 // Middle stage, ONE WARP PER POINT: the near phase's neighbourhood search (Chebyshev cubes of growing radius around the
@@ -531,9 +597,8 @@ extern "C" int cov_hpr_hull(const float* flipped, int64_t n, uint8_t* vertex_mas
     if (const char* e = getenv("COV_HULL_R_MID")) r_mid = atoi(e);
 #endif
     const int sms = cov_sm_count_cached();
-    hull_classify_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(G, w.cell_count, w.sorted, w.occ, w.n_occ,
-                                                                    w.rho_max_bits, w.n_valid, vertex_mask, info, w.key, w.n_mid,
-                                                                    r_near, budget);
+    hull_classify_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(G, w.cell_count, w.sorted, w.rho_max_bits, w.n_valid,
+                                                                    vertex_mask, info, w.key, w.n_mid, r_near, budget);
     hull_mid_kernel<<<(unsigned)(sms * 8), 128, 0, s>>>(G, w.cell_count, w.sorted, w.rho_max_bits, w.key, w.n_mid, vertex_mask,
                                                        info, w.far, w.n_far, r_mid);
     hull_far_kernel<<<(unsigned)(sms * 4), kFarThreads, 0, s>>>(G, w.cell_count, w.sorted, w.occ, w.n_occ, w.rho_max_bits,

@@ -93,6 +93,16 @@ HULL_HD bool hull_violated(const HullLP& L, double a, double b, double c) {
     return v < -1.0e-15 * (fabs(a * L.x0) + fabs(b * L.x1) + fabs(c));
 }
 
+// One constraint g s + h > 0 on the line parameter s: tightens lo (g > 0: s > -h/g), hi (g < 0: s < h/(-g)) or empties the
+// interval (g == 0 > h).  Bounds are fractions with positive denominators, compared by cross-multiplication.
+#define HULL_LP_BOUND(G_, H_, ID_)                                                                    \
+    {                                                                                                  \
+        const double g_ = (G_), h_ = (H_);                                                             \
+        if (g_ > 0.0) { if (-h_ * lo_d > lo_n * g_) { lo_n = -h_; lo_d = g_; ilo = (ID_); } }          \
+        else if (g_ < 0.0) { if (h_ * hi_d < hi_n * -g_) { hi_n = h_; hi_d = -g_; ihi = (ID_); } }     \
+        else if (h_ < 0.0) { empty = true; ilo = (ID_); ihi = (ID_); }                                 \
+    }
+
 // Add a violated half-plane (a,b,c) [candidate id cid].  Returns HULL_UNDECIDED (new optimum stored),
 // HULL_INSIDE (active set infeasible, L.cert filled) or HULL_OVERFLOW (active set full / tilt box hit).
 HULL_HD int hull_lp_add(HullLP& L, double a, double b, double c, int cid) {
@@ -127,18 +137,16 @@ HULL_HD int hull_lp_add(HullLP& L, double a, double b, double c, int cid) {
     double lo_n = -1e300, lo_d = 1.0, hi_n = 1e300, hi_d = 1.0;
     int ilo = -1, ihi = -1;
     bool empty = false;
-    // LP bounding box (ids -2: hitting it is not a proof of infeasibility -> HULL_OVERFLOW).  It is much wider than
-    // the tilt the rounding margin covers; a solution beyond L.tilt is re-done with the wider margin by the caller.
-    const double bx[4][3] = {{1, 0, HULL_BOX}, {-1, 0, HULL_BOX}, {0, 1, HULL_BOX}, {0, -1, HULL_BOX}};
-    for (int k = 0; k < 4 + L.n; ++k) {
-        double ai, bi, ci;
-        int idk;
-        if (k < 4) { ai = bx[k][0]; bi = bx[k][1]; ci = bx[k][2]; idk = -2; }
-        else { ai = L.a[k - 4]; bi = L.b[k - 4]; ci = L.c[k - 4]; idk = L.id[k - 4]; }
-        const double g = ai * t0 + bi * t1, h = ai * q0 + bi * q1 + ci;
-        if (g > 0.0) { if (-h * lo_d > lo_n * g) { lo_n = -h; lo_d = g; ilo = idk; } }        // -h/g > lo
-        else if (g < 0.0) { if (h * hi_d < hi_n * -g) { hi_n = h; hi_d = -g; ihi = idk; } }   // -h/g = h/(-g) < hi
-        else if (h < 0.0) { empty = true; ilo = idk; ihi = idk; break; }
+    // LP bounding box |alpha|, |beta| <= HULL_BOX (ids -2: hitting it is not a proof of infeasibility -> HULL_OVERFLOW),
+    // in straight-line code.  It is much wider than the tilt the rounding margin covers; a solution beyond L.tilt is
+    // re-done with the wider margin by the caller.
+    HULL_LP_BOUND(t0, q0 + HULL_BOX, -2)
+    HULL_LP_BOUND(-t0, HULL_BOX - q0, -2)
+    HULL_LP_BOUND(t1, q1 + HULL_BOX, -2)
+    HULL_LP_BOUND(-t1, HULL_BOX - q1, -2)
+    for (int k = 0; k < L.n && !empty; ++k) {
+        const double ai = L.a[k], bi = L.b[k];
+        HULL_LP_BOUND(ai * t0 + bi * t1, ai * q0 + bi * q1 + L.c[k], L.id[k])
     }
     const double lo = empty ? 1e300 : lo_n / lo_d, hi = empty ? -1e300 : hi_n / hi_d;
     if (lo > hi) {
