@@ -12,7 +12,9 @@
 //   hull_occupied  compact list of non-empty voxels (for the far phase)
 //   hull_scatter   counting-sort scatter into (x, y, z, original index) records
 //   hull_classify  one thread per point: hull_classify_point -> vertex mask, counters
-//   hull_origin    GJK distance from the origin to conv(F) in one block (is the origin a vertex?)
+//   hull_origin    GJK distance from the origin to conv(F) in one cluster of 8 blocks (is the origin a vertex?)
+#include <cooperative_groups.h>
+
 #include <cstdlib>
 
 #include "cov_common.cuh"
@@ -480,11 +482,23 @@ hull_far_kernel(int G, const int* __restrict__ cell_start, const float4* __restr
     }
 }
 
-__global__ void __launch_bounds__(1024)
+// Is the origin a vertex of conv(F U {0})?  GJK distance from the origin to conv(F).  The support search of an
+// iteration is a scan of the whole cloud; one block does that at one SM's load bandwidth (0.6-0.9 ms per call at 1 M
+// points), so the kernel runs as ONE THREAD-BLOCK CLUSTER of 8 CTAs: each scans an eighth, the 8 candidates meet in
+// CTA 0's shared memory (distributed shared memory), every CTA reads them back and updates its own copy of the simplex
+// (the update is deterministic, so the copies stay identical and the loop control is uniform over the cluster).
+constexpr int kOriginCtas = 8;
+
+__global__ void __cluster_dims__(kOriginCtas, 1, 1) __launch_bounds__(1024)
 hull_origin_kernel(const float* __restrict__ f, int64_t n, int* __restrict__ info) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned rank = cluster.block_rank();
     __shared__ HullSimplex S;
     __shared__ double rv[32];
     __shared__ long long ri[32];
+    __shared__ double slot_v[kOriginCtas];       // CTA 0's copies collect the cluster's candidates
+    __shared__ long long slot_i[kOriginCtas];
     __shared__ int state;  // 0 = iterate, 1 = done
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     if (t == 0) {
@@ -494,53 +508,74 @@ hull_origin_kernel(const float* __restrict__ f, int64_t n, int* __restrict__ inf
             if (q > 0.0 && q < 1e300) break;
         }
         state = 0;
-        if (j0 >= n) { info[0] = 1; state = 1; }
-        else {
+        if (j0 >= n) {
+            if (rank == 0) info[0] = 1;
+            state = 1;
+        } else {
             S.n = 1;
             for (int c = 0; c < 3; ++c) S.v[0][c] = S.x[c] = f[j0 * 3 + c];
         }
     }
     __syncthreads();
+    double* slot_v0 = cluster.map_shared_rank(slot_v, 0);
+    long long* slot_i0 = cluster.map_shared_rank(slot_i, 0);
     for (int it = 0; it < 64 && state == 0; ++it) {
         const double x0 = S.x[0], x1 = S.x[1], x2 = S.x[2];
         double best = 1e300;
         long long bj = -1;
-        for (int64_t j = t; j < n; j += 1024) {
+        for (int64_t j = (int64_t)rank * 1024 + t; j < n; j += (int64_t)kOriginCtas * 1024) {
             const double d = x0 * f[j * 3] + x1 * f[j * 3 + 1] + x2 * f[j * 3 + 2];
             if (d < best) { best = d; bj = j; }  // NaNs never compare smaller
         }
         for (int o = 16; o > 0; o >>= 1) {
             const double ob = __shfl_xor_sync(0xffffffffu, best, o);
             const long long oj = __shfl_xor_sync(0xffffffffu, bj, o);
-            if (ob < best || (ob == best && oj >= 0 && (bj < 0 || oj < bj))) { best = ob; bj = oj; }
+            if (oj >= 0 && (bj < 0 || ob < best || (ob == best && oj < bj))) { best = ob; bj = oj; }
         }
         if (lane == 0) { rv[warp] = best; ri[warp] = bj; }
         __syncthreads();
         if (t == 0) {
             for (int w = 1; w < 32; ++w)
-                if (rv[w] < best || (rv[w] == best && ri[w] >= 0 && (bj < 0 || ri[w] < bj))) { best = rv[w]; bj = ri[w]; }
+                if (ri[w] >= 0 && (bj < 0 || rv[w] < best || (rv[w] == best && ri[w] < bj))) { best = rv[w]; bj = ri[w]; }
+            slot_v0[rank] = best;
+            slot_i0[rank] = bj;
+        }
+        cluster.sync();  // the 8 candidates are in CTA 0's shared memory
+        if (t == 0) {
+            best = 1e300;
+            bj = -1;
+            for (int c = 0; c < kOriginCtas; ++c) {
+                const double ob = slot_v0[c];
+                const long long oj = slot_i0[c];
+                if (oj >= 0 && (bj < 0 || ob < best || (ob == best && oj < bj))) { best = ob; bj = oj; }
+            }
             const double xx = hull_dot3(S.x, S.x);
-            info[3] = it + 1;
+            if (rank == 0) info[3] = it + 1;
             if (bj < 0 || best >= xx * (1.0 - 1e-10)) {  // no point lies further towards the origin: x is the closest point
-                info[0] = 1;
-                if (!(best > 1e-9 * xx)) atomicAdd(info + 1, 1);  // separating margin not certified
+                if (rank == 0) {
+                    info[0] = 1;
+                    if (!(best > 1e-9 * xx)) atomicAdd(info + 1, 1);  // separating margin not certified
+                }
                 state = 1;
             } else {
                 for (int c = 0; c < 3; ++c) S.v[S.n][c] = f[bj * 3 + c];
                 S.n++;
                 if (hull_simplex_update(S)) {
-                    info[0] = 0;
-                    if (!hull_certify_origin_inside(S)) atomicAdd(info + 1, 1);
+                    if (rank == 0) {
+                        info[0] = 0;
+                        if (!hull_certify_origin_inside(S)) atomicAdd(info + 1, 1);
+                    }
                     state = 1;
                 }
             }
         }
-        __syncthreads();
+        cluster.sync();  // everybody has read the candidates (the next iteration overwrites them) and `state` is set
     }
-    if (t == 0 && state == 0) {  // did not converge in 64 iterations: decide by distance, flag as uncertified
+    if (t == 0 && rank == 0 && state == 0) {  // did not converge in 64 iterations: decide by distance, flag as uncertified
         info[0] = hull_dot3(S.x, S.x) > 0.0 ? 1 : 0;
         atomicAdd(info + 1, 1);
     }
+    cluster.sync();  // no CTA leaves while another may still read CTA 0's shared memory
 }
 
 }  // namespace
@@ -603,7 +638,7 @@ extern "C" int cov_hpr_hull(const float* flipped, int64_t n, uint8_t* vertex_mas
                                                        info, w.far, w.n_far, r_mid);
     hull_far_kernel<<<(unsigned)(sms * 4), kFarThreads, 0, s>>>(G, w.cell_count, w.sorted, w.occ, w.n_occ, w.rho_max_bits,
                                                                w.far, w.n_far, vertex_mask, info);
-    hull_origin_kernel<<<1, 1024, 0, s>>>(flipped, n, info);
+    hull_origin_kernel<<<kOriginCtas, 1024, 0, s>>>(flipped, n, info);
 #ifdef COV_HULL_KNOBS
     cudaMemcpyAsync(info + 3, w.n_mid, sizeof(int), cudaMemcpyDeviceToDevice, s);  // probe builds report the list lengths
     cudaMemcpyAsync(info + 2, w.n_far, sizeof(int), cudaMemcpyDeviceToDevice, s);
