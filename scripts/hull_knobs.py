@@ -41,8 +41,8 @@ for kind in ("shell", "halfspace"):
     P = torch.from_numpy(cloud(kind)).to(dev)
     flipped, _ = ops.spherical_flip(P, 2)
     base = None
-    for r_near, budget, r_mid in [(1, 1000, 16), (1, 1000, 16), (1, 600, 16), (1, 400, 16), (1, 300, 16), (1, 200, 16), (1, 150, 16),
-                                  (1, 100, 16), (1, 60, 16), (2, 300, 16), (2, 600, 16), (0, 0, 16)]:
+    for r_near, budget, r_mid in [(1, 1000, 16), (1, 1000, 16), (1, 2000, 16), (1, 700, 16), (1, 500, 16), (1, 400, 16), (1, 300, 16),
+                                  (1, 200, 16), (2, 1000, 16), (2, 2000, 16), (1, 1000, 24), (6, 0, 16)]:
         os.environ["COV_HULL_R_NEAR"] = str(r_near)
         os.environ["COV_HULL_BUDGET"] = str(budget)
         os.environ["COV_HULL_R_MID"] = str(r_mid)
@@ -50,4 +50,4 @@ for kind in ("shell", "halfspace"):
         if base is None:
             base = mask.clone()
         print(f"{kind:9s} r_near {r_near} budget {budget:5d} r_mid {r_mid:2d}: {ms:7.3f} ms  vertices {int(mask.sum())} uncertified {n_unc} "
-              f"same set {bool(torch.equal(mask, base))} handed to the warp stage {info[3]}, to the all-voxel stage {info[2]}", flush=True)
+              f"same set {bool(torch.equal(mask, base))} handed to the warp stage {info[3]}, to the block stage {info[2]}", flush=True)

@@ -25,11 +25,14 @@ namespace {
 
 constexpr int kHullMaxG = 128;
 // one-thread-per-point near phase: radius and evaluation budget after which a point is handed to the warp-per-point
-// stage.  Measured on 1 M-point clouds (scripts/hull_knobs.py): radius 6 / no budget 6.5 ms (shell) and 27.5 ms (half
-// space: the warp waits for its slowest lane); radius 1: 6.0 and 14.7 ms.  The budget bounds what one lane can cost
-// when a direction voxel is crowded.
+// stage.  Measured on 1 M-point clouds (scripts/hull_knobs.py, profiles/r02ab_hull_knobs.txt): a radius beyond 1 makes the
+// warp wait for its slowest lane (radius 6, no budget: 4.9 ms shell, 23 ms half space; radius 1: 3.9 and 7.7 ms).  The
+// budget bounds what one lane can cost; the best absolute value follows the density of the direction grid (shell cloud,
+// 13 records per voxel: 200-300; half-space cloud, 50 per voxel: 700-1000), hence a budget per record of an average
+// occupied voxel (a per-point budget from the point's OWN voxel was worse: 8.3 instead of 7.7 ms on the half-space cloud).
 constexpr int kNearRadius = 1;
-constexpr int kNearBudget = 1000;
+constexpr int kNearBudget = -20;   // < 0: evaluations per record of an average occupied voxel, clamped to [256, 4096]
+constexpr int kWarpRadius = 6;    // warp-per-point stage: largest Chebyshev radius; beyond it a block takes the point
 constexpr int kMidRadius = 16;   // warp-per-point stage: largest Chebyshev radius before the all-voxel sweep (half-space cloud: radius 6 leaves 747 points for it = 4.6 ms, radius 16 none)
 
 int hull_grid_size(int64_t n) {
@@ -48,6 +51,7 @@ struct HullWs {  // carve-up of the caller's workspace
     int* n_valid;         // 1
     int* n_far;           // 1: points handed on to the all-voxel sweep (their sorted ids: `far`)
     int* n_mid;           // 1: points the near phase gave up on (their sorted ids reuse `key`)
+    int* n_far2;          // 1: points the block stage hands to the all-voxel sweep (their sorted ids reuse `key` again)
     int* far;             // n
     int* block_tot;       // ceil(G^3 / 4096): chunk totals / offsets of the histogram scan
 };
@@ -71,6 +75,7 @@ size_t hull_carve(void* base, int64_t n, int G, HullWs* w) {
     t.n_valid = (int*)take(16);
     t.n_far = (int*)take(16);
     t.n_mid = (int*)take(16);
+    t.n_far2 = (int*)take(16);
     t.block_tot = (int*)take(((ncell + 4095) / 4096 + 1) * sizeof(int));
     if (w) *w = t;
     return off;
@@ -203,15 +208,21 @@ __device__ __forceinline__ void hull_pick_init(HullPick& pk) {
     pk.score = 0.0; pk.a = 0.0; pk.b = 0.0; pk.c = 0.0; pk.id = -1;
 }
 
-__device__ __forceinline__ void hull_consider(const HullFrame& F, const HullLP& L, const float4& sp, int j, HullPick& pk) {
-    double a, bq, c;
-    hull_constraint(F, L.tilt, (double)sp.x, (double)sp.y, (double)sp.z, a, bq, c);
+// half-plane (a, bq, c) of record j against the current LP: kept in pk when it is violated, not active yet, and more
+// violated than what pk holds
+__device__ __forceinline__ void hull_score(const HullLP& L, double a, double bq, double c, int j, HullPick& pk) {
     if (!hull_violated(L, a, bq, c)) return;
     bool active = false;
     for (int q = 0; q < L.n; ++q) active |= L.id[q] == j;
     if (active) return;  // the residual is evaluation noise of an optimum that sits on its line
     const double score = (a * L.x0 + bq * L.x1 + c) / (fabs(a * L.x0) + fabs(bq * L.x1) + fabs(c));
     if (score < pk.score || (score == pk.score && (pk.id < 0 || j < pk.id))) { pk.score = score; pk.a = a; pk.b = bq; pk.c = c; pk.id = j; }
+}
+
+__device__ __forceinline__ void hull_consider(const HullFrame& F, const HullLP& L, const float4& sp, int j, HullPick& pk) {
+    double a, bq, c;
+    hull_constraint(F, L.tilt, (double)sp.x, (double)sp.y, (double)sp.z, a, bq, c);
+    hull_score(L, a, bq, c, j, pk);
 }
 
 // the warp's most violated half-plane (ties: smallest id) — the same on every lane afterwards
@@ -229,6 +240,31 @@ __device__ __forceinline__ void hull_warp_pick(HullPick& pk) {
     pk.c = __shfl_sync(0xffffffffu, pk.c, src);
     pk.score = wbest;
     pk.id = wid;
+}
+
+// the GROUP's most violated half-plane, the same on every thread afterwards: a warp's pick, or the warps' picks joined
+// through shared memory (two block barriers)
+template <int GROUP>
+__device__ __forceinline__ void hull_group_pick(HullPick& pk, double* s_score, double (*s_abc)[3], int* s_id) {
+    hull_warp_pick(pk);
+    if (GROUP > 32) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (lane == 0) {
+            s_score[warp] = pk.score; s_id[warp] = pk.id;
+            s_abc[warp][0] = pk.a; s_abc[warp][1] = pk.b; s_abc[warp][2] = pk.c;
+        }
+        __syncthreads();
+        hull_pick_init(pk);
+#pragma unroll
+        for (int w = 0; w < GROUP / 32; ++w) {
+            const int oi = s_id[w];
+            const double ob = s_score[w];
+            if (oi >= 0 && (pk.id < 0 || ob < pk.score || (ob == pk.score && oi < pk.id))) {
+                pk.score = ob; pk.id = oi; pk.a = s_abc[w][0]; pk.b = s_abc[w][1]; pk.c = s_abc[w][2];
+            }
+        }
+        __syncthreads();  // everybody has read the picks before the next call overwrites them
+    }
 }
 
 // one thread writes the decision for sorted point `ps` (certifying an INSIDE answer first)
@@ -256,12 +292,12 @@ __device__ __forceinline__ void hull_finalize(int rc, const int* cert, const Hul
 // step at their first LP update and never met again (ncu: 3.0 active threads per instruction in the candidate loop,
 // 1.0 in the LP update); here the evaluation runs with every undecided lane and lanes that are violated in the same
 // iteration update together.  A point that exhausts its evaluation budget or needs a wider search, a wider tilt box or a
-// bigger active set goes on the list of the cooperative stages (hull_mid_kernel, hull_far_kernel).
+// bigger active set goes on the list of the cooperative stages (hull_local_kernel, hull_far_kernel).
 __global__ void __launch_bounds__(128)
 hull_classify_kernel(int G, const int* __restrict__ cell_start, const float4* __restrict__ sorted,
                      const unsigned long long* __restrict__ rho_max_bits, const int* __restrict__ n_valid,
-                     uint8_t* __restrict__ mask, int* __restrict__ info, int* __restrict__ mid_list, int* __restrict__ n_mid,
-                     int r_near, int budget) {
+                     const int* __restrict__ n_occ, uint8_t* __restrict__ mask, int* __restrict__ info,
+                     int* __restrict__ mid_list, int* __restrict__ n_mid, int r_near, int budget) {
     const int self = blockIdx.x * 128 + threadIdx.x;
     const bool mine = self < *n_valid;
     const double h = 2.0 / G;
@@ -276,6 +312,8 @@ hull_classify_kernel(int G, const int* __restrict__ cell_start, const float4* __
     int dx = 0, dy = 0, dz = 0; // next voxel of the cube of radius r (counters, no divisions: the cursor runs one lane at a time)
     int k = 0, e = 0;           // remaining records of the current voxel
     int work = 0;
+    if (budget < 0)  // relative budget: -budget evaluations per record of an average occupied voxel (the clouds differ in density)
+        budget = min(max(-budget * (*n_valid / max(*n_occ, 1)), 256), 4096);
     bool changed = false;       // the LP moved during the current sweep
     bool alive = mine, defer = false;
     int rc = HULL_UNDECIDED;
@@ -345,21 +383,30 @@ hull_classify_kernel(int G, const int* __restrict__ cell_start, const float4* __
     else hull_finalize(rc, L.cert, F, ps, sorted, mask, info);
 }
 
-// Middle stage, ONE WARP PER POINT: the near phase's neighbourhood search (Chebyshev cubes of growing radius around the
-// point's direction voxel, coverage bound after a clean sweep) with the candidates of a cube spread over the lanes.  The
-// voxels of a (dx, dy) column are consecutive in the counting sort, so a column is one contiguous run of records.
-// A point that needs a wider tilt box, a bigger active set or a radius beyond r_max goes on to the all-voxel stage.
-__global__ void __launch_bounds__(128)
-hull_mid_kernel(int G, const int* __restrict__ cell_start, const float4* __restrict__ sorted,
-                const unsigned long long* __restrict__ rho_max_bits, const int* __restrict__ mid_list,
-                const int* __restrict__ n_mid, uint8_t* __restrict__ mask, int* __restrict__ info, int* __restrict__ far_list,
-                int* __restrict__ n_far, int r_max) {
-    const int lane = threadIdx.x & 31;
-    const int warps = (gridDim.x * blockDim.x) >> 5;
+// Middle stages, a GROUP of threads per point (a warp, then a block of 256 for what the warp stage hands on): the near
+// phase's neighbourhood search (Chebyshev cubes of growing radius around the point's direction voxel, coverage bound
+// after a clean sweep) with the candidates of a cube spread over the group's threads.  The voxels of a (dx, dy) column
+// are consecutive in the counting sort, so a column is one contiguous run of records.  Every round scans the WHOLE
+// cube of the current radius, so a stage may start at any radius (the block stage starts where the warp stage ends).
+// A point that needs a wider tilt box, a bigger active set or a radius beyond r_max goes on the next stage's list.
+// (A single warp needs ~1 ms for a silhouette point whose search reaches radius 16; with only hundreds of such points
+// the warp stage alone left the GPU idle for 3 of its 3.9 ms on the half-space cloud.)
+template <int GROUP>
+__global__ void __launch_bounds__(GROUP == 32 ? 128 : GROUP)
+hull_local_kernel(int G, const int* __restrict__ cell_start, const float4* __restrict__ sorted,
+                  const unsigned long long* __restrict__ rho_max_bits, const int* __restrict__ list_in,
+                  const int* __restrict__ n_in, uint8_t* __restrict__ mask, int* __restrict__ info, int* __restrict__ list_out,
+                  int* __restrict__ n_out, int r_first, int r_max) {
+    __shared__ double s_score[8], s_abc[8][3];
+    __shared__ int s_id[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gtid = GROUP == 32 ? lane : (int)threadIdx.x;           // thread within the group
+    const int first = GROUP == 32 ? (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) : (int)blockIdx.x;
+    const int stride = GROUP == 32 ? (int)((gridDim.x * blockDim.x) >> 5) : (int)gridDim.x;
     const double h = 2.0 / G;
     const double rho_max = __longlong_as_double((long long)*rho_max_bits);
-    for (int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < *n_mid; item += warps) {
-        const int self = mid_list[item];
+    for (int item = first; item < *n_in; item += stride) {  // GROUP > 32: block-uniform control flow from here on
+        const int self = list_in[item];
         const float4 ps = sorted[self];
         HullFrame F;
         hull_frame_init(F, (double)ps.x, (double)ps.y, (double)ps.z);
@@ -368,21 +415,36 @@ hull_mid_kernel(int G, const int* __restrict__ cell_start, const float4* __restr
         hull_lp_init(L, HULL_TILT_NEAR);
         int rc = HULL_UNDECIDED;
         bool defer = false;
-        int r = 1;
+        int r = r_first;
         for (int round = 0; round < 4096 && rc == HULL_UNDECIDED && !defer; ++round) {
             HullPick pk;
             hull_pick_init(pk);
             const int side = 2 * r + 1;
             const int izlo = max(cz - r, 0), izhi = min(cz + r, G - 1);
-            for (int col = 0; col < side * side; ++col) {
-                const int ix = cx + col / side - r, iy = cy + col % side - r;
-                if (ix < 0 || ix >= G || iy < 0 || iy >= G) continue;
-                const int cbase = (ix * G + iy) * G;
-                const int b = cell_start[cbase + izlo], e = cell_start[cbase + izhi + 1];
-                for (int j = b + lane; j < e; j += 32)
-                    if (j != self) hull_consider(F, L, sorted[j], j, pk);
+            // a warp takes 32 columns at a time: every lane fetches the bounds of one column (one round trip to the L2 for 32
+            // columns instead of one per column: the dependent loads were what a round's time consisted of), then the
+            // warp walks the non-empty ones, its lanes striding over a column's records
+            for (int col0 = (GROUP == 32 ? 0 : warp * 32); col0 < side * side; col0 += GROUP) {
+                const int col = col0 + lane;
+                int cb = 0, ce = 0;
+                if (col < side * side) {
+                    const int ix = cx + col / side - r, iy = cy + col % side - r;
+                    if (ix >= 0 && ix < G && iy >= 0 && iy < G) {
+                        const int cbase = (ix * G + iy) * G;
+                        cb = cell_start[cbase + izlo];
+                        ce = cell_start[cbase + izhi + 1];
+                    }
+                }
+                unsigned todo = __ballot_sync(0xffffffffu, ce > cb);
+                while (todo) {
+                    const int q = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int b = __shfl_sync(0xffffffffu, cb, q), e = __shfl_sync(0xffffffffu, ce, q);
+                    for (int j = b + lane; j < e; j += 32)
+                        if (j != self) hull_consider(F, L, sorted[j], j, pk);
+                }
             }
-            hull_warp_pick(pk);
+            hull_group_pick<GROUP>(pk, s_score, s_abc, s_id);
             if (pk.id < 0) {  // clean sweep of the cube of radius r
                 const bool whole = (cx - r <= 0 && cx + r >= G - 1 && cy - r <= 0 && cy + r >= G - 1 && cz - r <= 0 && cz + r >= G - 1);
                 if (whole || hull_coverage_ok(L, F.rho, rho_max, r * h)) {
@@ -398,8 +460,8 @@ hull_mid_kernel(int G, const int* __restrict__ cell_start, const float4* __restr
             else if (ra == HULL_OVERFLOW) defer = true;
         }
         if (rc == HULL_UNDECIDED) defer = true;  // round limit
-        if (lane == 0) {
-            if (defer) far_list[atomicAdd(n_far, 1)] = self;
+        if (gtid == 0) {
+            if (defer) list_out[atomicAdd(n_out, 1)] = self;
             else hull_finalize(rc, L.cert, F, ps, sorted, mask, info);
         }
     }
@@ -609,7 +671,7 @@ extern "C" int cov_hpr_hull(const float* flipped, int64_t n, uint8_t* vertex_mas
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t ncell = (int64_t)G * G * G;
     // one memset clears histogram, cursors, occupied list and the three scalars (contiguous in the carve-up)
-    cudaMemsetAsync(w.cell_count, 0, (size_t)((char*)w.n_mid + 16 - (char*)w.cell_count), s);
+    cudaMemsetAsync(w.cell_count, 0, (size_t)((char*)w.n_far2 + 16 - (char*)w.cell_count), s);
     cudaMemsetAsync(info, 0, 4 * sizeof(int32_t), s);
     int64_t nb = (n + 255) / 256;
     const int64_t cap = (int64_t)cov_sm_count_cached() * 16;
@@ -633,15 +695,19 @@ extern "C" int cov_hpr_hull(const float* flipped, int64_t n, uint8_t* vertex_mas
 #endif
     const int sms = cov_sm_count_cached();
     hull_classify_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(G, w.cell_count, w.sorted, w.rho_max_bits, w.n_valid,
-                                                                    vertex_mask, info, w.key, w.n_mid, r_near, budget);
-    hull_mid_kernel<<<(unsigned)(sms * 8), 128, 0, s>>>(G, w.cell_count, w.sorted, w.rho_max_bits, w.key, w.n_mid, vertex_mask,
-                                                       info, w.far, w.n_far, r_mid);
+                                                                    w.n_occ, vertex_mask, info, w.key, w.n_mid, r_near, budget);
+    // warp per point up to radius kWarpRadius (list: key -> far), block per point beyond it (far -> key), then the all-voxel
+    // sweep for what is still open (key)
+    hull_local_kernel<32><<<(unsigned)(sms * 8), 128, 0, s>>>(G, w.cell_count, w.sorted, w.rho_max_bits, w.key, w.n_mid,
+                                                             vertex_mask, info, w.far, w.n_far, 1, min(kWarpRadius, r_mid));
+    hull_local_kernel<256><<<(unsigned)(sms * 4), 256, 0, s>>>(G, w.cell_count, w.sorted, w.rho_max_bits, w.far, w.n_far,
+                                                              vertex_mask, info, w.key, w.n_far2, min(kWarpRadius, r_mid) + 1, r_mid);
     hull_far_kernel<<<(unsigned)(sms * 4), kFarThreads, 0, s>>>(G, w.cell_count, w.sorted, w.occ, w.n_occ, w.rho_max_bits,
-                                                               w.far, w.n_far, vertex_mask, info);
+                                                               w.key, w.n_far2, vertex_mask, info);
     hull_origin_kernel<<<kOriginCtas, 1024, 0, s>>>(flipped, n, info);
 #ifdef COV_HULL_KNOBS
     cudaMemcpyAsync(info + 3, w.n_mid, sizeof(int), cudaMemcpyDeviceToDevice, s);  // probe builds report the list lengths
-    cudaMemcpyAsync(info + 2, w.n_far, sizeof(int), cudaMemcpyDeviceToDevice, s);
+    cudaMemcpyAsync(info + 2, w.n_far, sizeof(int), cudaMemcpyDeviceToDevice, s);   // handed to the block stage
 #endif
     return cov_check_launch("cov_hpr_hull");
 }
