@@ -85,6 +85,29 @@ def test_hidden_pts_removal_index_sets_bit_exact(name, dev, tools):
     assert np.array_equal(hull.vertices[:-1], g["out_idx"])
 
 
+def _hpr_shapes(gen, n):
+    yield "gaussian blob off centre", gen.standard_normal((n, 3)) * np.array([1.0, 2.0, 0.5]) + np.array([6.0, 0.0, 1.0])
+    yield "two clusters", np.concatenate([gen.standard_normal((n // 2, 3)) * 0.7 + np.array([4.0, 3.0, 0.0]),
+                                          gen.standard_normal((n - n // 2, 3)) * 1.5 + np.array([-5.0, -2.0, 1.0])])
+    yield "thick wall", gen.random((n, 3)) * np.array([0.3, 30, 10]) + np.array([5.0, -15, -5])
+    yield "camera inside a box", (gen.random((n, 3)) - 0.5) * np.array([12, 9, 5])
+    yield "ground plane with noise", np.stack([gen.uniform(-20, 20, n), gen.uniform(-20, 20, n),
+                                               -1.5 + 0.05 * gen.standard_normal(n)], 1)
+
+
+@pytest.mark.parametrize("n", [50, 1000, 20_000, 200_000])
+def test_hidden_pts_removal_on_other_cloud_shapes(n, dev, tools):
+    """Every stage of the hull pipeline (thread, warp, block per point, all-voxel sweep) sees work on these: clouds that do
+    not surround the camera, clusters of different density, a near-planar cloud.  Index sets equal Qhull's."""
+    gen = np.random.default_rng(n)
+    for name, pts in _hpr_shapes(gen, n):
+        pts = pts.astype(np.float32)
+        ref_idx, _ = orc.hidden_pts_removal(pts, 2)
+        vis, mask = tools.hidden_pts_removal(torch.from_numpy(pts).to(dev), dev, 2)
+        assert np.array_equal(torch.nonzero(mask).reshape(-1).cpu().numpy(), ref_idx), name
+        assert np.array_equal(vis.cpu().numpy(), pts[ref_idx]), name
+
+
 @pytest.mark.parametrize("kind,n", [("shell", 1_000_000), ("halfspace", 300_000), ("tiny", 5), ("tiny", 64)])
 def test_hidden_pts_removal_matches_oracle(kind, n, dev, tools):
     """BASELINE config 2 (1M-point shell cloud, camera inside) and a half-space cloud (origin is a hull vertex)."""
