@@ -8,10 +8,13 @@
 // few dozen..thousand points within a small cap around its direction; a counting sort by direction voxel
 // makes those contiguous.  Kernels:
 //   hull_prep      voxel key + histogram + max |f|                       (12 B/point read)
-//   hull_scan      exclusive scan of the G^3 histogram (one block, coalesced chunks with a running carry)
-//   hull_occupied  compact list of non-empty voxels (for the far phase)
+//   hull_scan      exclusive scan of the G^3 histogram (three small launches over 4096-voxel chunks)
+//   hull_occupied  compact list of non-empty voxels (for the all-voxel stage)
 //   hull_scatter   counting-sort scatter into (x, y, z, original index) records
-//   hull_classify  one thread per point: hull_classify_point -> vertex mask, counters
+//   hull_classify  stage 1, one thread per point: radius <= 1 and an evaluation budget, one flat loop per warp
+//   hull_local<32>   stage 2, one warp per point handed on: cubes up to radius 6, candidates spread over the lanes
+//   hull_local<256>  stage 3, one block per point handed on: radius 7..16
+//   hull_far       stage 4, one block per point: every occupied voxel, culled by a bound (wide tilt box, full active set)
 //   hull_origin    GJK distance from the origin to conv(F) in one cluster of 8 blocks (is the origin a vertex?)
 #include <cooperative_groups.h>
 
@@ -33,7 +36,8 @@ constexpr int kHullMaxG = 128;
 constexpr int kNearRadius = 1;
 constexpr int kNearBudget = -20;   // < 0: evaluations per record of an average occupied voxel, clamped to [256, 4096]
 constexpr int kWarpRadius = 6;    // warp-per-point stage: largest Chebyshev radius; beyond it a block takes the point
-constexpr int kMidRadius = 16;   // warp-per-point stage: largest Chebyshev radius before the all-voxel sweep (half-space cloud: radius 6 leaves 747 points for it = 4.6 ms, radius 16 none)
+constexpr int kMidRadius = 16;    // block-per-point stage: largest Chebyshev radius before the all-voxel sweep (half-space cloud:
+                                  // 747 points need more than radius 6, none more than 16)
 
 int hull_grid_size(int64_t n) {
     int G = (int)lround(sqrt((double)n / (12.0 * 3.141592653589793)));
