@@ -153,3 +153,101 @@ def test_two_rank_sweep_trajectory_and_point_sharding_match_the_oracle():
     for rank, by_traj, by_pts in results:
         assert by_traj.shape == ref.shape and by_pts.shape == ref.shape
         assert rel_err(by_traj, ref) < 1e-9 and rel_err(by_pts, ref) < 1e-9
+
+
+def _rig_case():
+    gen = np.random.default_rng(23)
+    d = gen.normal(size=(4000, 3))
+    pts = (d / np.linalg.norm(d, axis=1, keepdims=True) * gen.uniform(1.5, 9.0, (4000, 1))).astype(np.float32)
+    yaws = np.deg2rad([0, 72, -72, 144, -144])   # 5 cameras over 2 ranks: an uneven split (3 + 2)
+    quats = np.stack([np.cos(yaws / 2), 0 * yaws, 0 * yaws, np.sin(yaws / 2)], 1).astype(np.float32)
+    # rotate the optical axis (+z) into the horizontal plane first: q = q_yaw * q_tilt, q_tilt = rotation by -90 deg about x
+    s = np.float32(np.sqrt(0.5))
+    tilt = np.array([s, -s, 0, 0], np.float32)
+
+    def qmul(a, b):
+        w1, x1, y1, z1 = a
+        w2, x2, y2, z2 = b
+        return np.array([w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2, w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2,
+                         w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2, w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2], np.float32)
+
+    quats = np.stack([qmul(q, tilt) for q in quats])
+    trans = np.stack([[0.1 * i, -0.05 * i, 0.02 * i] for i in range(5)]).astype(np.float32)
+    return pts, trans, quats
+
+
+def _install_cpu_visibility_standins(ops, orc):
+    """Oracle-backed stand-ins for the three C-ABI wrappers the per-camera pipeline calls (tests only)."""
+    def frustum_cull(points_nx3, intrins, img_width, img_height, min_dist=1.0, max_dist=10.0):
+        p = points_nx3.detach().cpu().numpy().astype(np.float32)
+        _, dm, fm = orc.frustum_cull(p.T, img_height, img_width, intrins.detach().cpu().numpy(), min_dist, max_dist)
+        return torch.from_numpy(np.flatnonzero(dm & fm).astype(np.int64)), torch.from_numpy(dm), torch.from_numpy(fm)
+
+    def spherical_flip(points, param):
+        f, radius, _ = orc.spherical_flip(points.detach().cpu().numpy(), param)
+        return torch.from_numpy(f), torch.tensor(float(radius))
+
+    def hpr_hull_mask(flipped, return_info=False):
+        from scipy.spatial import ConvexHull
+        f = flipped.detach().cpu().numpy()
+        hull = ConvexHull(np.concatenate([f, np.zeros((1, 3), np.float32)], 0))
+        v = np.sort(hull.vertices)
+        mask = np.zeros(len(f), np.uint8)
+        mask[v[v < len(f)]] = 1
+        return torch.from_numpy(mask), bool(v[-1] == len(f)), 0
+
+    ops.frustum_cull, ops.spherical_flip, ops.hpr_hull_mask = frustum_cull, spherical_flip, hpr_hull_mask
+
+
+def _rig_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import coverage_oracle as orc
+        from trajectory_optimization_b200 import ops, tools
+        _install_cpu_visibility_standins(ops, orc)
+        pts, trans, quats = _rig_case()
+        K = torch.from_numpy(orc.K_DEFAULT.copy())
+        res = tools.multi_camera_visibility(torch.from_numpy(pts), torch.from_numpy(trans), torch.from_numpy(quats), K,
+                                            orc.IMG_HEIGHT, orc.IMG_WIDTH, 1.0, 10.0, device=torch.device("cpu"),
+                                            group=dist.group.WORLD)
+        q.put((rank, [(r["camera"], r["frustum_idx"].numpy(), r["visible_idx"].numpy()) for r in res]))
+    except Exception as e:
+        q.put((rank, repr(e)))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_multi_camera_visibility_replicates_cameras():
+    """Per-camera visibility over N > 1 ranks is REPLICATED work (HPR does not shard): rank r takes cameras
+    r, r + world, ...; together the ranks cover every camera once, and each camera's index sets are what one process
+    computes for it (reference src/pc_processor.py:158-182 per camera)."""
+    from oracle import coverage_oracle as orc
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rig_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted([q.get(timeout=240) for _ in range(world)], key=lambda t: t[0])
+    assert all(isinstance(r[1], list) for r in results), results
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [c for c, _, _ in results[0][1]] == [0, 2, 4] and [c for c, _, _ in results[1][1]] == [1, 3]
+    pts, trans, quats = _rig_case()
+    K, W, H = orc.load_intrinsics()
+    seen = 0
+    for _, cams in results:
+        for c, fr_idx, vis_idx in cams:
+            cam = orc.to_camera_frame(pts, quats[c], trans[c], dtype=np.float32)
+            cam = np.asarray(cam, np.float32).reshape(-1, 3)
+            culled, dm, fm = orc.frustum_cull(cam.T, H, W, K, 1.0, 10.0)
+            ref_idx = np.flatnonzero(dm & fm)
+            assert len(ref_idx) > 50 and np.array_equal(fr_idx, ref_idx)
+            vis, _ = orc.hidden_pts_removal(culled, 2)
+            assert np.array_equal(vis_idx, ref_idx[vis]) and 0 < len(vis) < len(ref_idx)
+            seen += 1
+    assert seen == 5
