@@ -297,12 +297,9 @@ __device__ __forceinline__ void hull_finalize(int rc, const int* cert, const Hul
 // 1.0 in the LP update); here the evaluation runs with every undecided lane and lanes that are violated in the same
 // iteration update together.  A point that exhausts its evaluation budget or needs a wider search, a wider tilt box or a
 // bigger active set goes on the list of the cooperative stages (hull_local_kernel, hull_far_kernel).
-// resident blocks per SM the register allocation aims at: 1 = the compiler's choice (91 registers, 5 blocks); 6 (80
-// registers) and 8 (64) measured within 2 % of it, 12 (40 registers, spills) 20 % slower
-#ifndef HULL_CLASSIFY_MINB
-#define HULL_CLASSIFY_MINB 1
-#endif
-__global__ void __launch_bounds__(128, HULL_CLASSIFY_MINB)
+// (register allocation: the compiler's choice is 91 registers = 5 blocks per SM; capping it at 80 or 64 registers measured
+// within 2 % of that, 40 registers with spills 20 % slower)
+__global__ void __launch_bounds__(128)
 hull_classify_kernel(int G, const int* __restrict__ cell_start, const float4* __restrict__ sorted,
                      const unsigned long long* __restrict__ rho_max_bits, const int* __restrict__ n_valid,
                      const int* __restrict__ n_occ, uint8_t* __restrict__ mask, int* __restrict__ info,
